@@ -1,0 +1,408 @@
+"""Minimal read-only HDF5 reader (no h5py / libhdf5 in this image, no network).
+
+Covers exactly the subset that Keras-2.2.4 ``save_weights`` files and Albacore
+single-read ``.fast5`` files use: superblock v0, object
+header v1 (+ continuation blocks), symbol-table groups (B-tree v1 / SNOD / local
+heap), dataspace v1, datatypes fixed/float/string/compound-v1/vlen-string,
+layout v3 contiguous + chunked (B-tree v1 node type 1) with the deflate filter,
+attribute v1, global heap (vlen string attributes).
+
+This replaces the ``h5py.File`` calls of the reference at
+``nanorevutils/nanorev_fast5_handeler.py:59-75,132-133,157-162`` and Keras'
+``load_weights``.  The API deliberately looks like the sliver of h5py those call
+sites touch: ``File(fn)[path]`` -> Group/Dataset, ``.attrs`` (dict), ``ds[()]``,
+``group.keys()/items()/values()``, ``close()``.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class H5Error(RuntimeError):
+    pass
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) & ~7
+
+
+class _Datatype:
+    """Parsed datatype message -> numpy dtype (+ vlen marker)."""
+
+    __slots__ = ("np_dtype", "size", "is_vlen_str", "nbytes_msg")
+
+    def __init__(self, np_dtype, size, is_vlen_str, nbytes_msg):
+        self.np_dtype = np_dtype
+        self.size = size
+        self.is_vlen_str = is_vlen_str
+        self.nbytes_msg = nbytes_msg
+
+
+def _parse_datatype(buf: bytes, off: int) -> _Datatype:
+    cls_ver = buf[off]
+    cls = cls_ver & 0x0F
+    ver = cls_ver >> 4
+    b1, b2, b3 = buf[off + 1], buf[off + 2], buf[off + 3]
+    size = struct.unpack_from("<I", buf, off + 4)[0]
+    p = off + 8
+    if cls == 0:  # fixed point
+        if b1 & 1:
+            raise H5Error("big-endian integers unsupported")
+        signed = bool(b1 & 0x08)
+        dt = np.dtype(("<i" if signed else "<u") + str(size))
+        return _Datatype(dt, size, False, 8 + 4)
+    if cls == 1:  # float
+        if b1 & 1:
+            raise H5Error("big-endian floats unsupported")
+        return _Datatype(np.dtype("<f" + str(size)), size, False, 8 + 12)
+    if cls == 3:  # fixed string
+        return _Datatype(np.dtype("S" + str(size)), size, False, 8)
+    if cls == 6:  # compound
+        if ver != 1:
+            raise H5Error("compound datatype version %d unsupported" % ver)
+        nmemb = b1 | (b2 << 8)
+        names, formats, offsets = [], [], []
+        for _ in range(nmemb):
+            end = buf.index(b"\x00", p)
+            name = buf[p:end].decode("ascii")
+            p += _pad8(end - p + 1)
+            boff = struct.unpack_from("<I", buf, p)[0]
+            ndims = buf[p + 4]
+            if ndims != 0:
+                raise H5Error("array members in compound unsupported")
+            p += 4 + 1 + 3 + 4 + 4 + 16
+            sub = _parse_datatype(buf, p)
+            p += sub.nbytes_msg
+            names.append(name)
+            formats.append(sub.np_dtype)
+            offsets.append(boff)
+        dt = np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": size})
+        return _Datatype(dt, size, False, p - off)
+    if cls == 9:  # variable length
+        base = _parse_datatype(buf, p)
+        is_str = (b1 & 0x0F) == 1
+        return _Datatype(np.dtype("V16"), size, is_str or True, 8 + base.nbytes_msg)
+    raise H5Error("datatype class %d unsupported" % cls)
+
+
+def _parse_dataspace(buf: bytes, off: int):
+    ver, rank, flags = buf[off], buf[off + 1], buf[off + 2]
+    if ver == 1:
+        p = off + 8
+    elif ver == 2:
+        p = off + 4
+    else:
+        raise H5Error("dataspace version %d unsupported" % ver)
+    dims = struct.unpack_from("<%dQ" % rank, buf, p) if rank else ()
+    return tuple(int(d) for d in dims)
+
+
+class _Object:
+    def __init__(self, f: "File", addr: int, name: str):
+        self._f = f
+        self._addr = addr
+        self.name = name
+        self._msgs = f._read_object_header(addr)
+        self._attrs = None
+
+    @property
+    def attrs(self) -> dict:
+        if self._attrs is None:
+            self._attrs = {}
+            for mtype, data in self._msgs:
+                if mtype == 0x000C:
+                    k, v = self._f._parse_attribute(data)
+                    self._attrs[k] = v
+        return self._attrs
+
+
+class Dataset(_Object):
+    def __init__(self, f, addr, name):
+        super().__init__(f, addr, name)
+        self.shape = ()
+        self._dt = None
+        self._layout = None
+        self._filters = []
+        for mtype, data in self._msgs:
+            if mtype == 0x0001:
+                self.shape = _parse_dataspace(data, 0)
+            elif mtype == 0x0003:
+                self._dt = _parse_datatype(data, 0)
+            elif mtype == 0x0008:
+                self._layout = data
+            elif mtype == 0x000B:
+                self._filters = self._parse_filters(data)
+        if self._dt is None or self._layout is None:
+            raise H5Error("object at %d is not a dataset" % addr)
+        self.dtype = self._dt.np_dtype
+
+    @staticmethod
+    def _parse_filters(data: bytes):
+        if data[0] != 1:
+            raise H5Error("filter pipeline version %d unsupported" % data[0])
+        n = data[1]
+        p = 8
+        out = []
+        for _ in range(n):
+            fid, name_len, _flags, ncd = struct.unpack_from("<HHHH", data, p)
+            p += 8 + _pad8(name_len)
+            p += 4 * ncd + (4 if ncd % 2 else 0)
+            out.append(fid)
+        return out
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        if key != ():
+            raise H5Error("only ds[()] is supported")
+        return self.read()
+
+    def read(self):
+        lay = self._layout
+        if lay[0] != 3:
+            raise H5Error("layout version %d unsupported" % lay[0])
+        cls = lay[1]
+        count = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        nbytes = count * self._dt.size
+        f = self._f
+        if cls == 1:  # contiguous
+            addr, size = struct.unpack_from("<QQ", lay, 2)
+            raw = b"" if addr == _UNDEF else f._buf[addr:addr + nbytes]
+            if len(raw) < nbytes:
+                raw = raw + b"\x00" * (nbytes - len(raw))
+        elif cls == 0:  # compact
+            size = struct.unpack_from("<H", lay, 2)[0]
+            raw = lay[4:4 + size][:nbytes]
+        elif cls == 2:  # chunked
+            raw = self._read_chunked(lay, nbytes)
+        else:
+            raise H5Error("layout class %d unsupported" % cls)
+        if self._dt.is_vlen_str:
+            vals = [f._read_vlen(raw[i * 16:(i + 1) * 16]) for i in range(count)]
+            return vals[0] if not self.shape else np.array(vals, dtype=object).reshape(self.shape)
+        arr = np.frombuffer(raw, dtype=self._dt.np_dtype, count=count)
+        if not self.shape:
+            return arr[0]
+        return arr.reshape(self.shape).copy()
+
+    def _read_chunked(self, lay: bytes, nbytes: int) -> bytes:
+        ndims = lay[2]
+        btree = struct.unpack_from("<Q", lay, 3)[0]
+        cdims = struct.unpack_from("<%dI" % ndims, lay, 11)
+        rank = ndims - 1
+        esize = cdims[-1]
+        if rank != 1:
+            raise H5Error("only rank-1 chunked datasets supported")
+        out = bytearray(nbytes)
+        if btree == _UNDEF:
+            return bytes(out)
+        for (csize, fmask, offs, caddr) in self._f._iter_chunks(btree, ndims):
+            payload = self._f._buf[caddr:caddr + csize]
+            for i, fid in enumerate(reversed(self._filters)):
+                if fmask & (1 << (len(self._filters) - 1 - i)):
+                    continue
+                if fid == 1:
+                    payload = zlib.decompress(payload)
+                else:
+                    raise H5Error("HDF5 filter id %d unsupported (only deflate)" % fid)
+            start = offs[0] * esize
+            # chunk may be larger than the dataset and the payload shorter than the chunk
+            n = min(len(payload), nbytes - start)
+            if n > 0:
+                out[start:start + n] = payload[:n]
+        return bytes(out)
+
+
+class Group(_Object):
+    def __init__(self, f, addr, name):
+        super().__init__(f, addr, name)
+        self._links = None
+
+    def _load(self):
+        if self._links is not None:
+            return
+        self._links = {}
+        for mtype, data in self._msgs:
+            if mtype == 0x0011:
+                btree, heap = struct.unpack_from("<QQ", data, 0)
+                for nm, oaddr in self._f._iter_group(btree, heap):
+                    self._links[nm] = oaddr
+
+    def keys(self):
+        self._load()
+        return list(self._links.keys())
+
+    def __contains__(self, k):
+        self._load()
+        return k in self._links
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def __getitem__(self, path: str):
+        obj = self
+        for part in [p for p in path.split("/") if p]:
+            if not isinstance(obj, Group):
+                raise KeyError(path)
+            obj._load()
+            if part not in obj._links:
+                raise KeyError("%s (no member %r in %s)" % (path, part, obj.name))
+            obj = obj._f._open(obj._links[part], (obj.name.rstrip("/") + "/" + part))
+        return obj
+
+
+class File(Group):
+    def __init__(self, fn, mode: str = "r"):
+        if mode != "r":
+            raise H5Error("h5mini is read-only")
+        with open(fn, "rb") as fp:
+            self._buf = fp.read()
+        b = self._buf
+        if b[:8] != _SIG:
+            raise H5Error("not an HDF5 file: %s" % fn)
+        if b[8] != 0:
+            raise H5Error("superblock version %d unsupported" % b[8])
+        if b[13] != 8 or b[14] != 8:
+            raise H5Error("only 8-byte offsets/lengths supported")
+        root = struct.unpack_from("<Q", b, 64)[0]
+        self._cache = {}
+        self.filename = fn
+        Group.__init__(self, self, root, "/")
+
+    def close(self):
+        self._buf = b""
+        self._cache = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- low level -------------------------------------------------------
+    def _open(self, addr: int, name: str):
+        if addr in self._cache:
+            return self._cache[addr]
+        msgs = self._read_object_header(addr)
+        types = {t for t, _ in msgs}
+        obj = Dataset(self, addr, name) if 0x0008 in types else Group(self, addr, name)
+        self._cache[addr] = obj
+        return obj
+
+    def _read_object_header(self, addr: int):
+        b = self._buf
+        ver, _, nmsg, _refc, hsize = struct.unpack_from("<BBHII", b, addr)
+        if ver != 1:
+            raise H5Error("object header version %d unsupported" % ver)
+        blocks = [(addr + 16, hsize)]
+        msgs = []
+        while blocks and len(msgs) < nmsg:
+            p, remaining = blocks.pop(0)
+            end = p + remaining
+            while p + 8 <= end and len(msgs) < nmsg:
+                mtype, msize, _flags = struct.unpack_from("<HHB", b, p)
+                data = b[p + 8:p + 8 + msize]
+                p += 8 + msize
+                if mtype == 0x0010:
+                    coff, clen = struct.unpack_from("<QQ", data, 0)
+                    blocks.append((coff, clen))
+                msgs.append((mtype, data))
+        return msgs
+
+    def _iter_group(self, btree: int, heap: int):
+        b = self._buf
+        if b[heap:heap + 4] != b"HEAP":
+            raise H5Error("bad local heap")
+        dseg = struct.unpack_from("<Q", b, heap + 24)[0]
+
+        def walk(node):
+            if b[node:node + 4] == b"TREE":
+                ntype, level, used = struct.unpack_from("<BBH", b, node + 4)
+                p = node + 24
+                for i in range(used):
+                    child = struct.unpack_from("<Q", b, p + 8)[0]
+                    p += 16
+                    yield from walk(child)
+            elif b[node:node + 4] == b"SNOD":
+                n = struct.unpack_from("<H", b, node + 6)[0]
+                for i in range(n):
+                    e = node + 8 + 40 * i
+                    noff, oaddr = struct.unpack_from("<QQ", b, e)
+                    s = dseg + noff
+                    nm = b[s:b.index(b"\x00", s)].decode("utf8")
+                    yield nm, oaddr
+            else:
+                raise H5Error("bad group node signature")
+
+        yield from walk(btree)
+
+    def _iter_chunks(self, node: int, ndims: int):
+        b = self._buf
+        if b[node:node + 4] != b"TREE":
+            raise H5Error("bad chunk b-tree")
+        ntype, level, used = struct.unpack_from("<BBH", b, node + 4)
+        if ntype != 1:
+            raise H5Error("expected chunk b-tree (type 1)")
+        keysz = 8 + 8 * ndims
+        p = node + 24
+        for i in range(used):
+            csize, fmask = struct.unpack_from("<II", b, p)
+            offs = struct.unpack_from("<%dQ" % ndims, b, p + 8)
+            child = struct.unpack_from("<Q", b, p + keysz)[0]
+            p += keysz + 8
+            if level > 0:
+                yield from self._iter_chunks(child, ndims)
+            else:
+                yield csize, fmask, offs, child
+
+    def _read_vlen(self, ref: bytes):
+        length, gaddr, idx = struct.unpack("<IQI", ref)
+        b = self._buf
+        if b[gaddr:gaddr + 4] != b"GCOL":
+            raise H5Error("bad global heap")
+        csize = struct.unpack_from("<Q", b, gaddr + 8)[0]
+        p = gaddr + 16
+        end = gaddr + csize
+        while p + 16 <= end:
+            oidx, _rc, _r, osize = struct.unpack_from("<HHIQ", b, p)
+            if oidx == idx:
+                return b[p + 16:p + 16 + length]
+            if oidx == 0:
+                break
+            p += 16 + _pad8(osize)
+        raise H5Error("global heap object %d not found" % idx)
+
+    def _parse_attribute(self, data: bytes):
+        ver = data[0]
+        if ver != 1:
+            raise H5Error("attribute version %d unsupported" % ver)
+        nsz, dtsz, dssz = struct.unpack_from("<HHH", data, 2)
+        p = 8
+        name = data[p:p + nsz].split(b"\x00")[0].decode("utf8")
+        p += _pad8(nsz)
+        dt = _parse_datatype(data, p)
+        p += _pad8(dtsz)
+        shape = _parse_dataspace(data, p)
+        p += _pad8(dssz)
+        count = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        raw = data[p:p + count * dt.size]
+        if dt.is_vlen_str:
+            vals = [self._read_vlen(raw[i * 16:(i + 1) * 16]) for i in range(count)]
+            return name, (vals[0] if not shape else np.array(vals, dtype=object))
+        if len(raw) < count * dt.size:
+            return name, np.zeros(shape, dtype=dt.np_dtype)
+        arr = np.frombuffer(raw, dtype=dt.np_dtype, count=count)
+        return name, (arr[0] if not shape else arr.reshape(shape).copy())
