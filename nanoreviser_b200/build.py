@@ -1,0 +1,74 @@
+"""In-tree build of libnrv.so (nvcc, sm_100a only).  ``python -m nanoreviser_b200.build [--force] [-v]``.
+
+The library links the CUDA runtime statically and depends on nothing else, so the built ``.so``
+travels with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "csrc", "_obj")
+LIB = os.path.join(PKG, "libnrv.so")
+
+SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_api.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "nrv.h"))
+    nvcc = _nvcc()
+    jobs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            jobs.append((src, cmd))
+
+    def run(job):
+        name, cmd = job
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        return name, p.returncode, p.stdout + p.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for name, rc, out in ex.map(run, jobs):
+                if verbose or rc != 0:
+                    sys.stderr.write("[nvcc %s]\n%s\n" % (name, out))
+                if rc != 0:
+                    raise RuntimeError("nvcc failed on %s" % name)
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("link of libnrv.so failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,599 @@
+// C-ABI of libnrv.so (include/nrv.h): handle, grow-only device arenas, weight re-packing, and the
+// orchestration of K1..K4 on one CUDA stream.  No allocation on the hot path after warm-up.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "nrv_common.cuh"
+
+using namespace nrv;
+
+namespace {
+
+std::string g_create_error;
+
+struct Arena {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedArena {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+enum { ST_STATS = 0, ST_FEAT, ST_CNN, ST_L0, ST_L1, ST_L2, ST_L3, ST_HEADS, ST_DECODE, ST_COUNT };
+
+}  // namespace
+
+struct nrv_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool sticky = false;
+    int window = 11;
+    ModelDev m[2];
+    std::vector<void*> weight_allocs;
+    int64_t launches = 0;
+    int64_t chunk_windows = 148 * 4 * 64;
+    // inputs / per-batch arenas
+    Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
+        d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag,
+        d_segmean, d_segstd, d_sigwin;
+    PinnedArena h_off, h_flag;
+    bool timing = false;
+    float stage_ms[ST_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(nrv_handle* h, int code, const std::string& msg) {
+    if (h) { h->err = msg; if (code == NRV_E_CUDA) h->sticky = true; }
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(h, NRV_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+template <class T>
+T* upload(nrv_handle* h, const std::vector<T>& v, cudaError_t* err) {
+    void* p = nullptr;
+    *err = cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 16));
+    if (*err != cudaSuccess) return nullptr;
+    *err = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    h->weight_allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+}
+
+void bn_fold(const float* bn, int n, std::vector<float>& scale, std::vector<float>& shift) {
+    // tf.nn.batch_normalization: inv = gamma * rsqrt(var + eps); y = x*inv + (beta - mean*inv); eps = 1e-3 (Keras)
+    scale.resize(n); shift.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const float gamma = bn[i], beta = bn[n + i], mean = bn[2 * n + i], var = bn[3 * n + i];
+        const float inv = gamma / sqrtf(var + 1e-3f);
+        scale[i] = inv;
+        shift[i] = beta - mean * inv;
+    }
+}
+
+int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
+    static const int IN_A[4] = {0, 32, 128, 256}, IN_B[4] = {6, 0, 64, 0}, UU[4] = {16, 64, 128, 64};
+    cudaError_t e = cudaSuccess;
+    out->window = w->window;
+    out->n_class = w->n_class;
+    // ---- CNN ----
+    std::vector<float> blob(264), s, t;
+    memcpy(&blob[0], w->conv1_k, 24 * sizeof(float));
+    memcpy(&blob[24], w->conv1_b, 8 * sizeof(float));
+    bn_fold(w->bn1, 8, s, t);
+    memcpy(&blob[32], s.data(), 32); memcpy(&blob[40], t.data(), 32);
+    memcpy(&blob[48], w->conv2_k, 192 * sizeof(float));
+    memcpy(&blob[240], w->conv2_b, 8 * sizeof(float));
+    bn_fold(w->bn2, 8, s, t);
+    memcpy(&blob[248], s.data(), 32); memcpy(&blob[256], t.data(), 32);
+    out->cnn.blob = upload(h, blob, &e); if (e) goto cuda_fail;
+    out->cnn.dense_k = upload(h, std::vector<float>(w->sig_dense_k, w->sig_dense_k + 400 * 64), &e); if (e) goto cuda_fail;
+    out->cnn.dense_b = upload(h, std::vector<float>(w->sig_dense_b, w->sig_dense_b + 64), &e); if (e) goto cuda_fail;
+    // ---- LSTM layers ----
+    for (int l = 0; l < 4; ++l) {
+        LstmLayerDev& L = out->lstm[l];
+        const int in = IN_A[l] + IN_B[l], u = UU[l];
+        L.in_a = IN_A[l]; L.in_b = IN_B[l]; L.u = u; L.k = in + u; L.k_pad = (L.k + 15) / 16 * 16;
+        for (int d = 0; d < 2; ++d) {
+            const nrv_lstm_dir& src = w->lstm[l][d];
+            std::vector<float> wc((size_t)L.k_pad * 4 * u, 0.f), bb(4 * u);
+            for (int r = 0; r < in; ++r)
+                for (int g = 0; g < 4; ++g)
+                    for (int j = 0; j < u; ++j) wc[(size_t)r * 4 * u + j * 4 + g] = src.kernel[(size_t)r * 4 * u + g * u + j];
+            for (int r = 0; r < u; ++r)
+                for (int g = 0; g < 4; ++g)
+                    for (int j = 0; j < u; ++j)
+                        wc[(size_t)(in + r) * 4 * u + j * 4 + g] = src.recurrent[(size_t)r * 4 * u + g * u + j];
+            for (int g = 0; g < 4; ++g)
+                for (int j = 0; j < u; ++j) bb[j * 4 + g] = src.bias[g * u + j];
+            L.wcat[d] = upload(h, wc, &e); if (e) goto cuda_fail;
+            L.bias[d] = upload(h, bb, &e); if (e) goto cuda_fail;
+        }
+        if (l < 3) {
+            bn_fold(w->bn_rnn[l], 2 * u, s, t);
+            L.bn_scale = upload(h, s, &e); if (e) goto cuda_fail;
+            L.bn_shift = upload(h, t, &e); if (e) goto cuda_fail;
+        } else {
+            L.bn_scale = nullptr; L.bn_shift = nullptr;
+        }
+    }
+    // ---- heads ----
+    {
+        HeadsDev& H = out->heads;
+        const int W = w->window, nc = w->n_class;
+        H.n_class = nc;
+        H.d1k = upload(h, std::vector<float>(w->dense1_k, w->dense1_k + 128 * 128), &e); if (e) goto cuda_fail;
+        H.d1b = upload(h, std::vector<float>(w->dense1_b, w->dense1_b + 128), &e); if (e) goto cuda_fail;
+        H.d2k = upload(h, std::vector<float>(w->dense2_k, w->dense2_k + 128 * 32), &e); if (e) goto cuda_fail;
+        H.d2b = upload(h, std::vector<float>(w->dense2_b, w->dense2_b + 32), &e); if (e) goto cuda_fail;
+        H.mk = upload(h, std::vector<float>(w->main_k, w->main_k + 32 * 6), &e); if (e) goto cuda_fail;
+        H.mb = upload(h, std::vector<float>(w->main_b, w->main_b + 6), &e); if (e) goto cuda_fail;
+        H.fk = upload(h, std::vector<float>(w->feat_k, w->feat_k + W * 6 * 16), &e); if (e) goto cuda_fail;
+        H.fb = upload(h, std::vector<float>(w->feat_b, w->feat_b + 16), &e); if (e) goto cuda_fail;
+        H.ok = upload(h, std::vector<float>(w->final_k, w->final_k + 16 * nc), &e); if (e) goto cuda_fail;
+        H.ob = upload(h, std::vector<float>(w->final_b, w->final_b + nc), &e); if (e) goto cuda_fail;
+    }
+    return NRV_OK;
+cuda_fail:
+    return fail(h, NRV_E_CUDA, std::string("weight upload: ") + cudaGetErrorString(e));
+}
+
+struct StageTimer {
+    nrv_handle* h; int stage;
+    StageTimer(nrv_handle* h_, int s) : h(h_), stage(s) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
+    ~StageTimer() {
+        if (!h->timing) return;
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->stage_ms[stage] += ms;
+    }
+};
+
+__global__ void iota_mul_kernel(int32_t* out, int64_t n, int mul) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(i * mul);
+}
+
+// Both models over all windows, chunk by chunk.  x [n_bases][6]; sig_feat[m] [n_bases][64].
+int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const float* x, float* const sig_feat[2],
+               float* const probs[2], uint8_t* const labels[2]) {
+    const int T = h->window;
+    const int64_t CH = std::min<int64_t>(h->chunk_windows, std::max<int64_t>(n_win, 1));
+    static const int widths[4] = {32, 128, 256, 128};
+    for (int l = 0; l < 4; ++l) CU(h, h->d_act[l].ensure((size_t)CH * T * widths[l] * sizeof(float)));
+    for (int64_t c0 = 0; c0 < n_win; c0 += CH) {
+        const int64_t nw = std::min(CH, n_win - c0);
+        for (int mi = 0; mi < 2; ++mi) {
+            const ModelDev& M = h->m[mi];
+            const float* in_prev = nullptr;
+            for (int l = 0; l < 4; ++l) {
+                StageTimer tm(h, ST_L0 + l);
+                const float* base_in = (l == 0) ? x : (l == 2 ? sig_feat[mi] : nullptr);
+                int n = launch_lstm_layer(l, M.lstm[l], in_prev, base_in, win_base + c0, nw, T, h->d_act[l].as<float>(),
+                                          h->stream);
+                h->launches += n;
+                in_prev = h->d_act[l].as<float>();
+            }
+            {
+                StageTimer tm(h, ST_HEADS);
+                int n = launch_heads(M.heads, in_prev, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
+                                     labels[mi] ? labels[mi] + c0 : nullptr, h->stream);
+                if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
+                h->launches += n;
+            }
+        }
+    }
+    CU(h, cudaGetLastError());
+    return NRV_OK;
+}
+
+struct Offsets {
+    int64_t n_reads = 0, n_samples = 0, n_bases = 0, n_win = 0;
+    const int64_t *d_sig_off = nullptr, *d_base_off = nullptr, *d_win_off = nullptr;
+};
+
+// host offsets -> pinned staging -> device; also derives the window CSR.
+int stage_offsets(nrv_handle* h, int64_t R, const int64_t* sig_off, const int64_t* base_off, Offsets* o) {
+    const size_t n = (size_t)R + 1;
+    CU(h, h->h_off.ensure(3 * n * sizeof(int64_t)));
+    CU(h, h->d_off.ensure(3 * n * sizeof(int64_t)));
+    // the previous batch's async upload from this staging buffer must be done before it is overwritten
+    CU(h, cudaStreamSynchronize(h->stream));
+    int64_t* hs = h->h_off.as<int64_t>();
+    int64_t* hb = hs + n;
+    int64_t* hw = hb + n;
+    for (size_t i = 0; i < n; ++i) { hs[i] = sig_off ? sig_off[i] : 0; hb[i] = base_off[i]; }
+    hw[0] = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        if (hb[r + 1] < hb[r] || hs[r + 1] < hs[r]) return fail(h, NRV_E_INVALID, "offsets must be non-decreasing");
+        const int64_t N = hb[r + 1] - hb[r];
+        hw[r + 1] = hw[r] + std::max<int64_t>(N - h->window, 0);
+    }
+    if (hb[0] != 0 || hs[0] != 0) return fail(h, NRV_E_INVALID, "offsets must start at 0");
+    CU(h, cudaMemcpyAsync(h->d_off.p, hs, 3 * n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    o->n_reads = R; o->n_samples = hs[R]; o->n_bases = hb[R]; o->n_win = hw[R];
+    o->d_sig_off = h->d_off.as<int64_t>();
+    o->d_base_off = o->d_sig_off + n;
+    o->d_win_off = o->d_base_off + n;
+    if (o->n_bases >= (int64_t)INT32_MAX || o->n_samples >= ((int64_t)1 << 40))
+        return fail(h, NRV_E_INVALID, "batch too large (total bases must be < 2^31)");
+    return NRV_OK;
+}
+
+int check_batch(nrv_handle* h, const nrv_batch* b) {
+    if (!h) return NRV_E_INVALID;
+    if (h->sticky) return NRV_E_CUDA;
+    if (!b || b->n_reads < 0 || !b->sig_off || !b->base_off) return fail(h, NRV_E_INVALID, "bad batch");
+    if (b->n_reads > 0 && (!b->signal || !b->starts || !b->bases || !b->ev_mean || !b->ev_std || !b->last_dur))
+        return fail(h, NRV_E_INVALID, "batch has NULL arrays");
+    return NRV_OK;
+}
+
+struct DevBatch {
+    const int16_t* signal; const int32_t* starts; const uint8_t* bases; const float* evm; const float* evs;
+    const int32_t* last_dur;
+};
+
+int upload_batch(nrv_handle* h, const nrv_batch* b, const Offsets& o, DevBatch* d) {
+    CU(h, h->d_signal.ensure((size_t)o.n_samples * 2 + 64));
+    CU(h, h->d_starts.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, h->d_bases.ensure((size_t)o.n_bases + 16));
+    CU(h, h->d_evm.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, h->d_evs.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, h->d_lastdur.ensure((size_t)o.n_reads * 4 + 16));
+    CU(h, cudaMemcpyAsync(h->d_signal.p, b->signal, (size_t)o.n_samples * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_starts.p, b->starts, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_bases.p, b->bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_evm.p, b->ev_mean, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_evs.p, b->ev_std, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_lastdur.p, b->last_dur, (size_t)o.n_reads * 4, cudaMemcpyHostToDevice, h->stream));
+    d->signal = h->d_signal.as<int16_t>(); d->starts = h->d_starts.as<int32_t>(); d->bases = h->d_bases.as<uint8_t>();
+    d->evm = h->d_evm.as<float>(); d->evs = h->d_evs.as<float>(); d->last_dur = h->d_lastdur.as<int32_t>();
+    return NRV_OK;
+}
+
+// K1: stats + maps (+ features).  Fills shift/scale/status/base_read arenas.
+int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x, double* seg_mean, double* seg_std) {
+    CU(h, h->d_shift.ensure((size_t)o.n_reads * 8 + 16));
+    CU(h, h->d_scale.ensure((size_t)o.n_reads * 8 + 16));
+    CU(h, h->d_status.ensure((size_t)o.n_reads * 4 + 16));
+    CU(h, h->d_base_read.ensure((size_t)o.n_bases * 4 + 16));
+    if (want_x) CU(h, h->d_x.ensure((size_t)o.n_bases * 6 * 4 + 16));
+    {
+        StageTimer tm(h, ST_STATS);
+        h->launches += launch_read_stats(d.signal, o.d_sig_off, o.d_base_off, d.starts, d.last_dur, h->window, o.n_reads,
+                                         h->d_shift.as<double>(), h->d_scale.as<double>(), h->d_status.as<int32_t>(),
+                                         h->stream);
+        h->launches += launch_base_read_map(o.d_base_off, o.n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
+    }
+    {
+        StageTimer tm(h, ST_FEAT);
+        h->launches += launch_base_features(d.signal, o.d_sig_off, d.starts, o.d_base_off, d.bases, d.evm, d.evs,
+                                            d.last_dur, h->d_base_read.as<int32_t>(), h->d_shift.as<double>(),
+                                            h->d_scale.as<double>(), o.n_bases, want_x ? h->d_x.as<float>() : nullptr,
+                                            seg_mean, seg_std, h->stream);
+    }
+    CU(h, cudaGetLastError());
+    return NRV_OK;
+}
+
+int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) {
+    int rc = check_batch(h, b);
+    if (rc) return rc;
+    if (!r || !r->revised || !r->out_off || !r->status) return fail(h, NRV_E_INVALID, "result needs revised/out_off/status");
+    CU(h, cudaSetDevice(h->device));
+    for (int i = 0; i < ST_COUNT; ++i) h->stage_ms[i] = 0.f;
+    Offsets o;
+    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o);
+    if (rc) return rc;
+    if (r->revised_cap < o.n_bases) return fail(h, NRV_E_CAPACITY, "revised_cap smaller than the number of bases");
+    DevBatch d;
+    if (host_io) {
+        rc = upload_batch(h, b, o, &d);
+        if (rc) return rc;
+    } else {
+        d.signal = b->signal; d.starts = b->starts; d.bases = b->bases; d.evm = b->ev_mean; d.evs = b->ev_std;
+        d.last_dur = b->last_dur;
+    }
+    rc = run_segment(h, d, o, true, nullptr, nullptr);
+    if (rc) return rc;
+    // ---- K2: CNN per base, both models -------------------------------------------------------
+    for (int mi = 0; mi < 2; ++mi) CU(h, h->d_sigfeat[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 4 + 16));
+    {
+        StageTimer tm(h, ST_CNN);
+        h->launches += launch_cnn(&h->m[0], &h->m[1], d.signal, o.d_sig_off, d.starts, o.d_base_off,
+                                  h->d_base_read.as<int32_t>(), h->d_shift.as<double>(), h->d_scale.as<double>(), nullptr,
+                                  o.n_bases, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), h->stream);
+    }
+    // ---- K3: window map + Bi-LSTM stack + heads --------------------------------------------------
+    CU(h, h->d_win_base.ensure((size_t)o.n_win * 4 + 16));
+    h->launches += launch_window_map(o.d_base_off, o.d_win_off, nullptr, o.n_reads, h->window, h->d_win_base.as<int32_t>(),
+                                     h->stream);
+    float* probs[2] = {nullptr, nullptr};
+    uint8_t* labels[2];
+    if (host_io) {
+        if (r->p1) { CU(h, h->d_probs[0].ensure((size_t)o.n_win * 6 * 4 + 16)); probs[0] = h->d_probs[0].as<float>(); }
+        if (r->p2) { CU(h, h->d_probs[1].ensure((size_t)o.n_win * 5 * 4 + 16)); probs[1] = h->d_probs[1].as<float>(); }
+        for (int mi = 0; mi < 2; ++mi) { CU(h, h->d_y[mi].ensure((size_t)o.n_win + 16)); labels[mi] = h->d_y[mi].as<uint8_t>(); }
+    } else {
+        probs[0] = r->p1; probs[1] = r->p2;
+        uint8_t* user[2] = {r->y1, r->y2};
+        for (int mi = 0; mi < 2; ++mi) {
+            if (user[mi]) labels[mi] = user[mi];
+            else { CU(h, h->d_y[mi].ensure((size_t)o.n_win + 16)); labels[mi] = h->d_y[mi].as<uint8_t>(); }
+        }
+    }
+    float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
+    rc = run_models(h, o.n_win, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels);
+    if (rc) return rc;
+    // ---- K4: decode --------------------------------------------------------------------------------
+    const int64_t n_tiles = decode_tile_count(o.n_bases);
+    CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
+    CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
+    CU(h, h->d_flag.ensure(16));
+    CU(h, cudaMemsetAsync(h->d_flag.p, 0, 4, h->stream));
+    uint8_t* d_rev; int64_t* d_outoff;
+    if (host_io) {
+        CU(h, h->d_revised.ensure((size_t)r->revised_cap + 16));
+        CU(h, h->d_outoff.ensure((size_t)(o.n_reads + 1) * 8));
+        d_rev = h->d_revised.as<uint8_t>(); d_outoff = h->d_outoff.as<int64_t>();
+    } else {
+        d_rev = r->revised; d_outoff = r->out_off;
+    }
+    {
+        StageTimer tm(h, ST_DECODE);
+        h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
+                                     h->d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
+                                     h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, h->d_flag.as<int>(),
+                                     h->stream);
+    }
+    CU(h, cudaGetLastError());
+    if (!host_io) {
+        CU(h, cudaMemcpyAsync(r->status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToDevice, h->stream));
+        return NRV_OK;
+    }
+    // ---- D2H ---------------------------------------------------------------------------------------
+    CU(h, h->h_flag.ensure(16));
+    CU(h, cudaMemcpyAsync(r->out_off, d_outoff, (size_t)(o.n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(r->status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_flag.p, h->d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    if (r->y1) CU(h, cudaMemcpyAsync(r->y1, labels[0], (size_t)o.n_win, cudaMemcpyDeviceToHost, h->stream));
+    if (r->y2) CU(h, cudaMemcpyAsync(r->y2, labels[1], (size_t)o.n_win, cudaMemcpyDeviceToHost, h->stream));
+    if (r->p1) CU(h, cudaMemcpyAsync(r->p1, probs[0], (size_t)o.n_win * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (r->p2) CU(h, cudaMemcpyAsync(r->p2, probs[1], (size_t)o.n_win * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (*h->h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
+    const int64_t total = r->out_off[o.n_reads];
+    CU(h, cudaMemcpyAsync(r->revised, d_rev, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NRV_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* nrv_version(void) { return "nanoreviser-b200 0.1 (sm_100a)"; }
+
+int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights* m2, nrv_handle** out) {
+    if (!out || !m1 || !m2) return fail(nullptr, NRV_E_INVALID, "NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, NRV_E_NODEVICE, "no CUDA device available (libnrv has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, NRV_E_INVALID, "bad device index");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, NRV_E_NODEVICE, "libnrv is built for sm_100a (B200) only");
+    if (m1->window != m2->window || m1->window < 5 || m1->window > NRV_MAX_T || (m1->window & 1) == 0)
+        return fail(nullptr, NRV_E_INVALID, "window must be odd, 5..13, and equal for both models");
+    if (m1->n_class != 6 || m2->n_class != 5) return fail(nullptr, NRV_E_INVALID, "model1 must have 6 classes, model2 5");
+    nrv_handle* h = new nrv_handle();
+    h->device = device;
+    h->window = m1->window;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("nrv_create: ") + cudaGetErrorString(e);
+        delete h;
+        return NRV_E_CUDA;
+    }
+    int rc = pack_model(h, m1, &h->m[0]);
+    if (rc == NRV_OK) rc = pack_model(h, m2, &h->m[1]);
+    if (rc != NRV_OK) { g_create_error = h->err; nrv_destroy(h); return rc; }
+    const char* ch = getenv("NRV_CHUNK_WINDOWS");
+    if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
+    *out = h;
+    return NRV_OK;
+}
+
+void nrv_destroy(nrv_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->weight_allocs) cudaFree(p);
+    Arena* arenas[] = {&h->d_signal, &h->d_starts, &h->d_bases, &h->d_evm, &h->d_evs, &h->d_lastdur, &h->d_off, &h->d_shift,
+                       &h->d_scale, &h->d_status, &h->d_base_read, &h->d_win_base, &h->d_x, &h->d_sigfeat[0],
+                       &h->d_sigfeat[1], &h->d_act[0], &h->d_act[1], &h->d_act[2], &h->d_act[3], &h->d_probs[0],
+                       &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff,
+                       &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin};
+    for (Arena* a : arenas) a->release();
+    h->h_off.release(); h->h_flag.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* nrv_last_error(const nrv_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t nrv_launch_count(const nrv_handle* h) { return h ? h->launches : 0; }
+int nrv_set_stage_timing(nrv_handle* h, int enable) { if (!h) return NRV_E_INVALID; h->timing = enable != 0; return NRV_OK; }
+int nrv_get_stage_ms(const nrv_handle* h, float out[9]) {
+    if (!h || !out) return NRV_E_INVALID;
+    for (int i = 0; i < ST_COUNT; ++i) out[i] = h->stage_ms[i];
+    return NRV_OK;
+}
+void* nrv_stream(const nrv_handle* h) { return h ? (void*)h->stream : nullptr; }
+int nrv_synchronize(nrv_handle* h) {
+    if (!h) return NRV_E_INVALID;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NRV_OK;
+}
+
+int nrv_segment(nrv_handle* h, const nrv_batch* b, double* shift, double* scale, double* seg_mean, double* seg_std,
+                float* x, float* sig_win, int32_t* status) {
+    int rc = check_batch(h, b);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    Offsets o;
+    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o);
+    if (rc) return rc;
+    DevBatch d;
+    rc = upload_batch(h, b, o, &d);
+    if (rc) return rc;
+    if (seg_mean) CU(h, h->d_segmean.ensure((size_t)o.n_bases * 8 + 16));
+    if (seg_std) CU(h, h->d_segstd.ensure((size_t)o.n_bases * 8 + 16));
+    rc = run_segment(h, d, o, true, seg_mean ? h->d_segmean.as<double>() : nullptr,
+                     seg_std ? h->d_segstd.as<double>() : nullptr);
+    if (rc) return rc;
+    if (sig_win) {
+        CU(h, h->d_sigwin.ensure((size_t)o.n_bases * NRV_SIG * 4 + 16));
+        h->launches += launch_sig_windows(d.signal, o.d_sig_off, d.starts, o.d_base_off, h->d_base_read.as<int32_t>(),
+                                          h->d_shift.as<double>(), h->d_scale.as<double>(), o.n_bases,
+                                          h->d_sigwin.as<float>(), h->stream);
+        CU(h, cudaMemcpyAsync(sig_win, h->d_sigwin.p, (size_t)o.n_bases * NRV_SIG * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (shift) CU(h, cudaMemcpyAsync(shift, h->d_shift.p, (size_t)o.n_reads * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (scale) CU(h, cudaMemcpyAsync(scale, h->d_scale.p, (size_t)o.n_reads * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (seg_mean) CU(h, cudaMemcpyAsync(seg_mean, h->d_segmean.p, (size_t)o.n_bases * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (seg_std) CU(h, cudaMemcpyAsync(seg_std, h->d_segstd.p, (size_t)o.n_bases * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (x) CU(h, cudaMemcpyAsync(x, h->d_x.p, (size_t)o.n_bases * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    return NRV_OK;
+}
+
+int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X, float* p1, float* p2) {
+    if (!h) return NRV_E_INVALID;
+    if (h->sticky) return NRV_E_CUDA;
+    if (n < 0 || (n > 0 && (!S || !X))) return fail(h, NRV_E_INVALID, "bad arguments");
+    if (n == 0) return NRV_OK;
+    CU(h, cudaSetDevice(h->device));
+    const int W = h->window;
+    const int64_t nb = n * W;
+    if (nb >= (int64_t)INT32_MAX) return fail(h, NRV_E_INVALID, "too many windows in one call");
+    CU(h, h->d_sigwin.ensure((size_t)nb * NRV_SIG * 4));
+    CU(h, h->d_x.ensure((size_t)nb * 6 * 4));
+    CU(h, h->d_win_base.ensure((size_t)n * 4));
+    for (int mi = 0; mi < 2; ++mi) CU(h, h->d_sigfeat[mi].ensure((size_t)nb * NRV_SIGFEAT * 4));
+    CU(h, h->d_probs[0].ensure((size_t)n * 6 * 4));
+    CU(h, h->d_probs[1].ensure((size_t)n * 5 * 4));
+    CU(h, cudaMemcpyAsync(h->d_sigwin.p, S, (size_t)nb * NRV_SIG * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_x.p, X, (size_t)nb * 6 * 4, cudaMemcpyHostToDevice, h->stream));
+    iota_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_win_base.as<int32_t>(), n, W);
+    h->launches += 1;
+    h->launches += launch_cnn(&h->m[0], &h->m[1], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              h->d_sigwin.as<float>(), nb, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(),
+                              h->stream);
+    float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
+    float* probs[2] = {h->d_probs[0].as<float>(), h->d_probs[1].as<float>()};
+    uint8_t* labels[2] = {nullptr, nullptr};
+    int rc = run_models(h, n, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels);
+    if (rc) return rc;
+    if (p1) CU(h, cudaMemcpyAsync(p1, probs[0], (size_t)n * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (p2) CU(h, cudaMemcpyAsync(p2, probs[1], (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    return NRV_OK;
+}
+
+int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const uint8_t* bases, const uint8_t* y1,
+               const uint8_t* y2, const int32_t* status, uint8_t* revised, int64_t revised_cap, int64_t* out_off) {
+    if (!h) return NRV_E_INVALID;
+    if (h->sticky) return NRV_E_CUDA;
+    if (n_reads < 0 || !base_off || !revised || !out_off) return fail(h, NRV_E_INVALID, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    Offsets o;
+    int rc = stage_offsets(h, n_reads, nullptr, base_off, &o);
+    if (rc) return rc;
+    if (o.n_bases > 0 && !bases) return fail(h, NRV_E_INVALID, "bases is NULL");
+    if (o.n_win > 0 && (!y1 || !y2)) return fail(h, NRV_E_INVALID, "labels are NULL");
+    if (revised_cap < o.n_bases) return fail(h, NRV_E_CAPACITY, "revised_cap smaller than the number of bases");
+    CU(h, h->d_bases.ensure((size_t)o.n_bases + 16));
+    CU(h, h->d_y[0].ensure((size_t)o.n_win + 16));
+    CU(h, h->d_y[1].ensure((size_t)o.n_win + 16));
+    CU(h, h->d_status.ensure((size_t)n_reads * 4 + 16));
+    CU(h, h->d_base_read.ensure((size_t)o.n_bases * 4 + 16));
+    const int64_t n_tiles = decode_tile_count(o.n_bases);
+    CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
+    CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
+    CU(h, h->d_flag.ensure(16));
+    CU(h, h->h_flag.ensure(16));
+    CU(h, h->d_revised.ensure((size_t)revised_cap + 16));
+    CU(h, h->d_outoff.ensure((size_t)(n_reads + 1) * 8));
+    CU(h, cudaMemsetAsync(h->d_flag.p, 0, 4, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_bases.p, bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_y[0].p, y1, (size_t)o.n_win, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_y[1].p, y2, (size_t)o.n_win, cudaMemcpyHostToDevice, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(h->d_status.p, status, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
+    else CU(h, cudaMemsetAsync(h->d_status.p, 0, (size_t)n_reads * 4 + 16, h->stream));
+    h->launches += launch_base_read_map(o.d_base_off, n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
+    h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), h->d_bases.as<uint8_t>(),
+                                 h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), h->d_status.as<int32_t>(), n_reads,
+                                 o.n_bases, h->window, h->d_counts.as<int32_t>(), h->d_tiles.as<int64_t>(),
+                                 h->d_revised.as<uint8_t>(), revised_cap, h->d_outoff.as<int64_t>(), h->d_flag.as<int>(),
+                                 h->stream);
+    CU(h, cudaMemcpyAsync(out_off, h->d_outoff.p, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_flag.p, h->d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (*h->h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
+    CU(h, cudaMemcpyAsync(revised, h->d_revised.p, (size_t)out_off[n_reads], cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    return NRV_OK;
+}
+
+int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return revise_impl(h, b, r, true); }
+int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return revise_impl(h, b, r, false); }
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Shared declarations of libnrv.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "nrv.h"
+
+#define NRV_MAX_T 13        // largest supported window W (odd 5..13); shipped weights: 11
+#define NRV_SIG 50
+#define NRV_CNN_CH 8
+#define NRV_SIGFEAT 64
+
+namespace nrv {
+
+// ---- packed device weights of one model ---------------------------------------------------
+struct LstmLayerDev {
+    int in_a, in_b, u, k, k_pad;       // K = in_a + in_b + u (x_t rows, then h rows); k_pad = roundup(K, 16)
+    float* wcat[2];                    // [k_pad][4u], column = unit*4 + gate (i,f,c,o), rows [x | h]
+    float* bias[2];                    // [4u] same column order
+    float* bn_scale;                   // [2u] gamma/sqrt(var+eps)  (identity for the last layer)
+    float* bn_shift;                   // [2u] beta - mean*scale
+};
+
+struct CnnDev {
+    // conv weights with the batch-norms kept separate (order is conv -> relu -> BN)
+    float* blob;                       // one allocation, offsets below (floats)
+    // [0..24) conv1_k[3][8]  [24..32) conv1_b  [32..40) bn1_scale  [40..48) bn1_shift
+    // [48..240) conv2_k[3][8][8]  [240..248) conv2_b  [248..256) bn2_scale  [256..264) bn2_shift
+    float* dense_k;                    // [400][64]
+    float* dense_b;                    // [64]
+};
+
+struct HeadsDev {
+    float *d1k, *d1b, *d2k, *d2b, *mk, *mb, *fk, *fb, *ok, *ob;
+    int n_class;
+};
+
+struct ModelDev {
+    int window, n_class;
+    CnnDev cnn;
+    LstmLayerDev lstm[4];
+    HeadsDev heads;
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) -----------------------
+// nrv_segment.cu
+int launch_read_stats(const int16_t* signal, const int64_t* sig_off, const int64_t* base_off,
+                      const int32_t* starts, const int32_t* last_dur, int window, int64_t n_reads,
+                      double* shift, double* scale, int32_t* status, cudaStream_t st);
+int launch_base_features(const int16_t* signal, const int64_t* sig_off, const int32_t* starts,
+                         const int64_t* base_off, const uint8_t* bases, const float* ev_mean,
+                         const float* ev_std, const int32_t* last_dur, const int32_t* base_read,
+                         const double* shift, const double* scale, int64_t n_bases,
+                         float* x, double* seg_mean, double* seg_std, cudaStream_t st);
+int launch_sig_windows(const int16_t* signal, const int64_t* sig_off, const int32_t* starts,
+                       const int64_t* base_off, const int32_t* base_read, const double* shift,
+                       const double* scale, int64_t n_bases, float* sig_win, cudaStream_t st);
+int launch_base_read_map(const int64_t* base_off, int64_t n_reads, int64_t n_bases, int32_t* base_read,
+                         cudaStream_t st);
+int launch_window_map(const int64_t* base_off, const int64_t* win_off, const int32_t* status,
+                      int64_t n_reads, int window, int32_t* win_base, cudaStream_t st);
+
+// nrv_cnn.cu: sig_feat[m][base][64] for both models.  If explicit_win != nullptr the windows are read
+// from it ([n_bases][50] fp32) instead of being gathered from the raw signal.
+int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, const int64_t* sig_off,
+               const int32_t* starts, const int64_t* base_off, const int32_t* base_read,
+               const double* shift, const double* scale, const float* explicit_win, int64_t n_bases,
+               float* sig_feat1, float* sig_feat2, cudaStream_t st);
+
+// nrv_lstm.cu: one Bi-LSTM layer over a chunk of windows.
+int launch_lstm_layer(int layer, const LstmLayerDev& L, const float* act_in, const float* base_in,
+                      const int32_t* win_base, int64_t n_win, int T, float* act_out, cudaStream_t st);
+
+// nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
+int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
+                 float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, cudaStream_t st);
+
+// nrv_decode.cu
+int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,
+                  const uint8_t* bases, const uint8_t* y1, const uint8_t* y2, const int32_t* status,
+                  int64_t n_reads, int64_t n_bases, int window, int32_t* counts_tmp, int64_t* tile_tmp,
+                  uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st);
+int64_t decode_tile_count(int64_t n_bases);
+
+}  // namespace nrv

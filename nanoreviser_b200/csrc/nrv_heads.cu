@@ -1,0 +1,162 @@
+// Dense heads of the predict model (lstmmodel.py:56-63 / :108-115), fused per tile of windows:
+//   per timestep Dense(128,relu) -> Dense(32,relu) -> main_out Dense(6,relu); Flatten (t*6+k);
+//   feature Dense(16,relu); final_out Dense(n_class, softmax); argmax (first maximum).
+#include "nrv_common.cuh"
+
+namespace nrv {
+
+constexpr int HD_WIN = 8;                 // windows per CTA
+constexpr int HD_THREADS = 256;
+constexpr int HD_LD = 132;                // 128 + 4 (float4 aligned, conflict-free row groups)
+
+template <int T>
+struct HeadsSmem {
+    float in[HD_WIN * T][HD_LD];
+    float d1[HD_WIN * T][HD_LD];
+    float d2[HD_WIN * T][36];
+    float d3[HD_WIN][T * 6 + 2];
+    float ft[HD_WIN][16];
+};
+
+template <int T>
+__global__ void __launch_bounds__(HD_THREADS)
+heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float* __restrict__ probs,
+             uint8_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeadsSmem<T>& s = *reinterpret_cast<HeadsSmem<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t w0 = (int64_t)blockIdx.x * HD_WIN;
+    constexpr int ROWS = HD_WIN * T;
+    // ---- load [ROWS][128] ------------------------------------------------------------------
+    for (int i = tid; i < ROWS * 32; i += HD_THREADS) {
+        const int row = i >> 5, q = i & 31;
+        const int64_t w = w0 + row / T;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w < n_win) v = __ldg(reinterpret_cast<const float4*>(act_in + (w0 * T + row) * 128) + q);
+        *reinterpret_cast<float4*>(&s.in[row][q * 4]) = v;
+    }
+    __syncthreads();
+    const int g = tid >> 5;          // window inside the tile (one warp per window)
+    const int tx = tid & 31;
+    // ---- Dense(128 -> 128, relu): thread = T rows x 4 cols -------------------------------------
+    {
+        float acc[T][4];
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(H.d1b) + tx);
+#pragma unroll
+        for (int r = 0; r < T; ++r) { acc[r][0] = bb.x; acc[r][1] = bb.y; acc[r][2] = bb.z; acc[r][3] = bb.w; }
+        const float4* Wp = reinterpret_cast<const float4*>(H.d1k) + tx;
+        for (int k = 0; k < 128; k += 4) {
+            const float4 wv0 = __ldg(Wp + (k + 0) * 32), wv1 = __ldg(Wp + (k + 1) * 32);
+            const float4 wv2 = __ldg(Wp + (k + 2) * 32), wv3 = __ldg(Wp + (k + 3) * 32);
+#pragma unroll
+            for (int r = 0; r < T; ++r) {
+                const float4 a = *reinterpret_cast<const float4*>(&s.in[g * T + r][k]);
+                acc[r][0] = fmaf(a.x, wv0.x, acc[r][0]); acc[r][1] = fmaf(a.x, wv0.y, acc[r][1]);
+                acc[r][2] = fmaf(a.x, wv0.z, acc[r][2]); acc[r][3] = fmaf(a.x, wv0.w, acc[r][3]);
+                acc[r][0] = fmaf(a.y, wv1.x, acc[r][0]); acc[r][1] = fmaf(a.y, wv1.y, acc[r][1]);
+                acc[r][2] = fmaf(a.y, wv1.z, acc[r][2]); acc[r][3] = fmaf(a.y, wv1.w, acc[r][3]);
+                acc[r][0] = fmaf(a.z, wv2.x, acc[r][0]); acc[r][1] = fmaf(a.z, wv2.y, acc[r][1]);
+                acc[r][2] = fmaf(a.z, wv2.z, acc[r][2]); acc[r][3] = fmaf(a.z, wv2.w, acc[r][3]);
+                acc[r][0] = fmaf(a.w, wv3.x, acc[r][0]); acc[r][1] = fmaf(a.w, wv3.y, acc[r][1]);
+                acc[r][2] = fmaf(a.w, wv3.z, acc[r][2]); acc[r][3] = fmaf(a.w, wv3.w, acc[r][3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < T; ++r)
+            *reinterpret_cast<float4*>(&s.d1[g * T + r][tx * 4]) =
+                make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f), fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+    }
+    __syncwarp();
+    // ---- Dense(128 -> 32, relu): thread = T rows x 1 col ---------------------------------------
+    {
+        float acc[T];
+        const float bb = __ldg(H.d2b + tx);
+#pragma unroll
+        for (int r = 0; r < T; ++r) acc[r] = bb;
+        for (int k = 0; k < 128; k += 4) {
+            const float w0v = __ldg(H.d2k + (k + 0) * 32 + tx), w1v = __ldg(H.d2k + (k + 1) * 32 + tx);
+            const float w2v = __ldg(H.d2k + (k + 2) * 32 + tx), w3v = __ldg(H.d2k + (k + 3) * 32 + tx);
+#pragma unroll
+            for (int r = 0; r < T; ++r) {
+                const float4 a = *reinterpret_cast<const float4*>(&s.d1[g * T + r][k]);
+                acc[r] = fmaf(a.x, w0v, acc[r]); acc[r] = fmaf(a.y, w1v, acc[r]);
+                acc[r] = fmaf(a.z, w2v, acc[r]); acc[r] = fmaf(a.w, w3v, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < T; ++r) s.d2[g * T + r][tx] = fmaxf(acc[r], 0.f);
+    }
+    __syncwarp();
+    // ---- main_out Dense(32 -> 6, relu) + Flatten (index t*6 + k) --------------------------------
+    for (int o = tx; o < T * 6; o += 32) {
+        const int t = o / 6, k = o - t * 6;
+        float a = __ldg(H.mb + k);
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) a = fmaf(s.d2[g * T + t][j], __ldg(H.mk + j * 6 + k), a);
+        s.d3[g][o] = fmaxf(a, 0.f);
+    }
+    __syncwarp();
+    // ---- feature Dense(T*6 -> 16, relu) ---------------------------------------------------------
+    if (tx < 16) {
+        float a = __ldg(H.fb + tx);
+        for (int j = 0; j < T * 6; ++j) a = fmaf(s.d3[g][j], __ldg(H.fk + j * 16 + tx), a);
+        s.ft[g][tx] = fmaxf(a, 0.f);
+    }
+    __syncwarp();
+    // ---- final_out Dense(16 -> n_class) + softmax + argmax --------------------------------------
+    const int nc = H.n_class;
+    float logit = -INFINITY;
+    if (tx < nc) {
+        float a = __ldg(H.ob + tx);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a = fmaf(s.ft[g][j], __ldg(H.ok + j * nc + tx), a);
+        logit = a;
+    }
+    float mx = logit;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e = (tx < nc) ? expf(logit - mx) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float p = e / sum;
+    // argmax with numpy semantics (first maximum)
+    float bp = (tx < nc) ? p : -1.f;
+    int bi = tx;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (op > bp || (op == bp && oi < bi)) { bp = op; bi = oi; }
+    }
+    const int64_t w = w0 + g;
+    if (w < n_win) {
+        if (probs && tx < nc) probs[w * nc + tx] = p;
+        if (labels && tx == 0) labels[w] = (uint8_t)bi;
+    }
+}
+
+template <int T>
+static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win, float* probs, uint8_t* labels,
+                          cudaStream_t st) {
+    auto kern = heads_kernel<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadsSmem<T>));
+    const unsigned grid = (unsigned)((n_win + HD_WIN - 1) / HD_WIN);
+    kern<<<grid, HD_THREADS, sizeof(HeadsSmem<T>), st>>>(H, act_in, n_win, probs, labels);
+    return 1;
+}
+
+int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, float* probs, uint8_t* labels,
+                 cudaStream_t st) {
+    if (n_win <= 0) return 0;
+    switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
+        case 5: return launch_heads_t<5>(H, act_in, n_win, probs, labels, st);
+        case 7: return launch_heads_t<7>(H, act_in, n_win, probs, labels, st);
+        case 9: return launch_heads_t<9>(H, act_in, n_win, probs, labels, st);
+        case 11: return launch_heads_t<11>(H, act_in, n_win, probs, labels, st);
+        case 13: return launch_heads_t<13>(H, act_in, n_win, probs, labels, st);
+    }
+    return -1;
+}
+
+}  // namespace nrv

@@ -1,0 +1,293 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI of libnrv.so) against the committed
+golden vectors (outputs of the reference's own functions, see oracle/pin_against_reference.py) and
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): segmentation / feature indices bit-exact; values computed in
+float64 by the reference bit-exact after the fp32 cast (np.std: <= 1 ulp fp32, it uses pairwise
+summation); softmax outputs max-abs <= 1e-3 vs the fp64 oracle (stated tolerance; measured ~1e-4);
+argmax labels >= 99.99 % identical; revised sequences identical on the unitest fast5 set.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P_TOL = 1e-3          # max-abs tolerance on softmax outputs vs the fp64 oracle (north_star)
+P_TOL_F32 = 2e-4      # vs the fp32 oracle on the same inputs (both fp32; only summation order differs)
+
+
+def _ulp_diff_f32(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+@pytest.fixture(scope="module")
+def unitest_batch(reads):
+    from nanoreviser_b200 import engine
+    return engine.pack_batch(reads)
+
+
+# --------------------------------------------------------------------------------------------------
+# K1: segmentation + features vs the reference's own signal_segmentation outputs
+# --------------------------------------------------------------------------------------------------
+def test_segment_matches_reference_goldens(reviser_by_species, unitest_batch, seg_golden):
+    rv = reviser_by_species("ecoli")
+    b = unitest_batch
+    shift, scale, mean, std, x, win, status = rv.segment(b, want_windows=True)
+    assert status.tolist() == [0] * 5
+    for k in range(5):
+        g = lambda n: seg_golden["r%d_%s" % (k, n)]
+        s, e = int(b.base_off[k]), int(b.base_off[k + 1])
+        assert shift[k] == float(g("shift")) and scale[k] == float(g("scale"))
+        assert np.array_equal(mean[s:e], g("seg_mean"))                      # exact integer sums / n
+        np.testing.assert_allclose(std[s:e], g("seg_std"), rtol=1e-13, atol=0)
+        gx = g("x").astype(np.float32)
+        for col in (0, 1, 3, 4, 5):
+            assert np.array_equal(x[s:e, col], gx[:, col]), "feature column %d read %d" % (col, k)
+        assert _ulp_diff_f32(x[s:e, 2], gx[:, 2]).max() <= 1
+        rows = g("win_rows")
+        assert np.array_equal(win[s:e][rows], g("win").astype(np.float32))   # indices + values bit-exact
+        assert hashlib.md5(win[s:e].tobytes()).hexdigest() == str(g("win_md5"))
+
+
+def _oracle_segment_read(b, i):
+    from oracle import nanorev_oracle as orc
+    s0, s1 = int(b.sig_off[i]), int(b.sig_off[i + 1])
+    b0, b1 = int(b.base_off[i]), int(b.base_off[i + 1])
+    return orc.signal_segmentation(b.signal[s0:s1], b.starts[b0:b1].astype(np.int64), int(b.last_dur[i]))
+
+
+def test_segment_edge_cases_vs_oracle(reviser_by_species):
+    """Ragged batch: tiny read (N <= W), constant signal (MAD = 0), a stalled base (long segment),
+    windows clipped at both signal ends, even/odd sample counts (x.5 medians), an empty read."""
+    from nanoreviser_b200 import engine, synth
+    rv = reviser_by_species("ecoli")
+    rng = np.random.default_rng(5)
+    parts = []
+    parts.append(synth.make_read(40, 1, 0))                     # ordinary
+    parts.append(synth.make_read(7, 1, 1))                      # N <= W
+    sig, st, ba, em, es, ld = synth.make_read(30, 1, 2)
+    parts.append((np.full_like(sig, 500), st, ba, em, es, ld))  # MAD == 0
+    sig, st, ba, em, es, ld = synth.make_read(50, 1, 3)         # stalled base: stretch one segment by 5000
+    cut = int(st[20])
+    sig2 = np.concatenate([sig[:cut], rng.integers(300, 900, 5000).astype(np.int16), sig[cut:]])
+    st2 = st.copy(); st2[21:] += 5000
+    parts.append((sig2, st2, ba, em, es, ld))
+    sig, st, ba, em, es, ld = synth.make_read(25, 1, 4)         # signal ends right after the last event
+    parts.append((sig[:int(st[-1]) + ld], st, ba, em, es, ld))
+    sig, st, ba, em, es, ld = synth.make_read(25, 1, 5)         # even number of samples with a .5 median
+    sig = sig[:(len(sig) // 2) * 2].copy()
+    parts.append((sig, st, ba, em, es, ld))
+    R = len(parts)
+    sig_off = np.zeros(R + 1, np.int64); base_off = np.zeros(R + 1, np.int64)
+    for i, p in enumerate(parts):
+        sig_off[i + 1] = sig_off[i] + len(p[0]); base_off[i + 1] = base_off[i] + len(p[1])
+    b = engine.Batch(np.concatenate([p[0] for p in parts]).astype(np.int16), sig_off,
+                     np.concatenate([p[1] for p in parts]).astype(np.int32), base_off,
+                     np.concatenate([p[2] for p in parts]), np.concatenate([p[3] for p in parts]),
+                     np.concatenate([p[4] for p in parts]), np.array([p[5] for p in parts], np.int32))
+    shift, scale, mean, std, x, win, status = rv.segment(b, want_windows=True)
+    assert status.tolist() == [0, engine.NRV_READ_TOO_SHORT, engine.NRV_READ_SCALE_ZERO, 0, 0, 0]
+    for i in range(R):
+        o_win, o_mean, o_std, o_shift, o_scale = _oracle_segment_read(b, i)
+        s, e = int(base_off[i]), int(base_off[i + 1])
+        assert shift[i] == o_shift and scale[i] == o_scale, i
+        assert np.array_equal(mean[s:e], o_mean), i
+        np.testing.assert_allclose(std[s:e], o_std, rtol=1e-13)
+        if status[i] != engine.NRV_READ_SCALE_ZERO:
+            assert np.array_equal(win[s:e], o_win.astype(np.float32)), i
+    # empty batch and a batch with an empty read are legal
+    e = engine.Batch(np.zeros(0, np.int16), np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(1, np.int64),
+                     np.zeros(0, np.uint8), np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32))
+    out = rv.revise_batch(e)
+    assert out.out_off.tolist() == [0]
+
+
+def test_median_mad_exact_random(reviser_by_species):
+    """shift/scale against numpy on adversarial int16 distributions (full range, ties, tiny n)."""
+    from nanoreviser_b200 import engine
+    rv = reviser_by_species("ecoli")
+    rng = np.random.default_rng(11)
+    sigs = [rng.integers(-32768, 32768, 10001).astype(np.int16), rng.integers(-32768, 32768, 10000).astype(np.int16),
+            rng.integers(0, 3, 999).astype(np.int16), np.array([5, 7], np.int16), np.array([-3], np.int16),
+            rng.integers(400, 420, 50000).astype(np.int16), np.array([32767, -32768, 0, 1], np.int16)]
+    R = len(sigs)
+    sig_off = np.zeros(R + 1, np.int64); base_off = np.arange(R + 1, dtype=np.int64)
+    for i, s in enumerate(sigs):
+        sig_off[i + 1] = sig_off[i] + len(s)
+    b = engine.Batch(np.concatenate(sigs), sig_off, np.zeros(R, np.int32), base_off, np.full(R, 65, np.uint8),
+                     np.zeros(R, np.float32), np.zeros(R, np.float32), np.ones(R, np.int32))
+    shift, scale, *_ = rv.segment(b)
+    for i, s in enumerate(sigs):
+        f = s.astype(np.float64)
+        assert shift[i] == np.median(f), i
+        assert scale[i] == np.median(np.abs(f - np.median(f))), i
+
+
+# --------------------------------------------------------------------------------------------------
+# K2 + K3: the model on explicit windows (Keras predict([S, X]) signature) vs the oracle
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("species", ["ecoli", "human"])
+def test_predict_windows_vs_oracle(reviser_by_species, weights_by_species, reads, species):
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import api
+    rv = reviser_by_species(species)
+    m1, m2 = weights_by_species(species)
+    r = reads[0]
+    sig = r.signal[r.a0:]
+    win, smean, sstd, shift, scale = orc.signal_segmentation(sig, r.starts, r.last_dur)
+    x = orc.feature_columns([chr(c) for c in r.bases], smean, sstd, shift, scale, r.length, r.ev_mean, r.ev_std)
+    X, S = orc.make_windows(x[:411], win[:411], m1.window)
+    assert X.shape[0] == 400
+    P1 = api.get_model1(reviser=rv).predict([S[..., None], X])
+    P2 = api.get_model2(reviser=rv).predict([S[..., None], X])
+    for P, m in ((P1, m1), (P2, m2)):
+        o32 = orc.forward_windows(m, S.astype(np.float32), X.astype(np.float32), np.float32)
+        o64 = orc.forward_windows(m, S.astype(np.float32).astype(np.float64), X.astype(np.float32).astype(np.float64), np.float64)
+        assert np.abs(P - o32).max() <= P_TOL_F32
+        assert np.abs(P - o64).max() <= P_TOL
+        assert np.array_equal(P.argmax(1), o64.argmax(1))
+    # single window, and random (non-physical) inputs
+    p1, p2 = rv.predict_windows(S[:1], X[:1])
+    assert np.abs(p1 - P1[:1]).max() <= 1e-6 and np.abs(p2 - P2[:1]).max() <= 1e-6
+    rng = np.random.default_rng(3)
+    Sr = rng.standard_normal((129, m1.window, 50)).astype(np.float32)
+    Xr = X[rng.integers(0, 400, 129)].astype(np.float32)
+    p1, p2 = rv.predict_windows(Sr, Xr)
+    assert np.abs(p1 - orc.forward_windows(m1, Sr, Xr, np.float32)).max() <= P_TOL_F32
+    assert np.abs(p2 - orc.forward_windows(m2, Sr, Xr, np.float32)).max() <= P_TOL_F32
+
+
+# --------------------------------------------------------------------------------------------------
+# K4: decode vs the restated (and reference-pinned) get_base_1
+# --------------------------------------------------------------------------------------------------
+def test_decode_vs_get_base_1(reviser_by_species):
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import api, engine
+    rv = reviser_by_species("ecoli")
+    rng = np.random.default_rng(21)
+    W = rv.window
+    # (a) the reference signature, many random cases incl. all-deletion, leading 'D' / '-'
+    for case in range(60):
+        M = int(rng.integers(1, 80))
+        bases = list(rng.choice(list("ACGT"), size=M))
+        y1 = rng.integers(0, 6, size=M); y2 = rng.integers(0, 5, size=M)
+        if case % 3 == 0:
+            y2 = np.clip(y1 - 1, 0, 4)
+        if case % 7 == 0:
+            y1[:] = 1; y2[:] = 0
+        assert api.get_base_1(bases, y1, y2 + 2, reviser=rv) == orc.get_base_1(bases, y1, y2 + 2), case
+    # (b) ragged multi-read batch with pass-through edges, short reads, failed reads, an empty read
+    lens = [0, 5, 11, 12, 30, 1, 2000, 64, 11, 3000]
+    base_off = np.zeros(len(lens) + 1, np.int64); base_off[1:] = np.cumsum(lens)
+    bases = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(base_off[-1]))
+    nw = int(np.maximum(np.array(lens) - W, 0).sum())
+    y1 = rng.integers(0, 6, nw).astype(np.uint8); y2 = rng.integers(0, 5, nw).astype(np.uint8)
+    agree = rng.random(nw) < 0.6
+    y2[agree] = np.clip(y1[agree].astype(int) - 1, 0, 4)
+    status = np.zeros(len(lens), np.int32); status[7] = engine.NRV_READ_SCALE_ZERO
+    rev, off = rv.decode(base_off, bases, y1, y2, status)
+    w0 = 0
+    for i, n in enumerate(lens):
+        seq = bases[base_off[i]:base_off[i + 1]].tobytes().decode()
+        M = max(n - W, 0)
+        if M > 0 and status[i] == 0:
+            core = orc.get_base_1(list(seq[5:5 + M]), y1[w0:w0 + M].astype(int), y2[w0:w0 + M].astype(int) + 2)
+            want = seq[:5] + core + seq[5 + M:]
+        else:
+            want = seq
+        assert rev[off[i]:off[i + 1]].tobytes().decode() == want, i
+        w0 += M
+    assert off[-1] == len(rev)
+
+
+# --------------------------------------------------------------------------------------------------
+# whole path on the unitest fast5 set (cfg1) vs the golden vectors
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("species", ["ecoli", "human"])
+def test_revise_unitest_set_matches_goldens(reviser_by_species, reads, golden_dir, species):
+    from nanoreviser_b200 import api
+    rv = reviser_by_species(species)
+    gold = np.load(os.path.join(golden_dir, "forward_%s.npz" % species))
+    out = api.revise_reads(reads, reviser=rv, want_labels=True, want_probs=True)
+    assert out.status.tolist() == [0] * 5
+    W = rv.window
+    w0 = 0
+    n_lab = n_same = 0
+    for k, r in enumerate(reads):
+        M = r.n_bases - W
+        p1, p2 = out.p1[w0:w0 + M], out.p2[w0:w0 + M]
+        y1, y2 = out.y1[w0:w0 + M], out.y2[w0:w0 + M]
+        assert np.abs(p1 - gold["r%d_P1_f64" % k]).max() <= P_TOL
+        assert np.abs(p2 - gold["r%d_P2_f64" % k]).max() <= P_TOL
+        n_lab += 2 * M
+        n_same += int((y1 == gold["r%d_y1_f64" % k]).sum()) + int((y2 == gold["r%d_y2_f64" % k]).sum())
+        # labels must be the argmax of the probabilities that were returned
+        assert np.array_equal(y1, p1.argmax(1)) and np.array_equal(y2, p2.argmax(1))
+        assert out.sequence(k) == gold["r%d_revised" % k].tobytes().decode(), "revised sequence of read %d" % k
+        w0 += M
+    assert n_same / n_lab >= 0.9999
+
+
+def test_batch_invariance_and_determinism(reviser_by_species, reads):
+    """Reads are independent: a ragged batch gives the same bytes as one read at a time, in any order."""
+    from nanoreviser_b200 import api
+    rv = reviser_by_species("ecoli")
+    whole = api.revise_reads(reads, reviser=rv).sequences()
+    again = api.revise_reads(reads, reviser=rv).sequences()
+    assert whole == again
+    order = [3, 0, 4]
+    sub = api.revise_reads([reads[i] for i in order], reviser=rv).sequences()
+    assert sub == [whole[i] for i in order]
+    one = api.revise_reads([reads[1]], reviser=rv).sequences()
+    assert one == [whole[1]]
+
+
+def test_synthetic_cfg2_shape_properties(reviser_by_species, weights_by_species):
+    """cfg2-shaped synthetic reads (10 kb): properties that hold at any size + oracle spot check."""
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import synth
+    rv = reviser_by_species("ecoli")
+    m1, m2 = weights_by_species("ecoli")
+    b = synth.make_batch([10_000, 10_000, 3_000, 10_000], seed=7)
+    out = rv.revise_batch(b, want_labels=True, want_probs=True)
+    W = rv.window
+    assert out.status.tolist() == [0, 0, 0, 0]
+    assert np.all(out.y1 <= 5) and np.all(out.y2 <= 4)
+    np.testing.assert_allclose(out.p1.sum(1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(out.p2.sum(1), 1.0, atol=1e-5)
+    woff = b.win_off(W)
+    for i in range(b.n_reads):
+        seq = out.sequence(i)
+        src = b.bases[b.base_off[i]:b.base_off[i + 1]].tobytes().decode()
+        assert seq[:5] == src[:5] and seq[-6:] == src[-6:]                      # pass-through edges
+        M = len(src) - W
+        y1 = out.y1[woff[i]:woff[i + 1]].astype(int); y2 = out.y2[woff[i]:woff[i + 1]].astype(int)
+        assert seq == src[:5] + orc.get_base_1(list(src[5:5 + M]), y1, y2 + 2) + src[5 + M:]
+    # oracle on the short read (3 kb): same labels
+    i = 2
+    s0, s1 = int(b.sig_off[i]), int(b.sig_off[i + 1]); b0, b1 = int(b.base_off[i]), int(b.base_off[i + 1])
+    length = np.diff(np.append(b.starts[b0:b1].astype(np.int64), b.starts[b1 - 1] + b.last_dur[i])).astype(float)
+    res = orc.revise_arrays(m1, m2, [chr(c) for c in b.bases[b0:b1]], b.starts[b0:b1].astype(np.int64), length,
+                            b.signal[s0:s1], b.ev_mean[b0:b1], b.ev_std[b0:b1], want=("probs",))
+    assert np.abs(res["P1"] - out.p1[woff[i]:woff[i + 1]]).max() <= P_TOL_F32
+    assert np.abs(res["P2"] - out.p2[woff[i]:woff[i + 1]]).max() <= P_TOL_F32
+    assert res["revised"] == out.sequence(i)
+
+
+def test_window_chunking_is_invisible(weights_by_species, reads, monkeypatch):
+    """The internal window-chunk size must not change a single byte."""
+    from nanoreviser_b200 import api, engine
+    m1, m2 = weights_by_species("ecoli")
+    monkeypatch.setenv("NRV_CHUNK_WINDOWS", "1000")
+    with engine.Reviser(m1, m2) as small:
+        a = api.revise_reads(reads[:2], reviser=small, want_probs=True)
+    monkeypatch.setenv("NRV_CHUNK_WINDOWS", "1000000")
+    with engine.Reviser(m1, m2) as big:
+        c = api.revise_reads(reads[:2], reviser=big, want_probs=True)
+    assert a.sequences() == c.sequences()
+    assert np.array_equal(a.p1, c.p1) and np.array_equal(a.p2, c.p2)
