@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- revised bases/s of the revision-inference hot path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads-per-step R]
+
+A *step* is one pass of the whole hot path (K1 segmentation -> K2 CNN -> K3 Bi-LSTM x2 models + heads
+-> K4 decode) over one ragged slab of synthetic reads of BASELINE.json's configs[1] shape ("ecoli
+model, synthetic 100k reads x 10 kb (4 kHz signal), 1xB200"): R reads x 10,000 bases per step, i.e.
+the steady state of the 100k-read job (a full 1e9-base pass would not fit the bench budget).
+
+  value : whole-job revised bases/s, inputs already resident in HBM (nrv_revise_batch_device),
+          timed with CUDA events on the library's stream, max over ranks.
+  e2e   : same metric through the reference-facing call with HOST buffers (nrv_revise_batch: pinned
+          host -> device copies, kernels, device -> host copy of the revised sequences), per step.
+  roofline     : dominant kernel = Bi-LSTM layer `total_rnn1` (57.7 % of the algorithmic FLOPs);
+                 achieved = algorithmic FLOPs per launch / CUDA-event duration of those launches.
+  cpu_baseline : the CPU oracle (numpy fp32 restatement, all host cores) on a bounded sample.
+
+--impl reference times the reference's own CPU algorithm for the path (the oracle port with the
+reference-faithful per-read python segmentation and per-window CNN recompute; Keras/TF cannot be
+installed here) on the host cores, same metric/unit/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "revised_bases_per_sec"
+UNIT = "bases/s"
+READ_LEN = 10_000
+# algorithmic MACs per window, per model; CNN is per base
+MAC_LSTM = (30_976, 540_672, 3_604_480, 1_802_240)
+MAC_HEADS = 228_448 + 96          # model1; model2 has 80 in the last layer
+MAC_CNN = 36_400
+FLOP_PER_BASE = 24.97e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_bases_per_sec(n_reads: int, read_len: int, faithful: bool, seed: int = 99):
+    """Time the CPU oracle on a bounded sample of the same workload.  Returns (bases/s, seconds, bases)."""
+    from nanoreviser_b200 import synth, weights
+    from oracle import nanorev_oracle as orc
+    m1, m2 = weights.load_species("ecoli", os.path.join(ROOT, "model"))
+    b = synth.make_batch([read_len] * n_reads, seed=seed)
+    t0 = time.perf_counter()
+    total = 0
+    for i in range(b.n_reads):
+        s0, s1 = int(b.sig_off[i]), int(b.sig_off[i + 1])
+        b0, b1 = int(b.base_off[i]), int(b.base_off[i + 1])
+        starts = b.starts[b0:b1].astype(np.int64)
+        length = np.diff(np.append(starts, starts[-1] + b.last_dur[i])).astype(float)
+        bases = [chr(c) for c in b.bases[b0:b1]]
+        if faithful:
+            # what signal_segmentation + model.predict([S, X]) do: per-base python loop, 11x window
+            # materialisation, CNN recomputed for every timestep of every window
+            win, mean, std, shift, scale = orc.signal_segmentation(b.signal[s0:s1], starts, int(b.last_dur[i]))
+            x = orc.feature_columns(bases, mean, std, shift, scale, length, b.ev_mean[b0:b1], b.ev_std[b0:b1])
+            X, S = orc.make_windows(x, win, m1.window)
+            P1 = np.concatenate([orc.forward_windows(m1, S[a:a + 2048], X[a:a + 2048]) for a in range(0, len(X), 2048)])
+            P2 = np.concatenate([orc.forward_windows(m2, S[a:a + 2048], X[a:a + 2048]) for a in range(0, len(X), 2048)])
+            M = len(X)
+            orc.get_base_1(bases[5:5 + M], P1.argmax(1), P2.argmax(1) + 2)
+        else:
+            orc.revise_arrays(m1, m2, bases, starts, length, b.signal[s0:s1], b.ev_mean[b0:b1], b.ev_std[b0:b1])
+        total += b1 - b0
+    dt = time.perf_counter() - t0
+    return total / dt, dt, total
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(1, args.ref_reads)
+    vals = []
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_oracle_bases_per_sec(1, 1000, True)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, nb = cpu_oracle_bases_per_sec(n, args.ref_read_len, True)
+        vals.append((v, dt, nb))
+    v = sum(x[2] for x in vals) / sum(x[1] for x in vals)
+    sample = "%d synthetic cfg2-shape read(s) x %d bases per step, %d steps" % (n, args.ref_read_len, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: ecoli model, synthetic 10 kb reads (4 kHz), CPU sample"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "oracle port of the reference algorithm (numpy fp32 + OpenBLAS, per-read python "
+                                     "segmentation, per-window CNN recompute); Keras 2.2.4/TF 1.12 not installable"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads-per-step", type=int, default=128)
+    ap.add_argument("--species", default="ecoli")
+    ap.add_argument("--ref-reads", type=int, default=1)
+    ap.add_argument("--ref-read-len", type=int, default=4000)
+    ap.add_argument("--cpu-sample-bases", type=int, default=10_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from nanoreviser_b200 import engine, synth, weights
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks, peak_src = load_peaks()
+
+    m1, m2 = weights.load_species(args.species, os.path.join(ROOT, "model"))
+    rv = engine.Reviser(m1, m2, device=local_rank)
+    W = rv.window
+    R = args.reads_per_step
+    # two distinct slabs per rank, alternated, so that no step re-reads the previous step's inputs from L2
+    slabs = [synth.make_batch([READ_LEN] * R, seed=1000 + 17 * rank + s) for s in range(2)]
+    n_bases = slabs[0].n_bases
+    n_win = slabs[0].n_windows(W)
+    cap = 2 * n_bases + R + 16
+    stream = torch.cuda.ExternalStream(rv.stream, device=local_rank)
+
+    # ---- device-resident copies (torch only as the allocator / stream plumbing) ---------------------
+    dev = torch.device("cuda", local_rank)
+    dslabs = []
+    for b in slabs:
+        t = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in ("signal", "starts", "bases", "ev_mean", "ev_std", "last_dur")}
+        dslabs.append(t)
+    d_rev = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(R + 1, dtype=torch.int64, device=dev)
+    d_status = torch.empty(R, dtype=torch.int32, device=dev)
+    dres = {"revised": d_rev.data_ptr(), "out_off": d_off.data_ptr(), "status": d_status.data_ptr()}
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        b, t = slabs[i & 1], dslabs[i & 1]
+        rv.revise_batch_device(R, b.sig_off, b.base_off, {k: v.data_ptr() for k, v in t.items()}, dres, cap)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    rv.synchronize()
+    # ---- timed region: `value` ---------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rv.set_stage_timing(True)
+    launches0 = rv.launch_count
+    barrier()
+    with torch.cuda.stream(stream):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            step_device(i)
+        e1.record(stream)
+    rv.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = rv.launch_count - launches0
+    stage_ms = rv.stage_ms()
+    stage_launches = rv.stage_launches()
+    rv.set_stage_timing(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n_bases * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through nrv_revise_batch (H2D + kernels + D2H inside the timed region) -----
+    pinned = []
+    for b in slabs:
+        pb = engine.Batch(**{k: torch.from_numpy(getattr(b, k)).pin_memory().numpy() for k in
+                             ("signal", "sig_off", "starts", "base_off", "bases", "ev_mean", "ev_std", "last_dur")})
+        pinned.append(pb)
+    out = engine.ReviseResult(torch.empty(cap, dtype=torch.uint8).pin_memory().numpy(),
+                              torch.empty(R + 1, dtype=torch.int64).pin_memory().numpy(),
+                              torch.empty(R, dtype=torch.int32).pin_memory().numpy())
+    for i in range(max(1, min(args.warmup, 2))):
+        rv.revise_batch(pinned[i & 1], out=out)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        rv.revise_batch(pinned[i & 1], out=out)
+        d2h += int(out.out_off[-1]) + out.out_off.nbytes + out.status.nbytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_bases * args.steps / float(t_e.item())
+    # sanity: the device-resident and the host path produce the same bytes
+    chk = rv.revise_batch(pinned[(args.steps - 1) & 1])
+    torch.cuda.synchronize()
+    same = bool(np.array_equal(d_off.cpu().numpy(), chk.out_off)) and \
+        bool(np.array_equal(d_rev.cpu().numpy()[:chk.out_off[-1]], chk.revised[:chk.out_off[-1]]))
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (Bi-LSTM layer 2 = total_rnn1) -------------------------------
+        l2_ms = stage_ms["lstm2"]
+        l2_launches = max(stage_launches["lstm2"], 1)
+        flops_total = 2.0 * MAC_LSTM[2] * n_win * 2 * args.steps          # 2 models
+        achieved = flops_total / (l2_ms * 1e-3) / 1e12 if l2_ms > 0 else 0.0
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        roofline = {"bound": "tensor", "kernel": "lstm_layer_kernel<128,64,128,64> (total_rnn1, fp32 SIMT)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peak_src,
+                    "launches": int(l2_launches), "avg_launch_ms": l2_ms / l2_launches,
+                    "flops_per_launch": flops_total / l2_launches, "traffic": None,
+                    "share_of_step": l2_ms / ms if ms > 0 else None}
+        whole = {"achieved_tflops": FLOP_PER_BASE * value / world / 1e12, "frac_of_bf16_sustained":
+                 FLOP_PER_BASE * value / world / 1e12 / peak}
+        cpu = None
+        if not args.no_cpu_baseline:
+            nreads = max(1, args.cpu_sample_bases // READ_LEN)
+            v, dt, nb = cpu_oracle_bases_per_sec(nreads, READ_LEN, False)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "%d synthetic cfg2 read(s) x %d bases (%.1f s), batched oracle (CNN once per base)" % (nreads, READ_LEN, dt)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg2: %s model, synthetic 10 kb reads (4 kHz signal), slab of %d reads "
+                                       "(%d bases) per step per GPU" % (args.species, R, n_bases),
+                           "reads_per_step": R, "bases_per_step": n_bases, "windows_per_step": n_win,
+                           "l2": "two alternating slabs; per-step activations (%.1f GB) exceed the 126 MB L2" %
+                                 (n_win * 11 * 544 * 4 / 1e9)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": slabs[0].h2d_bytes(),
+                        "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+                "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "whole_path": whole,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "device_vs_host_path_identical": same}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    rv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

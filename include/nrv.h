@@ -119,12 +119,15 @@ const char* nrv_version(void);
 
 /* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t nrv_launch_count(const nrv_handle* h);
-/* Device time (ms, CUDA events on the handle's stream) of the per-stage kernels of the LAST
- * nrv_revise_batch* call when stage timing was enabled with nrv_set_stage_timing(h, 1):
- * out[0]=read stats (median/MAD) out[1]=base features out[2]=CNN out[3..6]=LSTM layers 0..3
- * (both models) out[7]=dense heads+softmax out[8]=decode.  Enabling it serialises the stages. */
+/* Per-stage device time.  nrv_set_stage_timing(h, 1) resets the totals and makes every later call
+ * record CUDA-event pairs on the handle's stream around each stage's launches (no synchronisation on
+ * the hot path); nrv_get_stage_ms() synchronises once and returns the totals in ms since the reset:
+ * out[0]=read stats (median/MAD) out[1]=base features out[2]=CNN out[3..6]=Bi-LSTM layers 0..3
+ * out[7]=dense heads+softmax out[8]=decode.  nrv_get_stage_launches() gives the kernel launches of
+ * each stage over the same period. */
 int nrv_set_stage_timing(nrv_handle* h, int enable);
-int nrv_get_stage_ms(const nrv_handle* h, float out[9]);
+int nrv_get_stage_ms(nrv_handle* h, float out[9]);
+int nrv_get_stage_launches(const nrv_handle* h, int64_t out[9]);
 
 /* The CUDA stream all work of this handle is enqueued on (cudaStream_t as void*). */
 void* nrv_stream(const nrv_handle* h);

@@ -64,9 +64,23 @@ struct nrv_handle {
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag,
         d_segmean, d_segstd, d_sigwin;
     PinnedArena h_off, h_flag;
+    // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
+    // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
     float stage_ms[ST_COUNT] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t stage_launches[ST_COUNT] = {0};
+    struct EvPair { cudaEvent_t a, b; int stage; };
+    std::vector<EvPair> ev_pool;
+    size_t ev_used = 0;
+    void fold_events() {
+        if (ev_used == 0) return;
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i < ev_used; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b) == cudaSuccess) stage_ms[ev_pool[i].stage] += ms;
+        }
+        ev_used = 0;
+    }
 };
 
 namespace {
@@ -173,15 +187,24 @@ cuda_fail:
 }
 
 struct StageTimer {
-    nrv_handle* h; int stage;
-    StageTimer(nrv_handle* h_, int s) : h(h_), stage(s) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
-    ~StageTimer() {
+    nrv_handle* h; int stage; int64_t launches0; nrv_handle::EvPair* ev = nullptr;
+    StageTimer(nrv_handle* h_, int s) : h(h_), stage(s), launches0(h_->launches) {
         if (!h->timing) return;
-        cudaEventRecord(h->ev1, h->stream);
-        cudaEventSynchronize(h->ev1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-        h->stage_ms[stage] += ms;
+        if (h->ev_used == h->ev_pool.size()) {
+            if (h->ev_pool.size() >= 8192) h->fold_events();
+            else {
+                nrv_handle::EvPair p; p.stage = 0;
+                if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+                h->ev_pool.push_back(p);
+            }
+        }
+        ev = &h->ev_pool[h->ev_used++];
+        ev->stage = stage;
+        cudaEventRecord(ev->a, h->stream);
+    }
+    ~StageTimer() {
+        h->stage_launches[stage] += h->launches - launches0;
+        if (ev) cudaEventRecord(ev->b, h->stream);
     }
 };
 
@@ -318,7 +341,6 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
     if (rc) return rc;
     if (!r || !r->revised || !r->out_off || !r->status) return fail(h, NRV_E_INVALID, "result needs revised/out_off/status");
     CU(h, cudaSetDevice(h->device));
-    for (int i = 0; i < ST_COUNT; ++i) h->stage_ms[i] = 0.f;
     Offsets o;
     rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o);
     if (rc) return rc;
@@ -430,8 +452,6 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     h->window = m1->window;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) {
         g_create_error = std::string("nrv_create: ") + cudaGetErrorString(e);
         delete h;
@@ -458,18 +478,29 @@ void nrv_destroy(nrv_handle* h) {
                        &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin};
     for (Arena* a : arenas) a->release();
     h->h_off.release(); h->h_flag.release();
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 const char* nrv_last_error(const nrv_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int64_t nrv_launch_count(const nrv_handle* h) { return h ? h->launches : 0; }
-int nrv_set_stage_timing(nrv_handle* h, int enable) { if (!h) return NRV_E_INVALID; h->timing = enable != 0; return NRV_OK; }
-int nrv_get_stage_ms(const nrv_handle* h, float out[9]) {
+int nrv_set_stage_timing(nrv_handle* h, int enable) {
+    if (!h) return NRV_E_INVALID;
+    h->fold_events();
+    h->timing = enable != 0;
+    for (int i = 0; i < ST_COUNT; ++i) { h->stage_ms[i] = 0.f; h->stage_launches[i] = 0; }
+    return NRV_OK;
+}
+int nrv_get_stage_ms(nrv_handle* h, float out[9]) {
     if (!h || !out) return NRV_E_INVALID;
+    h->fold_events();
     for (int i = 0; i < ST_COUNT; ++i) out[i] = h->stage_ms[i];
+    return NRV_OK;
+}
+int nrv_get_stage_launches(const nrv_handle* h, int64_t out[9]) {
+    if (!h || !out) return NRV_E_INVALID;
+    for (int i = 0; i < ST_COUNT; ++i) out[i] = h->stage_launches[i];
     return NRV_OK;
 }
 void* nrv_stream(const nrv_handle* h) { return h ? (void*)h->stream : nullptr; }

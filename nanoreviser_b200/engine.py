@@ -57,7 +57,7 @@ class _Result(C.Structure):
 
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
-           "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_stream", "nrv_synchronize", "nrv_segment",
+           "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
            "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device")
 
 _lib = None
@@ -88,6 +88,8 @@ def load_library(path: Optional[str] = None):
     lib.nrv_set_stage_timing.restype = C.c_int
     lib.nrv_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.nrv_get_stage_ms.restype = C.c_int
+    lib.nrv_get_stage_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.nrv_get_stage_launches.restype = C.c_int
     lib.nrv_stream.argtypes = [vp]
     lib.nrv_stream.restype = vp
     lib.nrv_synchronize.argtypes = [vp]
@@ -277,6 +279,11 @@ class Reviser:
         buf = (C.c_float * 9)()
         self._check(self._lib.nrv_get_stage_ms(self._h, buf), "nrv_get_stage_ms")
         return dict(zip(STAGE_NAMES, [float(v) for v in buf]))
+
+    def stage_launches(self) -> dict:
+        buf = (C.c_int64 * 9)()
+        self._check(self._lib.nrv_get_stage_launches(self._h, buf), "nrv_get_stage_launches")
+        return dict(zip(STAGE_NAMES, [int(v) for v in buf]))
 
     @staticmethod
     def _cbatch(b: Batch, keep: list) -> _Batch:
