@@ -1,0 +1,210 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""NanoReviser command line on B200: same flags as the reference CLI (NanoReviser.py:42-95 there),
+same model files (./model/<S>/<S>_win13_50ep_model{1,2}.h5), same output files
+(<o><stem>_out.fasta|fastq), but the revision path runs in libnrv.so (CUDA, sm_100a): no Keras,
+no Guppy shell-out, no CPU fallback.
+
+Differences that are deliberate:
+  * the NN path is what runs (the shipped reference CLI builds un-weighted models and shells out to a
+    missing Guppy binary -- SURVEY.md F1);
+  * every fast5 in -d is processed (the reference silently drops ``len(files) % pool_size`` files,
+    NanoReviser.py:212-219);
+  * ``-e`` (failed reads file) is actually written;
+  * extra flags ``--devices`` (comma separated GPU ids, one worker process per GPU) and
+    ``--batch-bases`` (ragged batch budget per launch).
+"""
+import os
+import shutil
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+from optparse import OptionParser
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def get_args(argv=None):
+    optParser = OptionParser(usage="%prog [-d] [-o]", version="%prog 1.0",
+                             description="An Error-correction Tool for Nanopore Sequencing Based on a Deep Learning "
+                                         "Algorithm (B200-native revision path)")
+    optParser.add_option('-d', '--fast5_base_dir', action='store', type="string", dest='fast5_base_dir',
+                         help='path to the fast5 files')
+    optParser.add_option('-o', '--output_dir', action='store', type="string", dest='output_dir',
+                         default='./unitest/nanorev_output/', help='path to store the output files')
+    optParser.add_option('-F', '--output_format', action='store', type="string", dest='output_format',
+                         default='fasta', help='format of the output files, default is fasta')
+    optParser.add_option('-S', '--species', action='store', type="string", dest='species', default='human',
+                         help='species of the model (ecoli or human), default is human')
+    optParser.add_option("--thread", action="store", type="int", dest="thread", default=100,
+                         help='host threads for fast5 ingest, default is 100 (capped at the core count)')
+    optParser.add_option('-t', '--tmp_dir', action='store', type="string", dest='temp_dir', default='./unitest/tmp/',
+                         help='path to the tmp dir (accepted for compatibility; nothing is staged there)')
+    optParser.add_option('-e', '--failed_read', action='store', type="string", dest='failed_reads_filename',
+                         default='failed_reads.txt', help='document to log the failed reads')
+    optParser.add_option('-g', '--basecall_group', action='store', type="string", dest='basecall_group',
+                         default='Basecall_1D_000', help='group holding the events table')
+    optParser.add_option('-s', '--basecall_subgroup', action='store', type="string", dest='basecall_subgroup',
+                         default='BaseCalled_template', help='subgroup holding the events table')
+    optParser.add_option('--test_mode', action='store_true', default=False, help='just for unitest')
+    optParser.add_option('--model1_predict_dir', action='store', type="string", dest='model1_predict_dir',
+                         default='./model/human/human_win13_50ep_model1.h5', help='model dirs for model1')
+    optParser.add_option('--model2_predict_dir', action='store', type="string", dest='model2_predict_dir',
+                         default='./model/human/human_win13_50ep_model2.h5', help='model dirs for model2')
+    optParser.add_option("-v", "--virsion", action="store_true", dest="virsion", help="version of NanoReviser")
+    optParser.add_option('--devices', action='store', type="string", dest='devices', default='0',
+                         help='comma separated CUDA device ids; reads are sharded over them (no collectives)')
+    optParser.add_option('--batch-bases', action='store', type="int", dest='batch_bases', default=2_000_000,
+                         help='ragged batch budget (bases per GPU launch)')
+    (tmp_args, _) = optParser.parse_args(argv)
+    if tmp_args.virsion:
+        print("The virsion of NanoReviser : 1.0 ")
+        sys.exit()
+    elif tmp_args.fast5_base_dir and tmp_args.output_dir:
+        return tmp_args
+    else:
+        optParser.parse_args(['-h'])
+        sys.exit()
+
+
+def _test_logger():
+    import logging
+    logger = logging.getLogger('unitest')
+    if not logger.handlers:
+        logger.setLevel(logging.DEBUG)
+        os.makedirs('./unitest', exist_ok=True)
+        handler = logging.FileHandler('./unitest/unitest_log.txt', encoding='UTF-8')
+        handler.setLevel(logging.INFO)
+        handler.setFormatter(logging.Formatter('%(asctime)s - %(name)s - %(levelname)s - %(message)s'))
+        logger.addHandler(handler)
+        logger.addHandler(logging.StreamHandler())
+    return logger
+
+
+def _ingest(args, fn_sg):
+    from nanoreviser_b200 import fast5
+    path = os.path.join(args.fast5_base_dir, fn_sg)
+    try:
+        return fn_sg, fast5.read_fast5_arrays(path, args.basecall_group, args.basecall_subgroup), None
+    except Exception as e:          # per-read try/except, like provide_fasta (NanoReviser.py:114-118)
+        return fn_sg, None, e
+
+
+def _write_read(args, fn_sg, bases, qul=None):
+    from nanoreviser_b200 import api
+    if not os.path.exists(args.output_dir):
+        os.makedirs(args.output_dir)
+    fast5_fn = os.path.join(args.fast5_base_dir, fn_sg)
+    if args.output_format == 'fasta':
+        api.prep_read_fasta(fast5_fn, api.out_filename(args.output_dir, fn_sg, 'fasta'), bases)
+    else:
+        api.prep_read_fastq(fast5_fn, api.out_filename(args.output_dir, fn_sg, 'fastq'), bases, qul)
+
+
+def run_worker(args, file_list, device, logger=None):
+    """One GPU: ingest with host threads, ragged batches by base budget, revise, write."""
+    from nanoreviser_b200 import api, engine, fast5, weights, workqueue
+    m1 = weights.load_model_weights(args.model1_predict_dir)
+    m2 = weights.load_model_weights(args.model2_predict_dir)
+    n_ok = n_fallback = n_failed = 0
+    failed = []
+    with engine.Reviser(m1, m2, device=device) as rv:
+        nthreads = max(1, min(int(args.thread), os.cpu_count() or 4, 32))
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            loaded = list(ex.map(lambda f: _ingest(args, f), file_list))
+        good = []
+        for fn_sg, r, err in loaded:
+            if r is None:
+                print('！！！[Error] fast5 file: ' + fn_sg.split('.')[0] + str(err))
+                failed.append(fn_sg)
+                n_failed += 1
+                if logger:
+                    logger.error('[!!! Error] Basecalling')
+            else:
+                good.append((fn_sg, r))
+        lengths = [r.n_bases for _, r in good]
+        for batch in workqueue.make_batches(range(len(good)), lengths, int(args.batch_bases)):
+            reads = [good[i][1] for i in batch]
+            out = api.revise_reads(reads, reviser=rv)
+            for k, i in enumerate(batch):
+                fn_sg, r = good[i]
+                try:
+                    if out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT):
+                        seq = out.sequence(k)
+                        qul = 'I' * len(seq) if args.output_format == 'fastq' else None   # D6: provisional
+                        _write_read(args, fn_sg, list(seq), qul)
+                        n_ok += 1
+                    else:
+                        # fallback to the un-revised read (NanoReviser.py:146-154 / :172-181)
+                        if args.output_format == 'fasta':
+                            _write_read(args, fn_sg, [chr(c) for c in r.bases])
+                        else:
+                            seq, qul = fast5.extract_fastq(os.path.join(args.fast5_base_dir, fn_sg), None)
+                            _write_read(args, fn_sg, list(seq), list(qul))
+                        n_fallback += 1
+                        failed.append(fn_sg)
+                    if logger:
+                        logger.info("Congratulations, NanoReviser is installed properly")
+                    elif not args.test_mode:
+                        print('[p:::] ' + fn_sg.split('.')[0] + '_out.' + args.output_format + ' was saved......')
+                except Exception as e:
+                    print('[！！！Error] stroring : ' + fn_sg.split('.')[0] + ' ' + str(e))
+                    failed.append(fn_sg)
+                    if logger:
+                        logger.error('[!!! Error] Basecalling')
+    return n_ok, n_fallback, n_failed, failed
+
+
+def _worker_entry(payload):
+    args, files, device = payload
+    return run_worker(args, files, device, _test_logger() if args.test_mode else None)
+
+
+def main(ar_args):
+    logger = None
+    if ar_args.test_mode:
+        logger = _test_logger()
+        ar_args.model1_predict_dir = './model/ecoli/ecoli_win13_50ep_model1.h5'
+        ar_args.model2_predict_dir = './model/ecoli/ecoli_win13_50ep_model2.h5'
+    if ar_args.species:   # NanoReviser.py:191-193: -S (default 'human') overrides the model paths, also in test mode
+        ar_args.model1_predict_dir = './model/' + str(ar_args.species) + '/' + str(ar_args.species) + '_win13_50ep_model1.h5'
+        ar_args.model2_predict_dir = './model/' + str(ar_args.species) + '/' + str(ar_args.species) + '_win13_50ep_model2.h5'
+    if not (os.path.exists(ar_args.model1_predict_dir) and os.path.exists(ar_args.model2_predict_dir)):
+        raise RuntimeError('！！！[Error] model file: Please check the dir of models file!!')
+    os.makedirs(ar_args.output_dir, exist_ok=True)
+    fast5_fns = [f for f in sorted(os.listdir(ar_args.fast5_base_dir)) if not f.startswith('.')]
+    devices = [int(d) for d in str(ar_args.devices).split(',') if d != '']
+    start_time = time.time()
+    if len(devices) <= 1:
+        res = [run_worker(ar_args, fast5_fns, devices[0] if devices else 0, logger)]
+    else:
+        # reads shard naturally: length-balanced partition by file size (proxy for bases), one process per GPU
+        import multiprocessing as mp
+        from nanoreviser_b200 import workqueue
+        sizes = [os.path.getsize(os.path.join(ar_args.fast5_base_dir, f)) for f in fast5_fns]
+        parts = workqueue.lpt_partition(sizes, len(devices))
+        ctx = mp.get_context('spawn')
+        with ctx.Pool(len(devices)) as pool:
+            res = pool.map(_worker_entry, [(ar_args, [fast5_fns[i] for i in p], d) for p, d in zip(parts, devices)])
+    failed = [f for r in res for f in r[3]]
+    if failed and not ar_args.test_mode:
+        with open(os.path.join(ar_args.output_dir, ar_args.failed_reads_filename), 'w') as fp:
+            fp.write('\n'.join(failed) + '\n')
+    end_time = time.time()
+    if not ar_args.test_mode:
+        print('[s:::] All reads done: %d revised, %d written un-revised, %d unreadable.' % (
+            sum(r[0] for r in res), sum(r[1] for r in res), sum(r[2] for r in res)))
+        print('[s:::] NanoReviser time consuming:%.2f seconds' % (end_time - start_time))
+    else:
+        shutil.rmtree(ar_args.output_dir, ignore_errors=True)    # NanoReviser.py:231-232
+    return res
+
+
+if __name__ == '__main__':
+    ar_args = get_args()
+    try:
+        main(ar_args)
+    except Exception as e:
+        print(e)

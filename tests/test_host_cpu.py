@@ -1,0 +1,166 @@
+"""CPU: host logic of the product (HDF5 reader, ingest, weights, batching, writers, CLI flags,
+work queue) and the C-ABI surface (library loads and exports every symbol include/nrv.h declares)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_h5mini_structure(fast5_files):
+    from nanoreviser_b200 import h5mini
+    for fn in fast5_files:
+        with h5mini.File(fn) as f:
+            assert set(f.keys()) >= {"Analyses", "Raw"}
+            g = f["/Analyses/Basecall_1D_000"]
+            assert g.attrs["version"] == b"2.0.2"
+            ev = f["/Analyses/Basecall_1D_000/BaseCalled_template/Events"][()]
+            assert ev.dtype.itemsize == 41 and ev.dtype.names[:4] == ("mean", "start", "stdv", "length")
+            assert set(np.unique(ev["move"])) <= {0, 1, 2} and np.all(ev["length"] == 5)
+            summ = f["/Analyses/Basecall_1D_000/Summary/basecall_1d_template"].attrs
+            assert int(summ["num_events"]) == len(ev)
+            rd = list(f["/Raw/Reads"].values())[0]
+            sig = rd["Signal"][()]
+            assert sig.dtype == np.int16 and len(sig) == int(rd.attrs["duration"])
+            with pytest.raises(KeyError):
+                f["/Analyses/Nope"]
+    with pytest.raises(h5mini.H5Error):
+        h5mini.File(__file__)
+
+
+def test_weights_loader_all_files():
+    from nanoreviser_b200 import weights
+    for sp in ("ecoli", "human"):
+        m1, m2 = weights.load_species(sp, os.path.join(ROOT, "model"))
+        assert (m1.window, m1.n_class, m2.window, m2.n_class) == (11, 6, 11, 5)      # F3: W = 11, not 13
+        assert m1.n_params() == 595_300 and m2.n_params() == 595_283
+        assert m1.lstm[2][0].kernel.shape == (192, 512) and m1.lstm[2][1].recurrent.shape == (128, 512)
+    assert weights.model_paths("ecoli") == ("./model/ecoli/ecoli_win13_50ep_model1.h5",
+                                            "./model/ecoli/ecoli_win13_50ep_model2.h5")
+
+
+def test_product_ingest_matches_reference_outputs(fast5_files, seg_golden):
+    from nanoreviser_b200 import fast5
+    for k, fn in enumerate(fast5_files):
+        a0, starts, length, bases, signal, em, es = fast5.get_read_data(fn, "Basecall_1D_000", "BaseCalled_template")
+        g = lambda n: seg_golden["r%d_%s" % (k, n)]
+        assert a0 == int(g("a0")) and np.array_equal(starts, g("starts")) and np.array_equal(length, g("length"))
+        assert "".join(bases).encode() == g("bases").tobytes()
+        assert np.array_equal(np.asarray(em), g("ev_mean")) and np.array_equal(np.asarray(es), g("ev_std"))
+        seq, qul = fast5.extract_fastq(fn)
+        assert "".join(bases)[5:-5] == seq and len(seq) == len(qul)      # Fastq[7:-7] vs bases == Fastq[2:-2]
+    with pytest.raises(NotImplementedError):
+        fast5.get_read_data(__file__, "Basecall_1D_000", "BaseCalled_template")
+    with pytest.raises(RuntimeError):
+        fast5.get_read_data(fast5_files[0], "Basecall_1D_999", "BaseCalled_template")
+
+
+def test_collapse_events_moves():
+    from nanoreviser_b200 import fast5
+    st = np.array([100, 105, 110, 115, 120], np.uint64)
+    mv = np.array([1, 0, 2, 1, 3], np.int32)
+    ms = np.array([b"AACGT", b"ACGTA", b"CGTAC", b"GTACG", b"TACGA"], dtype="S5")
+    mean = np.arange(5, dtype=np.float32); sd = mean + 10
+    start, bases, m, s = fast5.collapse_events(st, mean, sd, ms, mv)
+    assert start.tolist() == [100, 110, 112, 115, 120]
+    assert bases.tobytes() == b"CGTAC"          # move2: state[1] then state[2]; move 3 treated as 1
+    assert m.tolist() == [0, 2, 2, 3, 4] and s.tolist() == [10, 12, 12, 13, 14]
+
+
+def test_pack_batch_and_synth(reads):
+    from nanoreviser_b200 import engine, synth
+    b = engine.pack_batch(reads)
+    assert b.n_reads == 5 and b.n_bases == 40_940 and b.n_windows(11) == 40_940 - 55
+    assert b.signal.dtype == np.int16 and b.starts.dtype == np.int32
+    for i, r in enumerate(reads):
+        assert np.array_equal(b.signal[b.sig_off[i]:b.sig_off[i + 1]], r.signal[r.a0:])
+        assert b.starts[b.base_off[i]] == 0 and b.last_dur[i] in (3, 5)
+    s1 = synth.make_batch([10_000, 500], seed=3)
+    s2 = synth.make_batch([10_000, 500], seed=3)
+    assert np.array_equal(s1.signal, s2.signal) and np.array_equal(s1.bases, s2.bases)
+    assert s1.n_bases == 10_500 and abs(s1.sig_off[1] / 10_000 - 8.89) < 0.3       # 4 kHz / 450 b/s
+    assert s1.signal.min() >= -605 and s1.signal.max() <= 1805
+    sub = synth.split_batch(s1, [1])
+    assert sub.n_bases == 500 and np.array_equal(sub.bases, s1.bases[10_000:])
+    L = synth.read_lengths("cfg3", 2000)
+    assert L.min() >= 500 and L.max() <= 300_000 and 8_300 < np.median(L) < 9_500   # exp(9.0935) = 8.9 k
+
+
+def test_writers_and_names(tmp_path):
+    from nanoreviser_b200 import api
+    fn = str(tmp_path / "o.fasta")
+    api.prep_read_fasta("/x/y/a b.fast5", fn, list("ACGT"))
+    assert open(fn).read() == ">a|||b.fast5\nACGT"                       # no trailing newline
+    api.prep_read_fastq("/x/y/a b.fast5", fn, list("ACGT"), list("!!!!"))
+    assert open(fn).read() == "@a|||b.fast5\nACGT+\n!!!!"               # no newline before '+'
+    assert api.out_filename("./out/", "r1.strand.fast5", "fasta") == "./out/r1_out.fasta"
+    assert api.get_base_color("G") == 180 and api.get_base_color("N") == 0 and api.get_base_label("-") == 1
+    with pytest.raises(NotImplementedError):
+        api.prep_read_fasta("a.fast5", str(tmp_path / "nodir" / "x"), list("A"))
+
+
+def test_cli_flags_match_reference():
+    sys.path.insert(0, ROOT)
+    import NanoReviser as cli
+    a = cli.get_args(["-d", "in/", "-o", "out/"])
+    assert (a.species, a.output_format, a.thread, a.basecall_group, a.basecall_subgroup) == \
+        ("human", "fasta", 100, "Basecall_1D_000", "BaseCalled_template")
+    a = cli.get_args(["-d", "in/", "-o", "out/", "-S", "ecoli", "-F", "fastq", "--thread", "4", "-t", "tmp/",
+                      "-e", "f.txt", "-g", "G", "-s", "S", "--test_mode", "--devices", "0,1"])
+    assert (a.species, a.output_format, a.thread, a.test_mode, a.devices) == ("ecoli", "fastq", 4, True, "0,1")
+    with pytest.raises(SystemExit):
+        cli.get_args([])
+
+
+def test_workqueue_partition_and_batches():
+    from nanoreviser_b200 import synth, workqueue
+    L = synth.read_lengths("cfg3", 4000).tolist()
+    for world in (1, 2, 4, 8):
+        parts = workqueue.lpt_partition(L, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(L)))        # disjoint and complete
+        assert workqueue.imbalance(L, parts) < 1.01
+        assert parts == workqueue.lpt_partition(L, world)                        # deterministic
+    batches = workqueue.make_batches(range(len(L)), L, 2_000_000)
+    assert [i for b in batches for i in b] == list(range(len(L)))
+    assert all(sum(L[i] for i in b) <= 2_000_000 or len(b) == 1 for b in batches)
+    assert workqueue.make_batches([0, 1], [5_000_000, 10], 1000) == [[0], [1]]
+    with pytest.raises(ValueError):
+        workqueue.lpt_partition(L, 0)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a CPU box and exports exactly what include/nrv.h declares."""
+    import ctypes
+    from nanoreviser_b200 import engine
+    hdr = open(os.path.join(ROOT, "include", "nrv.h")).read()
+    declared = set(re.findall(r"\b(nrv_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
+    if not os.path.exists(engine.LIB_PATH):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    engine.load_library()
+    assert b"sm_100a" in engine.load_library().nrv_version()
+
+
+def test_no_cpu_fallback_without_device(weights_by_species):
+    """Without a GPU the product fails loudly; it never routes through the oracle."""
+    import torch
+    from nanoreviser_b200 import api, engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m1, m2 = weights_by_species("ecoli")
+    with pytest.raises(engine.NrvError, match="no CUDA device"):
+        engine.Reviser(m1, m2)
+    api.set_default(None)
+    with pytest.raises(engine.NrvError):
+        api.signal_segmentation(np.zeros(100, np.int16), np.arange(0, 50, 5), 5)
+    for mod in ("engine", "api", "fast5", "weights", "synth", "workqueue", "h5mini", "build"):
+        src = open(os.path.join(ROOT, "nanoreviser_b200", mod + ".py")).read()
+        assert "import oracle" not in src and "from oracle" not in src, mod
