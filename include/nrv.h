@@ -162,6 +162,11 @@ int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r);
  * host).  Enqueues on nrv_stream(h) and returns without synchronising. */
 int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r);
 
+/* Diagnostic entry point (tests only): C[M][N] = A[M][K] . Bt[N][K]^T (+ bias[N]) through the split-fp16
+ * tcgen05 projection GEMM that the Bi-LSTM input projections use (csrc/nrv_gemm.cu).  Host fp32 buffers;
+ * N must be a multiple of 256 and K a multiple of 64. */
+int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const float* Bt, const float* bias, float* C);
+
 #ifdef __cplusplus
 }
 #endif

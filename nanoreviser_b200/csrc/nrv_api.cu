@@ -62,8 +62,10 @@ struct nrv_handle {
     // inputs / per-batch arenas
     Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag,
-        d_segmean, d_segstd, d_sigwin;
+        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a2[2], d_a3[2], d_zin;
     PinnedArena h_off, h_flag;
+    int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
+    int num_sms = 148;
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
@@ -156,6 +158,8 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
                 for (int j = 0; j < u; ++j) bb[j * 4 + g] = src.bias[g * u + j];
             L.wcat[d] = upload(h, wc, &e); if (e) goto cuda_fail;
             L.bias[d] = upload(h, bb, &e); if (e) goto cuda_fail;
+            std::vector<float> wr(wc.begin() + (size_t)in * 4 * u, wc.begin() + (size_t)(in + u) * 4 * u);
+            L.wrec[d] = upload(h, wr, &e); if (e) goto cuda_fail;
         }
         if (l < 3) {
             bn_fold(w->bn_rnn[l], 2 * u, s, t);
@@ -163,6 +167,42 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.bn_shift = upload(h, t, &e); if (e) goto cuda_fail;
         } else {
             L.bn_scale = nullptr; L.bn_shift = nullptr;
+        }
+        L.pb_hi = L.pb_lo = L.sb_hi = L.sb_lo = nullptr; L.bias_tc = nullptr;
+        if (l >= 2) {
+            // Tensor-core projection operand B^T [2*4u][in] (K-major), rows = dir*4u + unit*4 + gate.  The input of
+            // this layer is BN(h_prev) (+ the raw CNN features for layer 2): y = h*s + t  =>  fold s into the rows of
+            // Wk that multiply h_prev and t . Wk into the bias, so the GEMM consumes the raw h in [-1, 1].
+            std::vector<float> ps, pt;
+            bn_fold(w->bn_rnn[l - 1], IN_A[l], ps, pt);
+            const int N2 = 2 * 4 * u;
+            std::vector<float> bt((size_t)N2 * in), bias_tc(N2);
+            for (int d = 0; d < 2; ++d) {
+                const nrv_lstm_dir& src = w->lstm[l][d];
+                for (int g = 0; g < 4; ++g)
+                    for (int j = 0; j < u; ++j) {
+                        const int n = d * 4 * u + j * 4 + g;
+                        double bacc = src.bias[g * u + j];
+                        for (int r = 0; r < in; ++r) {
+                            const float wv = src.kernel[(size_t)r * 4 * u + g * u + j];
+                            if (r < IN_A[l]) {
+                                bt[(size_t)n * in + r] = ps[r] * wv;
+                                bacc += (double)pt[r] * (double)wv;
+                            } else {
+                                bt[(size_t)n * in + r] = wv;
+                            }
+                        }
+                        bias_tc[n] = (float)bacc;
+                    }
+            }
+            std::vector<__half> bh(bt.size()), bl(bt.size());
+            for (size_t i = 0; i < bt.size(); ++i) {
+                bh[i] = __float2half_rn(bt[i]);
+                bl[i] = __float2half_rn(bt[i] - __half2float(bh[i]));
+            }
+            L.pb_hi = upload(h, bh, &e); if (e) goto cuda_fail;
+            L.pb_lo = upload(h, bl, &e); if (e) goto cuda_fail;
+            L.bias_tc = upload(h, bias_tc, &e); if (e) goto cuda_fail;
         }
     }
     // ---- heads ----
@@ -213,29 +253,99 @@ __global__ void iota_mul_kernel(int32_t* out, int64_t n, int mul) {
     if (i < n) out[i] = (int32_t)(i * mul);
 }
 
-// Both models over all windows, chunk by chunk.  x [n_bases][6]; sig_feat[m] [n_bases][64].
+__global__ void gather_sig_kernel(const __half* __restrict__ sf_hi, const __half* __restrict__ sf_lo,
+                                  const int32_t* __restrict__ win_base, int64_t n_win, int T, int ld,
+                                  __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+    // columns [128, 192) of total_rnn1's input row (w, t) = CNN features of base win_base[w] + t; 8 x 16 B per half array
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = i >> 3;
+    const int q = (int)(i & 7);
+    if (row >= n_win * T) return;
+    const int64_t w = row / T;
+    const int t = (int)(row - w * T);
+    const int64_t b = (int64_t)win_base[w] + t;
+    reinterpret_cast<uint4*>(a_hi + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_hi + b * NRV_SIGFEAT) + q);
+    reinterpret_cast<uint4*>(a_lo + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_lo + b * NRV_SIGFEAT) + q);
+}
+
+// Both models over all windows, chunk by chunk.  x [n_bases][6]; sig_feat[m] [n_bases][64] (+ fp16 pairs).
 int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const float* x, float* const sig_feat[2],
                float* const probs[2], uint8_t* const labels[2]) {
     const int T = h->window;
     const int64_t CH = std::min<int64_t>(h->chunk_windows, std::max<int64_t>(n_win, 1));
+    const int64_t rows = CH * T;
     static const int widths[4] = {32, 128, 256, 128};
-    for (int l = 0; l < 4; ++l) CU(h, h->d_act[l].ensure((size_t)CH * T * widths[l] * sizeof(float)));
+    if (h->path == 0) {
+        for (int l = 0; l < 4; ++l) CU(h, h->d_act[l].ensure((size_t)rows * widths[l] * sizeof(float)));
+    } else {
+        CU(h, h->d_act[0].ensure((size_t)rows * 32 * sizeof(float)));
+        CU(h, h->d_act[3].ensure((size_t)rows * 128 * sizeof(float)));
+        CU(h, h->d_a2[0].ensure((size_t)rows * 192 * 2)); CU(h, h->d_a2[1].ensure((size_t)rows * 192 * 2));
+        CU(h, h->d_a3[0].ensure((size_t)rows * 256 * 2)); CU(h, h->d_a3[1].ensure((size_t)rows * 256 * 2));
+        CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
+    }
     for (int64_t c0 = 0; c0 < n_win; c0 += CH) {
         const int64_t nw = std::min(CH, n_win - c0);
         for (int mi = 0; mi < 2; ++mi) {
             const ModelDev& M = h->m[mi];
-            const float* in_prev = nullptr;
-            for (int l = 0; l < 4; ++l) {
-                StageTimer tm(h, ST_L0 + l);
-                const float* base_in = (l == 0) ? x : (l == 2 ? sig_feat[mi] : nullptr);
-                int n = launch_lstm_layer(l, M.lstm[l], in_prev, base_in, win_base + c0, nw, T, h->d_act[l].as<float>(),
-                                          h->stream);
-                h->launches += n;
-                in_prev = h->d_act[l].as<float>();
+            const float* heads_in = nullptr;
+            if (h->path == 0) {
+                // ---- fp32 SIMT path: projection fused into every recurrence step ----
+                const float* in_prev = nullptr;
+                for (int l = 0; l < 4; ++l) {
+                    StageTimer tm(h, ST_L0 + l);
+                    LstmIo io;
+                    io.act_in = in_prev; io.base_in = (l == 0) ? x : (l == 2 ? sig_feat[mi] : nullptr);
+                    io.win_base = win_base + c0; io.act_out = h->d_act[l].as<float>();
+                    int n = launch_lstm_layer(l, 0, M.lstm[l], io, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_INVALID, "lstm variant");
+                    h->launches += n;
+                    in_prev = h->d_act[l].as<float>();
+                }
+                heads_in = in_prev;
+            } else {
+                // ---- tensor-core path: tcgen05 projections for total_rnn1 / total_rnn2 ----
+                __half *a2h = h->d_a2[0].as<__half>(), *a2l = h->d_a2[1].as<__half>();
+                __half *a3h = h->d_a3[0].as<__half>(), *a3l = h->d_a3[1].as<__half>();
+                float* zin = h->d_zin.as<float>();
+                {   // read_rnn1 (fp32, fused) -> BN'd fp32
+                    StageTimer tm(h, ST_L0);
+                    LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.act_out = h->d_act[0].as<float>();
+                    h->launches += launch_lstm_layer(0, 0, M.lstm[0], io, nw, T, h->stream);
+                }
+                {   // read_rnn11 (fp32, fused) -> raw h as fp16 pairs, columns [0,128) of the next GEMM's A operand
+                    StageTimer tm(h, ST_L1);
+                    LstmIo io; io.act_in = h->d_act[0].as<float>(); io.win_base = win_base + c0;
+                    io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
+                    h->launches += launch_lstm_layer(1, 1, M.lstm[1], io, nw, T, h->stream);
+                }
+                {   // total_rnn1: gather CNN features, tcgen05 projection (K = 192), recurrence (K = 128)
+                    StageTimer tm(h, ST_L2);
+                    const int64_t items = nw * T * 8;
+                    gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
+                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, T, 192, a2h, a2l);
+                    h->launches += 1;
+                    int n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, nw * T, 1024, 192, zin,
+                                              M.lstm[2].bias_tc, 1, T, nw, 512, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
+                    h->launches += n;
+                    LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
+                    h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
+                }
+                {   // total_rnn2: tcgen05 projection (K = 256), recurrence (K = 64) -> fp32 for the heads
+                    StageTimer tm(h, ST_L3);
+                    int n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, nw * T, 512, 256, zin,
+                                              M.lstm[3].bias_tc, 1, T, nw, 256, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
+                    h->launches += n;
+                    LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.act_out = h->d_act[3].as<float>();
+                    h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
+                }
+                heads_in = h->d_act[3].as<float>();
             }
             {
                 StageTimer tm(h, ST_HEADS);
-                int n = launch_heads(M.heads, in_prev, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
+                int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
                                      labels[mi] ? labels[mi] + c0 : nullptr, h->stream);
                 if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
                 h->launches += n;
@@ -356,12 +466,18 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
     rc = run_segment(h, d, o, true, nullptr, nullptr);
     if (rc) return rc;
     // ---- K2: CNN per base, both models -------------------------------------------------------
-    for (int mi = 0; mi < 2; ++mi) CU(h, h->d_sigfeat[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 4 + 16));
+    for (int mi = 0; mi < 2; ++mi) {
+        CU(h, h->d_sigfeat[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 4 + 16));
+        CU(h, h->d_sfh[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 2 + 16));
+        CU(h, h->d_sfl[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 2 + 16));
+    }
     {
         StageTimer tm(h, ST_CNN);
+        __half* sfh[2] = {h->d_sfh[0].as<__half>(), h->d_sfh[1].as<__half>()};
+        __half* sfl[2] = {h->d_sfl[0].as<__half>(), h->d_sfl[1].as<__half>()};
         h->launches += launch_cnn(&h->m[0], &h->m[1], d.signal, o.d_sig_off, d.starts, o.d_base_off,
                                   h->d_base_read.as<int32_t>(), h->d_shift.as<double>(), h->d_scale.as<double>(), nullptr,
-                                  o.n_bases, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), h->stream);
+                                  o.n_bases, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), sfh, sfl, h->stream);
     }
     // ---- K3: window map + Bi-LSTM stack + heads --------------------------------------------------
     CU(h, h->d_win_base.ensure((size_t)o.n_win * 4 + 16));
@@ -462,6 +578,9 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (rc != NRV_OK) { g_create_error = h->err; nrv_destroy(h); return rc; }
     const char* ch = getenv("NRV_CHUNK_WINDOWS");
     if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
+    const char* pa = getenv("NRV_PATH");
+    if (pa && !strcmp(pa, "simt")) h->path = 0;
+    h->num_sms = prop.multiProcessorCount;
     *out = h;
     return NRV_OK;
 }
@@ -475,7 +594,8 @@ void nrv_destroy(nrv_handle* h) {
                        &h->d_scale, &h->d_status, &h->d_base_read, &h->d_win_base, &h->d_x, &h->d_sigfeat[0],
                        &h->d_sigfeat[1], &h->d_act[0], &h->d_act[1], &h->d_act[2], &h->d_act[3], &h->d_probs[0],
                        &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff,
-                       &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin};
+                       &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
+                       &h->d_sfl[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_zin};
     for (Arena* a : arenas) a->release();
     h->h_off.release(); h->h_flag.release();
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -556,7 +676,13 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     CU(h, h->d_sigwin.ensure((size_t)nb * NRV_SIG * 4));
     CU(h, h->d_x.ensure((size_t)nb * 6 * 4));
     CU(h, h->d_win_base.ensure((size_t)n * 4));
-    for (int mi = 0; mi < 2; ++mi) CU(h, h->d_sigfeat[mi].ensure((size_t)nb * NRV_SIGFEAT * 4));
+    for (int mi = 0; mi < 2; ++mi) {
+        CU(h, h->d_sigfeat[mi].ensure((size_t)nb * NRV_SIGFEAT * 4));
+        CU(h, h->d_sfh[mi].ensure((size_t)nb * NRV_SIGFEAT * 2 + 16));
+        CU(h, h->d_sfl[mi].ensure((size_t)nb * NRV_SIGFEAT * 2 + 16));
+    }
+    __half* sfh[2] = {h->d_sfh[0].as<__half>(), h->d_sfh[1].as<__half>()};
+    __half* sfl[2] = {h->d_sfl[0].as<__half>(), h->d_sfl[1].as<__half>()};
     CU(h, h->d_probs[0].ensure((size_t)n * 6 * 4));
     CU(h, h->d_probs[1].ensure((size_t)n * 5 * 4));
     CU(h, cudaMemcpyAsync(h->d_sigwin.p, S, (size_t)nb * NRV_SIG * 4, cudaMemcpyHostToDevice, h->stream));
@@ -564,7 +690,7 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     iota_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_win_base.as<int32_t>(), n, W);
     h->launches += 1;
     h->launches += launch_cnn(&h->m[0], &h->m[1], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                              h->d_sigwin.as<float>(), nb, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(),
+                              h->d_sigwin.as<float>(), nb, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), sfh, sfl,
                               h->stream);
     float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
     float* probs[2] = {h->d_probs[0].as<float>(), h->d_probs[1].as<float>()};
@@ -622,6 +748,37 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaGetLastError());
     return NRV_OK;
+}
+
+int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const float* Bt, const float* bias, float* C) {
+    if (!h) return NRV_E_INVALID;
+    if (h->sticky) return NRV_E_CUDA;
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !Bt || !C) return fail(h, NRV_E_INVALID, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    Arena a32, b32, ah, al, bh, bl, c32, bi;
+    int rc = NRV_OK;
+    auto cleanup = [&]() { a32.release(); b32.release(); ah.release(); al.release(); bh.release(); bl.release(); c32.release(); bi.release(); };
+    do {
+        if (a32.ensure((size_t)M * K * 4) || b32.ensure((size_t)N * K * 4) || ah.ensure((size_t)M * K * 2) ||
+            al.ensure((size_t)M * K * 2) || bh.ensure((size_t)N * K * 2) || bl.ensure((size_t)N * K * 2) ||
+            c32.ensure((size_t)M * N * 4) || bi.ensure((size_t)N * 4)) { rc = fail(h, NRV_E_CUDA, "debug gemm: cudaMalloc"); break; }
+        cudaMemcpyAsync(a32.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(b32.p, Bt, (size_t)N * K * 4, cudaMemcpyHostToDevice, h->stream);
+        if (bias) cudaMemcpyAsync(bi.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream);
+        cudaMemsetAsync(c32.p, 0xFF, (size_t)M * N * 4, h->stream);      // NaN pattern: unwritten outputs are visible
+        h->launches += launch_split_f16(a32.as<float>(), ah.as<__half>(), al.as<__half>(), M * K, h->stream);
+        h->launches += launch_split_f16(b32.as<float>(), bh.as<__half>(), bl.as<__half>(), (int64_t)N * K, h->stream);
+        int n = launch_gemm_f16x3(ah.as<__half>(), al.as<__half>(), bh.as<__half>(), bl.as<__half>(), M, N, K, c32.as<float>(),
+                                  bias ? bi.as<float>() : nullptr, 0, 1, M, N, h->num_sms, h->stream);
+        if (n < 0) { rc = fail(h, NRV_E_INVALID, "debug gemm: unsupported shape or tensor-map failure"); break; }
+        h->launches += n;
+        cudaMemcpyAsync(C, c32.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(h, NRV_E_CUDA, std::string("debug gemm: ") + cudaGetErrorString(e)); break; }
+    } while (0);
+    cleanup();
+    return rc;
 }
 
 int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return revise_impl(h, b, r, true); }

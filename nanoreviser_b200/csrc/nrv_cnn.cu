@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(CNN_THREADS, 2)
 cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
            const int32_t* __restrict__ starts, const int32_t* __restrict__ base_read,
            const double* __restrict__ shift, const double* __restrict__ scale,
-           const float* __restrict__ explicit_win, int64_t n_bases, float* __restrict__ sig_feat) {
+           const float* __restrict__ explicit_win, int64_t n_bases, float* __restrict__ sig_feat,
+           __half* __restrict__ sf_hi, __half* __restrict__ sf_lo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CnnSmem& s = *reinterpret_cast<CnnSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -132,13 +133,28 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
             reinterpret_cast<float4*>(sig_feat + ja * NRV_SIGFEAT)[tx] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
         if (jb < n_bases)
             reinterpret_cast<float4*>(sig_feat + jb * NRV_SIGFEAT)[tx] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        if (sf_hi) {   // fp16 (hi, lo) copy: A operand of the tensor-core projection of total_rnn1's per-base part
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (ja < n_bases) {
+                    const __half h = __float2half_rn(acc0[c]);
+                    sf_hi[ja * NRV_SIGFEAT + tx * 4 + c] = h;
+                    sf_lo[ja * NRV_SIGFEAT + tx * 4 + c] = __float2half_rn(acc0[c] - __half2float(h));
+                }
+                if (jb < n_bases) {
+                    const __half h = __float2half_rn(acc1[c]);
+                    sf_hi[jb * NRV_SIGFEAT + tx * 4 + c] = h;
+                    sf_lo[jb * NRV_SIGFEAT + tx * 4 + c] = __float2half_rn(acc1[c] - __half2float(h));
+                }
+            }
+        }
     }
 }
 
 int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, const int64_t* sig_off,
                const int32_t* starts, const int64_t* /*base_off*/, const int32_t* base_read,
                const double* shift, const double* scale, const float* explicit_win, int64_t n_bases,
-               float* sig_feat1, float* sig_feat2, cudaStream_t st) {
+               float* sig_feat1, float* sig_feat2, __half* const sf_hi[2], __half* const sf_lo[2], cudaStream_t st) {
     if (n_bases <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -149,12 +165,14 @@ int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, co
     int n = 0;
     if (m1 && sig_feat1) {
         cnn_kernel<<<grid, CNN_THREADS, sizeof(CnnSmem), st>>>(m1->cnn, signal, sig_off, starts, base_read, shift,
-                                                                scale, explicit_win, n_bases, sig_feat1);
+                                                                scale, explicit_win, n_bases, sig_feat1, sf_hi ? sf_hi[0] : nullptr,
+                                                                sf_lo ? sf_lo[0] : nullptr);
         ++n;
     }
     if (m2 && sig_feat2) {
         cnn_kernel<<<grid, CNN_THREADS, sizeof(CnnSmem), st>>>(m2->cnn, signal, sig_off, starts, base_read, shift,
-                                                                scale, explicit_win, n_bases, sig_feat2);
+                                                                scale, explicit_win, n_bases, sig_feat2, sf_hi ? sf_hi[1] : nullptr,
+                                                                sf_lo ? sf_lo[1] : nullptr);
         ++n;
     }
     return n;

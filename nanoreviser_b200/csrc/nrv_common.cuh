@@ -1,5 +1,6 @@
 // Shared declarations of libnrv.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,9 +20,27 @@ namespace nrv {
 struct LstmLayerDev {
     int in_a, in_b, u, k, k_pad;       // K = in_a + in_b + u (x_t rows, then h rows); k_pad = roundup(K, 16)
     float* wcat[2];                    // [k_pad][4u], column = unit*4 + gate (i,f,c,o), rows [x | h]
+    float* wrec[2];                    // [u][4u] recurrent rows only (used when the projection runs on tensor cores)
     float* bias[2];                    // [4u] same column order
     float* bn_scale;                   // [2u] gamma/sqrt(var+eps)  (identity for the last layer)
     float* bn_shift;                   // [2u] beta - mean*scale
+    // tensor-core projection operands (layers 2, 3): B^T = [2*4u][k_in] fp16 (hi, lo), rows = dir-major interleaved
+    // gate columns, the preceding BatchNormalization folded in; bias_tc [2*4u] = bias + bn_shift . Wk
+    __half* pb_hi; __half* pb_lo;      // main part (K = in_a)
+    __half* sb_hi; __half* sb_lo;      // per-base part (K = in_b), layer 2 only
+    float* bias_tc;
+};
+
+struct LstmIo {
+    const float* act_in = nullptr;     // [n_win][T][in_a] fp32 (fused variants)
+    const float* base_in = nullptr;    // [n_bases][in_b]
+    const int32_t* win_base = nullptr;
+    float* act_out = nullptr;          // fp32 [n_win][T][2u]
+    const float* zin = nullptr;        // [2][T][n_win][4u]
+    const float* zsig = nullptr;       // [n_bases][2][4u]
+    __half* out_hi = nullptr;          // fp16 pair [n_win][T][out_ld] (columns [0, 2u))
+    __half* out_lo = nullptr;
+    int out_ld = 0;
 };
 
 struct CnnDev {
@@ -68,11 +87,16 @@ int launch_window_map(const int64_t* base_off, const int64_t* win_off, const int
 int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, const int64_t* sig_off,
                const int32_t* starts, const int64_t* base_off, const int32_t* base_read,
                const double* shift, const double* scale, const float* explicit_win, int64_t n_bases,
-               float* sig_feat1, float* sig_feat2, cudaStream_t st);
+               float* sig_feat1, float* sig_feat2, __half* const sf_hi[2], __half* const sf_lo[2], cudaStream_t st);
 
 // nrv_lstm.cu: one Bi-LSTM layer over a chunk of windows.
-int launch_lstm_layer(int layer, const LstmLayerDev& L, const float* act_in, const float* base_in,
-                      const int32_t* win_base, int64_t n_win, int T, float* act_out, cudaStream_t st);
+int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T,
+                      cudaStream_t st);
+
+// nrv_gemm.cu: C[M][N] = A[M][K] . B[N][K]^T (+bias) with split-fp16 operands on tcgen05 (see file header)
+int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
+                      float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int num_sms, cudaStream_t st);
+int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,

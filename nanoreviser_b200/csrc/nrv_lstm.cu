@@ -10,6 +10,8 @@
 // shared memory k-major; weights stream from L2 through a double-buffered cp.async ring.
 // Windows overlap in the read, but every window restarts from a zero state, so nothing is shared
 // between windows except the per-base inputs (features / CNN output), which are indexed, not copied.
+#include <cuda_fp16.h>
+
 #include "nrv_common.cuh"
 
 namespace nrv {
@@ -39,13 +41,20 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ float hard_sigmoid(float x) { return __saturatef(fmaf(0.2f, x, 0.5f)); }
 
-template <int IN_A, int IN_B, int U, int TM>
+// ZMODE 0: the input projection is part of the per-step GEMM (K = in + u), accumulators start from the bias.
+// ZMODE 1: the input projection was computed by the tensor-core GEMM (nrv_gemm.cu): accumulators start from
+//          zin[dir][t][w][4u] (+ zsig[base][2][4u], the per-base part of total_rnn1's input), K = u only.
+// OMODE 0: fp32 output with the following BatchNormalization folded in.  OMODE 1: raw h as an fp16 (hi, lo)
+//          pair -- the A operand of the next layer's tensor-core projection (its BN is folded into that GEMM).
+template <int IN_A, int IN_B, int U, int TM, int ZMODE, int OMODE>
 __global__ void __launch_bounds__((LstmTile<IN_A, IN_B, U, TM>::NT), 1)
 lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ base_in,
                   const int32_t* __restrict__ win_base, const float* __restrict__ wcat0,
                   const float* __restrict__ wcat1, const float* __restrict__ bias0,
                   const float* __restrict__ bias1, const float* __restrict__ bn_scale,
-                  const float* __restrict__ bn_shift, float* __restrict__ act_out, int64_t n_win, int T) {
+                  const float* __restrict__ bn_shift, float* __restrict__ act_out,
+                  const float* __restrict__ zin, const float* __restrict__ zsig,
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t n_win, int T) {
     using C = LstmTile<IN_A, IN_B, U, TM>;
     extern __shared__ __align__(16) float smem[];
     float* As = smem;                       // [KP][A_LD]  rows [0,IN) = x_t, [IN,K) = h_{t-1}
@@ -109,10 +118,32 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
         }
         // ---- GEMM over K in chunks of KC, weights double-buffered ----------------------------
         float acc[8][8];
+        if (ZMODE == 0) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            acc[r][0] = bA.x; acc[r][1] = bA.y; acc[r][2] = bA.z; acc[r][3] = bA.w;
-            acc[r][4] = bB.x; acc[r][5] = bB.y; acc[r][6] = bB.z; acc[r][7] = bB.w;
+            for (int r = 0; r < 8; ++r) {
+                acc[r][0] = bA.x; acc[r][1] = bA.y; acc[r][2] = bA.z; acc[r][3] = bA.w;
+                acc[r][4] = bB.x; acc[r][5] = bB.y; acc[r][6] = bB.z; acc[r][7] = bB.w;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int64_t w = w0 + m0 + r;
+                float4 zA = make_float4(0.f, 0.f, 0.f, 0.f), zB = zA;
+                if (w < n_win) {
+                    const float* zp = zin + (((int64_t)dir * T + t) * n_win + w) * C::N;
+                    zA = __ldg(reinterpret_cast<const float4*>(zp + colA));
+                    zB = __ldg(reinterpret_cast<const float4*>(zp + colB));
+                    if (zsig) {
+                        const float* sp = zsig + ((int64_t)win_base[w] + t) * (2 * C::N) + dir * C::N;
+                        const float4 sA = __ldg(reinterpret_cast<const float4*>(sp + colA));
+                        const float4 sB = __ldg(reinterpret_cast<const float4*>(sp + colB));
+                        zA.x += sA.x; zA.y += sA.y; zA.z += sA.z; zA.w += sA.w;
+                        zB.x += sB.x; zB.y += sB.y; zB.z += sB.z; zB.w += sB.w;
+                    }
+                }
+                acc[r][0] = zA.x; acc[r][1] = zA.y; acc[r][2] = zA.z; acc[r][3] = zA.w;
+                acc[r][4] = zB.x; acc[r][5] = zB.y; acc[r][6] = zB.z; acc[r][7] = zB.w;
+            }
         }
         constexpr int CHUNK_V4 = C::KC * C::N / 4;
         for (int i = tid; i < CHUNK_V4; i += C::NT) cp_async16(Bs + i * 4, wcat + i * 4);
@@ -174,37 +205,52 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
         for (int r = 0; r < 8; ++r) {
             const int64_t w = w0 + m0 + r;
             if (w < n_win) {
-                float* o = act_out + (w * T + t) * (2 * U) + dir * U;
-                o[uA] = fmaf(hA[r], bnsA, bntA);
-                o[uB] = fmaf(hB[r], bnsB, bntB);
+                if (OMODE == 0) {
+                    const int64_t off = (w * T + t) * (2 * U) + dir * U;
+                    act_out[off + uA] = fmaf(hA[r], bnsA, bntA);
+                    act_out[off + uB] = fmaf(hB[r], bnsB, bntB);
+                } else {
+                    const int64_t off = (w * T + t) * out_ld + dir * U;
+                    const __half h1 = __float2half_rn(hA[r]), h2 = __float2half_rn(hB[r]);
+                    out_hi[off + uA] = h1; out_lo[off + uA] = __float2half_rn(hA[r] - __half2float(h1));
+                    out_hi[off + uB] = h2; out_lo[off + uB] = __float2half_rn(hB[r] - __half2float(h2));
+                }
             }
         }
         // the first __syncthreads of the next step's K loop orders these smem writes before any read
     }
 }
 
-template <int IN_A, int IN_B, int U, int TM>
-static int launch_one(const LstmLayerDev& L, const float* act_in, const float* base_in, const int32_t* win_base,
-                      int64_t n_win, int T, float* act_out, cudaStream_t st) {
+template <int IN_A, int IN_B, int U, int TM, int ZMODE, int OMODE>
+static int launch_one(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st) {
     using C = LstmTile<IN_A, IN_B, U, TM>;
-    auto kern = lstm_layer_kernel<IN_A, IN_B, U, TM>;
+    auto kern = lstm_layer_kernel<IN_A, IN_B, U, TM, ZMODE, OMODE>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     dim3 grid((unsigned)((n_win + TM - 1) / TM), 2);
-    kern<<<grid, C::NT, C::SMEM, st>>>(act_in, base_in, win_base, L.wcat[0], L.wcat[1], L.bias[0], L.bias[1],
-                                       L.bn_scale, L.bn_shift, act_out, n_win, T);
+    float* const* w = ZMODE ? L.wrec : L.wcat;
+    kern<<<grid, C::NT, C::SMEM, st>>>(io.act_in, io.base_in, io.win_base, w[0], w[1], L.bias[0], L.bias[1],
+                                       L.bn_scale, L.bn_shift, io.act_out, io.zin, io.zsig, io.out_hi, io.out_lo, io.out_ld,
+                                       n_win, T);
     return 1;
 }
 
-int launch_lstm_layer(int layer, const LstmLayerDev& L, const float* act_in, const float* base_in,
-                      const int32_t* win_base, int64_t n_win, int T, float* act_out, cudaStream_t st) {
+// variant 0: fused fp32 path (projection inside the recurrence GEMM), fp32+BN output
+// variant 1: fused fp32 path, raw fp16 (hi, lo) output             (feeds a tensor-core projection)
+// variant 2: recurrence only, pre-activations from the tensor-core projection, fp16 (hi, lo) output
+// variant 3: recurrence only, fp32 output (last layer; no BN follows)
+int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T,
+                      cudaStream_t st) {
     if (n_win <= 0) return 0;
-    switch (layer) {
-        case 0: return launch_one<0, 6, 16, 128>(L, act_in, base_in, win_base, n_win, T, act_out, st);
-        case 1: return launch_one<32, 0, 64, 128>(L, act_in, base_in, win_base, n_win, T, act_out, st);
-        case 2: return launch_one<128, 64, 128, 64>(L, act_in, base_in, win_base, n_win, T, act_out, st);
-        case 3: return launch_one<256, 0, 64, 128>(L, act_in, base_in, win_base, n_win, T, act_out, st);
+    switch (layer * 4 + variant) {
+        case 0 * 4 + 0: return launch_one<0, 6, 16, 128, 0, 0>(L, io, n_win, T, st);
+        case 1 * 4 + 0: return launch_one<32, 0, 64, 128, 0, 0>(L, io, n_win, T, st);
+        case 1 * 4 + 1: return launch_one<32, 0, 64, 128, 0, 1>(L, io, n_win, T, st);
+        case 2 * 4 + 0: return launch_one<128, 64, 128, 64, 0, 0>(L, io, n_win, T, st);
+        case 2 * 4 + 2: return launch_one<0, 0, 128, 64, 1, 1>(L, io, n_win, T, st);
+        case 3 * 4 + 0: return launch_one<256, 0, 64, 128, 0, 0>(L, io, n_win, T, st);
+        case 3 * 4 + 3: return launch_one<0, 0, 64, 128, 1, 0>(L, io, n_win, T, st);
     }
-    return 0;
+    return -1;
 }
 
 }  // namespace nrv

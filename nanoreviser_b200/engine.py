@@ -58,7 +58,7 @@ class _Result(C.Structure):
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
            "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
-           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device")
+           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_debug_gemm")
 
 _lib = None
 
@@ -104,6 +104,8 @@ def load_library(path: Optional[str] = None):
     lib.nrv_revise_batch.restype = C.c_int
     lib.nrv_revise_batch_device.argtypes = [vp, C.POINTER(_Batch), C.POINTER(_Result)]
     lib.nrv_revise_batch_device.restype = C.c_int
+    lib.nrv_debug_gemm.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.nrv_debug_gemm.restype = C.c_int
     if path is None:
         _lib = lib
     return lib
@@ -347,6 +349,17 @@ class Reviser:
                                   _ptr(revised), cap, _ptr(out_off))
         self._check(rc, "nrv_decode")
         return revised[:out_off[-1]], out_off
+
+    def debug_gemm(self, A: np.ndarray, Bt: np.ndarray, bias: Optional[np.ndarray] = None) -> np.ndarray:
+        """nrv_debug_gemm: A [M,K] . Bt[N,K]^T (+bias) through the tcgen05 split-fp16 projection GEMM."""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        Bt = np.ascontiguousarray(Bt, dtype=np.float32)
+        M, K = A.shape
+        N = Bt.shape[0]
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        Cm = np.empty((M, N), np.float32)
+        self._check(self._lib.nrv_debug_gemm(self._h, M, N, K, _ptr(A), _ptr(Bt), _ptr(b), _ptr(Cm)), "nrv_debug_gemm")
+        return Cm
 
     # -- the whole path -----------------------------------------------------------------------
     def revise_batch(self, b: Batch, want_labels: bool = False, want_probs: bool = False,
