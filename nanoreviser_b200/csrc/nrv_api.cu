@@ -66,6 +66,7 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
+    int rec_tc = 1;         // tcgen05 recurrence kernels where available (NRV_REC=simt disables)
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
@@ -169,6 +170,21 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.bn_scale = nullptr; L.bn_shift = nullptr;
         }
         L.pb_hi = L.pb_lo = L.sb_hi = L.sb_lo = nullptr; L.bias_tc = nullptr;
+        L.rt_hi = L.rt_lo = nullptr;
+        if (l >= 1) {
+            std::vector<__half> rh((size_t)2 * 4 * u * u), rl(rh.size());
+            for (int d = 0; d < 2; ++d)
+                for (int g = 0; g < 4; ++g)
+                    for (int j = 0; j < u; ++j)
+                        for (int k = 0; k < u; ++k) {
+                            const float wv = w->lstm[l][d].recurrent[(size_t)k * 4 * u + g * u + j];
+                            const size_t idx = ((size_t)d * 4 * u + j * 4 + g) * u + k;
+                            rh[idx] = __float2half_rn(wv);
+                            rl[idx] = __float2half_rn(wv - __half2float(rh[idx]));
+                        }
+            L.rt_hi = upload(h, rh, &e); if (e) goto cuda_fail;
+            L.rt_lo = upload(h, rl, &e); if (e) goto cuda_fail;
+        }
         if (l >= 2) {
             // Tensor-core projection operand B^T [2*4u][in] (K-major), rows = dir*4u + unit*4 + gate.  The input of
             // this layer is BN(h_prev) (+ the raw CNN features for layer 2): y = h*s + t  =>  fold s into the rows of
@@ -339,7 +355,13 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
                     h->launches += n;
                     LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.act_out = h->d_act[3].as<float>();
-                    h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
+                    if (h->rec_tc) {
+                        n = launch_lstm_rec_tc64(M.lstm[3], io, nw, T, h->stream);
+                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
+                        h->launches += n;
+                    } else {
+                        h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
+                    }
                 }
                 heads_in = h->d_act[3].as<float>();
             }
@@ -580,6 +602,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
     const char* pa = getenv("NRV_PATH");
     if (pa && !strcmp(pa, "simt")) h->path = 0;
+    const char* rc_env = getenv("NRV_REC");
+    if (rc_env && !strcmp(rc_env, "simt")) h->rec_tc = 0;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
     return NRV_OK;

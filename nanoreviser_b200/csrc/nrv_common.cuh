@@ -29,6 +29,8 @@ struct LstmLayerDev {
     __half* pb_hi; __half* pb_lo;      // main part (K = in_a)
     __half* sb_hi; __half* sb_lo;      // per-base part (K = in_b), layer 2 only
     float* bias_tc;
+    // tensor-core recurrence operand: Wr^T [2 dirs][4u][u] fp16 (hi, lo), row = unit*4 + gate (layers 1..3)
+    __half* rt_hi; __half* rt_lo;
 };
 
 struct LstmIo {
@@ -97,6 +99,9 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int num_sms, cudaStream_t st);
 int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
+
+// nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
+int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
