@@ -346,7 +346,13 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
                     h->launches += n;
                     LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
+                    if (h->rec_tc) {
+                        n = launch_lstm_rec_tc128(M.lstm[2], io, nw, T, h->stream);
+                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
+                        h->launches += n;
+                    } else {
+                        h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
+                    }
                 }
                 {   // total_rnn2: tcgen05 projection (K = 256), recurrence (K = 64) -> fp32 for the heads
                     StageTimer tm(h, ST_L3);

@@ -102,6 +102,7 @@ int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStre
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
 int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
+int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
