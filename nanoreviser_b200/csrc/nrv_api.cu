@@ -62,7 +62,7 @@ struct nrv_handle {
     // inputs / per-batch arenas
     Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag,
-        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a2[2], d_a3[2], d_zin;
+        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin;
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
@@ -185,14 +185,20 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.rt_hi = upload(h, rh, &e); if (e) goto cuda_fail;
             L.rt_lo = upload(h, rl, &e); if (e) goto cuda_fail;
         }
-        if (l >= 2) {
-            // Tensor-core projection operand B^T [2*4u][in] (K-major), rows = dir*4u + unit*4 + gate.  The input of
-            // this layer is BN(h_prev) (+ the raw CNN features for layer 2): y = h*s + t  =>  fold s into the rows of
-            // Wk that multiply h_prev and t . Wk into the bias, so the GEMM consumes the raw h in [-1, 1].
+        if (l >= 1) {
+            // Tensor-core projection operand B^T [2*4u][kin] (K-major, kin = in rounded up to 64 with zero columns),
+            // rows = dir*4u + unit*4 + gate.  The input of this layer is BN(h_prev) (+ the raw CNN features for layer
+            // 2): y = h*s + t  =>  fold s into the rows of Wk that multiply h_prev and t . Wk into the bias, so the GEMM
+            // consumes the raw h in [-1, 1].
             std::vector<float> ps, pt;
             bn_fold(w->bn_rnn[l - 1], IN_A[l], ps, pt);
+            if (l == 1) {   // read_rnn1's BN is applied by the producing kernel (see nrv_lstm.cu OMODE 2): no fold
+                std::fill(ps.begin(), ps.end(), 1.f);
+                std::fill(pt.begin(), pt.end(), 0.f);
+            }
             const int N2 = 2 * 4 * u;
-            std::vector<float> bt((size_t)N2 * in), bias_tc(N2);
+            const int kin = (in + 63) / 64 * 64;
+            std::vector<float> bt((size_t)N2 * kin, 0.f), bias_tc(N2);
             for (int d = 0; d < 2; ++d) {
                 const nrv_lstm_dir& src = w->lstm[l][d];
                 for (int g = 0; g < 4; ++g)
@@ -202,10 +208,10 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
                         for (int r = 0; r < in; ++r) {
                             const float wv = src.kernel[(size_t)r * 4 * u + g * u + j];
                             if (r < IN_A[l]) {
-                                bt[(size_t)n * in + r] = ps[r] * wv;
+                                bt[(size_t)n * kin + r] = ps[r] * wv;
                                 bacc += (double)pt[r] * (double)wv;
                             } else {
-                                bt[(size_t)n * in + r] = wv;
+                                bt[(size_t)n * kin + r] = wv;
                             }
                         }
                         bias_tc[n] = (float)bacc;
@@ -236,6 +242,15 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
         H.fb = upload(h, std::vector<float>(w->feat_b, w->feat_b + 16), &e); if (e) goto cuda_fail;
         H.ok = upload(h, std::vector<float>(w->final_k, w->final_k + 16 * nc), &e); if (e) goto cuda_fail;
         H.ob = upload(h, std::vector<float>(w->final_b, w->final_b + nc), &e); if (e) goto cuda_fail;
+        std::vector<__half> th(128 * 128), tl(128 * 128);
+        for (int o = 0; o < 128; ++o)
+            for (int i = 0; i < 128; ++i) {
+                const float wv = w->dense1_k[i * 128 + o];
+                th[o * 128 + i] = __float2half_rn(wv);
+                tl[o * 128 + i] = __float2half_rn(wv - __half2float(th[o * 128 + i]));
+            }
+        H.d1t_hi = upload(h, th, &e); if (e) goto cuda_fail;
+        H.d1t_lo = upload(h, tl, &e); if (e) goto cuda_fail;
     }
     return NRV_OK;
 cuda_fail:
@@ -296,6 +311,13 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
     } else {
         CU(h, h->d_act[0].ensure((size_t)rows * 32 * sizeof(float)));
         CU(h, h->d_act[3].ensure((size_t)rows * 128 * sizeof(float)));
+        for (int k = 0; k < 2; ++k) {
+            const size_t before = h->d_a1[k].cap;
+            CU(h, h->d_a1[k].ensure((size_t)rows * 64 * 2));
+            // columns [32, 64) of read_rnn11's operand are zero padding that no kernel ever writes
+            if (h->d_a1[k].cap != before) CU(h, cudaMemsetAsync(h->d_a1[k].p, 0, h->d_a1[k].cap, h->stream));
+            CU(h, h->d_a4[k].ensure((size_t)rows * 128 * 2));
+        }
         CU(h, h->d_a2[0].ensure((size_t)rows * 192 * 2)); CU(h, h->d_a2[1].ensure((size_t)rows * 192 * 2));
         CU(h, h->d_a3[0].ensure((size_t)rows * 256 * 2)); CU(h, h->d_a3[1].ensure((size_t)rows * 256 * 2));
         CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
@@ -305,6 +327,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
         for (int mi = 0; mi < 2; ++mi) {
             const ModelDev& M = h->m[mi];
             const float* heads_in = nullptr;
+            bool heads_d1_done = false;
             if (h->path == 0) {
                 // ---- fp32 SIMT path: projection fused into every recurrence step ----
                 const float* in_prev = nullptr;
@@ -319,62 +342,110 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     in_prev = h->d_act[l].as<float>();
                 }
                 heads_in = in_prev;
-            } else {
-                // ---- tensor-core path: tcgen05 projections for total_rnn1 / total_rnn2 ----
+            } else if (!h->rec_tc) {
+                // ---- tcgen05 projections for total_rnn1 / total_rnn2, fp32 SIMT recurrences (NRV_REC=simt) ----
                 __half *a2h = h->d_a2[0].as<__half>(), *a2l = h->d_a2[1].as<__half>();
                 __half *a3h = h->d_a3[0].as<__half>(), *a3l = h->d_a3[1].as<__half>();
                 float* zin = h->d_zin.as<float>();
-                {   // read_rnn1 (fp32, fused) -> BN'd fp32
+                {
                     StageTimer tm(h, ST_L0);
                     LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.act_out = h->d_act[0].as<float>();
                     h->launches += launch_lstm_layer(0, 0, M.lstm[0], io, nw, T, h->stream);
                 }
-                {   // read_rnn11 (fp32, fused) -> raw h as fp16 pairs, columns [0,128) of the next GEMM's A operand
+                {
                     StageTimer tm(h, ST_L1);
                     LstmIo io; io.act_in = h->d_act[0].as<float>(); io.win_base = win_base + c0;
                     io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
                     h->launches += launch_lstm_layer(1, 1, M.lstm[1], io, nw, T, h->stream);
                 }
-                {   // total_rnn1: gather CNN features, tcgen05 projection (K = 192), recurrence (K = 128)
+                {
                     StageTimer tm(h, ST_L2);
                     const int64_t items = nw * T * 8;
                     gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
                         h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, T, 192, a2h, a2l);
                     h->launches += 1;
                     int n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, nw * T, 1024, 192, zin,
-                                              M.lstm[2].bias_tc, 1, T, nw, 512, h->num_sms, h->stream);
+                                              M.lstm[2].bias_tc, 1, T, nw, 512, 0, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
                     h->launches += n;
                     LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    if (h->rec_tc) {
-                        n = launch_lstm_rec_tc128(M.lstm[2], io, nw, T, h->stream);
-                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
-                        h->launches += n;
-                    } else {
-                        h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
-                    }
+                    h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
                 }
-                {   // total_rnn2: tcgen05 projection (K = 256), recurrence (K = 64) -> fp32 for the heads
+                {
                     StageTimer tm(h, ST_L3);
                     int n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, nw * T, 512, 256, zin,
-                                              M.lstm[3].bias_tc, 1, T, nw, 256, h->num_sms, h->stream);
+                                              M.lstm[3].bias_tc, 1, T, nw, 256, 0, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
                     h->launches += n;
                     LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.act_out = h->d_act[3].as<float>();
-                    if (h->rec_tc) {
-                        n = launch_lstm_rec_tc64(M.lstm[3], io, nw, T, h->stream);
-                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
-                        h->launches += n;
-                    } else {
-                        h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
-                    }
+                    h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
                 }
                 heads_in = h->d_act[3].as<float>();
+            } else {
+                // ---- full tensor-core path: every projection is a tcgen05 GEMM, every recurrence with u >= 64 a tcgen05
+                //      recurrence kernel; activations travel between layers as raw h in fp16 (hi, lo) pairs ----
+                __half *a1h = h->d_a1[0].as<__half>(), *a1l = h->d_a1[1].as<__half>();
+                __half *a2h = h->d_a2[0].as<__half>(), *a2l = h->d_a2[1].as<__half>();
+                __half *a3h = h->d_a3[0].as<__half>(), *a3l = h->d_a3[1].as<__half>();
+                __half *a4h = h->d_a4[0].as<__half>(), *a4l = h->d_a4[1].as<__half>();
+                float* zin = h->d_zin.as<float>();
+                int n;
+                {   // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand
+                    StageTimer tm(h, ST_L0);
+                    LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.out_hi = a1h; io.out_lo = a1l; io.out_ld = 64;
+                    h->launches += launch_lstm_layer(0, 1, M.lstm[0], io, nw, T, h->stream);
+                }
+                {   // read_rnn11: projection (K = 32 -> 64) + recurrence (u = 64)
+                    StageTimer tm(h, ST_L1);
+                    n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, nw * T, 512, 64, zin, M.lstm[1].bias_tc, 1,
+                                          T, nw, 256, 0, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (read_rnn11) could not be launched");
+                    h->launches += n;
+                    LstmIo io; io.zin = zin; io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
+                    n = launch_lstm_rec_tc64(M.lstm[1], io, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (read_rnn11) could not be launched");
+                    h->launches += n;
+                }
+                {   // total_rnn1: gather CNN features, projection (K = 192), recurrence (u = 128)
+                    StageTimer tm(h, ST_L2);
+                    const int64_t items = nw * T * 8;
+                    gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
+                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, T, 192, a2h, a2l);
+                    h->launches += 1;
+                    n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, nw * T, 1024, 192, zin, M.lstm[2].bias_tc,
+                                          1, T, nw, 512, 0, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
+                    h->launches += n;
+                    LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
+                    n = launch_lstm_rec_tc128(M.lstm[2], io, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
+                    h->launches += n;
+                }
+                {   // total_rnn2: projection (K = 256), recurrence (u = 64)
+                    StageTimer tm(h, ST_L3);
+                    n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, nw * T, 512, 256, zin, M.lstm[3].bias_tc, 1,
+                                          T, nw, 256, 0, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
+                    h->launches += n;
+                    LstmIo io; io.zin = zin; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
+                    n = launch_lstm_rec_tc64(M.lstm[3], io, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
+                    h->launches += n;
+                }
+                {   // heads, first layer: relu(Dense(128 -> 128)) as a tcgen05 GEMM (85 % of the heads' work)
+                    StageTimer tm(h, ST_HEADS);
+                    n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, nw * T, 128, 128, h->d_act[3].as<float>(),
+                                          M.heads.d1b, 0, T, nw, 128, 1, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
+                    h->launches += n;
+                }
+                heads_in = h->d_act[3].as<float>();
+                heads_d1_done = true;
             }
             {
                 StageTimer tm(h, ST_HEADS);
                 int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
-                                     labels[mi] ? labels[mi] + c0 : nullptr, h->stream);
+                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_d1_done, h->stream);
                 if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
                 h->launches += n;
             }
@@ -625,7 +696,8 @@ void nrv_destroy(nrv_handle* h) {
                        &h->d_sigfeat[1], &h->d_act[0], &h->d_act[1], &h->d_act[2], &h->d_act[3], &h->d_probs[0],
                        &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff,
                        &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
-                       &h->d_sfl[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_zin};
+                       &h->d_sfl[1], &h->d_a1[0], &h->d_a1[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_a4[0],
+                       &h->d_a4[1], &h->d_zin};
     for (Arena* a : arenas) a->release();
     h->h_off.release(); h->h_flag.release();
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -799,7 +871,7 @@ int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const
         h->launches += launch_split_f16(a32.as<float>(), ah.as<__half>(), al.as<__half>(), M * K, h->stream);
         h->launches += launch_split_f16(b32.as<float>(), bh.as<__half>(), bl.as<__half>(), (int64_t)N * K, h->stream);
         int n = launch_gemm_f16x3(ah.as<__half>(), al.as<__half>(), bh.as<__half>(), bl.as<__half>(), M, N, K, c32.as<float>(),
-                                  bias ? bi.as<float>() : nullptr, 0, 1, M, N, h->num_sms, h->stream);
+                                  bias ? bi.as<float>() : nullptr, 0, 1, M, N, 0, h->num_sms, h->stream);
         if (n < 0) { rc = fail(h, NRV_E_INVALID, "debug gemm: unsupported shape or tensor-map failure"); break; }
         h->launches += n;
         cudaMemcpyAsync(C, c32.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, h->stream);

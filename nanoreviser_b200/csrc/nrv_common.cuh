@@ -56,6 +56,7 @@ struct CnnDev {
 
 struct HeadsDev {
     float *d1k, *d1b, *d2k, *d2b, *mk, *mb, *fk, *fb, *ok, *ob;
+    __half *d1t_hi, *d1t_lo;           // dense1 kernel transposed [128 out][128 in] fp16 (hi, lo): tensor-core B operand
     int n_class;
 };
 
@@ -97,7 +98,8 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
 
 // nrv_gemm.cu: C[M][N] = A[M][K] . B[N][K]^T (+bias) with split-fp16 operands on tcgen05 (see file header)
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
-                      float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int num_sms, cudaStream_t st);
+                      float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
+                      cudaStream_t st);
 int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
@@ -105,8 +107,10 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
+// d1_done = false: act_in is total_rnn2's output; true: act_in is already relu(Dense(128)) (tensor-core GEMM)
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
-                 float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, cudaStream_t st);
+                 float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, bool d1_done,
+                 cudaStream_t st);
 
 // nrv_decode.cu
 int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,

@@ -24,13 +24,18 @@ namespace nrv {
 
 using namespace tc;
 
-constexpr int G_TM = 128, G_TN = 256, G_KC = 64;
-constexpr int G_STAGES = 2;
+constexpr int G_TM = 128, G_KC = 64;
 constexpr int G_A_BYTES = G_TM * G_KC * 2;            // 16 KB (one of hi / lo)
-constexpr int G_B_BYTES = G_TN * G_KC * 2;            // 32 KB
-constexpr int G_STAGE_BYTES = 2 * G_A_BYTES + 2 * G_B_BYTES;   // 96 KB
 constexpr int G_THREADS = 192;
-constexpr size_t G_SMEM = (size_t)G_STAGES * G_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+template <int TN>
+struct GemmCfg {
+    static constexpr int B_BYTES = TN * G_KC * 2;                      // 32 KB (TN = 256) / 16 KB (TN = 128)
+    static constexpr int STAGE_BYTES = 2 * G_A_BYTES + 2 * B_BYTES;    // 96 KB / 64 KB
+    static constexpr int STAGES = (TN == 256) ? 2 : 3;
+    static constexpr int TMEM_COLS = 2 * TN;                           // double-buffered accumulator
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
 
 struct GemmOut {
     float* c;
@@ -40,12 +45,16 @@ struct GemmOut {
     int T;
     int64_t nw;
     int n_per_dir;
+    int relu;               // apply max(x, 0) after the bias (dense heads)
 };
 
+template <int G_TN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   GemmOut out, int64_t M, int N, int K) {
+    using Cfg = GemmCfg<G_TN>;
+    constexpr int G_STAGES = Cfg::STAGES, G_STAGE_BYTES = Cfg::STAGE_BYTES, G_B_BYTES = Cfg::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -68,7 +77,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -159,6 +168,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                             const float4 b = __ldg(reinterpret_cast<const float4*>(out.bias + n0 + cb * 32 + j));
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
+                        if (out.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         *reinterpret_cast<float4*>(dst + cb * 32 + j) = o;
                     }
                 }
@@ -171,7 +181,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ---- fp32 -> (hi, lo) fp16 split ------------------------------------------------------------------------
@@ -220,25 +230,37 @@ bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, i
     return r == CUDA_SUCCESS;
 }
 
-int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
-                      float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int num_sms, cudaStream_t st) {
-    if (M <= 0) return 0;
-    if (N % G_TN != 0 || K % G_KC != 0 || K <= 0) return -1;
-    if (mode == 1 && (n_per_dir % G_TN != 0)) return -1;
+template <int TN>
+static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
+                          const GemmOut& o, int num_sms, cudaStream_t st) {
+    using Cfg = GemmCfg<TN>;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_tmap_f16_k64(&ta_hi, a_hi, M, K, G_TM) || !make_tmap_f16_k64(&ta_lo, a_lo, M, K, G_TM) ||
-        !make_tmap_f16_k64(&tb_hi, b_hi, N, K, G_TN) || !make_tmap_f16_k64(&tb_lo, b_lo, N, K, G_TN))
+        !make_tmap_f16_k64(&tb_hi, b_hi, N, K, TN) || !make_tmap_f16_k64(&tb_lo, b_lo, N, K, TN))
         return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-        attr = true;
-    }
-    GemmOut o{c, bias, mode, T, nw, n_per_dir};
-    const int64_t n_tiles = ((M + G_TM - 1) / G_TM) * (N / G_TN);
+    auto kern = gemm_f16x3_kernel<TN>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    const int64_t n_tiles = ((M + G_TM - 1) / G_TM) * (N / TN);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, num_sms > 0 ? num_sms : 148);
-    gemm_f16x3_kernel<<<grid, G_THREADS, G_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, o, M, N, K);
+    kern<<<grid, G_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, o, M, N, K);
     return 1;
+}
+
+int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
+                      float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
+                      cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
+    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu};
+    if (N % 256 == 0) {
+        if (mode == 1 && (n_per_dir % 256 != 0)) return -1;
+        return launch_gemm_tn<256>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
+    }
+    if (N % 128 == 0) {
+        if (mode == 1 && (n_per_dir % 128 != 0)) return -1;
+        return launch_gemm_tn<128>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
+    }
+    return -1;
 }
 
 }  // namespace nrv

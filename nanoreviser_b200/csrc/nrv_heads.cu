@@ -18,7 +18,7 @@ struct HeadsSmem {
     float ft[HD_WIN][16];
 };
 
-template <int T>
+template <int T, bool D1_DONE>
 __global__ void __launch_bounds__(HD_THREADS)
 heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float* __restrict__ probs,
              uint8_t* __restrict__ labels) {
@@ -33,13 +33,14 @@ heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float*
         const int64_t w = w0 + row / T;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (w < n_win) v = __ldg(reinterpret_cast<const float4*>(act_in + (w0 * T + row) * 128) + q);
-        *reinterpret_cast<float4*>(&s.in[row][q * 4]) = v;
+        if (D1_DONE) *reinterpret_cast<float4*>(&s.d1[row][q * 4]) = v;
+        else *reinterpret_cast<float4*>(&s.in[row][q * 4]) = v;
     }
     __syncthreads();
     const int g = tid >> 5;          // window inside the tile (one warp per window)
     const int tx = tid & 31;
     // ---- Dense(128 -> 128, relu): thread = T rows x 4 cols -------------------------------------
-    {
+    if (!D1_DONE) {
         float acc[T][4];
         const float4 bb = __ldg(reinterpret_cast<const float4*>(H.d1b) + tx);
 #pragma unroll
@@ -136,10 +137,10 @@ heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float*
     }
 }
 
-template <int T>
+template <int T, bool D1>
 static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win, float* probs, uint8_t* labels,
                           cudaStream_t st) {
-    auto kern = heads_kernel<T>;
+    auto kern = heads_kernel<T, D1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadsSmem<T>));
     const unsigned grid = (unsigned)((n_win + HD_WIN - 1) / HD_WIN);
     kern<<<grid, HD_THREADS, sizeof(HeadsSmem<T>), st>>>(H, act_in, n_win, probs, labels);
@@ -147,15 +148,20 @@ static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win,
 }
 
 int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, float* probs, uint8_t* labels,
-                 cudaStream_t st) {
+                 bool d1_done, cudaStream_t st) {
     if (n_win <= 0) return 0;
+#define NRV_HEADS_CASE(TT)                                                                        \
+    case TT:                                                                                      \
+        return d1_done ? launch_heads_t<TT, true>(H, act_in, n_win, probs, labels, st)            \
+                       : launch_heads_t<TT, false>(H, act_in, n_win, probs, labels, st);
     switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
-        case 5: return launch_heads_t<5>(H, act_in, n_win, probs, labels, st);
-        case 7: return launch_heads_t<7>(H, act_in, n_win, probs, labels, st);
-        case 9: return launch_heads_t<9>(H, act_in, n_win, probs, labels, st);
-        case 11: return launch_heads_t<11>(H, act_in, n_win, probs, labels, st);
-        case 13: return launch_heads_t<13>(H, act_in, n_win, probs, labels, st);
+        NRV_HEADS_CASE(5)
+        NRV_HEADS_CASE(7)
+        NRV_HEADS_CASE(9)
+        NRV_HEADS_CASE(11)
+        NRV_HEADS_CASE(13)
     }
+#undef NRV_HEADS_CASE
     return -1;
 }
 

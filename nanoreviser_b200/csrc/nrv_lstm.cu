@@ -210,10 +210,15 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
                     act_out[off + uA] = fmaf(hA[r], bnsA, bntA);
                     act_out[off + uB] = fmaf(hB[r], bnsB, bntB);
                 } else {
+                    // OMODE 1: raw h.  OMODE 2: BatchNormalization applied in fp32 first (read_rnn1: its BN has
+                    // zero-variance channels with a x31.6 gain and large offsets -- folding it into the next GEMM
+                    // would cancel catastrophically in split-fp16), then split.
                     const int64_t off = (w * T + t) * out_ld + dir * U;
-                    const __half h1 = __float2half_rn(hA[r]), h2 = __float2half_rn(hB[r]);
-                    out_hi[off + uA] = h1; out_lo[off + uA] = __float2half_rn(hA[r] - __half2float(h1));
-                    out_hi[off + uB] = h2; out_lo[off + uB] = __float2half_rn(hB[r] - __half2float(h2));
+                    const float yA = (OMODE == 2) ? fmaf(hA[r], bnsA, bntA) : hA[r];
+                    const float yB = (OMODE == 2) ? fmaf(hB[r], bnsB, bntB) : hB[r];
+                    const __half h1 = __float2half_rn(yA), h2 = __float2half_rn(yB);
+                    out_hi[off + uA] = h1; out_lo[off + uA] = __float2half_rn(yA - __half2float(h1));
+                    out_hi[off + uB] = h2; out_lo[off + uB] = __float2half_rn(yB - __half2float(h2));
                 }
             }
         }
@@ -243,6 +248,7 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
     if (n_win <= 0) return 0;
     switch (layer * 4 + variant) {
         case 0 * 4 + 0: return launch_one<0, 6, 16, 128, 0, 0>(L, io, n_win, T, st);
+        case 0 * 4 + 1: return launch_one<0, 6, 16, 128, 0, 2>(L, io, n_win, T, st);
         case 1 * 4 + 0: return launch_one<32, 0, 64, 128, 0, 0>(L, io, n_win, T, st);
         case 1 * 4 + 1: return launch_one<32, 0, 64, 128, 0, 1>(L, io, n_win, T, st);
         case 2 * 4 + 0: return launch_one<128, 64, 128, 64, 0, 0>(L, io, n_win, T, st);

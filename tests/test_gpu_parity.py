@@ -313,7 +313,8 @@ def test_window_chunking_is_invisible(weights_by_species, reads, monkeypatch):
 # --------------------------------------------------------------------------------------------------
 # tcgen05 split-fp16 projection GEMM in isolation (fp32-equivalent contraction)
 # --------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 128), (1000, 1024, 192), (4096 + 17, 512, 256)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 128), (1000, 1024, 192), (4096 + 17, 512, 256), (777, 128, 128),
+                                   (50000, 384, 64)])
 def test_tcgen05_projection_gemm(reviser_by_species, M, N, K):
     rv = reviser_by_species("ecoli")
     rng = np.random.default_rng(M + N + K)
