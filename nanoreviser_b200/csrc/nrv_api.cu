@@ -66,7 +66,6 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
-    int rec_tc = 1;         // tcgen05 recurrence kernels where available (NRV_REC=simt disables)
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
@@ -285,16 +284,17 @@ __global__ void iota_mul_kernel(int32_t* out, int64_t n, int mul) {
 }
 
 __global__ void gather_sig_kernel(const __half* __restrict__ sf_hi, const __half* __restrict__ sf_lo,
-                                  const int32_t* __restrict__ win_base, int64_t n_win, int T, int ld,
+                                  const int32_t* __restrict__ win_base, int64_t n_win, int64_t nwp, int T, int ld,
                                   __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
-    // columns [128, 192) of total_rnn1's input row (w, t) = CNN features of base win_base[w] + t; 8 x 16 B per half array
+    // columns [128, 192) of total_rnn1's input row (t, w) = CNN features of base win_base[w] + t; 8 x 16 B per half array
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = i >> 3;
+    const int64_t item = i >> 3;
     const int q = (int)(i & 7);
-    if (row >= n_win * T) return;
-    const int64_t w = row / T;
-    const int t = (int)(row - w * T);
+    if (item >= n_win * T) return;
+    const int t = (int)(item / n_win);
+    const int64_t w = item - (int64_t)t * n_win;
     const int64_t b = (int64_t)win_base[w] + t;
+    const int64_t row = (int64_t)t * nwp + w;
     reinterpret_cast<uint4*>(a_hi + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_hi + b * NRV_SIGFEAT) + q);
     reinterpret_cast<uint4*>(a_lo + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_lo + b * NRV_SIGFEAT) + q);
 }
@@ -304,7 +304,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                float* const probs[2], uint8_t* const labels[2]) {
     const int T = h->window;
     const int64_t CH = std::min<int64_t>(h->chunk_windows, std::max<int64_t>(n_win, 1));
-    const int64_t rows = CH * T;
+    const int64_t rows = ((CH + 127) / 128 * 128) * T;     // padded time-major rows of one chunk
     static const int widths[4] = {32, 128, 256, 128};
     if (h->path == 0) {
         for (int l = 0; l < 4; ++l) CU(h, h->d_act[l].ensure((size_t)rows * widths[l] * sizeof(float)));
@@ -328,6 +328,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
             const ModelDev& M = h->m[mi];
             const float* heads_in = nullptr;
             bool heads_d1_done = false;
+            int64_t heads_nwp = 0;
             if (h->path == 0) {
                 // ---- fp32 SIMT path: projection fused into every recurrence step ----
                 const float* in_prev = nullptr;
@@ -342,48 +343,12 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     in_prev = h->d_act[l].as<float>();
                 }
                 heads_in = in_prev;
-            } else if (!h->rec_tc) {
-                // ---- tcgen05 projections for total_rnn1 / total_rnn2, fp32 SIMT recurrences (NRV_REC=simt) ----
-                __half *a2h = h->d_a2[0].as<__half>(), *a2l = h->d_a2[1].as<__half>();
-                __half *a3h = h->d_a3[0].as<__half>(), *a3l = h->d_a3[1].as<__half>();
-                float* zin = h->d_zin.as<float>();
-                {
-                    StageTimer tm(h, ST_L0);
-                    LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.act_out = h->d_act[0].as<float>();
-                    h->launches += launch_lstm_layer(0, 0, M.lstm[0], io, nw, T, h->stream);
-                }
-                {
-                    StageTimer tm(h, ST_L1);
-                    LstmIo io; io.act_in = h->d_act[0].as<float>(); io.win_base = win_base + c0;
-                    io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
-                    h->launches += launch_lstm_layer(1, 1, M.lstm[1], io, nw, T, h->stream);
-                }
-                {
-                    StageTimer tm(h, ST_L2);
-                    const int64_t items = nw * T * 8;
-                    gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
-                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, T, 192, a2h, a2l);
-                    h->launches += 1;
-                    int n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, nw * T, 1024, 192, zin,
-                                              M.lstm[2].bias_tc, 1, T, nw, 512, 0, h->num_sms, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
-                    h->launches += n;
-                    LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    h->launches += launch_lstm_layer(2, 2, M.lstm[2], io, nw, T, h->stream);
-                }
-                {
-                    StageTimer tm(h, ST_L3);
-                    int n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, nw * T, 512, 256, zin,
-                                              M.lstm[3].bias_tc, 1, T, nw, 256, 0, h->num_sms, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
-                    h->launches += n;
-                    LstmIo io; io.win_base = win_base + c0; io.zin = zin; io.act_out = h->d_act[3].as<float>();
-                    h->launches += launch_lstm_layer(3, 3, M.lstm[3], io, nw, T, h->stream);
-                }
-                heads_in = h->d_act[3].as<float>();
             } else {
-                // ---- full tensor-core path: every projection is a tcgen05 GEMM, every recurrence with u >= 64 a tcgen05
-                //      recurrence kernel; activations travel between layers as raw h in fp16 (hi, lo) pairs ----
+                // ---- tensor-core path: every projection is a tcgen05 GEMM, every recurrence with u >= 64 a tcgen05
+                //      recurrence kernel; activations travel between layers as fp16 (hi, lo) pairs in the padded
+                //      time-major layout row(t, w) = t*nwp + w (see nrv_rec_tc.cu) ----
+                const int64_t nwp = (nw + 127) / 128 * 128;
+                const int64_t R = nwp * T;
                 __half *a1h = h->d_a1[0].as<__half>(), *a1l = h->d_a1[1].as<__half>();
                 __half *a2h = h->d_a2[0].as<__half>(), *a2l = h->d_a2[1].as<__half>();
                 __half *a3h = h->d_a3[0].as<__half>(), *a3l = h->d_a3[1].as<__half>();
@@ -393,16 +358,17 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 {   // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand
                     StageTimer tm(h, ST_L0);
                     LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.out_hi = a1h; io.out_lo = a1l; io.out_ld = 64;
+                    io.out_nwp = nwp;
                     h->launches += launch_lstm_layer(0, 1, M.lstm[0], io, nw, T, h->stream);
                 }
                 {   // read_rnn11: projection (K = 32 -> 64) + recurrence (u = 64)
                     StageTimer tm(h, ST_L1);
-                    n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, nw * T, 512, 64, zin, M.lstm[1].bias_tc, 1,
-                                          T, nw, 256, 0, h->num_sms, h->stream);
+                    n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, R, 512, 64, zin, M.lstm[1].bias_tc, 1,
+                                          T, nwp, 256, 0, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (read_rnn11) could not be launched");
                     h->launches += n;
                     LstmIo io; io.zin = zin; io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
-                    n = launch_lstm_rec_tc64(M.lstm[1], io, nw, T, h->stream);
+                    n = launch_lstm_rec_tc64(M.lstm[1], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (read_rnn11) could not be launched");
                     h->launches += n;
                 }
@@ -410,42 +376,43 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     StageTimer tm(h, ST_L2);
                     const int64_t items = nw * T * 8;
                     gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
-                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, T, 192, a2h, a2l);
+                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
                     h->launches += 1;
-                    n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, nw * T, 1024, 192, zin, M.lstm[2].bias_tc,
-                                          1, T, nw, 512, 0, h->num_sms, h->stream);
+                    n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, R, 1024, 192, zin, M.lstm[2].bias_tc,
+                                          1, T, nwp, 512, 0, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
                     h->launches += n;
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    n = launch_lstm_rec_tc128(M.lstm[2], io, nw, T, h->stream);
+                    n = launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
                     h->launches += n;
                 }
                 {   // total_rnn2: projection (K = 256), recurrence (u = 64)
                     StageTimer tm(h, ST_L3);
-                    n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, nw * T, 512, 256, zin, M.lstm[3].bias_tc, 1,
-                                          T, nw, 256, 0, h->num_sms, h->stream);
+                    n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, R, 512, 256, zin, M.lstm[3].bias_tc, 1,
+                                          T, nwp, 256, 0, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
                     h->launches += n;
                     LstmIo io; io.zin = zin; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
-                    n = launch_lstm_rec_tc64(M.lstm[3], io, nw, T, h->stream);
+                    n = launch_lstm_rec_tc64(M.lstm[3], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
                     h->launches += n;
                 }
                 {   // heads, first layer: relu(Dense(128 -> 128)) as a tcgen05 GEMM (85 % of the heads' work)
                     StageTimer tm(h, ST_HEADS);
-                    n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, nw * T, 128, 128, h->d_act[3].as<float>(),
-                                          M.heads.d1b, 0, T, nw, 128, 1, h->num_sms, h->stream);
+                    n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
+                                          M.heads.d1b, 0, T, nwp, 128, 1, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
                     h->launches += n;
                 }
                 heads_in = h->d_act[3].as<float>();
                 heads_d1_done = true;
+                heads_nwp = nwp;
             }
             {
                 StageTimer tm(h, ST_HEADS);
                 int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
-                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_d1_done, h->stream);
+                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_d1_done, heads_nwp, h->stream);
                 if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
                 h->launches += n;
             }
@@ -679,8 +646,6 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
     const char* pa = getenv("NRV_PATH");
     if (pa && !strcmp(pa, "simt")) h->path = 0;
-    const char* rc_env = getenv("NRV_REC");
-    if (rc_env && !strcmp(rc_env, "simt")) h->rec_tc = 0;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
     return NRV_OK;

@@ -43,6 +43,7 @@ struct LstmIo {
     __half* out_hi = nullptr;          // fp16 pair [n_win][T][out_ld] (columns [0, 2u))
     __half* out_lo = nullptr;
     int out_ld = 0;
+    int64_t out_nwp = 0;               // != 0: time-major padded rows, row(t, w) = t*out_nwp + w
 };
 
 struct CnnDev {
@@ -110,7 +111,7 @@ int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win
 // d1_done = false: act_in is total_rnn2's output; true: act_in is already relu(Dense(128)) (tensor-core GEMM)
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
                  float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, bool d1_done,
-                 cudaStream_t st);
+                 int64_t in_nwp /* != 0: act_in rows are time-major, row(t, w) = t*in_nwp + w */, cudaStream_t st);
 
 // nrv_decode.cu
 int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,

@@ -40,8 +40,8 @@ struct GemmCfg {
 struct GemmOut {
     float* c;
     const float* bias;      // [N] or nullptr
-    int mode;               // 0: C[r][N] row-major.  1: rows are (w,t) = (r / T, r % T); column tile -> direction:
-                            //    C[dir][t][w][n_per_dir]
+    int mode;               // 0: C[r][N] row-major.  1: zin tiles C[dir][r / 128][col / 4][128][4] with
+                            //    dir = column / n_per_dir (M must be a multiple of 128)
     int T;
     int64_t nw;
     int n_per_dir;
@@ -144,15 +144,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             tc_fence_after();
             const int64_t r = m0 + q * 32 + lane;             // this thread's output row
             float* dst = nullptr;
-            if (r < M) {
-                if (out.mode == 0) {
-                    dst = out.c + r * (int64_t)N + n0;
-                } else {
-                    const int64_t w = r / out.T;
-                    const int t = (int)(r - w * out.T);
-                    const int dir = n0 / out.n_per_dir;
-                    dst = out.c + ((int64_t)dir * out.T + t) * out.nw * out.n_per_dir + w * out.n_per_dir + (n0 - dir * out.n_per_dir);
-                }
+            int64_t cstride = 4;                              // floats between consecutive column quads
+            if (out.mode == 0) {
+                if (r < M) dst = out.c + r * (int64_t)N + n0;   // row-major: a quad is 4 consecutive floats
+            } else {
+                // zin tiles [dir][m_tile][col/4][128 rows][4]: lanes (rows) are contiguous for a fixed column quad
+                const int dir = n0 / out.n_per_dir;
+                const int nloc = n0 - dir * out.n_per_dir;
+                const int64_t m_tile = m0 / G_TM;
+                dst = out.c + ((int64_t)dir * n_tiles_m + m_tile) * ((int64_t)out.n_per_dir * G_TM) + (int64_t)(nloc >> 2) * (G_TM * 4) +
+                      (q * 32 + lane) * 4;
+                cstride = G_TM * 4;
             }
 #pragma unroll 1
             for (int cb = 0; cb < G_TN / 32; ++cb) {
@@ -169,7 +171,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
                         if (out.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(dst + cb * 32 + j) = o;
+                        *reinterpret_cast<float4*>(dst + (int64_t)(cb * 8 + (j >> 2)) * cstride) = o;
                     }
                 }
             }
@@ -252,6 +254,7 @@ int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
     GemmOut o{c, bias, mode, T, nw, n_per_dir, relu};
+    if (mode == 1 && (M % G_TM != 0)) return -1;
     if (N % 256 == 0) {
         if (mode == 1 && (n_per_dir % 256 != 0)) return -1;
         return launch_gemm_tn<256>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);

@@ -20,7 +20,7 @@ struct HeadsSmem {
 
 template <int T, bool D1_DONE>
 __global__ void __launch_bounds__(HD_THREADS)
-heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float* __restrict__ probs,
+heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, int64_t in_nwp, float* __restrict__ probs,
              uint8_t* __restrict__ labels) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadsSmem<T>& s = *reinterpret_cast<HeadsSmem<T>*>(smem_raw);
@@ -32,7 +32,10 @@ heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float*
         const int row = i >> 5, q = i & 31;
         const int64_t w = w0 + row / T;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w < n_win) v = __ldg(reinterpret_cast<const float4*>(act_in + (w0 * T + row) * 128) + q);
+        if (w < n_win) {
+            const int64_t grow = in_nwp ? ((int64_t)(row % T) * in_nwp + w) : (w0 * T + row);
+            v = __ldg(reinterpret_cast<const float4*>(act_in + grow * 128) + q);
+        }
         if (D1_DONE) *reinterpret_cast<float4*>(&s.d1[row][q * 4]) = v;
         else *reinterpret_cast<float4*>(&s.in[row][q * 4]) = v;
     }
@@ -138,22 +141,22 @@ heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, float*
 }
 
 template <int T, bool D1>
-static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win, float* probs, uint8_t* labels,
-                          cudaStream_t st) {
+static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win, int64_t in_nwp, float* probs,
+                          uint8_t* labels, cudaStream_t st) {
     auto kern = heads_kernel<T, D1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadsSmem<T>));
     const unsigned grid = (unsigned)((n_win + HD_WIN - 1) / HD_WIN);
-    kern<<<grid, HD_THREADS, sizeof(HeadsSmem<T>), st>>>(H, act_in, n_win, probs, labels);
+    kern<<<grid, HD_THREADS, sizeof(HeadsSmem<T>), st>>>(H, act_in, n_win, in_nwp, probs, labels);
     return 1;
 }
 
 int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, float* probs, uint8_t* labels,
-                 bool d1_done, cudaStream_t st) {
+                 bool d1_done, int64_t in_nwp, cudaStream_t st) {
     if (n_win <= 0) return 0;
 #define NRV_HEADS_CASE(TT)                                                                        \
     case TT:                                                                                      \
-        return d1_done ? launch_heads_t<TT, true>(H, act_in, n_win, probs, labels, st)            \
-                       : launch_heads_t<TT, false>(H, act_in, n_win, probs, labels, st);
+        return d1_done ? launch_heads_t<TT, true>(H, act_in, n_win, in_nwp, probs, labels, st)    \
+                       : launch_heads_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st);
     switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
         NRV_HEADS_CASE(5)
         NRV_HEADS_CASE(7)

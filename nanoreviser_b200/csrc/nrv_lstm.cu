@@ -54,7 +54,8 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
                   const float* __restrict__ bias1, const float* __restrict__ bn_scale,
                   const float* __restrict__ bn_shift, float* __restrict__ act_out,
                   const float* __restrict__ zin, const float* __restrict__ zsig,
-                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t n_win, int T) {
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t out_nwp,
+                  int64_t n_win, int T) {
     using C = LstmTile<IN_A, IN_B, U, TM>;
     extern __shared__ __align__(16) float smem[];
     float* As = smem;                       // [KP][A_LD]  rows [0,IN) = x_t, [IN,K) = h_{t-1}
@@ -213,7 +214,8 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
                     // OMODE 1: raw h.  OMODE 2: BatchNormalization applied in fp32 first (read_rnn1: its BN has
                     // zero-variance channels with a x31.6 gain and large offsets -- folding it into the next GEMM
                     // would cancel catastrophically in split-fp16), then split.
-                    const int64_t off = (w * T + t) * out_ld + dir * U;
+                    // row(t, w) = t*nwp + w when a padded time-major layout is requested, else (w, t)
+                    const int64_t off = (out_nwp ? ((int64_t)t * out_nwp + w) : (w * T + t)) * out_ld + dir * U;
                     const float yA = (OMODE == 2) ? fmaf(hA[r], bnsA, bntA) : hA[r];
                     const float yB = (OMODE == 2) ? fmaf(hB[r], bnsB, bntB) : hB[r];
                     const __half h1 = __float2half_rn(yA), h2 = __float2half_rn(yB);
@@ -235,7 +237,7 @@ static int launch_one(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, in
     float* const* w = ZMODE ? L.wrec : L.wcat;
     kern<<<grid, C::NT, C::SMEM, st>>>(io.act_in, io.base_in, io.win_base, w[0], w[1], L.bias[0], L.bias[1],
                                        L.bn_scale, L.bn_shift, io.act_out, io.zin, io.zsig, io.out_hi, io.out_lo, io.out_ld,
-                                       n_win, T);
+                                       io.out_nwp, n_win, T);
     return 1;
 }
 

@@ -1,9 +1,18 @@
 // K3 recurrence on the 5th-generation tensor cores (tcgen05 + TMEM), the "persistent recurrence kernel that
 // keeps the recurrent weights resident in shared memory" of BASELINE.json's north_star.
 //
-// The input projection x_t.Wk (+bias, with the preceding BatchNormalization folded in) has already been
-// computed for all timesteps by the time-batched GEMM (nrv_gemm.cu) into zin[dir][t][w][4u].  What is left
-// per step is  z = zin[t] + h_{t-1} . Wr ;  gates ;  c, h  -- sequential in t, independent across windows.
+// The input projection x_t.Wk (+bias, BatchNormalization folded) has already been computed for all timesteps by
+// the time-batched GEMM (nrv_gemm.cu).  What is left per step is  z = zin[t] + h_{t-1} . Wr ; gates ; c, h  --
+// sequential in t, independent across windows.
+//
+// Data layout (all kernels of the tensor-core path):
+//   * activations between layers: raw h as an fp16 (hi, lo) pair, TIME-MAJOR and padded:  row(t, w) = t*nwp + w,
+//     nwp = windows of the chunk rounded up to 128.  A tile of 128 windows at one timestep is 128 consecutive rows,
+//     so the recurrence publishes h with ONE bulk-tensor (TMA) store per 128x64 block straight from the swizzled
+//     shared-memory tile that is also the A operand of the next MMA, and the GEMM reads it back with TMA.
+//   * zin[dir][t][tile][col/4][128 rows][4]: "column-quad major inside a 128-row tile" -- the accumulator layout
+//     of both kernels is one TMEM lane (= one thread) per row, so a warp touching one column quad reads/writes
+//     32 x 16 B contiguous: coalesced 128-bit accesses without any staging.
 //
 // u = 64 variant (read_rnn11, total_rnn2; lstmmodel.py:46,51).  One CTA = one direction x TWO tiles of 128
 // windows that ping-pong:
@@ -12,9 +21,9 @@
 //   * h_{t-1} of each tile lives in shared memory as an fp16 (hi, lo) pair in the same swizzled K-major
 //     layout (the A operand), written by that tile's epilogue warps;
 //   * the accumulator of each tile is a 128-lane x 256-column fp32 block of TMEM;
-//   * warp 0 issues, per tile and step, 12 tcgen05.mma (4 K-steps x {lo*hi, hi*lo, hi*hi}) from one lane and
-//     commits to an mbarrier; warps 1-4 / 5-8 are the epilogue of tile A / B: tcgen05.ld -> + zin ->
-//     hard_sigmoid / tanh -> c (registers, never leaves the thread) -> h -> shared memory + global.
+//   * warp 0: per tile and step, one elected lane TMA-stores h_{t-1} to global, issues 12 tcgen05.mma
+//     (4 K-steps x {lo*hi, hi*lo, hi*hi}) and commits to an mbarrier; warps 1-4 / 5-8 are the epilogue of
+//     tile A / B: tcgen05.ld -> + zin -> hard_sigmoid / tanh -> c (registers) -> h -> shared memory.
 // While the epilogue of tile A runs on the CUDA cores, the tensor core works on tile B, and vice versa.
 #include "nrv_common.cuh"
 #include "nrv_tc.cuh"
@@ -22,6 +31,8 @@
 namespace nrv {
 
 using namespace tc;
+
+bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);   // nrv_gemm.cu
 
 constexpr int RT_THREADS = 288;                 // 1 MMA warp + 2 x 4 epilogue warps
 constexpr int RT_W_BYTES = 256 * 64 * 2;        // 32 KB: Wr^T hi (or lo)
@@ -51,11 +62,31 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-template <int OMODE>
+// One 32-column block (8 units x gates i,f,c,o) of the Keras-2.2.4 LSTM cell for this thread's row:
+// z = acc (if any) + zin ; c, h update ; h -> fp16 (hi, lo) packed as 2 x 16 bytes.
+__device__ __forceinline__ void lstm_cell_block(const uint32_t (&v)[32], bool have_acc, const float4 (&zq)[8], float* c8,
+                                                uint4& phi, uint4& plo) {
+    __half hh[8], hl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float zi = zq[j].x, zf = zq[j].y, zc = zq[j].z, zo = zq[j].w;
+        if (have_acc) {
+            zi += __uint_as_float(v[4 * j + 0]); zf += __uint_as_float(v[4 * j + 1]);
+            zc += __uint_as_float(v[4 * j + 2]); zo += __uint_as_float(v[4 * j + 3]);
+        }
+        const float ig = hsig(zi), fg = hsig(zf), gg = tanh_fast(zc), og = hsig(zo);
+        const float cn = fmaf(fg, c8[j], ig * gg);
+        c8[j] = cn;
+        split_f16(og * tanh_fast(cn), hh[j], hl[j]);
+    }
+    phi = make_uint4(pack_half2(hh[0], hh[1]), pack_half2(hh[2], hh[3]), pack_half2(hh[4], hh[5]), pack_half2(hh[6], hh[7]));
+    plo = make_uint4(pack_half2(hl[0], hl[1]), pack_half2(hl[2], hl[3]), pack_half2(hl[4], hl[5]), pack_half2(hl[6], hl[7]));
+}
+
 __global__ void __launch_bounds__(RT_THREADS, 1)
-lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict__ wr_lo,
-                     const float* __restrict__ zin, float* __restrict__ act_out, __half* __restrict__ out_hi,
-                     __half* __restrict__ out_lo, int out_ld, int64_t nw, int T) {
+lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict__ wr_lo, const float* __restrict__ zin,
+                     const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo,
+                     int64_t nwp, int T) {
     constexpr int U = 64, N = 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -64,69 +95,79 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
     uint8_t* s_h = smem + 2 * RT_W_BYTES;               // [tile][hi|lo][16 KB]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RT_W_BYTES + 4 * RT_H_BYTES);
     uint64_t* h_ready = bars;                           // [2] count 4 (one arrive per epilogue warp)
-    uint64_t* acc_ready = bars + 2;                     // [2] count 1 (tcgen05.commit)
+    uint64_t* acc_ready = bars + 2;                     // [2] count 2 (tcgen05.commit + "h store has left smem")
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    const int64_t w0[2] = {(int64_t)blockIdx.x * 256, (int64_t)blockIdx.x * 256 + 128};
-    const bool valid[2] = {w0[0] < nw, w0[1] < nw};
+    const int64_t ntw = nwp >> 7;
+    const int64_t wt[2] = {(int64_t)blockIdx.x * 2, (int64_t)blockIdx.x * 2 + 1};
+    const bool valid[2] = {wt[0] < ntw, wt[1] < ntw};
 
     if (threadIdx.x == 0) {
         mbar_init(&h_ready[0], 4); mbar_init(&h_ready[1], 4);
-        mbar_init(&acc_ready[0], 1); mbar_init(&acc_ready[1], 1);
+        mbar_init(&acc_ready[0], 2); mbar_init(&acc_ready[1], 2);
         fence_mbar_init();
+        tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
-    // resident recurrent weights: [256 rows][64 halves] -> K-major 128-byte-swizzled tiles
-    {
+    {   // resident recurrent weights: [256 rows][64 halves] -> K-major 128-byte-swizzled tiles
         const uint4* gh = reinterpret_cast<const uint4*>(wr_hi + (size_t)dir * N * U);
         const uint4* gl = reinterpret_cast<const uint4*>(wr_lo + (size_t)dir * N * U);
         for (int i = threadIdx.x; i < N * 8; i += RT_THREADS) {
-            const int row = i >> 3, c = i & 7;
-            const uint32_t off = sw128_offset(row, c);
+            const uint32_t off = sw128_offset(i >> 3, i & 7);
             *reinterpret_cast<uint4*>(s_whi + off) = __ldg(gh + i);
             *reinterpret_cast<uint4*>(s_wlo + off) = __ldg(gl + i);
         }
     }
-    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core / TMA (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== MMA issuer =====================
+        // ===================== h store + MMA issuer =====================
         constexpr uint32_t idesc = umma_idesc_f16_f32(128, N);
         const uint64_t b_hi = umma_desc_k_sw128(smem_u32(s_whi)), b_lo = umma_desc_k_sw128(smem_u32(s_wlo));
-        for (int s = 1; s < T; ++s) {
+        for (int s = 1; s <= T; ++s) {
+            const int t_prev = dir ? (T - s) : (s - 1);               // timestep whose h is in shared memory
             for (int X = 0; X < 2; ++X) {
                 if (!valid[X]) continue;
-                mbar_wait(&h_ready[X], (uint32_t)((s - 1) & 1));      // h_{s-1} of tile X is in shared memory
+                mbar_wait(&h_ready[X], (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t a_hi = umma_desc_k_sw128(smem_u32(s_h + (X * 2 + 0) * RT_H_BYTES));
-                    const uint64_t a_lo = umma_desc_k_sw128(smem_u32(s_h + (X * 2 + 1) * RT_H_BYTES));
-                    const uint32_t d = tmem_base + (uint32_t)(X * N);
+                    const uint8_t* hh = s_h + (X * 2 + 0) * RT_H_BYTES;
+                    const uint8_t* hl = s_h + (X * 2 + 1) * RT_H_BYTES;
+                    const int grow = (int)(t_prev * nwp + wt[X] * 128);
+                    tma_store_2d(&tm_out_hi, hh, dir * U, grow);
+                    tma_store_2d(&tm_out_lo, hl, dir * U, grow);
+                    tma_store_commit();
+                    if (s < T) {
+                        const uint64_t a_hi = umma_desc_k_sw128(smem_u32(hh)), a_lo = umma_desc_k_sw128(smem_u32(hl));
+                        const uint32_t d = tmem_base + (uint32_t)(X * N);
 #pragma unroll
-                    for (int k = 0; k < U / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);            // +32 B along K (16-byte units)
-                        umma_f16_ss(d, a_lo + adv, b_hi + adv, idesc, k != 0);
-                        umma_f16_ss(d, a_hi + adv, b_lo + adv, idesc, 1);
-                        umma_f16_ss(d, a_hi + adv, b_hi + adv, idesc, 1);
+                        for (int k = 0; k < U / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);        // +32 B along K (16-byte units)
+                            umma_f16_ss(d, a_lo + adv, b_hi + adv, idesc, k != 0);
+                            umma_f16_ss(d, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_f16_ss(d, a_hi + adv, b_hi + adv, idesc, 1);
+                        }
+                        umma_commit(&acc_ready[X]);                        // arrival 1: MMAs retired
+                        tma_store_wait_read();
+                        mbar_arrive(&acc_ready[X]);                        // arrival 2: the store has read the h tile
                     }
-                    umma_commit(&acc_ready[X]);
                 }
                 __syncwarp();
             }
         }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     } else {
         // ===================== epilogue: warps 1-4 -> tile 0, warps 5-8 -> tile 1 =====================
         const int X = (warp - 1) >> 2;
         const int q = warp & 3;                          // TMEM lane quarter accessible to this warp
         const int row = q * 32 + lane;
-        const int64_t w = w0[X] + row;
-        const bool live = w < nw;
         if (valid[X]) {
             uint8_t* hs_hi = s_h + (X * 2 + 0) * RT_H_BYTES;
             uint8_t* hs_lo = s_h + (X * 2 + 1) * RT_H_BYTES;
@@ -135,7 +176,7 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
             for (int j = 0; j < U; ++j) c[j] = 0.f;
             for (int s = 0; s < T; ++s) {
                 const int t = dir ? (T - 1 - s) : s;
-                const float* zrow = zin + (((int64_t)dir * T + t) * nw + (live ? w : 0)) * N;
+                const float4* ztile = reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t) * ntw + wt[X]) * (N * 128)) + row;
                 if (s > 0) {
                     mbar_wait(&acc_ready[X], (uint32_t)((s - 1) & 1));
                     tc_fence_after();
@@ -146,54 +187,18 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
                     if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
                     float4 z[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        z[j] = live ? __ldg(reinterpret_cast<const float4*>(zrow + cb * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s > 0) {
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            z[j].x += __uint_as_float(v[4 * j + 0]); z[j].y += __uint_as_float(v[4 * j + 1]);
-                            z[j].z += __uint_as_float(v[4 * j + 2]); z[j].w += __uint_as_float(v[4 * j + 3]);
-                        }
-                    }
-                    float h[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {                     // Keras 2.2.4 LSTM cell, gates i,f,c,o
-                        const float ig = hsig(z[j].x), fg = hsig(z[j].y), gg = tanh_fast(z[j].z), og = hsig(z[j].w);
-                        const float cn = fmaf(fg, c[cb * 8 + j], ig * gg);
-                        c[cb * 8 + j] = cn;
-                        h[j] = og * tanh_fast(cn);
-                    }
-                    __half hh[8], hl[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) split_f16(h[j], hh[j], hl[j]);
-                    const uint4 phi = make_uint4(pack_half2(hh[0], hh[1]), pack_half2(hh[2], hh[3]), pack_half2(hh[4], hh[5]),
-                                                 pack_half2(hh[6], hh[7]));
-                    const uint4 plo = make_uint4(pack_half2(hl[0], hl[1]), pack_half2(hl[2], hl[3]), pack_half2(hl[4], hl[5]),
-                                                 pack_half2(hl[6], hl[7]));
-                    if (s + 1 < T) {                                   // A operand of the next step
-                        const uint32_t off = sw128_offset(row, cb);
-                        *reinterpret_cast<uint4*>(hs_hi + off) = phi;
-                        *reinterpret_cast<uint4*>(hs_lo + off) = plo;
-                    }
-                    if (live) {
-                        if (OMODE == 0) {
-                            float* o = act_out + (w * T + t) * (2 * U) + dir * U + cb * 8;
-                            *reinterpret_cast<float4*>(o) = make_float4(h[0], h[1], h[2], h[3]);
-                            *reinterpret_cast<float4*>(o + 4) = make_float4(h[4], h[5], h[6], h[7]);
-                        } else {
-                            const int64_t off = (w * T + t) * out_ld + dir * U + cb * 8;
-                            *reinterpret_cast<uint4*>(out_hi + off) = phi;
-                            *reinterpret_cast<uint4*>(out_lo + off) = plo;
-                        }
-                    }
+                    for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + (cb * 8 + j) * 128);
+                    if (s > 0) tmem_ld_wait();
+                    uint4 phi, plo;
+                    lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
+                    const uint32_t off = sw128_offset(row, cb);
+                    *reinterpret_cast<uint4*>(hs_hi + off) = phi;
+                    *reinterpret_cast<uint4*>(hs_lo + off) = plo;
                 }
-                if (s + 1 < T) {
-                    tc_fence_before();           // our tcgen05.ld of this step precede the next MMA's writes
-                    fence_proxy_async_smem();    // our h writes are visible to the tensor core
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&h_ready[X]);
-                }
+                tc_fence_before();           // our tcgen05.ld of this step precede the next MMA's writes
+                fence_proxy_async_smem();    // our h writes are visible to the tensor core and to TMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_ready[X]);
             }
         }
     }
@@ -202,19 +207,20 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st) {
-    if (n_win <= 0) return 0;
-    if (L.u != 64 || !L.rt_hi) return -1;
-    dim3 grid((unsigned)((n_win + 255) / 256), 2);
-    if (io.out_hi) {
-        auto kern = lstm_rec_tc64_kernel<1>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
-        kern<<<grid, RT_THREADS, RT_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, nullptr, io.out_hi, io.out_lo, io.out_ld, n_win, T);
-    } else {
-        auto kern = lstm_rec_tc64_kernel<0>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
-        kern<<<grid, RT_THREADS, RT_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, io.act_out, nullptr, nullptr, 0, n_win, T);
+int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, int T, cudaStream_t st) {
+    if (nwp <= 0) return 0;
+    if (L.u != 64 || !L.rt_hi || !io.out_hi || (nwp & 127)) return -1;
+    CUtensorMap tmh, tml;
+    if (!make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
+        !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
+        return -2;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_rec_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
+        attr = true;
     }
+    dim3 grid((unsigned)(((nwp >> 7) + 1) / 2), 2);
+    lstm_rec_tc64_kernel<<<grid, RT_THREADS, RT_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, tmh, tml, nwp, T);
     return 1;
 }
 
@@ -225,8 +231,10 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 // streamed from L2 every step through a 2-stage TMA ring of [128 columns][64 K] boxes (16 KB), issued by a
 // dedicated producer warp that never waits on the recurrence (weights do not depend on h).
 // One CTA = one direction x one tile of 128 windows; the accumulator fills all 512 TMEM columns, split in two
-// 256-column halves (units 0-63 / 64-127) with their own "accumulator ready" barriers, so that the epilogue of
-// half 0 overlaps the MMAs of half 1.  Eight epilogue warps: two per TMEM lane quarter, one per column half.
+// 256-column halves H0 (units 0-63) / H1 (units 64-127) with their own "accumulator ready" barriers.  MMA order
+// per step:  H1 x K-chunk 0  ->  H0 (all of K)  -> commit H0 ->  H1 x K-chunk 1 -> commit H1,  so that when H0's
+// epilogue starts, nothing reads K-chunk 0 of h any more (it is the chunk H0's epilogue overwrites with its new
+// h) and it overlaps the remaining H1 MMAs.  Eight epilogue warps: two per TMEM lane quarter, one per half.
 // ============================================================================================================
 constexpr int R2_THREADS = 320;                       // MMA warp, TMA warp, 8 epilogue warps
 constexpr int R2_WHI_BYTES = 2 * 512 * 64 * 2;        // 128 KB: two K-chunks of [512 rows][64]
@@ -235,10 +243,14 @@ constexpr int R2_BOX_BYTES = 128 * 64 * 2;            // 16 KB: streamed W_lo bo
 constexpr int R2_STAGES = 2;
 constexpr size_t R2_SMEM = (size_t)R2_WHI_BYTES + 4 * R2_H_BYTES + R2_STAGES * R2_BOX_BYTES + 1024 + 128;
 
+// streamed W_lo boxes of one step, in consumption order: (n-quarter, K-chunk)
+__device__ __forceinline__ int r2_box_nq(int p) { return (0x32110032 >> (4 * p)) & 0xF; }   // {2,3,0,0,1,1,2,3}
+__device__ __forceinline__ int r2_box_kc(int p) { return (0xE8 >> p) & 1; }                 // {0,0,0,1,0,1,1,1}
+
 __global__ void __launch_bounds__(R2_THREADS, 1)
 lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ CUtensorMap tm_wlo,
-                      const float* __restrict__ zin, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                      int out_ld, int64_t nw, int T) {
+                      const float* __restrict__ zin, const __grid_constant__ CUtensorMap tm_out_hi,
+                      const __grid_constant__ CUtensorMap tm_out_lo, int64_t nwp, int T) {
     constexpr int U = 128, N = 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -247,29 +259,29 @@ lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ 
     uint8_t* s_ring = s_h + 4 * R2_H_BYTES;                  // [stage][128 rows][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + R2_STAGES * R2_BOX_BYTES);
     uint64_t* h_ready = bars;                                // count 8
-    uint64_t* acc_ready = bars + 1;                          // [2] count 1
+    uint64_t* acc_ready = bars + 1;                          // [2] count 2
     uint64_t* full = bars + 3;                               // [R2_STAGES]
     uint64_t* empty = bars + 3 + R2_STAGES;                  // [R2_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * R2_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    const int64_t w0 = (int64_t)blockIdx.x * 128;
+    const int64_t ntw = nwp >> 7;
+    const int64_t wtile = blockIdx.x;
 
     if (threadIdx.x == 0) {
         mbar_init(h_ready, 8);
-        mbar_init(&acc_ready[0], 1); mbar_init(&acc_ready[1], 1);
+        mbar_init(&acc_ready[0], 2); mbar_init(&acc_ready[1], 2);
         for (int s = 0; s < R2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         fence_mbar_init();
-        tma_prefetch_desc(&tm_wlo);
+        tma_prefetch_desc(&tm_wlo); tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     {
         const uint4* gh = reinterpret_cast<const uint4*>(wr_hi + (size_t)dir * N * U);   // [512][128] halves: 16 chunks per row
         for (int i = threadIdx.x; i < N * 16; i += R2_THREADS) {
             const int row = i >> 4, c16 = i & 15;
-            const int kc = c16 >> 3, c = c16 & 7;
-            *reinterpret_cast<uint4*>(s_whi + kc * (512 * 128) + sw128_offset(row, c)) = __ldg(gh + i);
+            *reinterpret_cast<uint4*>(s_whi + (c16 >> 3) * (512 * 128) + sw128_offset(row, c16 & 7)) = __ldg(gh + i);
         }
     }
     fence_proxy_async_smem();
@@ -279,72 +291,98 @@ lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 1) {
-        // ===================== TMA producer: W_lo boxes, (step, half, n-quarter-in-half, k-chunk) order ==========
+        // ===================== TMA producer: W_lo boxes in consumption order ==========
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int s = 1; s < T; ++s)
                 for (int p = 0; p < 8; ++p) {
-                    const int nq = p >> 1, kc = p & 1;           // rows nq*128.., K chunk kc
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], R2_BOX_BYTES);
-                    tma_load_2d(s_ring + stage * R2_BOX_BYTES, &tm_wlo, &full[stage], kc * 64, dir * N + nq * 128);
+                    tma_load_2d(s_ring + stage * R2_BOX_BYTES, &tm_wlo, &full[stage], r2_box_kc(p) * 64, dir * N + r2_box_nq(p) * 128);
                     if (++stage == R2_STAGES) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == 0) {
-        // ===================== MMA issuer =====================
+        // ===================== h store + MMA issuer =====================
         constexpr uint32_t idesc256 = umma_idesc_f16_f32(128, 256), idesc128 = umma_idesc_f16_f32(128, 128);
         int stage = 0; uint32_t phase = 0;
         const uint32_t a_base = smem_u32(s_h), w_base = smem_u32(s_whi);
-        for (int s = 1; s < T; ++s) {
+        // resident passes (lo*hi, hi*hi) of column half hf over K-steps [k0, k1)
+        auto resident = [&](int hf, int k0, int k1, bool zero_first) {
+            const uint32_t d = tmem_base + (uint32_t)(hf * 256);
+            for (int k = k0; k < k1; ++k) {
+                const int kc = k >> 2, kk = k & 3;
+                const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * R2_H_BYTES + kk * 32);
+                const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * R2_H_BYTES + kk * 32);
+                const uint64_t b_hi = umma_desc_k_sw128(w_base + kc * (512 * 128) + hf * (256 * 128) + kk * 32);
+                umma_f16_ss(d, a_lo, b_hi, idesc256, (zero_first && k == k0) ? 0u : 1u);
+                umma_f16_ss(d, a_hi, b_hi, idesc256, 1);
+            }
+        };
+        for (int s = 1; s <= T; ++s) {
+            const int t_prev = dir ? (T - s) : (s - 1);
             mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
             tc_fence_after();
-            for (int hf = 0; hf < 2; ++hf) {
-                const uint32_t d = tmem_base + (uint32_t)(hf * 256);
-                if (elect_one()) {
+            if (elect_one()) {
+                const int grow = (int)(t_prev * nwp + wtile * 128);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {                 // resident W_hi: lo*hi and hi*hi
-                        const int kc = k >> 2, kk = k & 3;
-                        const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * R2_H_BYTES + kk * 32);
-                        const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * R2_H_BYTES + kk * 32);
-                        const uint64_t b_hi = umma_desc_k_sw128(w_base + kc * (512 * 128) + hf * (256 * 128) + kk * 32);
-                        umma_f16_ss(d, a_lo, b_hi, idesc256, k != 0);
-                        umma_f16_ss(d, a_hi, b_hi, idesc256, 1);
-                    }
+                for (int kc = 0; kc < 2; ++kc) {
+                    tma_store_2d(&tm_out_hi, s_h + (0 * 2 + kc) * R2_H_BYTES, dir * U + kc * 64, grow);
+                    tma_store_2d(&tm_out_lo, s_h + (1 * 2 + kc) * R2_H_BYTES, dir * U + kc * 64, grow);
+                }
+                tma_store_commit();
+            }
+            __syncwarp();
+            if (s == T) break;
+            for (int p = 0; p < 8; ++p) {
+                // resident MMAs that precede streamed box p
+                if (elect_one()) {
+                    if (p == 0) resident(1, 0, 4, true);          // H1 x K-chunk 0
+                    if (p == 2) resident(0, 0, 8, true);          // H0, all of K
+                    if (p == 6) resident(1, 4, 8, false);         // H1 x K-chunk 1
                 }
                 __syncwarp();
-                for (int p = 0; p < 4; ++p) {                     // streamed W_lo: hi*lo, four [128 x 64] boxes per half
-                    const int nq = p >> 1, kc = p & 1;
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t bst = smem_u32(s_ring + stage * R2_BOX_BYTES);
+                const int nq = r2_box_nq(p), kc = r2_box_kc(p);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t bst = smem_u32(s_ring + stage * R2_BOX_BYTES);
+                    const uint32_t d = tmem_base + (uint32_t)(nq * 128);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * R2_H_BYTES + kk * 32);
-                            umma_f16_ss(d + (uint32_t)(nq * 128), a_hi, umma_desc_k_sw128(bst + kk * 32), idesc128, 1);
-                        }
-                        umma_commit(&empty[stage]);
-                        if (p == 3) umma_commit(&acc_ready[hf]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * R2_H_BYTES + kk * 32);
+                        umma_f16_ss(d, a_hi, umma_desc_k_sw128(bst + kk * 32), idesc128, 1);
                     }
-                    __syncwarp();
-                    if (++stage == R2_STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&empty[stage]);
+                    if (p == 5) umma_commit(&acc_ready[0]);       // H0 complete (and every read of h K-chunk 0)
+                    if (p == 7) umma_commit(&acc_ready[1]);       // everything complete
                 }
+                __syncwarp();
+                if (++stage == R2_STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) {
+                tma_store_wait_read();                            // the h_{s-1} stores have left shared memory
+                mbar_arrive(&acc_ready[0]);
+                mbar_arrive(&acc_ready[1]);
+            }
+            __syncwarp();
         }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     } else {
         // ===================== epilogue: warps 2..9; lane quarter = warp % 4, column half = (warp - 2) / 4 ===========
         const int q = warp & 3;
         const int hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        const int64_t w = w0 + row;
-        const bool live = w < nw;
+        uint8_t* hs_hi = s_h + (0 * 2 + hf) * R2_H_BYTES;       // units hf*64.. -> K chunk hf of the h tile
+        uint8_t* hs_lo = s_h + (1 * 2 + hf) * R2_H_BYTES;
         float c[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) c[j] = 0.f;
         for (int s = 0; s < T; ++s) {
             const int t = dir ? (T - 1 - s) : s;
-            const float* zrow = zin + (((int64_t)dir * T + t) * nw + (live ? w : 0)) * N + hf * 256;
+            const float4* ztile = reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t) * ntw + wtile) * (N * 128)) +
+                                  (hf * 64) * 128 + row;
             if (s > 0) {
                 mbar_wait(&acc_ready[hf], (uint32_t)((s - 1) & 1));
                 tc_fence_after();
@@ -355,64 +393,18 @@ lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ 
                 if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
                 float4 z[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    z[j] = live ? __ldg(reinterpret_cast<const float4*>(zrow + cb * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s > 0) {
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        z[j].x += __uint_as_float(v[4 * j + 0]); z[j].y += __uint_as_float(v[4 * j + 1]);
-                        z[j].z += __uint_as_float(v[4 * j + 2]); z[j].w += __uint_as_float(v[4 * j + 3]);
-                    }
-                }
-                float h[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float ig = hsig(z[j].x), fg = hsig(z[j].y), gg = tanh_fast(z[j].z), og = hsig(z[j].w);
-                    const float cn = fmaf(fg, c[cb * 8 + j], ig * gg);
-                    c[cb * 8 + j] = cn;
-                    h[j] = og * tanh_fast(cn);
-                }
-                __half hh[8], hl[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) split_f16(h[j], hh[j], hl[j]);
-                const uint4 phi = make_uint4(pack_half2(hh[0], hh[1]), pack_half2(hh[2], hh[3]), pack_half2(hh[4], hh[5]),
-                                             pack_half2(hh[6], hh[7]));
-                const uint4 plo = make_uint4(pack_half2(hl[0], hl[1]), pack_half2(hl[2], hl[3]), pack_half2(hl[4], hl[5]),
-                                             pack_half2(hl[6], hl[7]));
-                if (s + 1 < T && hf == 1) {
-                    // units 64 + cb*8 .. +8  ->  K chunk 1 of the h tile, 16-byte chunk cb.  Safe to overwrite now:
-                    // acc_ready[1] fires after ALL MMAs of this step, i.e. nothing reads h_{s-1} any more.
-                    const uint32_t off = sw128_offset(row, cb);
-                    *reinterpret_cast<uint4*>(s_h + (0 * 2 + 1) * R2_H_BYTES + off) = phi;
-                    *reinterpret_cast<uint4*>(s_h + (1 * 2 + 1) * R2_H_BYTES + off) = plo;
-                }
-                if (live) {
-                    const int64_t off = (w * T + t) * out_ld + dir * U + hf * 64 + cb * 8;
-                    *reinterpret_cast<uint4*>(out_hi + off) = phi;
-                    *reinterpret_cast<uint4*>(out_lo + off) = plo;
-                }
+                for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + (cb * 8 + j) * 128);
+                if (s > 0) tmem_ld_wait();
+                uint4 phi, plo;
+                lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
+                const uint32_t off = sw128_offset(row, cb);
+                *reinterpret_cast<uint4*>(hs_hi + off) = phi;
+                *reinterpret_cast<uint4*>(hs_lo + off) = plo;
             }
-            if (s + 1 < T && hf == 0) {
-                // Half 0 ran while the MMAs of half 1 were still reading h_{s-1}: publish its part of h_s only after
-                // they have retired, from the copy it has just written to global memory (own writes, program order).
-                if (s > 0) mbar_wait(&acc_ready[1], (uint32_t)((s - 1) & 1));
-                if (live) {
-                    const int64_t goff = (w * T + t) * out_ld + dir * U;
-#pragma unroll
-                    for (int cb = 0; cb < 8; ++cb) {
-                        const uint32_t off = sw128_offset(row, cb);
-                        *reinterpret_cast<uint4*>(s_h + (0 * 2 + 0) * R2_H_BYTES + off) = *reinterpret_cast<const uint4*>(out_hi + goff + cb * 8);
-                        *reinterpret_cast<uint4*>(s_h + (1 * 2 + 0) * R2_H_BYTES + off) = *reinterpret_cast<const uint4*>(out_lo + goff + cb * 8);
-                    }
-                }
-            }
-            if (s + 1 < T) {
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(h_ready);
-            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_ready);
         }
     }
     tc_fence_before();
@@ -420,20 +412,21 @@ lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ 
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);   // nrv_gemm.cu
-
-int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st) {
-    if (n_win <= 0) return 0;
-    if (L.u != 128 || !L.rt_hi || !io.out_hi) return -1;
-    CUtensorMap tm;
-    if (!make_tmap_f16_k64(&tm, L.rt_lo, 2 * 512, 128, 128)) return -2;
+int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, int T, cudaStream_t st) {
+    if (nwp <= 0) return 0;
+    if (L.u != 128 || !L.rt_hi || !io.out_hi || (nwp & 127)) return -1;
+    CUtensorMap tm, tmh, tml;
+    if (!make_tmap_f16_k64(&tm, L.rt_lo, 2 * 512, 128, 128) ||
+        !make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
+        !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
+        return -2;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(lstm_rec_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM);
         attr = true;
     }
-    dim3 grid((unsigned)((n_win + 127) / 128), 2);
-    lstm_rec_tc128_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(L.rt_hi, tm, io.zin, io.out_hi, io.out_lo, io.out_ld, n_win, T);
+    dim3 grid((unsigned)(nwp >> 7), 2);
+    lstm_rec_tc128_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(L.rt_hi, tm, io.zin, tmh, tml, nwp, T);
     return 1;
 }
 
