@@ -121,13 +121,17 @@ const char* nrv_version(void);
 int64_t nrv_launch_count(const nrv_handle* h);
 /* Per-stage device time.  nrv_set_stage_timing(h, 1) resets the totals and makes every later call
  * record CUDA-event pairs on the handle's stream around each stage's launches (no synchronisation on
- * the hot path); nrv_get_stage_ms() synchronises once and returns the totals in ms since the reset:
- * out[0]=read stats (median/MAD) out[1]=base features out[2]=CNN out[3..6]=Bi-LSTM layers 0..3
- * out[7]=dense heads+softmax out[8]=decode.  nrv_get_stage_launches() gives the kernel launches of
- * each stage over the same period. */
+ * the hot path); nrv_get_stage_ms() synchronises once and returns the totals in ms since the reset,
+ * nrv_get_stage_launches() the kernel launches of each stage over the same period.  Stages are named
+ * by nrv_stage_name(0 .. nrv_stage_count()-1): read_stats, base_features, cnn, lstm0, proj1, rec1,
+ * proj2, rec2, proj3, rec3, heads_gemm, heads, decode (projN / recN = input-projection GEMM and
+ * recurrence of Bi-LSTM layer N; on the fp32 SIMT path the fused layer kernels report under recN).
+ * `n` is the capacity of `out` and must be >= nrv_stage_count(). */
+int nrv_stage_count(void);
+const char* nrv_stage_name(int i);
 int nrv_set_stage_timing(nrv_handle* h, int enable);
-int nrv_get_stage_ms(nrv_handle* h, float out[9]);
-int nrv_get_stage_launches(const nrv_handle* h, int64_t out[9]);
+int nrv_get_stage_ms(nrv_handle* h, float* out, int n);
+int nrv_get_stage_launches(const nrv_handle* h, int64_t* out, int n);
 
 /* The CUDA stream all work of this handle is enqueued on (cudaStream_t as void*). */
 void* nrv_stream(const nrv_handle* h);

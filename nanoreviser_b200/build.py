@@ -18,7 +18,7 @@ LIB = os.path.join(PKG, "libnrv.so")
 
 SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo"] + os.environ.get("NRV_EXTRA_NVCC", "").split() + [ "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 
 def _nvcc() -> str:

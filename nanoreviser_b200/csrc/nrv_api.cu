@@ -45,7 +45,10 @@ struct PinnedArena {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
-enum { ST_STATS = 0, ST_FEAT, ST_CNN, ST_L0, ST_L1, ST_L2, ST_L3, ST_HEADS, ST_DECODE, ST_COUNT };
+enum { ST_STATS = 0, ST_FEAT, ST_CNN, ST_L0, ST_PROJ1, ST_REC1, ST_PROJ2, ST_REC2, ST_PROJ3, ST_REC3, ST_HEADS_GEMM,
+       ST_HEADS, ST_DECODE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"read_stats", "base_features", "cnn", "lstm0", "proj1", "rec1", "proj2", "rec2",
+                                           "proj3", "rec3", "heads_gemm", "heads", "decode"};
 
 }  // namespace
 
@@ -333,7 +336,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 // ---- fp32 SIMT path: projection fused into every recurrence step ----
                 const float* in_prev = nullptr;
                 for (int l = 0; l < 4; ++l) {
-                    StageTimer tm(h, ST_L0 + l);
+                    static const int simt_stage[4] = {ST_L0, ST_REC1, ST_REC2, ST_REC3};
+                    StageTimer tm(h, simt_stage[l]);
                     LstmIo io;
                     io.act_in = in_prev; io.base_in = (l == 0) ? x : (l == 2 ? sig_feat[mi] : nullptr);
                     io.win_base = win_base + c0; io.act_out = h->d_act[l].as<float>();
@@ -362,44 +366,52 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     h->launches += launch_lstm_layer(0, 1, M.lstm[0], io, nw, T, h->stream);
                 }
                 {   // read_rnn11: projection (K = 32 -> 64) + recurrence (u = 64)
-                    StageTimer tm(h, ST_L1);
-                    n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, R, 512, 64, zin, M.lstm[1].bias_tc, 1,
-                                          T, nwp, 256, 0, h->num_sms, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (read_rnn11) could not be launched");
-                    h->launches += n;
+                    {
+                        StageTimer tm(h, ST_PROJ1);
+                        n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, R, 512, 64, zin, M.lstm[1].bias_tc, 1,
+                                              T, nwp, 256, 0, h->num_sms, h->stream);
+                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (read_rnn11) could not be launched");
+                        h->launches += n;
+                    }
+                    StageTimer tm(h, ST_REC1);
                     LstmIo io; io.zin = zin; io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
                     n = launch_lstm_rec_tc64(M.lstm[1], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (read_rnn11) could not be launched");
                     h->launches += n;
                 }
                 {   // total_rnn1: gather CNN features, projection (K = 192), recurrence (u = 128)
-                    StageTimer tm(h, ST_L2);
+                    StageTimer* tp = new StageTimer(h, ST_PROJ2);
                     const int64_t items = nw * T * 8;
                     gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
                         h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
                     h->launches += 1;
                     n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, R, 1024, 192, zin, M.lstm[2].bias_tc,
                                           1, T, nwp, 512, 0, h->num_sms, h->stream);
+                    if (n >= 0) h->launches += n;
+                    delete tp;
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
-                    h->launches += n;
+                    StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
                     n = launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
                     h->launches += n;
                 }
                 {   // total_rnn2: projection (K = 256), recurrence (u = 64)
-                    StageTimer tm(h, ST_L3);
-                    n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, R, 512, 256, zin, M.lstm[3].bias_tc, 1,
-                                          T, nwp, 256, 0, h->num_sms, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
-                    h->launches += n;
+                    {
+                        StageTimer tm(h, ST_PROJ3);
+                        n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, R, 512, 256, zin, M.lstm[3].bias_tc, 1,
+                                              T, nwp, 256, 0, h->num_sms, h->stream);
+                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn2) could not be launched");
+                        h->launches += n;
+                    }
+                    StageTimer tm(h, ST_REC3);
                     LstmIo io; io.zin = zin; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
                     n = launch_lstm_rec_tc64(M.lstm[3], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
                     h->launches += n;
                 }
                 {   // heads, first layer: relu(Dense(128 -> 128)) as a tcgen05 GEMM (85 % of the heads' work)
-                    StageTimer tm(h, ST_HEADS);
+                    StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
                                           M.heads.d1b, 0, T, nwp, 128, 1, h->num_sms, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
@@ -679,14 +691,16 @@ int nrv_set_stage_timing(nrv_handle* h, int enable) {
     for (int i = 0; i < ST_COUNT; ++i) { h->stage_ms[i] = 0.f; h->stage_launches[i] = 0; }
     return NRV_OK;
 }
-int nrv_get_stage_ms(nrv_handle* h, float out[9]) {
-    if (!h || !out) return NRV_E_INVALID;
+int nrv_stage_count(void) { return ST_COUNT; }
+const char* nrv_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int nrv_get_stage_ms(nrv_handle* h, float* out, int n) {
+    if (!h || !out || n < ST_COUNT) return NRV_E_INVALID;
     h->fold_events();
     for (int i = 0; i < ST_COUNT; ++i) out[i] = h->stage_ms[i];
     return NRV_OK;
 }
-int nrv_get_stage_launches(const nrv_handle* h, int64_t out[9]) {
-    if (!h || !out) return NRV_E_INVALID;
+int nrv_get_stage_launches(const nrv_handle* h, int64_t* out, int n) {
+    if (!h || !out || n < ST_COUNT) return NRV_E_INVALID;
     for (int i = 0; i < ST_COUNT; ++i) out[i] = h->stage_launches[i];
     return NRV_OK;
 }

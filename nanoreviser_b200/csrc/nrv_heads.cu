@@ -1,6 +1,8 @@
 // Dense heads of the predict model (lstmmodel.py:56-63 / :108-115), fused per tile of windows:
 //   per timestep Dense(128,relu) -> Dense(32,relu) -> main_out Dense(6,relu); Flatten (t*6+k);
 //   feature Dense(16,relu); final_out Dense(n_class, softmax); argmax (first maximum).
+#include <algorithm>
+
 #include "nrv_common.cuh"
 
 namespace nrv {
@@ -140,6 +142,141 @@ heads_kernel(HeadsDev H, const float* __restrict__ act_in, int64_t n_win, int64_
     }
 }
 
+// ---- tail of the heads when relu(Dense(128)) already ran on the tensor cores (nrv_gemm.cu) ---------------------
+// Persistent CTAs, all small weights resident in shared memory, one warp per window.
+template <int T>
+struct TailSmem {
+    float d1[HD_WIN * T][HD_LD];
+    float d2[HD_WIN * T][36];
+    float d3[HD_WIN][T * 6 + 2];
+    float ft[HD_WIN][16];
+    float w2[128][32];
+    float b2[32];
+    float mk[32][6];
+    float mb[8];
+    float fk[T * 6][16];
+    float fb[16];
+    float ok[16][8];
+    float ob[8];
+};
+
+template <int T>
+__global__ void __launch_bounds__(HD_THREADS, 2)
+heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, int64_t in_nwp, float* __restrict__ probs,
+                  uint8_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TailSmem<T>& s = *reinterpret_cast<TailSmem<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nc = H.n_class;
+    for (int i = tid; i < 128 * 32; i += HD_THREADS) (&s.w2[0][0])[i] = __ldg(H.d2k + i);
+    for (int i = tid; i < 32 * 6; i += HD_THREADS) (&s.mk[0][0])[i] = __ldg(H.mk + i);
+    for (int i = tid; i < T * 6 * 16; i += HD_THREADS) (&s.fk[0][0])[i] = __ldg(H.fk + i);
+    if (tid < 32) s.b2[tid] = __ldg(H.d2b + tid);
+    if (tid < 6) s.mb[tid] = __ldg(H.mb + tid);
+    if (tid < 16) s.fb[tid] = __ldg(H.fb + tid);
+    if (tid < 16 * 8) s.ok[tid >> 3][tid & 7] = ((tid & 7) < nc) ? __ldg(H.ok + (tid >> 3) * nc + (tid & 7)) : 0.f;
+    if (tid < 8) s.ob[tid] = (tid < nc) ? __ldg(H.ob + tid) : 0.f;
+    const int g = tid >> 5, tx = tid & 31;
+    constexpr int ROWS = HD_WIN * T;
+    const int64_t n_groups = (n_win + HD_WIN - 1) / HD_WIN;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t w0 = grp * HD_WIN;
+        __syncthreads();                                   // previous group's tile fully consumed / weights loaded
+        for (int i = tid; i < ROWS * 32; i += HD_THREADS) {
+            const int row = i >> 5, q = i & 31;
+            const int64_t w = w0 + row / T;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w < n_win) {
+                const int64_t grow = in_nwp ? ((int64_t)(row % T) * in_nwp + w) : (w * T + row % T);
+                v = __ldg(reinterpret_cast<const float4*>(d1_in + grow * 128) + q);
+            }
+            *reinterpret_cast<float4*>(&s.d1[row][q * 4]) = v;
+        }
+        __syncthreads();
+        // ---- Dense(128 -> 32, relu): lane = output column, T rows per lane ----
+        {
+            float acc[T];
+#pragma unroll
+            for (int r = 0; r < T; ++r) acc[r] = s.b2[tx];
+#pragma unroll 4
+            for (int k = 0; k < 128; k += 4) {
+                const float w0v = s.w2[k][tx], w1v = s.w2[k + 1][tx], w2v = s.w2[k + 2][tx], w3v = s.w2[k + 3][tx];
+#pragma unroll
+                for (int r = 0; r < T; ++r) {
+                    const float4 a = *reinterpret_cast<const float4*>(&s.d1[g * T + r][k]);
+                    acc[r] = fmaf(a.x, w0v, acc[r]); acc[r] = fmaf(a.y, w1v, acc[r]);
+                    acc[r] = fmaf(a.z, w2v, acc[r]); acc[r] = fmaf(a.w, w3v, acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < T; ++r) s.d2[g * T + r][tx] = fmaxf(acc[r], 0.f);
+        }
+        __syncwarp();
+        // ---- main_out Dense(32 -> 6, relu) + Flatten (index t*6 + k) ----
+        for (int o = tx; o < T * 6; o += 32) {
+            const int t = o / 6, k = o - t * 6;
+            float a0 = s.mb[k], a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                a0 = fmaf(s.d2[g * T + t][j], s.mk[j][k], a0);
+                a1 = fmaf(s.d2[g * T + t][j + 1], s.mk[j + 1][k], a1);
+            }
+            s.d3[g][o] = fmaxf(a0 + a1, 0.f);
+        }
+        __syncwarp();
+        // ---- feature Dense(T*6 -> 16, relu): two half-sums per output, combined by shuffle ----
+        {
+            const int o = tx & 15, half = tx >> 4;
+            constexpr int HALF = (T * 6 + 1) / 2;
+            float a = 0.f;
+            for (int j = half * HALF; j < min((half + 1) * HALF, T * 6); ++j) a = fmaf(s.d3[g][j], s.fk[j][o], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            if (tx < 16) s.ft[g][tx] = fmaxf(a + s.fb[tx], 0.f);
+        }
+        __syncwarp();
+        // ---- final_out Dense(16 -> n_class) + softmax + argmax (first maximum) ----
+        float logit = -INFINITY;
+        if (tx < nc) {
+            float a = s.ob[tx];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a = fmaf(s.ft[g][j], s.ok[j][tx], a);
+            logit = a;
+        }
+        float mx = logit;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = (tx < nc) ? expf(logit - mx) : 0.f;
+        float sum = e;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float pr = e / sum;
+        float bp = (tx < nc) ? pr : -1.f;
+        int bi = tx;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (op > bp || (op == bp && oi < bi)) { bp = op; bi = oi; }
+        }
+        const int64_t w = w0 + g;
+        if (w < n_win) {
+            if (probs && tx < nc) probs[w * nc + tx] = pr;
+            if (labels && tx == 0) labels[w] = (uint8_t)bi;
+        }
+    }
+}
+
+template <int T>
+static int launch_heads_tail_t(const HeadsDev& H, const float* d1, int64_t n_win, int64_t in_nwp, float* probs,
+                               uint8_t* labels, cudaStream_t st) {
+    auto kern = heads_tail_kernel<T>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem<T>));
+    const int64_t n_groups = (n_win + HD_WIN - 1) / HD_WIN;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_groups, 2 * 148);
+    kern<<<grid, HD_THREADS, sizeof(TailSmem<T>), st>>>(H, d1, n_win, in_nwp, probs, labels);
+    return 1;
+}
+
 template <int T, bool D1>
 static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win, int64_t in_nwp, float* probs,
                           uint8_t* labels, cudaStream_t st) {
@@ -155,7 +292,7 @@ int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, f
     if (n_win <= 0) return 0;
 #define NRV_HEADS_CASE(TT)                                                                        \
     case TT:                                                                                      \
-        return d1_done ? launch_heads_t<TT, true>(H, act_in, n_win, in_nwp, probs, labels, st)    \
+        return d1_done ? launch_heads_tail_t<TT>(H, act_in, n_win, in_nwp, probs, labels, st)     \
                        : launch_heads_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st);
     switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
         NRV_HEADS_CASE(5)

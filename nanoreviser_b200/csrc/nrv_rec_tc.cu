@@ -174,27 +174,46 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
             float c[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) c[j] = 0.f;
+            // zin of this thread's row, one 16-byte quad per 128-row stride; block cb = quads [8cb, 8cb+8).
+            // Loads are software-pipelined one block ahead (the next step's first block is requested before the
+            // wait on the accumulator barrier), so their latency hides behind the cell arithmetic / the MMA.
+            auto ztile_of = [&](int s_) {
+                const int t_ = dir ? (T - 1 - s_) : s_;
+                return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wt[X]) * (N * 128)) + row;
+            };
+            const float4* ztile = ztile_of(0);
+            float4 z[8], zn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + j * 128);
             for (int s = 0; s < T; ++s) {
-                const int t = dir ? (T - 1 - s) : s;
-                const float4* ztile = reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t) * ntw + wt[X]) * (N * 128)) + row;
+                const float4* znext_tile = (s + 1 < T) ? ztile_of(s + 1) : ztile;
                 if (s > 0) {
                     mbar_wait(&acc_ready[X], (uint32_t)((s - 1) & 1));
                     tc_fence_after();
                 }
 #pragma unroll
                 for (int cb = 0; cb < N / 32; ++cb) {
-                    uint32_t v[32];
-                    if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
-                    float4 z[8];
+                    if (cb + 1 < N / 32) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + (cb * 8 + j) * 128);
-                    if (s > 0) tmem_ld_wait();
+                        for (int j = 0; j < 8; ++j) zn[j] = __ldg(ztile + ((cb + 1) * 8 + j) * 128);
+                    } else if (s + 1 < T) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zn[j] = __ldg(znext_tile + j * 128);
+                    }
+                    uint32_t v[32];
+                    if (s > 0) {
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
+                        tmem_ld_wait();
+                    }
                     uint4 phi, plo;
                     lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
                     const uint32_t off = sw128_offset(row, cb);
                     *reinterpret_cast<uint4*>(hs_hi + off) = phi;
                     *reinterpret_cast<uint4*>(hs_lo + off) = plo;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = zn[j];
                 }
+                ztile = znext_tile;
                 tc_fence_before();           // our tcgen05.ld of this step precede the next MMA's writes
                 fence_proxy_async_smem();    // our h writes are visible to the tensor core and to TMA
                 __syncwarp();
@@ -379,28 +398,43 @@ lstm_rec_tc128_kernel(const __half* __restrict__ wr_hi, const __grid_constant__ 
         float c[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) c[j] = 0.f;
+        auto ztile_of = [&](int s_) {
+            const int t_ = dir ? (T - 1 - s_) : s_;
+            return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wtile) * (N * 128)) + (hf * 64) * 128 + row;
+        };
+        const float4* ztile = ztile_of(0);
+        float4 z[8], zn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + j * 128);
         for (int s = 0; s < T; ++s) {
-            const int t = dir ? (T - 1 - s) : s;
-            const float4* ztile = reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t) * ntw + wtile) * (N * 128)) +
-                                  (hf * 64) * 128 + row;
+            const float4* znext_tile = (s + 1 < T) ? ztile_of(s + 1) : ztile;
             if (s > 0) {
                 mbar_wait(&acc_ready[hf], (uint32_t)((s - 1) & 1));
                 tc_fence_after();
             }
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
-                uint32_t v[32];
-                if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
-                float4 z[8];
+                if (cb + 1 < 8) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + (cb * 8 + j) * 128);
-                if (s > 0) tmem_ld_wait();
+                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(ztile + ((cb + 1) * 8 + j) * 128);
+                } else if (s + 1 < T) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(znext_tile + j * 128);
+                }
+                uint32_t v[32];
+                if (s > 0) {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
+                    tmem_ld_wait();
+                }
                 uint4 phi, plo;
                 lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
                 const uint32_t off = sw128_offset(row, cb);
                 *reinterpret_cast<uint4*>(hs_hi + off) = phi;
                 *reinterpret_cast<uint4*>(hs_lo + off) = plo;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = zn[j];
             }
+            ztile = znext_tile;
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();

@@ -77,6 +77,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // ... have completed entirely (global writes performed)
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
+// contiguous global range -> L2 (no destination; size multiple of 16 B)
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------
 // whole warp; writes the TMEM base address to *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

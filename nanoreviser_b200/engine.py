@@ -19,7 +19,6 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libnrv.so")
 
 NRV_READ_OK, NRV_READ_TOO_SHORT, NRV_READ_SCALE_ZERO, NRV_READ_BAD_EVENTS = 0, 1, 2, 3
-STAGE_NAMES = ("read_stats", "base_features", "cnn", "lstm0", "lstm1", "lstm2", "lstm3", "heads", "decode")
 
 
 class NrvError(RuntimeError):
@@ -57,7 +56,7 @@ class _Result(C.Structure):
 
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
-           "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
+           "nrv_stage_count", "nrv_stage_name", "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
            "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_debug_gemm")
 
 _lib = None
@@ -86,9 +85,13 @@ def load_library(path: Optional[str] = None):
     lib.nrv_launch_count.restype = C.c_int64
     lib.nrv_set_stage_timing.argtypes = [vp, C.c_int]
     lib.nrv_set_stage_timing.restype = C.c_int
-    lib.nrv_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.nrv_stage_count.argtypes = []
+    lib.nrv_stage_count.restype = C.c_int
+    lib.nrv_stage_name.argtypes = [C.c_int]
+    lib.nrv_stage_name.restype = C.c_char_p
+    lib.nrv_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.nrv_get_stage_ms.restype = C.c_int
-    lib.nrv_get_stage_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.nrv_get_stage_launches.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
     lib.nrv_get_stage_launches.restype = C.c_int
     lib.nrv_stream.argtypes = [vp]
     lib.nrv_stream.restype = vp
@@ -278,14 +281,16 @@ class Reviser:
         self._check(self._lib.nrv_set_stage_timing(self._h, int(enable)), "nrv_set_stage_timing")
 
     def stage_ms(self) -> dict:
-        buf = (C.c_float * 9)()
-        self._check(self._lib.nrv_get_stage_ms(self._h, buf), "nrv_get_stage_ms")
-        return dict(zip(STAGE_NAMES, [float(v) for v in buf]))
+        n = self._lib.nrv_stage_count()
+        buf = (C.c_float * n)()
+        self._check(self._lib.nrv_get_stage_ms(self._h, buf, n), "nrv_get_stage_ms")
+        return {self._lib.nrv_stage_name(i).decode(): float(buf[i]) for i in range(n)}
 
     def stage_launches(self) -> dict:
-        buf = (C.c_int64 * 9)()
-        self._check(self._lib.nrv_get_stage_launches(self._h, buf), "nrv_get_stage_launches")
-        return dict(zip(STAGE_NAMES, [int(v) for v in buf]))
+        n = self._lib.nrv_stage_count()
+        buf = (C.c_int64 * n)()
+        self._check(self._lib.nrv_get_stage_launches(self._h, buf, n), "nrv_get_stage_launches")
+        return {self._lib.nrv_stage_name(i).decode(): int(buf[i]) for i in range(n)}
 
     @staticmethod
     def _cbatch(b: Batch, keep: list) -> _Batch:
