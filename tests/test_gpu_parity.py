@@ -330,3 +330,42 @@ def test_tcgen05_projection_gemm(reviser_by_species, M, N, K):
     assert err <= 2e-5 * max(scale, 1.0), (err, scale)      # fp32 class; single-pass fp16 would be ~1e-3
     C2 = rv.debug_gemm(A, Bt, None)
     assert np.abs(C2 - (ref - bias)).max() <= 2e-5 * max(scale, 1.0)
+
+
+# --------------------------------------------------------------------------------------------------
+# the CLI, end to end: fast5 directory -> *_out.fasta files, byte-identical to the oracle's (cfg1)
+# --------------------------------------------------------------------------------------------------
+def test_cli_fasta_bytes_match_goldens(tmp_path, golden_dir, monkeypatch):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(root)                               # the CLI resolves ./model/<S>/... like the reference
+    sys.path.insert(0, root)
+    import NanoReviser as cli
+    out_dir = str(tmp_path) + "/"
+    args = cli.get_args(["-d", os.path.join(golden_dir, "fast5") + "/", "-o", out_dir, "-F", "fasta", "-S", "ecoli"])
+    res = cli.main(args)
+    assert sum(r[0] for r in res) == 5 and sum(r[1] + r[2] for r in res) == 0
+    gold = np.load(os.path.join(golden_dir, "forward_ecoli.npz"))
+    files = sorted(f for f in os.listdir(os.path.join(golden_dir, "fast5")) if f.endswith(".fast5"))
+    for k, f in enumerate(files):
+        out_fn = out_dir + f.split(".")[0] + "_out.fasta"
+        assert open(out_fn, "rb").read() == gold["r%d_fasta" % k].tobytes(), f
+    # fastq mode writes the same sequence (qualities on the NN path are a documented builder decision, D6)
+    args = cli.get_args(["-d", os.path.join(golden_dir, "fast5") + "/", "-o", out_dir, "-F", "fastq", "-S", "ecoli"])
+    cli.main(args)
+    txt = open(out_dir + files[0].split(".")[0] + "_out.fastq").read()
+    seq = gold["r0_revised"].tobytes().decode()
+    assert txt.startswith("@" + files[0] + "\n" + seq + "+\n") and len(txt.split("+\n")[1]) == len(seq)
+
+
+def test_stage_timing_api(reviser_by_species, reads):
+    from nanoreviser_b200 import api
+    rv = reviser_by_species("ecoli")
+    rv.set_stage_timing(True)
+    n0 = rv.launch_count
+    api.revise_reads(reads[:1], reviser=rv)
+    ms, nl = rv.stage_ms(), rv.stage_launches()
+    rv.set_stage_timing(False)
+    assert set(ms) == set(nl) and {"read_stats", "cnn", "rec2", "heads", "decode"} <= set(ms)
+    assert sum(nl.values()) <= rv.launch_count - n0 and nl["decode"] == 4 and nl["read_stats"] == 2
+    assert all(v >= 0 for v in ms.values()) and ms["rec2"] > 0
