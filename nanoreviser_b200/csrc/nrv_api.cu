@@ -330,7 +330,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
         for (int mi = 0; mi < 2; ++mi) {
             const ModelDev& M = h->m[mi];
             const float* heads_in = nullptr;
-            bool heads_d1_done = false;
+            int heads_stage = 0;
             int64_t heads_nwp = 0;
             if (h->path == 0) {
                 // ---- fp32 SIMT path: projection fused into every recurrence step ----
@@ -410,21 +410,21 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn2) could not be launched");
                     h->launches += n;
                 }
-                {   // heads, first layer: relu(Dense(128 -> 128)) as a tcgen05 GEMM (85 % of the heads' work)
+                {   // heads: relu(Dense(128 -> 128)) as a tcgen05 GEMM with relu(Dense(128 -> 32)) fused into its epilogue
                     StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
-                                          M.heads.d1b, 0, T, nwp, 128, 1, h->num_sms, h->stream);
+                                          M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2k, M.heads.d2b);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
                     h->launches += n;
                 }
                 heads_in = h->d_act[3].as<float>();
-                heads_d1_done = true;
+                heads_stage = 2;
                 heads_nwp = nwp;
             }
             {
                 StageTimer tm(h, ST_HEADS);
                 int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
-                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_d1_done, heads_nwp, h->stream);
+                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_stage, heads_nwp, h->stream);
                 if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
                 h->launches += n;
             }

@@ -100,7 +100,7 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
 // nrv_gemm.cu: C[M][N] = A[M][K] . B[N][K]^T (+bias) with split-fp16 operands on tcgen05 (see file header)
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st);
+                      cudaStream_t st, const float* w2 = nullptr, const float* b2 = nullptr);
 int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
@@ -108,9 +108,10 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
-// d1_done = false: act_in is total_rnn2's output; true: act_in is already relu(Dense(128)) (tensor-core GEMM)
+// stage = 0: act_in is total_rnn2's output [..][128]; 1: act_in is relu(Dense(128)) [..][128];
+// 2: act_in is relu(Dense(32)) [..][32] (both dense layers ran in the tensor-core GEMM and its epilogue)
 int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int64_t n_win, int T,
-                 float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, bool d1_done,
+                 float* probs /*[n_win][n_class] or null*/, uint8_t* labels /*[n_win] or null*/, int stage,
                  int64_t in_nwp /* != 0: act_in rows are time-major, row(t, w) = t*in_nwp + w */, cudaStream_t st);
 
 // nrv_decode.cu

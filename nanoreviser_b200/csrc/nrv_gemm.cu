@@ -34,7 +34,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = 2 * G_A_BYTES + 2 * B_BYTES;    // 96 KB / 64 KB
     static constexpr int STAGES = (TN == 256) ? 2 : 3;
     static constexpr int TMEM_COLS = 2 * TN;                           // double-buffered accumulator
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                                   (TN == 128 ? 128 * 32 * 4 : 0) /* w2 of the fused dense head */;
 };
 
 struct GemmOut {
@@ -46,6 +47,10 @@ struct GemmOut {
     int64_t nw;
     int n_per_dir;
     int relu;               // apply max(x, 0) after the bias (dense heads)
+    // mode 2 (dense heads, TN = N = 128): the epilogue applies bias + relu and immediately the NEXT dense layer
+    // out2[r][32] = relu(relu(acc + bias) . w2[128][32] + b2), so the 128-wide intermediate never leaves the SM
+    const float* w2;
+    const float* b2;
 };
 
 template <int G_TN>
@@ -78,6 +83,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    float* s_w2 = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES + 256);
+    if (G_TN == 128 && out.mode == 2)
+        for (int i = threadIdx.x; i < 128 * 32; i += G_THREADS) s_w2[i] = __ldg(out.w2 + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -145,7 +153,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const int64_t r = m0 + q * 32 + lane;             // this thread's output row
             float* dst = nullptr;
             int64_t cstride = 4;                              // floats between consecutive column quads
-            if (out.mode == 0) {
+            if (out.mode == 0 || out.mode == 2) {
                 if (r < M) dst = out.c + r * (int64_t)N + n0;   // row-major: a quad is 4 consecutive floats
             } else {
                 // zin tiles [dir][m_tile][col/4][128 rows][4]: lanes (rows) are contiguous for a fixed column quad
@@ -156,8 +164,38 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                       (q * 32 + lane) * 4;
                 cstride = G_TM * 4;
             }
+            if (G_TN == 128 && out.mode == 2) {
+                float a2[32];
+#pragma unroll
+                for (int o = 0; o < 32; ++o) a2[o] = __ldg(out.b2 + o);
 #pragma unroll 1
-            for (int cb = 0; cb < G_TN / 32; ++cb) {
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d1 = fmaxf(__uint_as_float(v[j]) + __ldg(out.bias + cb * 32 + j), 0.f);
+                        const float4* wrow = reinterpret_cast<const float4*>(s_w2 + (cb * 32 + j) * 32);
+#pragma unroll
+                        for (int o4 = 0; o4 < 8; ++o4) {
+                            const float4 w = wrow[o4];                      // broadcast: all lanes read the same row
+                            a2[4 * o4 + 0] = fmaf(d1, w.x, a2[4 * o4 + 0]); a2[4 * o4 + 1] = fmaf(d1, w.y, a2[4 * o4 + 1]);
+                            a2[4 * o4 + 2] = fmaf(d1, w.z, a2[4 * o4 + 2]); a2[4 * o4 + 3] = fmaf(d1, w.w, a2[4 * o4 + 3]);
+                        }
+                    }
+                }
+                if (r < M) {
+                    float4* o = reinterpret_cast<float4*>(out.c + r * 32);
+#pragma unroll
+                    for (int o4 = 0; o4 < 8; ++o4)
+                        o[o4] = make_float4(fmaxf(a2[4 * o4], 0.f), fmaxf(a2[4 * o4 + 1], 0.f), fmaxf(a2[4 * o4 + 2], 0.f),
+                                            fmaxf(a2[4 * o4 + 3], 0.f));
+                }
+                dst = nullptr;
+            }
+#pragma unroll 1
+            for (int cb = 0; cb < ((G_TN == 128 && out.mode == 2) ? 0 : G_TN / 32); ++cb) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
                 tmem_ld_wait();
@@ -250,10 +288,11 @@ static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* 
 
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* w2, const float* b2) {
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
-    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu};
+    if (mode == 2 && (N != 128 || !w2 || !b2 || !bias)) return -1;
+    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2, b2};
     if (mode == 1 && (M % G_TM != 0)) return -1;
     if (N % 256 == 0) {
         if (mode == 1 && (n_per_dir % 256 != 0)) return -1;

@@ -160,7 +160,7 @@ struct TailSmem {
     float ob[8];
 };
 
-template <int T>
+template <int T, bool D2_DONE>
 __global__ void __launch_bounds__(HD_THREADS, 2)
 heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, int64_t in_nwp, float* __restrict__ probs,
                   uint8_t* __restrict__ labels) {
@@ -168,7 +168,8 @@ heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, in
     TailSmem<T>& s = *reinterpret_cast<TailSmem<T>*>(smem_raw);
     const int tid = threadIdx.x;
     const int nc = H.n_class;
-    for (int i = tid; i < 128 * 32; i += HD_THREADS) (&s.w2[0][0])[i] = __ldg(H.d2k + i);
+    if (!D2_DONE)
+        for (int i = tid; i < 128 * 32; i += HD_THREADS) (&s.w2[0][0])[i] = __ldg(H.d2k + i);
     for (int i = tid; i < 32 * 6; i += HD_THREADS) (&s.mk[0][0])[i] = __ldg(H.mk + i);
     for (int i = tid; i < T * 6 * 16; i += HD_THREADS) (&s.fk[0][0])[i] = __ldg(H.fk + i);
     if (tid < 32) s.b2[tid] = __ldg(H.d2b + tid);
@@ -182,19 +183,32 @@ heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, in
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int64_t w0 = grp * HD_WIN;
         __syncthreads();                                   // previous group's tile fully consumed / weights loaded
-        for (int i = tid; i < ROWS * 32; i += HD_THREADS) {
-            const int row = i >> 5, q = i & 31;
-            const int64_t w = w0 + row / T;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (w < n_win) {
-                const int64_t grow = in_nwp ? ((int64_t)(row % T) * in_nwp + w) : (w * T + row % T);
-                v = __ldg(reinterpret_cast<const float4*>(d1_in + grow * 128) + q);
+        if (D2_DONE) {
+            // input is relu(Dense(32)) [rows][32]: 8 float4 per row
+            for (int i = tid; i < ROWS * 8; i += HD_THREADS) {
+                const int row = i >> 3, q = i & 7;
+                const int64_t w = w0 + row / T;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (w < n_win) {
+                    const int64_t grow = in_nwp ? ((int64_t)(row % T) * in_nwp + w) : (w * T + row % T);
+                    v = __ldg(reinterpret_cast<const float4*>(d1_in + grow * 32) + q);
+                }
+                *reinterpret_cast<float4*>(&s.d2[row][q * 4]) = v;
             }
-            *reinterpret_cast<float4*>(&s.d1[row][q * 4]) = v;
-        }
-        __syncthreads();
-        // ---- Dense(128 -> 32, relu): lane = output column, T rows per lane ----
-        {
+            __syncthreads();
+        } else {
+            for (int i = tid; i < ROWS * 32; i += HD_THREADS) {
+                const int row = i >> 5, q = i & 31;
+                const int64_t w = w0 + row / T;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (w < n_win) {
+                    const int64_t grow = in_nwp ? ((int64_t)(row % T) * in_nwp + w) : (w * T + row % T);
+                    v = __ldg(reinterpret_cast<const float4*>(d1_in + grow * 128) + q);
+                }
+                *reinterpret_cast<float4*>(&s.d1[row][q * 4]) = v;
+            }
+            __syncthreads();
+            // ---- Dense(128 -> 32, relu): lane = output column, T rows per lane ----
             float acc[T];
 #pragma unroll
             for (int r = 0; r < T; ++r) acc[r] = s.b2[tx];
@@ -266,10 +280,10 @@ heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, in
     }
 }
 
-template <int T>
+template <int T, bool D2_DONE>
 static int launch_heads_tail_t(const HeadsDev& H, const float* d1, int64_t n_win, int64_t in_nwp, float* probs,
                                uint8_t* labels, cudaStream_t st) {
-    auto kern = heads_tail_kernel<T>;
+    auto kern = heads_tail_kernel<T, D2_DONE>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem<T>));
     const int64_t n_groups = (n_win + HD_WIN - 1) / HD_WIN;
     const unsigned grid = (unsigned)std::min<int64_t>(n_groups, 2 * 148);
@@ -288,12 +302,13 @@ static int launch_heads_t(const HeadsDev& H, const float* act_in, int64_t n_win,
 }
 
 int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, float* probs, uint8_t* labels,
-                 bool d1_done, int64_t in_nwp, cudaStream_t st) {
+                 int stage, int64_t in_nwp, cudaStream_t st) {
     if (n_win <= 0) return 0;
 #define NRV_HEADS_CASE(TT)                                                                        \
     case TT:                                                                                      \
-        return d1_done ? launch_heads_tail_t<TT>(H, act_in, n_win, in_nwp, probs, labels, st)     \
-                       : launch_heads_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st);
+        return stage == 2   ? launch_heads_tail_t<TT, true>(H, act_in, n_win, in_nwp, probs, labels, st)   \
+               : stage == 1 ? launch_heads_tail_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st)  \
+                            : launch_heads_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st);
     switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
         NRV_HEADS_CASE(5)
         NRV_HEADS_CASE(7)
