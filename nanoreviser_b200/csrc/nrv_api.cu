@@ -253,6 +253,15 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             }
         H.d1t_hi = upload(h, th, &e); if (e) goto cuda_fail;
         H.d1t_lo = upload(h, tl, &e); if (e) goto cuda_fail;
+        std::vector<__half> uh(32 * 128), ul(32 * 128);
+        for (int o = 0; o < 32; ++o)
+            for (int i = 0; i < 128; ++i) {
+                const float wv = w->dense2_k[i * 32 + o];
+                uh[o * 128 + i] = __float2half_rn(wv);
+                ul[o * 128 + i] = __float2half_rn(wv - __half2float(uh[o * 128 + i]));
+            }
+        H.d2t_hi = upload(h, uh, &e); if (e) goto cuda_fail;
+        H.d2t_lo = upload(h, ul, &e); if (e) goto cuda_fail;
     }
     return NRV_OK;
 cuda_fail:
@@ -413,7 +422,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 {   // heads: relu(Dense(128 -> 128)) as a tcgen05 GEMM with relu(Dense(128 -> 32)) fused into its epilogue
                     StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
-                                          M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2k, M.heads.d2b);
+                                          M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2t_hi, M.heads.d2t_lo,
+                                          M.heads.d2b);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
                     h->launches += n;
                 }

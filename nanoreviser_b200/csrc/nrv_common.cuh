@@ -58,6 +58,7 @@ struct CnnDev {
 struct HeadsDev {
     float *d1k, *d1b, *d2k, *d2b, *mk, *mb, *fk, *fb, *ok, *ob;
     __half *d1t_hi, *d1t_lo;           // dense1 kernel transposed [128 out][128 in] fp16 (hi, lo): tensor-core B operand
+    __half *d2t_hi, *d2t_lo;           // dense2 kernel transposed [32 out][128 in]
     int n_class;
 };
 
@@ -100,7 +101,7 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
 // nrv_gemm.cu: C[M][N] = A[M][K] . B[N][K]^T (+bias) with split-fp16 operands on tcgen05 (see file header)
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st, const float* w2 = nullptr, const float* b2 = nullptr);
+                      cudaStream_t st, const __half* w2t_hi = nullptr, const __half* w2t_lo = nullptr, const float* b2 = nullptr);
 int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin

@@ -28,14 +28,17 @@ constexpr int G_TM = 128, G_KC = 64;
 constexpr int G_A_BYTES = G_TM * G_KC * 2;            // 16 KB (one of hi / lo)
 constexpr int G_THREADS = 192;
 
-template <int TN>
+constexpr int G_A2_BYTES = 4 * G_A_BYTES;            // fused head: relu(Dense128) tile [128][128] as fp16 (hi, lo), 2 K-chunks each
+constexpr int G_W2_BYTES = 4 * 32 * 128;              // fused head: W2^T [32][128] as fp16 (hi, lo), 2 K-chunks each (4 x 4 KB)
+
+template <int TN, bool FUSE2>
 struct GemmCfg {
     static constexpr int B_BYTES = TN * G_KC * 2;                      // 32 KB (TN = 256) / 16 KB (TN = 128)
     static constexpr int STAGE_BYTES = 2 * G_A_BYTES + 2 * B_BYTES;    // 96 KB / 64 KB
-    static constexpr int STAGES = (TN == 256) ? 2 : 3;
-    static constexpr int TMEM_COLS = 2 * TN;                           // double-buffered accumulator
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                                   (TN == 128 ? 128 * 32 * 4 : 0) /* w2 of the fused dense head */;
+    static constexpr int STAGES = (TN == 256 || FUSE2) ? 2 : 3;
+    static constexpr int TMEM_COLS = FUSE2 ? 512 : 2 * TN;             // double-buffered accumulator (+ 32 columns for the fused head)
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (FUSE2 ? G_A2_BYTES + G_W2_BYTES : 0) + 1024 /*alignment slack*/ +
+                                   256 /*barriers*/;
 };
 
 struct GemmOut {
@@ -47,28 +50,36 @@ struct GemmOut {
     int64_t nw;
     int n_per_dir;
     int relu;               // apply max(x, 0) after the bias (dense heads)
-    // mode 2 (dense heads, TN = N = 128): the epilogue applies bias + relu and immediately the NEXT dense layer
-    // out2[r][32] = relu(relu(acc + bias) . w2[128][32] + b2), so the 128-wide intermediate never leaves the SM
-    const float* w2;
+    // mode 2 (dense heads, TN = N = 128, FUSE2 kernel): the epilogue applies bias + relu, re-splits the 128-wide row into an
+    // fp16 (hi, lo) A tile in shared memory and the MMA warp runs the NEXT dense layer back to back on the tensor core:
+    // c[r][32] = relu(relu(acc + bias) . W2 + b2) -- the 128-wide intermediate never leaves the SM
+    const __half* w2t_hi;   // W2^T [32][128]
+    const __half* w2t_lo;
     const float* b2;
 };
 
-template <int G_TN>
+template <int G_TN, bool FUSE2>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   GemmOut out, int64_t M, int N, int K) {
-    using Cfg = GemmCfg<G_TN>;
+    using Cfg = GemmCfg<G_TN, FUSE2>;
     constexpr int G_STAGES = Cfg::STAGES, G_STAGE_BYTES = Cfg::STAGE_BYTES, G_B_BYTES = Cfg::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);
+    // swizzled tiles need 1024-byte alignment: ring stages first, then the fused head's tiles, barriers last
+    uint8_t* s_a2 = smem + G_STAGES * G_STAGE_BYTES;                 // [hi|lo][kc][128 rows][64]   (FUSE2 only)
+    uint8_t* s_w2 = s_a2 + (FUSE2 ? G_A2_BYTES : 0);                 // [hi|lo][kc][32 rows][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w2 + (FUSE2 ? G_W2_BYTES : 0));
     uint64_t* full = bars;                  // [G_STAGES]
     uint64_t* empty = bars + G_STAGES;      // [G_STAGES]
     uint64_t* tfull = bars + 2 * G_STAGES;  // [2]
     uint64_t* tempty = tfull + 2;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* a2_ready = tempty + 2;        // fused head: epilogue -> MMA warp ("A tile of the second dense is in smem")
+    uint64_t* d2_ready = a2_ready + 1;      // fused head: MMA warp -> epilogue ("second accumulator complete")
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_ready + 1);
+    constexpr uint32_t D2_COL = 2 * G_TN;                            // TMEM columns of the fused head's accumulator
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = N / G_TN;
@@ -80,12 +91,18 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(a2_ready, 4); mbar_init(d2_ready, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    float* s_w2 = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES + 256);
-    if (G_TN == 128 && out.mode == 2)
-        for (int i = threadIdx.x; i < 128 * 32; i += G_THREADS) s_w2[i] = __ldg(out.w2 + i);
+    if (FUSE2) {   // W2^T [32 rows][128 halves] -> two K-major swizzled [32][64] tiles per part
+        for (int i = threadIdx.x; i < 2 * 32 * 16; i += G_THREADS) {
+            const int part = i >> 9, row = (i >> 4) & 31, c16 = i & 15;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(part ? out.w2t_lo : out.w2t_hi) + row * 16 + c16);
+            *reinterpret_cast<uint4*>(s_w2 + (part * 2 + (c16 >> 3)) * 4096 + sw128_offset(row, c16 & 7)) = v;
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -114,6 +131,31 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         constexpr uint32_t idesc = umma_idesc_f16_f32(G_TM, G_TN);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t a2_phase = 0;
+        bool pending_head = false;
+        // second dense of the fused head for the tile whose epilogue is running: D2[128][32] = A2[128][128] . W2^T
+        auto issue_head = [&]() {
+            mbar_wait(a2_ready, a2_phase);
+            a2_phase ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+                constexpr uint32_t idesc2 = umma_idesc_f16_f32(G_TM, 32);
+                const uint32_t a2 = smem_u32(s_a2), w2 = smem_u32(s_w2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int kc = k >> 2, kk = k & 3;
+                    const uint64_t ah = umma_desc_k_sw128(a2 + (0 * 2 + kc) * G_A_BYTES + kk * 32);
+                    const uint64_t al = umma_desc_k_sw128(a2 + (1 * 2 + kc) * G_A_BYTES + kk * 32);
+                    const uint64_t bh = umma_desc_k_sw128(w2 + (0 * 2 + kc) * 4096 + kk * 32);
+                    const uint64_t bl = umma_desc_k_sw128(w2 + (1 * 2 + kc) * 4096 + kk * 32);
+                    umma_f16_ss(tmem_base + D2_COL, al, bh, idesc2, k != 0);
+                    umma_f16_ss(tmem_base + D2_COL, ah, bl, idesc2, 1);
+                    umma_f16_ss(tmem_base + D2_COL, ah, bh, idesc2, 1);
+                }
+                umma_commit(d2_ready);
+            }
+            __syncwarp();
+        };
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
             tc_fence_after();
@@ -140,11 +182,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (FUSE2) {
+                if (pending_head) issue_head();              // previous tile's second dense (its epilogue ran meanwhile)
+                pending_head = true;
+            }
         }
+        if (FUSE2 && pending_head) issue_head();
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t head_phase = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t m0 = (tile / n_tiles_n) * G_TM;
             const int n0 = (int)((tile % n_tiles_n) * G_TN);
@@ -164,38 +212,57 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                       (q * 32 + lane) * 4;
                 cstride = G_TM * 4;
             }
-            if (G_TN == 128 && out.mode == 2) {
-                float a2[32];
-#pragma unroll
-                for (int o = 0; o < 32; ++o) a2[o] = __ldg(out.b2 + o);
+            if (FUSE2) {
+                // (1) relu(acc + bias1) -> fp16 (hi, lo) A tile of the second dense, K index = column of this layer
 #pragma unroll 1
                 for (int cb = 0; cb < 4; ++cb) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d1 = fmaxf(__uint_as_float(v[j]) + __ldg(out.bias + cb * 32 + j), 0.f);
-                        const float4* wrow = reinterpret_cast<const float4*>(s_w2 + (cb * 32 + j) * 32);
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        uint32_t ph[4], pl[4];
 #pragma unroll
-                        for (int o4 = 0; o4 < 8; ++o4) {
-                            const float4 w = wrow[o4];                      // broadcast: all lanes read the same row
-                            a2[4 * o4 + 0] = fmaf(d1, w.x, a2[4 * o4 + 0]); a2[4 * o4 + 1] = fmaf(d1, w.y, a2[4 * o4 + 1]);
-                            a2[4 * o4 + 2] = fmaf(d1, w.z, a2[4 * o4 + 2]); a2[4 * o4 + 3] = fmaf(d1, w.w, a2[4 * o4 + 3]);
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = g8 * 8 + e * 2;
+                            const float x0 = fmaxf(__uint_as_float(v[j]) + __ldg(out.bias + cb * 32 + j), 0.f);
+                            const float x1 = fmaxf(__uint_as_float(v[j + 1]) + __ldg(out.bias + cb * 32 + j + 1), 0.f);
+                            __half h0, l0, h1, l1;
+                            split_f16(x0, h0, l0); split_f16(x1, h1, l1);
+                            ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                         }
+                        const uint32_t off = ((cb >> 1) * G_A_BYTES) + sw128_offset(q * 32 + lane, (cb & 1) * 4 + g8);
+                        *reinterpret_cast<uint4*>(s_a2 + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(s_a2 + 2 * G_A_BYTES + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(a2_ready); mbar_arrive(&tempty[acc]); }   // main accumulator is drained
+                // (2) second accumulator -> + b2, relu -> out[r][32]
+                mbar_wait(d2_ready, head_phase);
+                head_phase ^= 1;
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + D2_COL, v);
+                tmem_ld_wait();
                 if (r < M) {
                     float4* o = reinterpret_cast<float4*>(out.c + r * 32);
 #pragma unroll
-                    for (int o4 = 0; o4 < 8; ++o4)
-                        o[o4] = make_float4(fmaxf(a2[4 * o4], 0.f), fmaxf(a2[4 * o4 + 1], 0.f), fmaxf(a2[4 * o4 + 2], 0.f),
-                                            fmaxf(a2[4 * o4 + 3], 0.f));
+                    for (int o4 = 0; o4 < 8; ++o4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(out.b2) + o4);
+                        o[o4] = make_float4(fmaxf(__uint_as_float(v[4 * o4]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * o4 + 1]) + b.y, 0.f),
+                                            fmaxf(__uint_as_float(v[4 * o4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * o4 + 3]) + b.w, 0.f));
+                    }
                 }
-                dst = nullptr;
+                tc_fence_before();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
             }
 #pragma unroll 1
-            for (int cb = 0; cb < ((G_TN == 128 && out.mode == 2) ? 0 : G_TN / 32); ++cb) {
+            for (int cb = 0; cb < G_TN / 32; ++cb) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
                 tmem_ld_wait();
@@ -270,15 +337,15 @@ bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, i
     return r == CUDA_SUCCESS;
 }
 
-template <int TN>
+template <int TN, bool FUSE2>
 static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                           const GemmOut& o, int num_sms, cudaStream_t st) {
-    using Cfg = GemmCfg<TN>;
+    using Cfg = GemmCfg<TN, FUSE2>;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_tmap_f16_k64(&ta_hi, a_hi, M, K, G_TM) || !make_tmap_f16_k64(&ta_lo, a_lo, M, K, G_TM) ||
         !make_tmap_f16_k64(&tb_hi, b_hi, N, K, TN) || !make_tmap_f16_k64(&tb_lo, b_lo, N, K, TN))
         return -2;
-    auto kern = gemm_f16x3_kernel<TN>;
+    auto kern = gemm_f16x3_kernel<TN, FUSE2>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     const int64_t n_tiles = ((M + G_TM - 1) / G_TM) * (N / TN);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, num_sms > 0 ? num_sms : 148);
@@ -288,19 +355,22 @@ static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* 
 
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st, const float* w2, const float* b2) {
+                      cudaStream_t st, const __half* w2t_hi, const __half* w2t_lo, const float* b2) {
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
-    if (mode == 2 && (N != 128 || !w2 || !b2 || !bias)) return -1;
-    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2, b2};
+    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2};
+    if (mode == 2) {
+        if (N != 128 || !w2t_hi || !w2t_lo || !b2 || !bias) return -1;
+        return launch_gemm_tn<128, true>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
+    }
     if (mode == 1 && (M % G_TM != 0)) return -1;
     if (N % 256 == 0) {
         if (mode == 1 && (n_per_dir % 256 != 0)) return -1;
-        return launch_gemm_tn<256>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
+        return launch_gemm_tn<256, false>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
     }
     if (N % 128 == 0) {
         if (mode == 1 && (n_per_dir % 128 != 0)) return -1;
-        return launch_gemm_tn<128>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
+        return launch_gemm_tn<128, false>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
     }
     return -1;
 }
