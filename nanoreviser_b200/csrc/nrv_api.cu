@@ -69,6 +69,7 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
+    int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
@@ -401,7 +402,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
                     StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    n = launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
+                    n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
+                                       : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
                     h->launches += n;
                 }
@@ -668,6 +670,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
     const char* pa = getenv("NRV_PATH");
     if (pa && !strcmp(pa, "simt")) h->path = 0;
+    const char* r128 = getenv("NRV_REC128");
+    if (r128 && !strcmp(r128, "single")) h->rec128_pair = 0;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
     return NRV_OK;

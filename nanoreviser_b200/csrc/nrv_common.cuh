@@ -107,6 +107,7 @@ int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStre
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
 int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
+int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 
 // nrv_heads.cu: dense heads + flatten + feature + final softmax + argmax.
 // stage = 0: act_in is total_rnn2's output [..][128]; 1: act_in is relu(Dense(128)) [..][128];

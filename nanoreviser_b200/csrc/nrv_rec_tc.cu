@@ -464,4 +464,250 @@ int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, 
     return 1;
 }
 
+// ============================================================================================================
+// u = 128, CTA-PAIR variant (tcgen05 cta_group::2, thread-block cluster of 2 on one TPC).
+// One cluster = one direction x TWO tiles of 128 windows (one per CTA).  A single tcgen05.mma.cta_group::2
+// covers M = 256 rows (both CTAs' windows) x N = 256 gate columns and reads the B operand half from each CTA's
+// shared memory -- so each SM holds only HALF of Wr^T (hi and lo: 128 KB), all of it resident, and the W_lo
+// stream of the single-CTA kernel (and its latency) disappears.  Every CTA keeps its own windows' h tile (A
+// operand) and accumulator (its 128 TMEM lanes x 512 columns) and runs its own epilogue; no activation ever
+// crosses the pair.  Synchronisation: per-CTA "h tile written" mbarrier -> warp 0 of each CTA TMA-stores its h
+// and arrives (peer: remotely) on the leader's pair barrier; the leader issues the MMAs and commits with
+// .multicast::cluster to the accumulator barriers of both CTAs.
+// ============================================================================================================
+constexpr int RP_THREADS = 288;                        // warp 0: store + MMA issue; warps 1..8: epilogue
+constexpr int RP_W_BYTES = 8 * 128 * 64 * 2;           // 128 KB: [hi|lo][half][kc][128 rows][64]
+constexpr int RP_H_BYTES = 128 * 64 * 2;               // 16 KB: one K-chunk of h (hi or lo)
+constexpr size_t RP_SMEM = (size_t)RP_W_BYTES + 4 * RP_H_BYTES + 1024 + 128;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+}
+// arrive (release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, 256 rows over the pair] (+)= A[smem of both CTAs] * B[smem halves of both CTAs]^T ; leader CTA, one thread
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier at this offset in BOTH CTAs arrives when all tcgen05 ops issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
+lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __restrict__ wr_lo, const float* __restrict__ zin,
+                           const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo,
+                           int64_t nwp, int T) {
+    constexpr int U = 128, N = 512;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                     // [part][half][kc][128 rows][64]
+    uint8_t* s_h = smem + RP_W_BYTES;                        // [part][kc][128 rows][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + 4 * RP_H_BYTES);
+    uint64_t* h_local = bars;                                // count 8: this CTA's epilogue warps wrote h_t
+    uint64_t* h_pair = bars + 1;                             // count 2 (leader's copy is used): both CTAs' h tiles are ready
+    uint64_t* acc_ready = bars + 2;                          // [2] count 2: multicast commit + local "h store left smem"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int dir = blockIdx.y;
+    const int64_t ntw = nwp >> 7;
+    const int64_t wtile = min((int64_t)blockIdx.x, ntw - 1);     // odd tile count: the last peer repeats the last tile
+
+    if (threadIdx.x == 0) {
+        mbar_init(h_local, 8);
+        mbar_init(h_pair, 2);
+        mbar_init(&acc_ready[0], 2); mbar_init(&acc_ready[1], 2);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
+    }
+    if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+    {   // this CTA's half of Wr^T: for column half hf, global rows hf*256 + rank*128 .. +128 (hi and lo)
+        for (int i = threadIdx.x; i < 2 * 2 * 128 * 16; i += RP_THREADS) {
+            const int c16 = i & 15, row = (i >> 4) & 127, hf = (i >> 11) & 1, part = i >> 12;
+            const __half* src = (part ? wr_lo : wr_hi) + ((size_t)dir * N + hf * 256 + rank * 128 + row) * U;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + c16);
+            *reinterpret_cast<uint4*>(s_w + (((part * 2 + hf) * 2 + (c16 >> 3)) * (128 * 128)) + sw128_offset(row, c16 & 7)) = v;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // barriers initialised, weights in place and TMEM allocated in BOTH CTAs
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== h store (both CTAs) + MMA issue (leader) =====================
+        constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
+        const uint32_t a_base = smem_u32(s_h), w_base = smem_u32(s_w);
+        auto mma_block = [&](int hf, int k0, int k1, bool zero_first) {
+            const uint32_t d = tmem_base + (uint32_t)(hf * 256);
+            for (int k = k0; k < k1; ++k) {
+                const int kc = k >> 2, kk = k & 3;
+                const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * RP_H_BYTES + kk * 32);
+                const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * RP_H_BYTES + kk * 32);
+                const uint64_t b_hi = umma_desc_k_sw128(w_base + ((0 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
+                const uint64_t b_lo = umma_desc_k_sw128(w_base + ((1 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
+                umma_f16_ss_pair(d, a_lo, b_hi, idesc, (zero_first && k == k0) ? 0u : 1u);
+                umma_f16_ss_pair(d, a_hi, b_lo, idesc, 1);
+                umma_f16_ss_pair(d, a_hi, b_hi, idesc, 1);
+            }
+        };
+        for (int s = 1; s <= T; ++s) {
+            const int t_prev = dir ? (T - s) : (s - 1);
+            mbar_wait(h_local, (uint32_t)((s - 1) & 1));          // this CTA's h_{s-1} tile is written and fenced
+            tc_fence_after();
+            if (elect_one()) {
+                const int grow = (int)(t_prev * nwp + wtile * 128);
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    tma_store_2d(&tm_out_hi, s_h + (0 * 2 + kc) * RP_H_BYTES, dir * U + kc * 64, grow);
+                    tma_store_2d(&tm_out_lo, s_h + (1 * 2 + kc) * RP_H_BYTES, dir * U + kc * 64, grow);
+                }
+                tma_store_commit();
+                if (s < T) mbar_arrive_cluster(h_pair, 0);        // tell the leader this CTA's A operand is ready
+            }
+            __syncwarp();
+            if (s == T) break;
+            if (rank == 0) {
+                mbar_wait_cluster(h_pair, (uint32_t)((s - 1) & 1));
+                tc_fence_after();
+                if (elect_one()) {
+                    mma_block(1, 0, 4, true);                     // H1 x K-chunk 0
+                    mma_block(0, 0, 8, true);                     // H0, all of K
+                    umma_commit_pair(&acc_ready[0]);
+                    mma_block(1, 4, 8, false);                    // H1 x K-chunk 1
+                    umma_commit_pair(&acc_ready[1]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) {
+                tma_store_wait_read();                            // this CTA's h_{s-1} stores have left shared memory
+                mbar_arrive(&acc_ready[0]);
+                mbar_arrive(&acc_ready[1]);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else {
+        // ===================== epilogue: warps 1..8; lane quarter = warp % 4, column half = (warp - 1) / 4 ===========
+        const int q = warp & 3;
+        const int hf = (warp - 1) >> 2;
+        const int row = q * 32 + lane;
+        uint8_t* hs_hi = s_h + (0 * 2 + hf) * RP_H_BYTES;       // units hf*64.. -> K chunk hf of the h tile
+        uint8_t* hs_lo = s_h + (1 * 2 + hf) * RP_H_BYTES;
+        float c[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) c[j] = 0.f;
+        auto ztile_of = [&](int s_) {
+            const int t_ = dir ? (T - 1 - s_) : s_;
+            return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wtile) * (N * 128)) + (hf * 64) * 128 + row;
+        };
+        const float4* ztile = ztile_of(0);
+        float4 z[8], zn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + j * 128);
+        for (int s = 0; s < T; ++s) {
+            const float4* znext_tile = (s + 1 < T) ? ztile_of(s + 1) : ztile;
+            if (s > 0) {
+                mbar_wait_cluster(&acc_ready[hf], (uint32_t)((s - 1) & 1));
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+                if (cb + 1 < 8) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(ztile + ((cb + 1) * 8 + j) * 128);
+                } else if (s + 1 < T) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(znext_tile + j * 128);
+                }
+                uint32_t v[32];
+                if (s > 0) {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
+                    tmem_ld_wait();
+                }
+                uint4 phi, plo;
+                lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
+                const uint32_t off = sw128_offset(row, cb);
+                *reinterpret_cast<uint4*>(hs_hi + off) = phi;
+                *reinterpret_cast<uint4*>(hs_lo + off) = plo;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = zn[j];
+            }
+            ztile = znext_tile;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_local);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the leader's MMAs read the peer's shared memory: nobody leaves early
+    if (warp == 0) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
+int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, int T, cudaStream_t st) {
+    if (nwp <= 0) return 0;
+    if (L.u != 128 || !L.rt_hi || !io.out_hi || (nwp & 127)) return -1;
+    CUtensorMap tmh, tml;
+    if (!make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
+        !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
+        return -2;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_rec_tc128_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM);
+        attr = true;
+    }
+    const int64_t ntw = nwp >> 7;
+    dim3 grid((unsigned)((ntw + 1) / 2 * 2), 2);
+    lstm_rec_tc128_pair_kernel<<<grid, RP_THREADS, RP_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, tmh, tml, nwp, T);
+    return 1;
+}
+
 }  // namespace nrv
