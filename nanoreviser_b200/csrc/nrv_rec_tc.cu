@@ -34,10 +34,12 @@ using namespace tc;
 
 bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);   // nrv_gemm.cu
 
-constexpr int RT_THREADS = 288;                 // 1 MMA warp + 2 x 4 epilogue warps
+constexpr int RT_THREADS = 352;                 // 1 MMA warp + 2 x 4 epilogue warps + 2 zin producer warps
 constexpr int RT_W_BYTES = 256 * 64 * 2;        // 32 KB: Wr^T hi (or lo)
 constexpr int RT_H_BYTES = 128 * 64 * 2;        // 16 KB: h tile hi (or lo)
-constexpr size_t RT_SMEM = 2 * RT_W_BYTES + 4 * RT_H_BYTES + 1024 + 128;
+constexpr int RT_ZS = 3;                        // zin ring stages per tile
+constexpr int RT_Z_BYTES = 8 * 128 * 16;        // 16 KB: one 32-column block of a zin tile (8 quads x 128 rows x 16 B)
+constexpr size_t RT_SMEM = 2 * RT_W_BYTES + 4 * RT_H_BYTES + 2 * RT_ZS * RT_Z_BYTES + 1024 + 256;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -93,10 +95,13 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
     uint8_t* s_whi = smem;
     uint8_t* s_wlo = smem + RT_W_BYTES;
     uint8_t* s_h = smem + 2 * RT_W_BYTES;               // [tile][hi|lo][16 KB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RT_W_BYTES + 4 * RT_H_BYTES);
+    uint8_t* s_z = s_h + 4 * RT_H_BYTES;                // [tile][stage][16 KB] zin blocks landed by cp.async.bulk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 2 * RT_ZS * RT_Z_BYTES);
     uint64_t* h_ready = bars;                           // [2] count 4 (one arrive per epilogue warp)
     uint64_t* acc_ready = bars + 2;                     // [2] count 2 (tcgen05.commit + "h store has left smem")
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* zfull = bars + 4;                         // [2][RT_ZS] count 1 + tx bytes
+    uint64_t* zempty = bars + 4 + 2 * RT_ZS;            // [2][RT_ZS] count 4 (one arrive per epilogue warp of the tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 4 * RT_ZS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -107,6 +112,7 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
     if (threadIdx.x == 0) {
         mbar_init(&h_ready[0], 4); mbar_init(&h_ready[1], 4);
         mbar_init(&acc_ready[0], 2); mbar_init(&acc_ready[1], 2);
+        for (int i = 0; i < 2 * RT_ZS; ++i) { mbar_init(&zfull[i], 1); mbar_init(&zempty[i], 4); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
     }
@@ -163,6 +169,26 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
+    } else if (warp >= 9) {
+        // ===================== zin producers: warp 9 -> tile 0, warp 10 -> tile 1 =====================
+        // The whole zin stream of a tile (T steps x 8 blocks of 16 KB, each contiguous in the tiled layout) goes through a
+        // 3-stage shared-memory ring with cp.async.bulk: bytes in flight are no longer limited by registers, which is what
+        // bounded this kernel (ncu: ~64 KB in flight per SM against ~2 us of loaded HBM latency).
+        const int X = warp - 9;
+        if (valid[X] && elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 0; s < T; ++s) {
+                const int t = dir ? (T - 1 - s) : s;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(zin + (((int64_t)dir * T + t) * ntw + wt[X]) * (N * 128));
+                for (int cb = 0; cb < 8; ++cb) {
+                    uint64_t* fb = &zfull[X * RT_ZS + stage];
+                    mbar_wait(&zempty[X * RT_ZS + stage], phase ^ 1);
+                    mbar_arrive_expect_tx(fb, RT_Z_BYTES);
+                    bulk_load_1d(s_z + (X * RT_ZS + stage) * RT_Z_BYTES, src + (size_t)cb * RT_Z_BYTES, RT_Z_BYTES, fb);
+                    if (++stage == RT_ZS) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
     } else {
         // ===================== epilogue: warps 1-4 -> tile 0, warps 5-8 -> tile 1 =====================
         const int X = (warp - 1) >> 2;
@@ -174,46 +200,32 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
             float c[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) c[j] = 0.f;
-            // zin of this thread's row, one 16-byte quad per 128-row stride; block cb = quads [8cb, 8cb+8).
-            // Loads are software-pipelined one block ahead (the next step's first block is requested before the
-            // wait on the accumulator barrier), so their latency hides behind the cell arithmetic / the MMA.
-            auto ztile_of = [&](int s_) {
-                const int t_ = dir ? (T - 1 - s_) : s_;
-                return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wt[X]) * (N * 128)) + row;
-            };
-            const float4* ztile = ztile_of(0);
-            float4 z[8], zn[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + j * 128);
+            int stage = 0; uint32_t zphase = 0;
             for (int s = 0; s < T; ++s) {
-                const float4* znext_tile = (s + 1 < T) ? ztile_of(s + 1) : ztile;
                 if (s > 0) {
                     mbar_wait(&acc_ready[X], (uint32_t)((s - 1) & 1));
                     tc_fence_after();
                 }
 #pragma unroll
                 for (int cb = 0; cb < N / 32; ++cb) {
-                    if (cb + 1 < N / 32) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zn[j] = __ldg(ztile + ((cb + 1) * 8 + j) * 128);
-                    } else if (s + 1 < T) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zn[j] = __ldg(znext_tile + j * 128);
-                    }
                     uint32_t v[32];
-                    if (s > 0) {
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
-                        tmem_ld_wait();
-                    }
+                    if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
+                    // zin block from the ring: quad j of this row at j*2 KB + row*16 B (conflict-free 128-bit reads)
+                    mbar_wait(&zfull[X * RT_ZS + stage], zphase);
+                    const float4* zs = reinterpret_cast<const float4*>(s_z + (X * RT_ZS + stage) * RT_Z_BYTES) + row;
+                    float4 z[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = zs[j * 128];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&zempty[X * RT_ZS + stage]);
+                    if (++stage == RT_ZS) { stage = 0; zphase ^= 1; }
+                    if (s > 0) tmem_ld_wait();
                     uint4 phi, plo;
                     lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
                     const uint32_t off = sw128_offset(row, cb);
                     *reinterpret_cast<uint4*>(hs_hi + off) = phi;
                     *reinterpret_cast<uint4*>(hs_lo + off) = plo;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] = zn[j];
                 }
-                ztile = znext_tile;
                 tc_fence_before();           // our tcgen05.ld of this step precede the next MMA's writes
                 fence_proxy_async_smem();    // our h writes are visible to the tensor core and to TMA
                 __syncwarp();
