@@ -17,6 +17,10 @@
 //               the MMAs from one elected lane; tcgen05.commit releases ring slots / publishes accumulators
 //   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> (+bias) -> global, one TMEM
 //               lane quarter per warp; overlaps the next tile's MMAs through the second accumulator
+#include <string.h>
+
+#include <algorithm>
+
 #include "nrv_common.cuh"
 #include "nrv_tc.cuh"
 
@@ -291,6 +295,166 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
+// ============================================================================================================
+// CTA-PAIR projection GEMM (tcgen05 cta_group::2, cluster of 2): the kernel used for the Bi-LSTM input projections.
+//   * one tcgen05.mma covers M = 256 rows (128 per CTA) x N = 256 columns and reads half of the B operand from each
+//     CTA's shared memory, so each SM keeps only HALF of the 256-column weight tile -- all of K, hi and lo -- RESIDENT
+//     (K = 192: 96 KB, K = 256: 128 KB).  A cluster owns one column tile for its whole life and walks over row pairs;
+//     the clusters of the 2-4 column tiles walk in lockstep, so an A tile is fetched from HBM once and hits L2 after.
+//   * only the A operand streams: 32 KB chunks ([128 rows][64] hi + lo) through a 3-6 stage TMA ring per CTA, both
+//     CTAs' loads credited to the LEADER's "full" barrier; tcgen05.commit.multicast frees the slot in both CTAs.
+//   * the single-CTA kernel above is load-latency-bound (2 x 96 KB stages, A and B streamed: tensor pipe 52 %);
+//     here the bytes per MMA halve twice (B resident, A per CTA) and the ring is deep enough to cover HBM latency.
+//   * epilogue per CTA: its 128 rows of the double-buffered accumulator -> (+bias) -> zin tiles, coalesced.
+// ============================================================================================================
+constexpr int GP_THREADS = 192;
+constexpr int GP_A_STAGE = 2 * G_A_BYTES;             // 32 KB: A_hi + A_lo chunk
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GP_THREADS, 1)
+gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                       const __half* __restrict__ b_hi, const __half* __restrict__ b_lo, GemmOut out, int64_t M, int N, int K,
+                       int n_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int n_chunks = K / G_KC;
+    uint8_t* s_b = smem;                                              // [part][kc][128 rows][64]  resident
+    uint8_t* s_a = smem + (size_t)2 * n_chunks * G_A_BYTES;           // [stage][hi|lo][128 rows][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)n_stages * GP_A_STAGE);
+    uint64_t* full = bars;                  // [n_stages] leader's copy is used: 1 arrive (leader producer) + 64 KB of tx
+    uint64_t* empty = bars + 8;             // [n_stages] both CTAs: multicast commit
+    uint64_t* tfull = bars + 16;            // [2] both CTAs: multicast commit
+    uint64_t* tempty = bars + 18;           // [2] leader's copy is used: 8 arrivals (4 epilogue warps x 2 CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_tiles_n = N / 256;
+    const int64_t n_tiles_m = M / G_TM;
+    const int64_t n_mpairs = (n_tiles_m + 1) / 2;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_tile = cluster_id % n_tiles_n;
+    const int wi = cluster_id / n_tiles_n;                                 // worker index among the clusters of this column tile
+    const int n_workers = (n_clusters - n_tile + n_tiles_n - 1) / n_tiles_n;
+    const int n0 = n_tile * 256;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+        for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    {   // resident B: this CTA's 128 rows of the column tile, all of K, hi and lo -> swizzled K-major [128][64] tiles
+        const int per_row = K / 8;                                         // 16-byte chunks per row
+        for (int i = threadIdx.x; i < 2 * 128 * per_row; i += GP_THREADS) {
+            const int part = i / (128 * per_row), rem = i - part * (128 * per_row);
+            const int row = rem / per_row, c = rem - row * per_row;
+            const __half* src = (part ? b_lo : b_hi) + ((size_t)(n0 + rank * 128 + row)) * K;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + c);
+            *reinterpret_cast<uint4*>(s_b + ((size_t)(part * n_chunks + (c >> 3))) * G_A_BYTES + sw128_offset(row, c & 7)) = v;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own 128 rows of the A operand =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
+                const int m0 = (int)((mp * 2 + rank) * G_TM);             // rows beyond M are zero-filled by TMA
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    mbar_wait_cluster(&empty[stage], phase ^ 1);
+                    uint8_t* st = s_a + (size_t)stage * GP_A_STAGE;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * GP_A_STAGE);    // both CTAs' bytes
+                    tma_load_2d_pair(st, &tm_a_hi, &full[stage], 0, kc * G_KC, m0);
+                    tma_load_2d_pair(st + G_A_BYTES, &tm_a_lo, &full[stage], 0, kc * G_KC, m0);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t b_base = smem_u32(s_b);
+            for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
+                mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    mbar_wait_cluster(&full[stage], phase);              // both CTAs' A chunks have landed
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t st = smem_u32(s_a + (size_t)stage * GP_A_STAGE);
+#pragma unroll
+                        for (int k = 0; k < G_KC / 16; ++k) {
+                            const uint64_t a_hi = umma_desc_k_sw128(st + k * 32), a_lo = umma_desc_k_sw128(st + G_A_BYTES + k * 32);
+                            const uint64_t bh = umma_desc_k_sw128(b_base + (uint32_t)((0 * n_chunks + kc) * G_A_BYTES) + k * 32);
+                            const uint64_t bl = umma_desc_k_sw128(b_base + (uint32_t)((1 * n_chunks + kc) * G_A_BYTES) + k * 32);
+                            umma_f16_ss_pair(d_tmem, a_lo, bh, idesc, (kc | k) != 0);
+                            umma_f16_ss_pair(d_tmem, a_hi, bl, idesc, 1);
+                            umma_f16_ss_pair(d_tmem, a_hi, bh, idesc, 1);
+                        }
+                        umma_commit_pair(&empty[stage]);                  // frees the ring slot in both CTAs
+                        if (kc == n_chunks - 1) umma_commit_pair(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs): own 128 rows -> zin tile =====================
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const int dir = n0 / out.n_per_dir;
+        const int nloc = n0 - dir * out.n_per_dir;
+        for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
+            const int64_t m_tile = mp * 2 + rank;
+            mbar_wait_cluster(&tfull[acc], acc_phase);
+            tc_fence_after();
+            float* dst = nullptr;
+            if (m_tile < n_tiles_m)
+                dst = out.c + ((int64_t)dir * n_tiles_m + m_tile) * ((int64_t)out.n_per_dir * G_TM) + (int64_t)(nloc >> 2) * (G_TM * 4) +
+                      (q * 32 + lane) * 4;
+#pragma unroll 1
+            for (int cb = 0; cb < 8; ++cb) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + cb * 32), v);
+                tmem_ld_wait();
+                if (dst) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                               __uint_as_float(v[j + 3]));
+                        if (out.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(out.bias + n0 + cb * 32 + j));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + (int64_t)(cb * 8 + (j >> 2)) * (G_TM * 4)) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
 // ---- fp32 -> (hi, lo) fp16 split ------------------------------------------------------------------------
 __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,6 +523,25 @@ int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
     GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2};
+    static const bool use_pair = getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "pair");   // measured: no gain, the GEMMs are HBM-write-bound
+    if (mode == 1 && use_pair && N % 256 == 0 && n_per_dir % 256 == 0 && M % G_TM == 0 && K <= 256) {
+        CUtensorMap ta_hi, ta_lo;
+        if (!make_tmap_f16_k64(&ta_hi, a_hi, M, K, G_TM) || !make_tmap_f16_k64(&ta_lo, a_lo, M, K, G_TM)) return -2;
+        const int n_chunks = K / G_KC;
+        const size_t b_bytes = (size_t)2 * n_chunks * G_A_BYTES;
+        int n_stages = (int)((232448 - 2048 - b_bytes) / GP_A_STAGE);
+        if (n_stages > 6) n_stages = 6;
+        if (n_stages < 2) return -1;
+        const size_t smem = b_bytes + (size_t)n_stages * GP_A_STAGE + 1024 + 256;
+        cudaFuncSetAttribute(gemm_f16x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int sms = num_sms > 0 ? num_sms : 148;
+        const int n_tiles_n = N / 256;
+        const int64_t n_mpairs = (M / G_TM + 1) / 2;
+        int64_t n_clusters = std::min<int64_t>(sms / 2, n_mpairs * n_tiles_n);
+        if (n_clusters < n_tiles_n) n_clusters = n_tiles_n;                // every column tile needs a worker
+        gemm_f16x3_pair_kernel<<<(unsigned)(2 * n_clusters), GP_THREADS, smem, st>>>(ta_hi, ta_lo, b_hi, b_lo, o, M, N, K, n_stages);
+        return 1;
+    }
     if (mode == 2) {
         if (N != 128 || !w2t_hi || !w2t_lo || !b2 || !bias) return -1;
         return launch_gemm_tn<128, true>(a_hi, a_lo, b_hi, b_lo, M, N, K, o, num_sms, st);
