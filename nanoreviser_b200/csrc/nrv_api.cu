@@ -218,6 +218,10 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
                             }
                         }
                         bias_tc[n] = (float)bacc;
+                        if (l == 1) {   // fused kernel: the operand's column 32 is the constant 1.0, its weight row is the bias
+                            bt[(size_t)n * kin + 32] = (float)bacc;
+                            bias_tc[n] = 0.f;
+                        }
                     }
             }
             std::vector<__half> bh(bt.size()), bl(bt.size());
@@ -296,6 +300,11 @@ __global__ void iota_mul_kernel(int32_t* out, int64_t n, int mul) {
     if (i < n) out[i] = (int32_t)(i * mul);
 }
 
+__global__ void set_half_column_kernel(__half* a, int64_t rows, int ld, int col, float v) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) a[r * ld + col] = __float2half_rn(v);
+}
+
 __global__ void gather_sig_kernel(const __half* __restrict__ sf_hi, const __half* __restrict__ sf_lo,
                                   const int32_t* __restrict__ win_base, int64_t n_win, int64_t nwp, int T, int ld,
                                   __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
@@ -328,7 +337,14 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
             const size_t before = h->d_a1[k].cap;
             CU(h, h->d_a1[k].ensure((size_t)rows * 64 * 2));
             // columns [32, 64) of read_rnn11's operand are zero padding that no kernel ever writes
-            if (h->d_a1[k].cap != before) CU(h, cudaMemsetAsync(h->d_a1[k].p, 0, h->d_a1[k].cap, h->stream));
+            if (h->d_a1[k].cap != before) {
+                CU(h, cudaMemsetAsync(h->d_a1[k].p, 0, h->d_a1[k].cap, h->stream));
+                if (k == 0) {   // hi part: column 32 = 1.0 (bias column of read_rnn11's fused projection)
+                    const int64_t nrows = (int64_t)(h->d_a1[k].cap / (64 * 2));
+                    set_half_column_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, h->stream>>>(h->d_a1[k].as<__half>(), nrows, 64, 32, 1.0f);
+                    h->launches += 1;
+                }
+            }
             CU(h, h->d_a4[k].ensure((size_t)rows * 128 * 2));
         }
         CU(h, h->d_a2[0].ensure((size_t)rows * 192 * 2)); CU(h, h->d_a2[1].ensure((size_t)rows * 192 * 2));
@@ -375,18 +391,12 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     io.out_nwp = nwp;
                     h->launches += launch_lstm_layer(0, 1, M.lstm[0], io, nw, T, h->stream);
                 }
-                {   // read_rnn11: projection (K = 32 -> 64) + recurrence (u = 64)
-                    {
-                        StageTimer tm(h, ST_PROJ1);
-                        n = launch_gemm_f16x3(a1h, a1l, M.lstm[1].pb_hi, M.lstm[1].pb_lo, R, 512, 64, zin, M.lstm[1].bias_tc, 1,
-                                              T, nwp, 256, 0, h->num_sms, h->stream);
-                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (read_rnn11) could not be launched");
-                        h->launches += n;
-                    }
+                {   // read_rnn11: projection (K = 32 -> 64, bias as the weight row of a constant-1 column) and recurrence
+                    // (u = 64) fused in one tcgen05 kernel -- no zin round trip for this layer
                     StageTimer tm(h, ST_REC1);
-                    LstmIo io; io.zin = zin; io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
-                    n = launch_lstm_rec_tc64(M.lstm[1], io, nwp, T, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (read_rnn11) could not be launched");
+                    LstmIo io; io.out_hi = a2h; io.out_lo = a2l; io.out_ld = 192;
+                    n = launch_lstm_fused_tc64(M.lstm[1], a1h, a1l, io, nwp, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (read_rnn11) could not be launched");
                     h->launches += n;
                 }
                 {   // total_rnn1: gather CNN features, projection (K = 192), recurrence (u = 128)

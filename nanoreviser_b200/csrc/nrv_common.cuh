@@ -106,6 +106,9 @@ int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStre
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
 int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
+// fused projection + recurrence for read_rnn11 (K_in = 32 padded to 64 with a constant-1 bias column)
+int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
+                           cudaStream_t st);
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 

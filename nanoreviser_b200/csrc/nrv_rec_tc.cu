@@ -256,6 +256,193 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, i
 }
 
 // ============================================================================================================
+// u = 64 FUSED variant (read_rnn11, lstmmodel.py:46): input projection AND recurrence in one kernel, no zin at all.
+// The layer's input is only 32 wide (read_rnn1's BN'd output, zero-padded to K = 64, with column 32 fixed to 1.0 so
+// that the bias rides along as a weight row), so Wk^T (64 KB as an fp16 pair) fits next to Wr^T (64 KB):
+//   z_t = [x_t | 1 | 0..] . Wk  +  h_{t-1} . Wr          -- 12 + 12 tcgen05.mma per step into one TMEM accumulator
+// One CTA = one direction x one tile of 128 windows.  x_t tiles ([128][64] hi + lo, 32 KB) arrive through a 2-stage TMA
+// ring; the accumulator is double-buffered over timesteps so that the projection MMAs of step s+1 (independent of h)
+// are issued right behind the recurrent MMAs of step s and run while the epilogue of step s is busy.  Compared with
+// GEMM + recurrence this removes 2 x 22.5 KB of HBM traffic per window and a kernel launch.
+// ============================================================================================================
+constexpr int RF_THREADS = 192;                       // warp 0: store + MMA issue, warp 1: TMA producer, warps 2..5: epilogue
+constexpr int RF_W_BYTES = 256 * 64 * 2;              // 32 KB per weight tile (Wk hi, Wk lo, Wr hi, Wr lo)
+constexpr int RF_H_BYTES = 128 * 64 * 2;              // 16 KB per h / x tile part
+constexpr int RF_XS = 2;                              // x ring stages
+constexpr size_t RF_SMEM = 4 * RF_W_BYTES + 2 * RF_H_BYTES + RF_XS * 2 * RF_H_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
+                       const __half* __restrict__ wr_lo, const __grid_constant__ CUtensorMap tm_x_hi,
+                       const __grid_constant__ CUtensorMap tm_x_lo, const __grid_constant__ CUtensorMap tm_out_hi,
+                       const __grid_constant__ CUtensorMap tm_out_lo, int64_t nwp, int T) {
+    constexpr int U = 64, N = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                  // [Wk hi | Wk lo | Wr hi | Wr lo] x [256 rows][64]
+    uint8_t* s_h = smem + 4 * RF_W_BYTES;                 // [hi | lo][128 rows][64]
+    uint8_t* s_x = s_h + 2 * RF_H_BYTES;                  // [stage][hi | lo][128 rows][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + RF_XS * 2 * RF_H_BYTES);
+    uint64_t* h_ready = bars;                             // count 4
+    uint64_t* acc_ready = bars + 1;                       // count 2 (commit + "h store left smem"); step 0: see below
+    uint64_t* xfull = bars + 2;                           // [RF_XS]
+    uint64_t* xempty = bars + 2 + RF_XS;                  // [RF_XS] count 1 (commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * RF_XS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+    const int64_t wtile = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        mbar_init(h_ready, 4);
+        mbar_init(acc_ready, 2);
+        for (int i = 0; i < RF_XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    {
+        const __half* srcs[4] = {wk_hi + (size_t)dir * N * U, wk_lo + (size_t)dir * N * U, wr_hi + (size_t)dir * N * U,
+                                 wr_lo + (size_t)dir * N * U};
+        for (int i = threadIdx.x; i < 4 * N * 8; i += RF_THREADS) {
+            const int m = i / (N * 8), r = i - m * (N * 8);
+            *reinterpret_cast<uint4*>(s_w + m * RF_W_BYTES + sw128_offset(r >> 3, r & 7)) = __ldg(reinterpret_cast<const uint4*>(srcs[m]) + r);
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        // ===================== TMA producer: x_t tiles in step order =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 0; s < T; ++s) {
+                const int t = dir ? (T - 1 - s) : s;
+                const int grow = (int)(t * nwp + wtile * 128);
+                mbar_wait(&xempty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&xfull[stage], 2 * RF_H_BYTES);
+                tma_load_2d(s_x + (stage * 2 + 0) * RF_H_BYTES, &tm_x_hi, &xfull[stage], 0, grow);
+                tma_load_2d(s_x + (stage * 2 + 1) * RF_H_BYTES, &tm_x_lo, &xfull[stage], 0, grow);
+                if (++stage == RF_XS) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== h store + MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_f16_f32(128, N);
+        const uint32_t w_base = smem_u32(s_w);
+        int xstage = 0; uint32_t xphase = 0;
+        // projection of step s: acc[s & 1] = x_s . Wk   (zero-initialises the accumulator)
+        auto proj = [&](int s) {
+            mbar_wait(&xfull[xstage], xphase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t xa = smem_u32(s_x + (xstage * 2) * RF_H_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)((s & 1) * N);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t a_hi = umma_desc_k_sw128(xa + k * 32), a_lo = umma_desc_k_sw128(xa + RF_H_BYTES + k * 32);
+                    const uint64_t b_hi = umma_desc_k_sw128(w_base + 0 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 1 * RF_W_BYTES + k * 32);
+                    umma_f16_ss(d, a_lo, b_hi, idesc, k != 0);
+                    umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                    umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                }
+                umma_commit(&xempty[xstage]);
+            }
+            __syncwarp();
+            if (++xstage == RF_XS) { xstage = 0; xphase ^= 1; }
+        };
+        proj(0);
+        if (elect_one()) { umma_commit(acc_ready); mbar_arrive(acc_ready); }      // step 0: projection only, no store pending
+        __syncwarp();
+        if (T > 1) proj(1);
+        for (int s = 1; s <= T; ++s) {
+            const int t_prev = dir ? (T - s) : (s - 1);
+            mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const int grow = (int)(t_prev * nwp + wtile * 128);
+                tma_store_2d(&tm_out_hi, s_h, dir * U, grow);
+                tma_store_2d(&tm_out_lo, s_h + RF_H_BYTES, dir * U, grow);
+                tma_store_commit();
+                if (s < T) {
+                    const uint32_t ha = smem_u32(s_h);
+                    const uint32_t d = tmem_base + (uint32_t)((s & 1) * N);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
+                        const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
+                        umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
+                        umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                        umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                    }
+                    umma_commit(acc_ready);
+                }
+            }
+            __syncwarp();
+            if (s < T) {
+                if (s + 1 < T) proj(s + 1);                                // runs on the tensor core during epilogue(s)
+                if (elect_one()) { tma_store_wait_read(); mbar_arrive(acc_ready); }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else {
+        // ===================== epilogue: warps 2..5 =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float c[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) c[j] = 0.f;
+        const float4 zero4[8] = {};
+        for (int s = 0; s < T; ++s) {
+            mbar_wait(acc_ready, (uint32_t)(s & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < N / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((s & 1) * N + cb * 32), v);
+                tmem_ld_wait();
+                uint4 phi, plo;
+                lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
+                const uint32_t off = sw128_offset(row, cb);
+                *reinterpret_cast<uint4*>(s_h + off) = phi;
+                *reinterpret_cast<uint4*>(s_h + RF_H_BYTES + off) = plo;
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_ready);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
+                           cudaStream_t st) {
+    if (nwp <= 0) return 0;
+    if (L.u != 64 || !L.rt_hi || !L.pb_hi || !io.out_hi || (nwp & 127)) return -1;
+    CUtensorMap txh, txl, tmh, tml;
+    if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, 64, 128) || !make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, 64, 128) ||
+        !make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
+        !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
+        return -2;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_fused_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        attr = true;
+    }
+    dim3 grid((unsigned)(nwp >> 7), 2);
+    lstm_fused_tc64_kernel<<<grid, RF_THREADS, RF_SMEM, st>>>(L.pb_hi, L.pb_lo, L.rt_hi, L.rt_lo, txh, txl, tmh, tml, nwp, T);
+    return 1;
+}
+
+// ============================================================================================================
 // u = 128 variant (total_rnn1, lstmmodel.py:49): N = 512 gate columns, K = 128.
 // Wr^T as an fp16 (hi, lo) pair is 2 x 128 KB -- more than one SM's shared memory -- so the hi half stays
 // resident (128 KB, used by the lo*hi and hi*hi passes) and the lo half (used only by the hi*lo pass) is
