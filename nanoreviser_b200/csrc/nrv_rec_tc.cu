@@ -25,6 +25,8 @@
 //     (4 K-steps x {lo*hi, hi*lo, hi*hi}) and commits to an mbarrier; warps 1-4 / 5-8 are the epilogue of
 //     tile A / B: tcgen05.ld -> + zin -> hard_sigmoid / tanh -> c (registers) -> h -> shared memory.
 // While the epilogue of tile A runs on the CUDA cores, the tensor core works on tile B, and vice versa.
+#include <algorithm>
+
 #include "nrv_common.cuh"
 #include "nrv_tc.cuh"
 
@@ -265,7 +267,7 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, i
 // are issued right behind the recurrent MMAs of step s and run while the epilogue of step s is busy.  Compared with
 // GEMM + recurrence this removes 2 x 22.5 KB of HBM traffic per window and a kernel launch.
 // ============================================================================================================
-constexpr int RF_THREADS = 192;                       // warp 0: store + MMA issue, warp 1: TMA producer, warps 2..5: epilogue
+constexpr int RF_THREADS = 320;                       // warp 0: store + MMA issue, warp 1: TMA producer, warps 2..9: epilogue
 constexpr int RF_W_BYTES = 256 * 64 * 2;              // 32 KB per weight tile (Wk hi, Wk lo, Wr hi, Wr lo)
 constexpr int RF_H_BYTES = 128 * 64 * 2;              // 16 KB per h / x tile part
 constexpr int RF_XS = 2;                              // x ring stages
@@ -283,7 +285,7 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     uint8_t* s_h = smem + 4 * RF_W_BYTES;                 // [hi | lo][128 rows][64]
     uint8_t* s_x = s_h + 2 * RF_H_BYTES;                  // [stage][hi | lo][128 rows][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + RF_XS * 2 * RF_H_BYTES);
-    uint64_t* h_ready = bars;                             // count 4
+    uint64_t* h_ready = bars;                             // count 8 (one arrive per epilogue warp)
     uint64_t* acc_ready = bars + 1;                       // count 2 (commit + "h store left smem"); step 0: see below
     uint64_t* xfull = bars + 2;                           // [RF_XS]
     uint64_t* xempty = bars + 2 + RF_XS;                  // [RF_XS] count 1 (commit)
@@ -291,10 +293,9 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    const int64_t wtile = blockIdx.x;
 
     if (threadIdx.x == 0) {
-        mbar_init(h_ready, 4);
+        mbar_init(h_ready, 8);
         mbar_init(acc_ready, 2);
         for (int i = 0; i < RF_XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
         fence_mbar_init();
@@ -315,32 +316,36 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Persistent over tiles: the weights are loaded once per CTA.  g = running step counter over all of this CTA's tiles;
+    // every barrier completes exactly once per step, so all parities derive from g.
+    const int64_t ntw = nwp >> 7;
     if (warp == 1) {
         // ===================== TMA producer: x_t tiles in step order =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int s = 0; s < T; ++s) {
-                const int t = dir ? (T - 1 - s) : s;
-                const int grow = (int)(t * nwp + wtile * 128);
-                mbar_wait(&xempty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&xfull[stage], 2 * RF_H_BYTES);
-                tma_load_2d(s_x + (stage * 2 + 0) * RF_H_BYTES, &tm_x_hi, &xfull[stage], 0, grow);
-                tma_load_2d(s_x + (stage * 2 + 1) * RF_H_BYTES, &tm_x_lo, &xfull[stage], 0, grow);
-                if (++stage == RF_XS) { stage = 0; phase ^= 1; }
-            }
+            for (int64_t wtile = blockIdx.x; wtile < ntw; wtile += gridDim.x)
+                for (int s = 0; s < T; ++s) {
+                    const int t = dir ? (T - 1 - s) : s;
+                    const int grow = (int)(t * nwp + wtile * 128);
+                    mbar_wait(&xempty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&xfull[stage], 2 * RF_H_BYTES);
+                    tma_load_2d(s_x + (stage * 2 + 0) * RF_H_BYTES, &tm_x_hi, &xfull[stage], 0, grow);
+                    tma_load_2d(s_x + (stage * 2 + 1) * RF_H_BYTES, &tm_x_lo, &xfull[stage], 0, grow);
+                    if (++stage == RF_XS) { stage = 0; phase ^= 1; }
+                }
         }
     } else if (warp == 0) {
         // ===================== h store + MMA issuer =====================
         constexpr uint32_t idesc = umma_idesc_f16_f32(128, N);
         const uint32_t w_base = smem_u32(s_w);
         int xstage = 0; uint32_t xphase = 0;
-        // projection of step s: acc[s & 1] = x_s . Wk   (zero-initialises the accumulator)
-        auto proj = [&](int s) {
+        // projection of global step gs: acc[gs & 1] = x . Wk   (zero-initialises the accumulator)
+        auto proj = [&](uint32_t gs) {
             mbar_wait(&xfull[xstage], xphase);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t xa = smem_u32(s_x + (xstage * 2) * RF_H_BYTES);
-                const uint32_t d = tmem_base + (uint32_t)((s & 1) * N);
+                const uint32_t d = tmem_base + (gs & 1) * N;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t a_hi = umma_desc_k_sw128(xa + k * 32), a_lo = umma_desc_k_sw128(xa + RF_H_BYTES + k * 32);
@@ -354,68 +359,79 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
             __syncwarp();
             if (++xstage == RF_XS) { xstage = 0; xphase ^= 1; }
         };
-        proj(0);
-        if (elect_one()) { umma_commit(acc_ready); mbar_arrive(acc_ready); }      // step 0: projection only, no store pending
-        __syncwarp();
-        if (T > 1) proj(1);
-        for (int s = 1; s <= T; ++s) {
-            const int t_prev = dir ? (T - s) : (s - 1);
-            mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
-            tc_fence_after();
-            if (elect_one()) {
-                const int grow = (int)(t_prev * nwp + wtile * 128);
-                tma_store_2d(&tm_out_hi, s_h, dir * U, grow);
-                tma_store_2d(&tm_out_lo, s_h + RF_H_BYTES, dir * U, grow);
-                tma_store_commit();
-                if (s < T) {
-                    const uint32_t ha = smem_u32(s_h);
-                    const uint32_t d = tmem_base + (uint32_t)((s & 1) * N);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
-                        const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
-                        umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
-                        umma_f16_ss(d, a_hi, b_lo, idesc, 1);
-                        umma_f16_ss(d, a_hi, b_hi, idesc, 1);
-                    }
-                    umma_commit(acc_ready);
-                }
-            }
+        uint32_t g = 0;                                                    // global step of the current tile's step 0
+        for (int64_t wtile = blockIdx.x; wtile < ntw; wtile += gridDim.x, g += (uint32_t)T) {
+            // step 0 of this tile: projection only.  (The previous tile's last h store has been waited for below.)
+            proj(g);
+            if (elect_one()) { umma_commit(acc_ready); mbar_arrive(acc_ready); }
             __syncwarp();
-            if (s < T) {
-                if (s + 1 < T) proj(s + 1);                                // runs on the tensor core during epilogue(s)
-                if (elect_one()) { tma_store_wait_read(); mbar_arrive(acc_ready); }
+            if (T > 1) proj(g + 1);
+            for (int s = 1; s <= T; ++s) {
+                const int t_prev = dir ? (T - s) : (s - 1);
+                mbar_wait(h_ready, (g + (uint32_t)s - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const int grow = (int)(t_prev * nwp + wtile * 128);
+                    tma_store_2d(&tm_out_hi, s_h, dir * U, grow);
+                    tma_store_2d(&tm_out_lo, s_h + RF_H_BYTES, dir * U, grow);
+                    tma_store_commit();
+                    if (s < T) {
+                        const uint32_t ha = smem_u32(s_h);
+                        const uint32_t d = tmem_base + ((g + (uint32_t)s) & 1) * N;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
+                            const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
+                            umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
+                            umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                            umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                        }
+                        umma_commit(acc_ready);
+                    }
+                }
                 __syncwarp();
+                if (s < T) {
+                    if (s + 1 < T) proj(g + (uint32_t)s + 1);               // runs on the tensor core during epilogue(s)
+                    if (elect_one()) { tma_store_wait_read(); mbar_arrive(acc_ready); }
+                    __syncwarp();
+                } else {
+                    if (elect_one()) tma_store_wait_read();                // h tile may be overwritten by the next tile's step 0
+                    __syncwarp();
+                }
             }
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     } else {
-        // ===================== epilogue: warps 2..5 =====================
+        // ===================== epilogue: warps 2..9; lane quarter = warp % 4, column half = (warp - 2) / 4 =====================
         const int q = warp & 3;
+        const int hf = (warp - 2) >> 2;                  // units hf*32 .. +32  (128 gate columns, 4 blocks)
         const int row = q * 32 + lane;
-        float c[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) c[j] = 0.f;
         const float4 zero4[8] = {};
-        for (int s = 0; s < T; ++s) {
-            mbar_wait(acc_ready, (uint32_t)(s & 1));
-            tc_fence_after();
+        uint32_t g = 0;
+        for (int64_t wtile = blockIdx.x; wtile < ntw; wtile += gridDim.x) {
+            float c[32];
 #pragma unroll
-            for (int cb = 0; cb < N / 32; ++cb) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((s & 1) * N + cb * 32), v);
-                tmem_ld_wait();
-                uint4 phi, plo;
-                lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
-                const uint32_t off = sw128_offset(row, cb);
-                *reinterpret_cast<uint4*>(s_h + off) = phi;
-                *reinterpret_cast<uint4*>(s_h + RF_H_BYTES + off) = plo;
+            for (int j = 0; j < 32; ++j) c[j] = 0.f;
+            for (int s = 0; s < T; ++s, ++g) {
+                mbar_wait(acc_ready, g & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * N + (uint32_t)(hf * 128 + cb * 32), v);
+                    tmem_ld_wait();
+                    uint4 phi, plo;
+                    lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
+                    const uint32_t off = sw128_offset(row, hf * 4 + cb);
+                    *reinterpret_cast<uint4*>(s_h + off) = phi;
+                    *reinterpret_cast<uint4*>(s_h + RF_H_BYTES + off) = plo;
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_ready);
             }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(h_ready);
         }
     }
     tc_fence_before();
@@ -437,7 +453,7 @@ int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __ha
         cudaFuncSetAttribute(lstm_fused_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
         attr = true;
     }
-    dim3 grid((unsigned)(nwp >> 7), 2);
+    dim3 grid((unsigned)std::min<int64_t>(nwp >> 7, 74), 2);       // persistent: 148 CTAs, weights loaded once each
     lstm_fused_tc64_kernel<<<grid, RF_THREADS, RF_SMEM, st>>>(L.pb_hi, L.pb_lo, L.rt_hi, L.rt_lo, txh, txl, tmh, tml, nwp, T);
     return 1;
 }
