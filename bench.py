@@ -153,7 +153,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: ecoli model, synthetic 10 kb reads (4 kHz), CPU sample"},
+            "config": {"workload": "cfg2: ecoli model, synthetic 10 kb reads (4 kHz signal); bounded CPU sample of the slab",
+                       "reads_per_step": n, "bases_per_step": n * args.ref_read_len},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "oracle port of the reference algorithm (numpy fp32 + OpenBLAS, per-read python "
                                      "segmentation, per-window CNN recompute); Keras 2.2.4/TF 1.12 not installable"},
@@ -296,18 +297,24 @@ def main():
             macs = {"lstm0": 30_976, "proj1": 180_224, "rec1": 360_448, "proj2": 2_162_688, "rec2": 1_441_792,
                     "proj3": 1_441_792, "rec3": 360_448, "heads_gemm": 180_224, "heads": 48_320}
             names = {"proj2": "gemm_f16x3_kernel<256> (total_rnn1 input projection, tcgen05 3-pass split-fp16)",
-                     "rec2": "lstm_rec_tc128_kernel (total_rnn1 recurrence, tcgen05)",
+                     "rec2": "lstm_rec_tc128_pair_kernel (total_rnn1 recurrence, tcgen05 cta_group::2)",
                      "proj3": "gemm_f16x3_kernel<256> (total_rnn2 input projection, tcgen05)",
                      "rec3": "lstm_rec_tc64_kernel (total_rnn2 recurrence, tcgen05)",
                      "proj1": "gemm_f16x3_kernel<256> (read_rnn11 input projection, tcgen05)",
-                     "rec1": "lstm_rec_tc64_kernel (read_rnn11 recurrence, tcgen05)",
-                     "heads_gemm": "gemm_f16x3_kernel<128> (dense head 128->128, tcgen05)",
-                     "heads": "heads_kernel (dense 128->32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
+                     "rec1": "lstm_fused_tc64_kernel (read_rnn11 projection+recurrence, tcgen05)",
+                     "heads_gemm": "gemm_f16x3_kernel<128,FUSE2> (dense head 128->128->32, tcgen05)",
+                     "heads": "heads_tail_kernel (dense 32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
                      "lstm0": "lstm_layer_kernel<0,6,16,...> (read_rnn1, fp32 SIMT)"}
         else:
             macs = {"lstm0": 30_976, "rec1": 540_672, "rec2": 3_604_480, "rec3": 1_802_240, "heads": 228_544}
             names = {k: "lstm_layer_kernel (fp32 SIMT, fused projection+recurrence)" for k in macs}
             names["heads"] = "heads_kernel (fp32 SIMT)"
+        # algorithmic HBM bytes per window and per model of each stage (activations
+        # are fp16 hi/lo pairs = 4 B per value, pre-activations fp32; 11 timesteps; weights are L2-resident)
+        abytes = {"lstm0": 11 * (6 + 32) * 4, "rec1": 11 * (32 + 128) * 4, "proj2": 11 * (192 + 1024) * 4,
+                  "rec2": 11 * (1024 + 256) * 4, "proj3": 11 * (256 + 512) * 4, "rec3": 11 * (512 + 128) * 4,
+                  "heads_gemm": 11 * (128 + 32) * 4, "heads": 11 * 32 * 4 + 32} if tc_path else {}
+        hbm_peak = float(peaks.get("hbm_gbs"))
         traffic_db = {}
         tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
         if os.path.exists(tp):
@@ -322,6 +329,10 @@ def main():
             nl = max(stage_launches.get(k, 1), 1)
             kernels[k] = {"kernel": names.get(k, k), "achieved": ach, "frac": ach / peak, "launches": int(nl),
                           "avg_launch_ms": t_ms / nl, "flops_per_launch": fl / nl, "share_of_step": t_ms / ms if ms > 0 else None}
+            if k in abytes:
+                gbs = abytes[k] * n_win * 2 * args.steps / (t_ms * 1e-3) / 1e9
+                kernels[k].update(hbm_bytes_per_launch=abytes[k] * n_win * 2 * args.steps / nl, hbm_achieved_gbs=gbs,
+                                  hbm_frac=gbs / hbm_peak)
         dom = max(kernels, key=lambda k: stage_ms[k])
         roofline = {"bound": "tensor", "kernel": kernels[dom]["kernel"], "stage": dom, "achieved": kernels[dom]["achieved"],
                     "peak": peak, "unit": "TFLOP/s", "frac": kernels[dom]["frac"],
@@ -330,9 +341,23 @@ def main():
                     "flops_per_launch": kernels[dom]["flops_per_launch"],
                     "traffic": traffic_db.get(dom, {}).get("dram_bytes_per_launch"),
                     "share_of_step": kernels[dom]["share_of_step"],
+                    "hbm": {"achieved": kernels[dom].get("hbm_achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
+                            "frac": kernels[dom].get("hbm_frac"), "bytes_per_launch": kernels[dom].get("hbm_bytes_per_launch")},
                     "note": "algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay "
                             "fp32-equivalent, and is HBM-bound on the fp32 pre-activations (see traffic)",
                     "all_model_kernels": kernels}
+        # K1 (segmentation) and K4 (decode) are the HBM-bound kernels of SURVEY.md section 8(d)
+        n_samp = int(slabs[0].sig_off[-1])
+        hbm_kernels = {}
+        for k, nbytes in (("read_stats", 2 * n_samp * 2),                       # median pass + MAD pass over int16
+                          ("base_features", 2 * n_samp + n_bases * (4 + 1 + 8 + 24)),   # samples, starts, base, ev_mean/std, 6 features
+                          ("decode", n_bases * (2 + 1 + 2) + 8 * R)):
+            t_ms = stage_ms.get(k, 0.0)
+            if t_ms > 0:
+                gbs = nbytes * args.steps / (t_ms * 1e-3) / 1e9
+                hbm_kernels[k] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                  "bytes_per_step": nbytes, "ms_per_step": t_ms / args.steps}
+        roofline["hbm_kernels"] = hbm_kernels
         whole = {"achieved_tflops": FLOP_PER_BASE * value / world / 1e12, "frac_of_bf16_sustained":
                  FLOP_PER_BASE * value / world / 1e12 / peak}
         cpu = None
