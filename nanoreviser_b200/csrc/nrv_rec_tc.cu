@@ -36,6 +36,12 @@ using namespace tc;
 
 bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);   // nrv_gemm.cu
 
+#ifndef NRV_ZIN_PF_DIST
+#define NRV_ZIN_PF_DIST 4     // u = 128 pair kernel: L2 prefetch distance (32-column blocks) ahead of the demand loads of zin;
+#endif                        // measured on B200: 0 -> 46.4 ms, 2 -> 42.9, 4 -> 41.1, 7 -> 52.2 ms per step (far prefetch thrashes)
+#ifndef NRV_REC_PASSES
+#define NRV_REC_PASSES 3      // fp16 split passes of the recurrent product h.Wr: 3 = lo*hi + hi*lo + hi*hi (fp32-equivalent)
+#endif
 constexpr int RT_THREADS = 352;                 // 1 MMA warp + 2 x 4 epilogue warps + 2 zin producer warps
 constexpr int RT_W_BYTES = 256 * 64 * 2;        // 32 KB: Wr^T hi (or lo)
 constexpr int RT_H_BYTES = 128 * 64 * 2;        // 16 KB: h tile hi (or lo)
@@ -157,9 +163,13 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
 #pragma unroll
                         for (int k = 0; k < U / 16; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);        // +32 B along K (16-byte units)
+#if NRV_REC_PASSES >= 3
                             umma_f16_ss(d, a_lo + adv, b_hi + adv, idesc, k != 0);
                             umma_f16_ss(d, a_hi + adv, b_lo + adv, idesc, 1);
-                            umma_f16_ss(d, a_hi + adv, b_hi + adv, idesc, 1);
+#elif NRV_REC_PASSES == 2
+                            umma_f16_ss(d, a_hi + adv, b_lo + adv, idesc, k != 0);
+#endif
+                            umma_f16_ss(d, a_hi + adv, b_hi + adv, idesc, (NRV_REC_PASSES > 1) || k != 0);
                         }
                         umma_commit(&acc_ready[X]);                        // arrival 1: MMAs retired
                         tma_store_wait_read();
@@ -382,8 +392,12 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
                             const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
+#if NRV_REC_PASSES >= 3
                             umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
+#endif
+#if NRV_REC_PASSES >= 2
                             umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+#endif
                             umma_f16_ss(d, a_hi, b_hi, idesc, 1);
                         }
                         umma_commit(acc_ready);
@@ -680,17 +694,28 @@ int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, 
 }
 
 // ============================================================================================================
-// u = 128, CTA-PAIR variant (tcgen05 cta_group::2, thread-block cluster of 2 on one TPC).
-// One cluster = one direction x TWO tiles of 128 windows (one per CTA).  A single tcgen05.mma.cta_group::2
+// u = 128, CTA-PAIR variant (tcgen05 cta_group::2, thread-block cluster of 2 on one TPC), persistent over tiles.
+// One cluster = one direction x TWO tiles of 128 windows (one per CTA) at a time.  A single tcgen05.mma.cta_group::2
 // covers M = 256 rows (both CTAs' windows) x N = 256 gate columns and reads the B operand half from each CTA's
-// shared memory -- so each SM holds only HALF of Wr^T (hi and lo: 128 KB), all of it resident, and the W_lo
-// stream of the single-CTA kernel (and its latency) disappears.  Every CTA keeps its own windows' h tile (A
-// operand) and accumulator (its 128 TMEM lanes x 512 columns) and runs its own epilogue; no activation ever
-// crosses the pair.  Synchronisation: per-CTA "h tile written" mbarrier -> warp 0 of each CTA TMA-stores its h
-// and arrives (peer: remotely) on the leader's pair barrier; the leader issues the MMAs and commits with
-// .multicast::cluster to the accumulator barriers of both CTAs.
+// shared memory -- so each SM holds only HALF of Wr^T (hi and lo: 128 KB), all of it resident.  Every CTA keeps its
+// own windows' h tile (A operand, 64 KB) and accumulator (its 128 TMEM lanes x 512 columns) and runs its own
+// epilogue; no activation ever crosses the pair.
+//
+// The accumulator fills TMEM and the h tile fills the rest of shared memory, so two tiles cannot ping-pong.  Instead
+// the step is software-pipelined over the two column halves H0 / H1 (units 0-63 / 64-127 = K-chunks 0 / 1 of h):
+//     all 8 epilogue warps:  epi H0(s) ................ epi H1(s) ................ | epi H0(s+1) ...
+//     tensor core         :                            K0->H0(s+1)                | K0->H1, K1->H0 (commit H0), K1->H1 (commit H1)
+// i.e. as soon as the epilogue has produced K-chunk 0 of h_s (and thereby drained accumulator H0) the leader issues the
+// quarter of step s+1 that needs nothing else, hidden under the H1 epilogue; after H1 only 2/4 of the MMAs stand between
+// the epilogue and its next accumulator half, and the last quarter runs under epi H0(s+1).  (ncu before: epilogue warps
+// 42 % of their time waiting for the accumulator, tensor pipe idle while they worked.)
+//
+// Barriers (all complete exactly once per step; parity from a running step counter):
+//   h_half[hf]  (local, 8)    epilogue warps wrote K-chunk hf of h_s            -> store warp
+//   h_pair[hf]  (leader, 16)  the same, from both CTAs                          -> MMA issuer
+//   acc_ready[hf] (local, 2)  multicast tcgen05.commit + "the TMA store of the old K-chunk hf has left smem" -> epilogue
 // ============================================================================================================
-constexpr int RP_THREADS = 288;                        // warp 0: store + MMA issue; warps 1..8: epilogue
+constexpr int RP_THREADS = 320;                        // warp 0: MMA issue (leader); warps 1..8: epilogue; warp 9: h stores
 constexpr int RP_W_BYTES = 8 * 128 * 64 * 2;           // 128 KB: [hi|lo][half][kc][128 rows][64]
 constexpr int RP_H_BYTES = 128 * 64 * 2;               // 16 KB: one K-chunk of h (hi or lo)
 constexpr size_t RP_SMEM = (size_t)RP_W_BYTES + 4 * RP_H_BYTES + 1024 + 128;
@@ -705,21 +730,20 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
     uint8_t* s_w = smem;                                     // [part][half][kc][128 rows][64]
     uint8_t* s_h = smem + RP_W_BYTES;                        // [part][kc][128 rows][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + 4 * RP_H_BYTES);
-    uint64_t* h_local = bars;                                // count 8: this CTA's epilogue warps wrote h_t
-    uint64_t* h_pair = bars + 1;                             // count 2 (leader's copy is used): both CTAs' h tiles are ready
-    uint64_t* acc_ready = bars + 2;                          // [2] count 2: multicast commit + local "h store left smem"
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* h_half = bars;                                 // [2] count 8
+    uint64_t* h_pair = bars + 2;                             // [2] count 16 (leader's copy is used)
+    uint64_t* acc_ready = bars + 4;                          // [2] count 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int dir = blockIdx.y;
     const int64_t ntw = nwp >> 7;
-    const int64_t wtile = min((int64_t)blockIdx.x, ntw - 1);     // odd tile count: the last peer repeats the last tile
+    const int64_t n_pairs = (ntw + 1) >> 1;
+    const int64_t cl0 = blockIdx.x >> 1, cl_stride = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        mbar_init(h_local, 8);
-        mbar_init(h_pair, 2);
-        mbar_init(&acc_ready[0], 2); mbar_init(&acc_ready[1], 2);
+        for (int i = 0; i < 2; ++i) { mbar_init(&h_half[i], 8); mbar_init(&h_pair[i], 16); mbar_init(&acc_ready[i], 2); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
     }
@@ -740,110 +764,151 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== h store (both CTAs) + MMA issue (leader) =====================
-        constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
-        const uint32_t a_base = smem_u32(s_h), w_base = smem_u32(s_w);
-        auto mma_block = [&](int hf, int k0, int k1, bool zero_first) {
-            const uint32_t d = tmem_base + (uint32_t)(hf * 256);
-            for (int k = k0; k < k1; ++k) {
-                const int kc = k >> 2, kk = k & 3;
-                const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * RP_H_BYTES + kk * 32);
-                const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * RP_H_BYTES + kk * 32);
-                const uint64_t b_hi = umma_desc_k_sw128(w_base + ((0 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
-                const uint64_t b_lo = umma_desc_k_sw128(w_base + ((1 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
-                umma_f16_ss_pair(d, a_lo, b_hi, idesc, (zero_first && k == k0) ? 0u : 1u);
-                umma_f16_ss_pair(d, a_hi, b_lo, idesc, 1);
-                umma_f16_ss_pair(d, a_hi, b_hi, idesc, 1);
-            }
-        };
-        for (int s = 1; s <= T; ++s) {
-            const int t_prev = dir ? (T - s) : (s - 1);
-            mbar_wait(h_local, (uint32_t)((s - 1) & 1));          // this CTA's h_{s-1} tile is written and fenced
-            tc_fence_after();
-            if (elect_one()) {
-                const int grow = (int)(t_prev * nwp + wtile * 128);
+        // ===================== MMA issue (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
+            const uint32_t a_base = smem_u32(s_h), w_base = smem_u32(s_w);
+            // acc[hf] (+)= h[K-chunk kc] . Wr[kc, hf]   (4 K-steps x 3 split passes)
+            auto mma_block = [&](int hf, int kc, bool zero_first) {
+                const uint32_t d = tmem_base + (uint32_t)(hf * 256);
 #pragma unroll
-                for (int kc = 0; kc < 2; ++kc) {
-                    tma_store_2d(&tm_out_hi, s_h + (0 * 2 + kc) * RP_H_BYTES, dir * U + kc * 64, grow);
-                    tma_store_2d(&tm_out_lo, s_h + (1 * 2 + kc) * RP_H_BYTES, dir * U + kc * 64, grow);
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * RP_H_BYTES + kk * 32);
+                    const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * RP_H_BYTES + kk * 32);
+                    const uint64_t b_hi = umma_desc_k_sw128(w_base + ((0 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
+                    const uint64_t b_lo = umma_desc_k_sw128(w_base + ((1 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
+#if NRV_REC_PASSES >= 3
+                    umma_f16_ss_pair(d, a_lo, b_hi, idesc, (zero_first && kk == 0) ? 0u : 1u);
+                    umma_f16_ss_pair(d, a_hi, b_lo, idesc, 1);
+                    umma_f16_ss_pair(d, a_hi, b_hi, idesc, 1);
+#elif NRV_REC_PASSES == 2
+                    umma_f16_ss_pair(d, a_hi, b_lo, idesc, (zero_first && kk == 0) ? 0u : 1u);
+                    umma_f16_ss_pair(d, a_hi, b_hi, idesc, 1);
+#else
+                    umma_f16_ss_pair(d, a_hi, b_hi, idesc, (zero_first && kk == 0) ? 0u : 1u);
+#endif
                 }
-                tma_store_commit();
-                if (s < T) mbar_arrive_cluster(h_pair, 0);        // tell the leader this CTA's A operand is ready
-            }
-            __syncwarp();
-            if (s == T) break;
-            if (rank == 0) {
-                mbar_wait_cluster(h_pair, (uint32_t)((s - 1) & 1));
-                tc_fence_after();
-                if (elect_one()) {
-                    mma_block(1, 0, 4, true);                     // H1 x K-chunk 0
-                    mma_block(0, 0, 8, true);                     // H0, all of K
-                    umma_commit_pair(&acc_ready[0]);
-                    mma_block(1, 4, 8, false);                    // H1 x K-chunk 1
-                    umma_commit_pair(&acc_ready[1]);
+            };
+            uint32_t g = 0;                                       // phase counter of h_pair (one phase per step and half)
+            for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride)
+                for (int s = 1; s <= T; ++s, ++g) {
+                    mbar_wait(&h_pair[0], g & 1);         // K-chunk 0 of h_{s-1} in both CTAs; accumulator H0 drained
+                    tc_fence_after();
+                    if (s < T && elect_one()) mma_block(0, 0, true);
+                    __syncwarp();
+                    mbar_wait(&h_pair[1], g & 1);         // K-chunk 1; accumulator H1 drained
+                    tc_fence_after();
+                    if (s < T && elect_one()) {
+                        mma_block(1, 0, true);
+                        mma_block(0, 1, false);
+                        umma_commit_pair(&acc_ready[0]);          // H0 complete, and every read of K-chunk 0 of h_{s-1}
+                        mma_block(1, 1, false);
+                        umma_commit_pair(&acc_ready[1]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+        }
+    } else if (warp == 9) {
+        // ===================== h stores (both CTAs): K-chunk hf of h_s as soon as the epilogue has written it =====================
+        uint32_t g = 0;
+        for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
+            const int64_t wtile = min(tp * 2 + (int64_t)rank, ntw - 1);
+            for (int s = 0; s < T; ++s, ++g) {
+                const int t = dir ? (T - 1 - s) : s;
+                const int grow = (int)(t * nwp + wtile * 128);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    mbar_wait(&h_half[hf], g & 1);
+                    if (elect_one()) {
+                        tma_store_2d(&tm_out_hi, s_h + (0 * 2 + hf) * RP_H_BYTES, dir * U + hf * 64, grow);
+                        tma_store_2d(&tm_out_lo, s_h + (1 * 2 + hf) * RP_H_BYTES, dir * U + hf * 64, grow);
+                        tma_store_commit();
+                        tma_store_wait_read();                    // the store has left shared memory: the chunk may be overwritten
+                        mbar_arrive(&acc_ready[hf]);              // (the other arrival is the commit of step s+1's MMAs; at the last
+                        if (s == T - 1) mbar_arrive(&acc_ready[hf]);   // step there are none, so this warp completes the phase alone)
+                    }
+                    __syncwarp();
+                }
             }
-            if (elect_one()) {
-                tma_store_wait_read();                            // this CTA's h_{s-1} stores have left shared memory
-                mbar_arrive(&acc_ready[0]);
-                mbar_arrive(&acc_ready[1]);
-            }
-            __syncwarp();
         }
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     } else {
-        // ===================== epilogue: warps 1..8; lane quarter = warp % 4, column half = (warp - 1) / 4 ===========
+        // ===================== epilogue: warps 1..8; TMEM lane quarter = warp % 4; 4 of the 8 column blocks of each half ===========
         const int q = warp & 3;
-        const int hf = (warp - 1) >> 2;
+        const int sub = (warp - 1) >> 2;
         const int row = q * 32 + lane;
-        uint8_t* hs_hi = s_h + (0 * 2 + hf) * RP_H_BYTES;       // units hf*64.. -> K chunk hf of the h tile
-        uint8_t* hs_lo = s_h + (1 * 2 + hf) * RP_H_BYTES;
-        float c[64];
+        uint32_t g = 0;                                           // phase counter of acc_ready (per step; step 0 of a tile has none)
+        for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
+            const int64_t wtile = min(tp * 2 + (int64_t)rank, ntw - 1);   // odd tile count: the last peer repeats the last tile
+            float c[64];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) c[j] = 0.f;
-        auto ztile_of = [&](int s_) {
-            const int t_ = dir ? (T - 1 - s_) : s_;
-            return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wtile) * (N * 128)) + (hf * 64) * 128 + row;
-        };
-        const float4* ztile = ztile_of(0);
-        float4 z[8], zn[8];
+            for (int j = 0; j < 64; ++j) c[j] = 0.f;
+            // this thread's zin quads of linear block i = s*8 + hf*4 + b (b = 0..3): 8 float4, 2 KB apart
+            auto zaddr = [&](int i) {
+                const int s_ = i >> 3, hf_ = (i >> 2) & 1, b_ = i & 3;
+                const int t_ = dir ? (T - 1 - s_) : s_;
+                return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wtile) * (N * 128)) +
+                       (hf_ * 64 + (sub * 4 + b_) * 8) * 128 + row;
+            };
+            const int n_blk = T * 8;
+            float4 z[8], zn[8];
+            {
+                const float4* z0 = zaddr(0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = __ldg(ztile + j * 128);
-        for (int s = 0; s < T; ++s) {
-            const float4* znext_tile = (s + 1 < T) ? ztile_of(s + 1) : ztile;
-            if (s > 0) {
-                mbar_wait_cluster(&acc_ready[hf], (uint32_t)((s - 1) & 1));
-                tc_fence_after();
+                for (int j = 0; j < 8; ++j) z[j] = __ldg(z0 + j * 128);
             }
+            for (int s = 0; s < T; ++s) {
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                if (cb + 1 < 8) {
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (s > 0) {
+                        mbar_wait(&acc_ready[hf], (g + (uint32_t)s - 1) & 1);
+                        tc_fence_after();
+                    } else if (tp != cl0) {
+                        // first step of a later tile: the previous tile's last h store must have left shared memory
+                        mbar_wait(&acc_ready[hf], (g - 1) & 1);
+                    }
+                    const uint32_t hs_hi = smem_u32(s_h + (0 * 2 + hf) * RP_H_BYTES);
+                    const uint32_t hs_lo = smem_u32(s_h + (1 * 2 + hf) * RP_H_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(ztile + ((cb + 1) * 8 + j) * 128);
-                } else if (s + 1 < T) {
+                    for (int b = 0; b < 4; ++b) {
+                        const int i = s * 8 + hf * 4 + b;
+#if NRV_ZIN_PF_DIST > 0
+                        if (i + 1 + NRV_ZIN_PF_DIST < n_blk) {   // paced L2 prefetch ahead of the demand loads
+                            const float4* pt = zaddr(i + 1 + NRV_ZIN_PF_DIST);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) zn[j] = __ldg(znext_tile + j * 128);
+                            for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + j * 128));
+                        }
+#endif
+                        if (i + 1 < n_blk) {
+                            const float4* zp = zaddr(i + 1);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) zn[j] = __ldg(zp + j * 128);
+                        }
+                        const int cb = sub * 4 + b;
+                        uint32_t v[32];
+                        if (s > 0) {
+                            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
+                            tmem_ld_wait();
+                        }
+                        uint4 phi, plo;
+                        lstm_cell_block(v, s > 0, z, &c[(hf * 4 + b) * 8], phi, plo);
+                        const uint32_t off = sw128_offset(row, cb);
+                        st_shared_v4(hs_hi + off, phi);
+                        st_shared_v4(hs_lo + off, plo);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] = zn[j];
+                    }
+                    tc_fence_before();           // our tcgen05.ld of this half precede the MMAs that overwrite it
+                    fence_proxy_async_smem();    // our h writes are visible to the tensor core (of the leader) and to TMA
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&h_half[hf]);
+                        mbar_arrive_remote(&h_pair[hf], 0);
+                    }
                 }
-                uint32_t v[32];
-                if (s > 0) {
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256 + cb * 32), v);
-                    tmem_ld_wait();
-                }
-                uint4 phi, plo;
-                lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
-                const uint32_t off = sw128_offset(row, cb);
-                *reinterpret_cast<uint4*>(hs_hi + off) = phi;
-                *reinterpret_cast<uint4*>(hs_lo + off) = plo;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) z[j] = zn[j];
             }
-            ztile = znext_tile;
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(h_local);
+            g += (uint32_t)T;
         }
     }
     tc_fence_before();
@@ -864,8 +929,8 @@ int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t 
         cudaFuncSetAttribute(lstm_rec_tc128_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM);
         attr = true;
     }
-    const int64_t ntw = nwp >> 7;
-    dim3 grid((unsigned)((ntw + 1) / 2 * 2), 2);
+    const int64_t n_pairs = ((nwp >> 7) + 1) / 2;
+    dim3 grid((unsigned)(2 * std::min<int64_t>(n_pairs, 37)), 2);   // persistent: 74 clusters = 148 CTAs, weights loaded once each
     lstm_rec_tc128_pair_kernel<<<grid, RP_THREADS, RP_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, tmh, tml, nwp, T);
     return 1;
 }

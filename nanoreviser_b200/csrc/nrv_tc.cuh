@@ -167,6 +167,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "r"(cta)
         : "memory");
 }
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` WITHOUT cluster-scope release (no MEMBAR.GPU /
+// ERRBAR): enough when the data being published lives in shared memory / TMEM and has already been ordered by
+// fence.proxy.async / tcgen05.fence::before_thread_sync (the pattern of 2-SM UMMA pipelines)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
