@@ -718,7 +718,7 @@ int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, 
 constexpr int RP_THREADS = 320;                        // warp 0: MMA issue (leader); warps 1..8: epilogue; warp 9: h stores
 constexpr int RP_W_BYTES = 8 * 128 * 64 * 2;           // 128 KB: [hi|lo][half][kc][128 rows][64]
 constexpr int RP_H_BYTES = 128 * 64 * 2;               // 16 KB: one K-chunk of h (hi or lo)
-constexpr size_t RP_SMEM = (size_t)RP_W_BYTES + 4 * RP_H_BYTES + 1024 + 128;
+constexpr size_t RP_SMEM = (size_t)RP_W_BYTES + 6 * RP_H_BYTES + 1024 + 128;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
 lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __restrict__ wr_lo, const float* __restrict__ zin,
@@ -728,8 +728,9 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;                                     // [part][half][kc][128 rows][64]
-    uint8_t* s_h = smem + RP_W_BYTES;                        // [part][kc][128 rows][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + 4 * RP_H_BYTES);
+    uint8_t* s_h = smem + RP_W_BYTES;                        // [part][kc][128 rows][64]; K-chunk 0 of odd steps: s_h0b[part]
+    uint8_t* s_h0b = s_h + 4 * RP_H_BYTES;                   // K-chunk 0 is double-buffered over steps (see below)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + 6 * RP_H_BYTES);
     uint64_t* h_half = bars;                                 // [2] count 8
     uint64_t* h_pair = bars + 2;                             // [2] count 16 (leader's copy is used)
     uint64_t* acc_ready = bars + 4;                          // [2] count 2
@@ -768,13 +769,15 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
         if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
             const uint32_t a_base = smem_u32(s_h), w_base = smem_u32(s_w);
-            // acc[hf] (+)= h[K-chunk kc] . Wr[kc, hf]   (4 K-steps x 3 split passes)
-            auto mma_block = [&](int hf, int kc, bool zero_first) {
+            // acc[hf] (+)= h[K-chunk kc] . Wr[kc, hf]   (4 K-steps x 3 split passes); K-chunk 0 of h_{s-1} is in buffer (s-1) & 1
+            auto mma_block = [&](int hf, int kc, int buf, bool zero_first) {
                 const uint32_t d = tmem_base + (uint32_t)(hf * 256);
+                const uint32_t a_hi0 = (kc == 0 && buf) ? smem_u32(s_h0b) : a_base + (0 * 2 + kc) * RP_H_BYTES;
+                const uint32_t a_lo0 = (kc == 0 && buf) ? smem_u32(s_h0b) + RP_H_BYTES : a_base + (1 * 2 + kc) * RP_H_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t a_hi = umma_desc_k_sw128(a_base + (0 * 2 + kc) * RP_H_BYTES + kk * 32);
-                    const uint64_t a_lo = umma_desc_k_sw128(a_base + (1 * 2 + kc) * RP_H_BYTES + kk * 32);
+                    const uint64_t a_hi = umma_desc_k_sw128(a_hi0 + kk * 32);
+                    const uint64_t a_lo = umma_desc_k_sw128(a_lo0 + kk * 32);
                     const uint64_t b_hi = umma_desc_k_sw128(w_base + ((0 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
                     const uint64_t b_lo = umma_desc_k_sw128(w_base + ((1 * 2 + hf) * 2 + kc) * (128 * 128) + kk * 32);
 #if NRV_REC_PASSES >= 3
@@ -792,18 +795,19 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
             uint32_t g = 0;                                       // phase counter of h_pair (one phase per step and half)
             for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride)
                 for (int s = 1; s <= T; ++s, ++g) {
-                    mbar_wait(&h_pair[0], g & 1);         // K-chunk 0 of h_{s-1} in both CTAs; accumulator H0 drained
+                    const int buf = (s - 1) & 1;
+                    mbar_wait(&h_pair[0], g & 1);                 // K-chunk 0 of h_{s-1} in both CTAs; accumulator H0 drained
                     tc_fence_after();
-                    if (s < T && elect_one()) mma_block(0, 0, true);
+                    if (s < T && elect_one()) mma_block(0, 0, buf, true);
                     __syncwarp();
-                    mbar_wait(&h_pair[1], g & 1);         // K-chunk 1; accumulator H1 drained
+                    mbar_wait(&h_pair[1], g & 1);                 // K-chunk 1; accumulator H1 drained
                     tc_fence_after();
                     if (s < T && elect_one()) {
-                        mma_block(1, 0, true);
-                        mma_block(0, 1, false);
-                        umma_commit_pair(&acc_ready[0]);          // H0 complete, and every read of K-chunk 0 of h_{s-1}
-                        mma_block(1, 1, false);
-                        umma_commit_pair(&acc_ready[1]);
+                        mma_block(0, 1, buf, false);
+                        umma_commit_pair(&acc_ready[0]);          // H0 complete -> epi H0(s) starts (it writes the OTHER K-chunk-0 buffer)
+                        mma_block(1, 0, buf, true);
+                        mma_block(1, 1, buf, false);
+                        umma_commit_pair(&acc_ready[1]);          // H1 complete, and every read of K-chunk 1 of h_{s-1}
                     }
                     __syncwarp();
                 }
@@ -820,8 +824,10 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
                 for (int hf = 0; hf < 2; ++hf) {
                     mbar_wait(&h_half[hf], g & 1);
                     if (elect_one()) {
-                        tma_store_2d(&tm_out_hi, s_h + (0 * 2 + hf) * RP_H_BYTES, dir * U + hf * 64, grow);
-                        tma_store_2d(&tm_out_lo, s_h + (1 * 2 + hf) * RP_H_BYTES, dir * U + hf * 64, grow);
+                        const uint8_t* src_hi = (hf == 0 && (s & 1)) ? s_h0b : s_h + (0 * 2 + hf) * RP_H_BYTES;
+                        const uint8_t* src_lo = (hf == 0 && (s & 1)) ? s_h0b + RP_H_BYTES : s_h + (1 * 2 + hf) * RP_H_BYTES;
+                        tma_store_2d(&tm_out_hi, src_hi, dir * U + hf * 64, grow);
+                        tma_store_2d(&tm_out_lo, src_lo, dir * U + hf * 64, grow);
                         tma_store_commit();
                         tma_store_wait_read();                    // the store has left shared memory: the chunk may be overwritten
                         mbar_arrive(&acc_ready[hf]);              // (the other arrival is the commit of step s+1's MMAs; at the last
@@ -838,27 +844,21 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
         const int q = warp & 3;
         const int sub = (warp - 1) >> 2;
         const int row = q * 32 + lane;
-        uint32_t g = 0;                                           // phase counter of acc_ready (per step; step 0 of a tile has none)
+        const int64_t zstep = (dir ? -1 : 1) * ntw * (int64_t)(N * 128 / 4);      // float4s between consecutive steps of a tile
+        uint32_t g = 0;                                           // phase counter of acc_ready
         for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
             const int64_t wtile = min(tp * 2 + (int64_t)rank, ntw - 1);   // odd tile count: the last peer repeats the last tile
             float c[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) c[j] = 0.f;
-            // this thread's zin quads of linear block i = s*8 + hf*4 + b (b = 0..3): 8 float4, 2 KB apart
-            auto zaddr = [&](int i) {
-                const int s_ = i >> 3, hf_ = (i >> 2) & 1, b_ = i & 3;
-                const int t_ = dir ? (T - 1 - s_) : s_;
-                return reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + t_) * ntw + wtile) * (N * 128)) +
-                       (hf_ * 64 + (sub * 4 + b_) * 8) * 128 + row;
-            };
-            const int n_blk = T * 8;
-            float4 z[8], zn[8];
-            {
-                const float4* z0 = zaddr(0);
+            // this thread's zin quads of step s: block (hf, b) at zs + (hf*64 + b*8 + j) * 128, j = 0..7 (2 KB apart)
+            const float4* zs = reinterpret_cast<const float4*>(zin + (((int64_t)dir * T + (dir ? T - 1 : 0)) * ntw + wtile) * (N * 128)) +
+                               (sub * 32) * 128 + row;
+            float4 z[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) z[j] = __ldg(z0 + j * 128);
-            }
-            for (int s = 0; s < T; ++s) {
+            for (int j = 0; j < 8; ++j) z[j] = __ldg(zs + j * 128);
+            for (int s = 0; s < T; ++s, zs += zstep) {
+                const bool more = s + 1 < T;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     if (s > 0) {
@@ -868,22 +868,23 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
                         // first step of a later tile: the previous tile's last h store must have left shared memory
                         mbar_wait(&acc_ready[hf], (g - 1) & 1);
                     }
-                    const uint32_t hs_hi = smem_u32(s_h + (0 * 2 + hf) * RP_H_BYTES);
-                    const uint32_t hs_lo = smem_u32(s_h + (1 * 2 + hf) * RP_H_BYTES);
+                    const uint32_t hs_hi = (hf == 0 && (s & 1)) ? smem_u32(s_h0b) : smem_u32(s_h + (0 * 2 + hf) * RP_H_BYTES);
+                    const uint32_t hs_lo = (hf == 0 && (s & 1)) ? smem_u32(s_h0b) + RP_H_BYTES : smem_u32(s_h + (1 * 2 + hf) * RP_H_BYTES);
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int i = s * 8 + hf * 4 + b;
 #if NRV_ZIN_PF_DIST > 0
-                        if (i + 1 + NRV_ZIN_PF_DIST < n_blk) {   // paced L2 prefetch ahead of the demand loads
-                            const float4* pt = zaddr(i + 1 + NRV_ZIN_PF_DIST);
+                        {   // paced L2 prefetch one half (4 blocks) ahead of the demand loads
+                            const float4* pt = (hf == 0) ? zs + (64 + b * 8) * 128 : zs + zstep + (b * 8) * 128;
+                            if (hf == 0 || more) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + j * 128));
+                                for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + j * 128));
+                            }
                         }
 #endif
-                        if (i + 1 < n_blk) {
-                            const float4* zp = zaddr(i + 1);
+                        float4 zn[8];
+                        if (b < 3) {             // next block of this half: in flight while this one is computed
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) zn[j] = __ldg(zp + j * 128);
+                            for (int j = 0; j < 8; ++j) zn[j] = __ldg(zs + (hf * 64 + (b + 1) * 8 + j) * 128);
                         }
                         const int cb = sub * 4 + b;
                         uint32_t v[32];
@@ -896,8 +897,10 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
                         const uint32_t off = sw128_offset(row, cb);
                         st_shared_v4(hs_hi + off, phi);
                         st_shared_v4(hs_lo + off, plo);
+                        if (b < 3) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) z[j] = zn[j];
+                            for (int j = 0; j < 8; ++j) z[j] = zn[j];
+                        }
                     }
                     tc_fence_before();           // our tcgen05.ld of this half precede the MMAs that overwrite it
                     fence_proxy_async_smem();    // our h writes are visible to the tensor core (of the leader) and to TMA
@@ -905,6 +908,15 @@ lstm_rec_tc128_pair_kernel(const __half* __restrict__ wr_hi, const __half* __res
                     if (lane == 0) {
                         mbar_arrive(&h_half[hf]);
                         mbar_arrive_remote(&h_pair[hf], 0);
+                    }
+                    // first block of the next half: issued AFTER the proxy fence (its MEMBAR would wait for the loads) and, for
+                    // hf == 1, in flight while this warp waits for the next accumulator
+                    if (hf == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] = __ldg(zs + (64 + j) * 128);
+                    } else if (more) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] = __ldg(zs + zstep + j * 128);
                     }
                 }
             }
