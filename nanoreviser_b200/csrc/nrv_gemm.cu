@@ -307,7 +307,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 //     here the bytes per MMA halve twice (B resident, A per CTA) and the ring is deep enough to cover HBM latency.
 //   * epilogue per CTA: its 128 rows of the double-buffered accumulator -> (+bias) -> zin tiles, coalesced.
 // ============================================================================================================
-constexpr int GP_THREADS = 192;
+constexpr int GP_THREADS = 320;                       // warp 0: TMA producer, warp 1: MMA issue, warps 2..9: epilogue
 constexpr int GP_A_STAGE = 2 * G_A_BYTES;             // 32 KB: A_hi + A_lo chunk
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GP_THREADS, 1)
@@ -323,8 +323,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     uint64_t* full = bars;                  // [n_stages] leader's copy is used: 1 arrive (leader producer) + 64 KB of tx
     uint64_t* empty = bars + 8;             // [n_stages] both CTAs: multicast commit
     uint64_t* tfull = bars + 16;            // [2] both CTAs: multicast commit
-    uint64_t* tempty = bars + 18;           // [2] leader's copy is used: 8 arrivals (4 epilogue warps x 2 CTAs)
+    uint64_t* tempty = bars + 18;           // [2] leader's copy is used: 16 arrivals (8 epilogue warps x 2 CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* s_bias = reinterpret_cast<float*>(bars + 22);             // [256] bias of this cluster's column tile (1 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -340,10 +341,11 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
         for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    if (threadIdx.x < 256) s_bias[threadIdx.x] = out.bias ? __ldg(out.bias + n0 + threadIdx.x) : 0.f;
     {   // resident B: this CTA's 128 rows of the column tile, all of K, hi and lo -> swizzled K-major [128][64] tiles
         const int per_row = K / 8;                                         // 16-byte chunks per row
         for (int i = threadIdx.x; i < 2 * 128 * per_row; i += GP_THREADS) {
@@ -361,6 +363,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Cross-CTA signalling uses plain mbarrier arrives / waits: everything that is published lives in shared memory or TMEM and
+    // is ordered by the async proxy (TMA complete_tx, tcgen05.commit) or tcgen05.fence -- cluster-scope acquire/release would
+    // cost a MEMBAR.GPU + ERRBAR per arrive and an L1 invalidation (CCTL.IVALL) per wait (ncu: 20 % of the epilogue's samples).
     if (warp == 0) {
         // ===================== TMA producer (both CTAs): own 128 rows of the A operand =====================
         if (elect_one()) {
@@ -368,7 +373,7 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
                 const int m0 = (int)((mp * 2 + rank) * G_TM);             // rows beyond M are zero-filled by TMA
                 for (int kc = 0; kc < n_chunks; ++kc) {
-                    mbar_wait_cluster(&empty[stage], phase ^ 1);
+                    mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = s_a + (size_t)stage * GP_A_STAGE;
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * GP_A_STAGE);    // both CTAs' bytes
                     tma_load_2d_pair(st, &tm_a_hi, &full[stage], 0, kc * G_KC, m0);
@@ -385,11 +390,11 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             int acc = 0; uint32_t acc_phase = 0;
             const uint32_t b_base = smem_u32(s_b);
             for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
-                mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
+                mbar_wait(&tempty[acc], acc_phase ^ 1);                  // both CTAs' epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 for (int kc = 0; kc < n_chunks; ++kc) {
-                    mbar_wait_cluster(&full[stage], phase);              // both CTAs' A chunks have landed
+                    mbar_wait(&full[stage], phase);                      // both CTAs' A chunks have landed
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t st = smem_u32(s_a + (size_t)stage * GP_A_STAGE);
@@ -412,40 +417,41 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5, both CTAs): own 128 rows -> zin tile =====================
+        // ===================== epilogue (warps 2..9, both CTAs): own 128 rows -> zin tile =====================
+        // TMEM lane quarter = warp % 4; column half (4 blocks of 32 columns) = (warp - 2) / 4
         const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         const int dir = n0 / out.n_per_dir;
         const int nloc = n0 - dir * out.n_per_dir;
+        const uint32_t sb = smem_u32(s_bias);
         for (int64_t mp = wi; mp < n_mpairs; mp += n_workers) {
             const int64_t m_tile = mp * 2 + rank;
-            mbar_wait_cluster(&tfull[acc], acc_phase);
+            mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             float* dst = nullptr;
             if (m_tile < n_tiles_m)
                 dst = out.c + ((int64_t)dir * n_tiles_m + m_tile) * ((int64_t)out.n_per_dir * G_TM) + (int64_t)(nloc >> 2) * (G_TM * 4) +
                       (q * 32 + lane) * 4;
-#pragma unroll 1
-            for (int cb = 0; cb < 8; ++cb) {
+#pragma unroll 2
+            for (int cbi = 0; cbi < 4; ++cbi) {
+                const int cb = ch * 4 + cbi;
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + cb * 32), v);
                 tmem_ld_wait();
                 if (dst) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                               __uint_as_float(v[j + 3]));
-                        if (out.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(out.bias + n0 + cb * 32 + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
+                        const float4 bq = ld_shared_f4(sb + (uint32_t)(cb * 32 + j) * 4);
+                        const float4 o = make_float4(__uint_as_float(v[j]) + bq.x, __uint_as_float(v[j + 1]) + bq.y,
+                                                     __uint_as_float(v[j + 2]) + bq.z, __uint_as_float(v[j + 3]) + bq.w);
                         *reinterpret_cast<float4*>(dst + (int64_t)(cb * 8 + (j >> 2)) * (G_TM * 4)) = o;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);
+            if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -523,16 +529,17 @@ int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
     GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2};
-    static const bool use_pair = getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "pair");   // measured: no gain, the GEMMs are HBM-write-bound
+    // CTA-pair kernel (B resident, 8 epilogue warps) unless NRV_GEMM=single: proj2 36.7 -> 30.8 ms, proj3 21.3 -> 17.9 ms per step
+    static const bool use_pair = !(getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "single"));
     if (mode == 1 && use_pair && N % 256 == 0 && n_per_dir % 256 == 0 && M % G_TM == 0 && K <= 256) {
         CUtensorMap ta_hi, ta_lo;
         if (!make_tmap_f16_k64(&ta_hi, a_hi, M, K, G_TM) || !make_tmap_f16_k64(&ta_lo, a_lo, M, K, G_TM)) return -2;
         const int n_chunks = K / G_KC;
         const size_t b_bytes = (size_t)2 * n_chunks * G_A_BYTES;
-        int n_stages = (int)((232448 - 2048 - b_bytes) / GP_A_STAGE);
+        int n_stages = (int)((232448 - 2304 - b_bytes) / GP_A_STAGE);
         if (n_stages > 6) n_stages = 6;
         if (n_stages < 2) return -1;
-        const size_t smem = b_bytes + (size_t)n_stages * GP_A_STAGE + 1024 + 256;
+        const size_t smem = b_bytes + (size_t)n_stages * GP_A_STAGE + 1024 + 256 + 1024;
         cudaFuncSetAttribute(gemm_f16x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int sms = num_sms > 0 ? num_sms : 148;
         const int n_tiles_n = N / 256;

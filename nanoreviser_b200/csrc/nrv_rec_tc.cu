@@ -207,8 +207,8 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
         const int q = warp & 3;                          // TMEM lane quarter accessible to this warp
         const int row = q * 32 + lane;
         if (valid[X]) {
-            uint8_t* hs_hi = s_h + (X * 2 + 0) * RT_H_BYTES;
-            uint8_t* hs_lo = s_h + (X * 2 + 1) * RT_H_BYTES;
+            const uint32_t hs_hi = smem_u32(s_h + (X * 2 + 0) * RT_H_BYTES);
+            const uint32_t hs_lo = smem_u32(s_h + (X * 2 + 1) * RT_H_BYTES);
             float c[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) c[j] = 0.f;
@@ -224,10 +224,10 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
                     if (s > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(X * N + cb * 32), v);
                     // zin block from the ring: quad j of this row at j*2 KB + row*16 B (conflict-free 128-bit reads)
                     mbar_wait(&zfull[X * RT_ZS + stage], zphase);
-                    const float4* zs = reinterpret_cast<const float4*>(s_z + (X * RT_ZS + stage) * RT_Z_BYTES) + row;
+                    const uint32_t zs = smem_u32(s_z + (X * RT_ZS + stage) * RT_Z_BYTES) + row * 16;
                     float4 z[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] = zs[j * 128];
+                    for (int j = 0; j < 8; ++j) z[j] = ld_shared_f4(zs + j * 2048);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&zempty[X * RT_ZS + stage]);
                     if (++stage == RT_ZS) { stage = 0; zphase ^= 1; }
@@ -235,8 +235,8 @@ lstm_rec_tc64_kernel(const __half* __restrict__ wr_hi, const __half* __restrict_
                     uint4 phi, plo;
                     lstm_cell_block(v, s > 0, z, &c[cb * 8], phi, plo);
                     const uint32_t off = sw128_offset(row, cb);
-                    *reinterpret_cast<uint4*>(hs_hi + off) = phi;
-                    *reinterpret_cast<uint4*>(hs_lo + off) = plo;
+                    st_shared_v4(hs_hi + off, phi);
+                    st_shared_v4(hs_lo + off, plo);
                 }
                 tc_fence_before();           // our tcgen05.ld of this step precede the next MMA's writes
                 fence_proxy_async_smem();    // our h writes are visible to the tensor core and to TMA
@@ -422,6 +422,7 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const int hf = (warp - 2) >> 2;                  // units hf*32 .. +32  (128 gate columns, 4 blocks)
         const int row = q * 32 + lane;
         const float4 zero4[8] = {};
+        const uint32_t sh_base = smem_u32(s_h);
         uint32_t g = 0;
         for (int64_t wtile = blockIdx.x; wtile < ntw; wtile += gridDim.x) {
             float c[32];
@@ -438,8 +439,8 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     uint4 phi, plo;
                     lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
                     const uint32_t off = sw128_offset(row, hf * 4 + cb);
-                    *reinterpret_cast<uint4*>(s_h + off) = phi;
-                    *reinterpret_cast<uint4*>(s_h + RF_H_BYTES + off) = plo;
+                    st_shared_v4(sh_base + off, phi);
+                    st_shared_v4(sh_base + RF_H_BYTES + off, plo);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
