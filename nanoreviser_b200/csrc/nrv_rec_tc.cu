@@ -74,9 +74,11 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
 
 // One 32-column block (8 units x gates i,f,c,o) of the Keras-2.2.4 LSTM cell for this thread's row:
 // z = acc (if any) + zin ; c, h update ; h -> fp16 (hi, lo) packed as 2 x 16 bytes.
+__device__ __forceinline__ uint32_t half2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
 __device__ __forceinline__ void lstm_cell_block(const uint32_t (&v)[32], bool have_acc, const float4 (&zq)[8], float* c8,
                                                 uint4& phi, uint4& plo) {
-    __half hh[8], hl[8];
+    float hv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float zi = zq[j].x, zf = zq[j].y, zc = zq[j].z, zo = zq[j].w;
@@ -87,10 +89,20 @@ __device__ __forceinline__ void lstm_cell_block(const uint32_t (&v)[32], bool ha
         const float ig = hsig(zi), fg = hsig(zf), gg = tanh_fast(zc), og = hsig(zo);
         const float cn = fmaf(fg, c8[j], ig * gg);
         c8[j] = cn;
-        split_f16(og * tanh_fast(cn), hh[j], hl[j]);
+        hv[j] = og * tanh_fast(cn);
     }
-    phi = make_uint4(pack_half2(hh[0], hh[1]), pack_half2(hh[2], hh[3]), pack_half2(hh[4], hh[5]), pack_half2(hh[6], hh[7]));
-    plo = make_uint4(pack_half2(hl[0], hl[1]), pack_half2(hl[2], hl[3]), pack_half2(hl[4], hl[5]), pack_half2(hl[6], hl[7]));
+    // h = hi + lo as fp16 pairs.  Packed conversions (cvt.rn.f16x2.f32 -> F2FP, ALU pipe): the scalar F2F.F16.F32 runs on the
+    // quarter-rate XU pipe next to the four MUFU ops of every unit, which is what bounds this epilogue (ncu: XU 43 %).
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(hv[2 * p] - hf.x, hv[2 * p + 1] - hf.y);
+        ph[p] = half2_bits(hi); pl[p] = half2_bits(lo);
+    }
+    phi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
 __global__ void __launch_bounds__(RT_THREADS, 1)
@@ -277,7 +289,8 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, i
 // are issued right behind the recurrent MMAs of step s and run while the epilogue of step s is busy.  Compared with
 // GEMM + recurrence this removes 2 x 22.5 KB of HBM traffic per window and a kernel launch.
 // ============================================================================================================
-constexpr int RF_THREADS = 320;                       // warp 0: store + MMA issue, warp 1: TMA producer, warps 2..9: epilogue
+constexpr int RF_EPI_WARPS = 16;                      // 4 per TMEM lane quarter, 16 units (2 blocks of 32 gate columns) each
+constexpr int RF_THREADS = 64 + 32 * RF_EPI_WARPS;    // warp 0: store + MMA issue, warp 1: TMA producer, warps 2..: epilogue
 constexpr int RF_W_BYTES = 256 * 64 * 2;              // 32 KB per weight tile (Wk hi, Wk lo, Wr hi, Wr lo)
 constexpr int RF_H_BYTES = 128 * 64 * 2;              // 16 KB per h / x tile part
 constexpr int RF_XS = 2;                              // x ring stages
@@ -295,7 +308,7 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     uint8_t* s_h = smem + 4 * RF_W_BYTES;                 // [hi | lo][128 rows][64]
     uint8_t* s_x = s_h + 2 * RF_H_BYTES;                  // [stage][hi | lo][128 rows][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + RF_XS * 2 * RF_H_BYTES);
-    uint64_t* h_ready = bars;                             // count 8 (one arrive per epilogue warp)
+    uint64_t* h_ready = bars;                             // count RF_EPI_WARPS (one arrive per epilogue warp)
     uint64_t* acc_ready = bars + 1;                       // count 2 (commit + "h store left smem"); step 0: see below
     uint64_t* xfull = bars + 2;                           // [RF_XS]
     uint64_t* xempty = bars + 2 + RF_XS;                  // [RF_XS] count 1 (commit)
@@ -305,7 +318,7 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     const int dir = blockIdx.y;
 
     if (threadIdx.x == 0) {
-        mbar_init(h_ready, 8);
+        mbar_init(h_ready, RF_EPI_WARPS);
         mbar_init(acc_ready, 2);
         for (int i = 0; i < RF_XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
         fence_mbar_init();
@@ -417,28 +430,31 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     } else {
-        // ===================== epilogue: warps 2..9; lane quarter = warp % 4, column half = (warp - 2) / 4 =====================
+        // ===================== epilogue: warps 2..17; lane quarter = warp % 4, column group = (warp - 2) / 4 =====================
+        // 16 warps (4 per scheduler) instead of 8: the cell math is a chain of dependent MUFU / FMA ops, and with 2 warps per
+        // scheduler it issued at ~0.5 IPC (ncu) -- the epilogue, not the tensor core, set the step time
+        constexpr int NB = 8 / (RF_EPI_WARPS / 4);        // 32-column blocks per warp
         const int q = warp & 3;
-        const int hf = (warp - 2) >> 2;                  // units hf*32 .. +32  (128 gate columns, 4 blocks)
+        const int cg = (warp - 2) >> 2;                  // units cg*8*NB .. +8*NB
         const int row = q * 32 + lane;
         const float4 zero4[8] = {};
         const uint32_t sh_base = smem_u32(s_h);
         uint32_t g = 0;
         for (int64_t wtile = blockIdx.x; wtile < ntw; wtile += gridDim.x) {
-            float c[32];
+            float c[8 * NB];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) c[j] = 0.f;
+            for (int j = 0; j < 8 * NB; ++j) c[j] = 0.f;
             for (int s = 0; s < T; ++s, ++g) {
                 mbar_wait(acc_ready, g & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
+                for (int cb = 0; cb < NB; ++cb) {
                     uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * N + (uint32_t)(hf * 128 + cb * 32), v);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * N + (uint32_t)((cg * NB + cb) * 32), v);
                     tmem_ld_wait();
                     uint4 phi, plo;
                     lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
-                    const uint32_t off = sw128_offset(row, hf * 4 + cb);
+                    const uint32_t off = sw128_offset(row, cg * NB + cb);
                     st_shared_v4(sh_base + off, phi);
                     st_shared_v4(sh_base + RF_H_BYTES + off, plo);
                 }
