@@ -389,7 +389,9 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     StageTimer tm(h, ST_L0);
                     LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.out_hi = a1h; io.out_lo = a1l; io.out_ld = 64;
                     io.out_nwp = nwp;
-                    h->launches += launch_lstm_layer(0, 1, M.lstm[0], io, nw, T, h->stream);
+                    n = launch_read_rnn1(M.lstm[0], io, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
+                    h->launches += n;
                 }
                 {   // read_rnn11: projection (K = 32 -> 64, bias as the weight row of a constant-1 column) and recurrence
                     // (u = 64) fused in one tcgen05 kernel -- no zin round trip for this layer

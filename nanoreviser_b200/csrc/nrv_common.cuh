@@ -109,6 +109,7 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 // fused projection + recurrence for read_rnn11 (K_in = 32 padded to 64 with a constant-1 bias column)
 int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                            cudaStream_t st);
+int launch_read_rnn1(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 

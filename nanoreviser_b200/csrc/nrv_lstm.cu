@@ -228,6 +228,139 @@ lstm_layer_kernel(const float* __restrict__ act_in, const float* __restrict__ ba
     }
 }
 
+// ============================================================================================================
+// read_rnn1 (lstmmodel.py:44: Bidirectional(LSTM(16)) on the 6 feature columns) for the tensor-core path.
+// The layer is tiny (K = 6 + 16, N = 64): the generic tile kernel above pads K to 32, re-streams the weights every
+// step and scatters 2-byte stores.  Here ONE THREAD owns one (window, direction): x_t comes straight from the
+// per-base feature table (indexed by first base + t, never materialised per window), h and c stay in registers
+// for all T steps, the 22 x 64 weights sit in shared memory and are read as warp-wide broadcasts (LDS.128), and
+// each step ends in two 32-byte stores of BatchNormalization(h) as an fp16 (hi, lo) pair into row (t, w) of the
+// padded time-major operand of read_rnn11 (BN is applied here, not folded: see nrv_api.cu pack_model).
+// ============================================================================================================
+constexpr int R1_THREADS = 128;
+
+__device__ __forceinline__ float r1_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float r1_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// tanh(|x|) = 1 - 2 / (exp(2|x|) + 1): abs error ~2e-7 (same form as the tensor-core recurrences)
+__device__ __forceinline__ float r1_tanh(float x) {
+    const float e = r1_ex2(fabsf(x) * 2.8853900817779268f);
+    return copysignf(fmaf(-2.f, r1_rcp(e + 1.f), 1.f), x);
+}
+
+constexpr int R1_WPT = 2;                              // windows per thread: every weight broadcast (LDS.128) feeds 4 x R1_WPT FMAs
+
+__global__ void __launch_bounds__(R1_THREADS, 3)
+read_rnn1_kernel(const float* __restrict__ x, const int32_t* __restrict__ win_base, const float* __restrict__ wcat0,
+                 const float* __restrict__ wcat1, const float* __restrict__ bias0, const float* __restrict__ bias1,
+                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, __half* __restrict__ out_hi,
+                 __half* __restrict__ out_lo, int out_ld, int64_t nwp, int64_t n_win, int T) {
+    constexpr int U = 16, IN = 6, K = IN + U, N = 4 * U, P = R1_WPT;
+    __shared__ __align__(16) float s_w[K * N];        // [k][unit*4 + gate]
+    __shared__ __align__(16) float s_b[N];
+    __shared__ float s_bn[2 * U];                      // scale | shift of this direction
+    const int dir = blockIdx.y;
+    const float* wcat = dir ? wcat1 : wcat0;
+    const float* bias = dir ? bias1 : bias0;
+    for (int i = threadIdx.x; i < K * N; i += R1_THREADS) s_w[i] = wcat[i];
+    if (threadIdx.x < N) s_b[threadIdx.x] = bias[threadIdx.x];
+    if (threadIdx.x < U) {
+        s_bn[threadIdx.x] = bn_scale[dir * U + threadIdx.x];
+        s_bn[U + threadIdx.x] = bn_shift[dir * U + threadIdx.x];
+    }
+    __syncthreads();
+    int64_t w[P], b0[P];
+    bool ok[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        w[p] = ((int64_t)blockIdx.x * P + p) * R1_THREADS + threadIdx.x;
+        ok[p] = w[p] < n_win;
+        b0[p] = ok[p] ? win_base[w[p]] : 0;
+    }
+    if (!ok[0]) return;
+    float in[P][K];                                    // x_t (6) | h_{t-1} (16)
+    float c[P][U];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int j = 0; j < U; ++j) { in[p][IN + j] = 0.f; c[p][j] = 0.f; }
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? (T - 1 - s) : s;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float2* xp = reinterpret_cast<const float2*>(x + (b0[p] + t) * IN);
+            const float2 x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+            in[p][0] = x0.x; in[p][1] = x0.y; in[p][2] = x1.x; in[p][3] = x1.y; in[p][4] = x2.x; in[p][5] = x2.y;
+        }
+        float hn[P][U];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {                  // 2 units = 8 gate columns at a time
+            float z[P][8];
+            {
+                const float4 ba = *reinterpret_cast<const float4*>(s_b + g * 8), bb = *reinterpret_cast<const float4*>(s_b + g * 8 + 4);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    z[p][0] = ba.x; z[p][1] = ba.y; z[p][2] = ba.z; z[p][3] = ba.w;
+                    z[p][4] = bb.x; z[p][5] = bb.y; z[p][6] = bb.z; z[p][7] = bb.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 wa = *reinterpret_cast<const float4*>(s_w + k * N + g * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(s_w + k * N + g * 8 + 4);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const float a = in[p][k];
+                    z[p][0] = fmaf(a, wa.x, z[p][0]); z[p][1] = fmaf(a, wa.y, z[p][1]);
+                    z[p][2] = fmaf(a, wa.z, z[p][2]); z[p][3] = fmaf(a, wa.w, z[p][3]);
+                    z[p][4] = fmaf(a, wb.x, z[p][4]); z[p][5] = fmaf(a, wb.y, z[p][5]);
+                    z[p][6] = fmaf(a, wb.z, z[p][6]); z[p][7] = fmaf(a, wb.w, z[p][7]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int j = g * 2 + q;
+                    const float ig = hard_sigmoid(z[p][q * 4 + 0]), fg = hard_sigmoid(z[p][q * 4 + 1]);
+                    const float gg = r1_tanh(z[p][q * 4 + 2]), og = hard_sigmoid(z[p][q * 4 + 3]);
+                    const float cn = fmaf(fg, c[p][j], ig * gg);
+                    c[p][j] = cn;
+                    hn[p][j] = og * r1_tanh(cn);
+                }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int p2 = 0; p2 < 8; ++p2) {
+                in[p][IN + 2 * p2] = hn[p][2 * p2]; in[p][IN + 2 * p2 + 1] = hn[p][2 * p2 + 1];
+                const float y0 = fmaf(hn[p][2 * p2], s_bn[2 * p2], s_bn[U + 2 * p2]);
+                const float y1 = fmaf(hn[p][2 * p2 + 1], s_bn[2 * p2 + 1], s_bn[U + 2 * p2 + 1]);
+                const __half2 hi = __floats2half2_rn(y0, y1);
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+                ph[p2] = *reinterpret_cast<const uint32_t*>(&hi); pl[p2] = *reinterpret_cast<const uint32_t*>(&lo);
+            }
+            if (ok[p]) {
+                const int64_t off = ((int64_t)t * nwp + w[p]) * out_ld + dir * U;
+                uint4* oh = reinterpret_cast<uint4*>(out_hi + off);
+                uint4* ol = reinterpret_cast<uint4*>(out_lo + off);
+                oh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); oh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            }
+        }
+    }
+}
+
+int launch_read_rnn1(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st) {
+    if (n_win <= 0) return 0;
+    if (L.u != 16 || L.in_b != 6 || L.in_a != 0 || !io.out_hi || !io.out_lo || !io.out_nwp || (io.out_ld & 7) || !L.bn_scale) return -1;
+    dim3 grid((unsigned)((n_win + R1_THREADS * R1_WPT - 1) / (R1_THREADS * R1_WPT)), 2);
+    read_rnn1_kernel<<<grid, R1_THREADS, 0, st>>>(io.base_in, io.win_base, L.wcat[0], L.wcat[1], L.bias[0], L.bias[1], L.bn_scale,
+                                                   L.bn_shift, io.out_hi, io.out_lo, io.out_ld, io.out_nwp, n_win, T);
+    return 1;
+}
+
 template <int IN_A, int IN_B, int U, int TM, int ZMODE, int OMODE>
 static int launch_one(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st) {
     using C = LstmTile<IN_A, IN_B, U, TM>;
