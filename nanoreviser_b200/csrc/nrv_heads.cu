@@ -280,6 +280,104 @@ heads_tail_kernel(HeadsDev H, const float* __restrict__ d1_in, int64_t n_win, in
     }
 }
 
+// ---- tail of the heads when relu(Dense(128)) AND relu(Dense(32)) already ran on the tensor cores ---------------------
+// One THREAD per window: main_out Dense(32 -> 6, relu) for the T timesteps, Flatten (t*6 + k), feature Dense(16, relu),
+// final_out Dense(n_class) + softmax + argmax, all in registers; the small weights are warp-wide broadcasts from shared
+// memory.  (The warp-per-window kernel above spent 6 ms per step on 0.3 ms worth of FMAs: 66 outputs over 32 lanes,
+// two shared-memory reads per FMA.)  Input rows are time-major: row(t, w) = t*nwp + w, 32 floats each.
+constexpr int HT_THREADS = 128;
+
+template <int T>
+__global__ void __launch_bounds__(HT_THREADS)
+heads_tail_thread_kernel(HeadsDev H, const float* __restrict__ d2_in, int64_t n_win, int64_t in_nwp, float* __restrict__ probs,
+                         uint8_t* __restrict__ labels) {
+    __shared__ __align__(16) float s_mk[32][8];        // main_out kernel, 6 columns padded to 8
+    __shared__ __align__(16) float s_fk[T * 6][16];
+    __shared__ __align__(16) float s_ok[16][8];
+    __shared__ __align__(16) float s_mb[8], s_fb[16], s_ob[8];
+    const int tid = threadIdx.x;
+    const int nc = H.n_class;
+    for (int i = tid; i < 32 * 8; i += HT_THREADS) s_mk[i >> 3][i & 7] = ((i & 7) < 6) ? __ldg(H.mk + (i >> 3) * 6 + (i & 7)) : 0.f;
+    for (int i = tid; i < T * 6 * 16; i += HT_THREADS) (&s_fk[0][0])[i] = __ldg(H.fk + i);
+    for (int i = tid; i < 16 * 8; i += HT_THREADS) s_ok[i >> 3][i & 7] = ((i & 7) < nc) ? __ldg(H.ok + (i >> 3) * nc + (i & 7)) : 0.f;
+    if (tid < 8) { s_mb[tid] = (tid < 6) ? __ldg(H.mb + tid) : 0.f; s_ob[tid] = (tid < nc) ? __ldg(H.ob + tid) : 0.f; }
+    if (tid < 16) s_fb[tid] = __ldg(H.fb + tid);
+    __syncthreads();
+    const int64_t w = (int64_t)blockIdx.x * HT_THREADS + tid;
+    if (w >= n_win) return;
+    float ft[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) ft[o] = s_fb[o];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        const float4* rowp = reinterpret_cast<const float4*>(d2_in + ((int64_t)t * in_nwp + w) * 32);
+        float4 r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = __ldg(rowp + q);
+        float m[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) m[k] = s_mb[k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float a[4] = {r[q].x, r[q].y, r[q].z, r[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 wa = *reinterpret_cast<const float4*>(&s_mk[q * 4 + e][0]);
+                const float2 wb = *reinterpret_cast<const float2*>(&s_mk[q * 4 + e][4]);
+                m[0] = fmaf(a[e], wa.x, m[0]); m[1] = fmaf(a[e], wa.y, m[1]); m[2] = fmaf(a[e], wa.z, m[2]);
+                m[3] = fmaf(a[e], wa.w, m[3]); m[4] = fmaf(a[e], wb.x, m[4]); m[5] = fmaf(a[e], wb.y, m[5]);
+            }
+        }
+        // feature Dense: flattened index t*6 + k
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float a = fmaxf(m[k], 0.f);
+#pragma unroll
+            for (int o4 = 0; o4 < 4; ++o4) {
+                const float4 fw = *reinterpret_cast<const float4*>(&s_fk[t * 6 + k][o4 * 4]);
+                ft[o4 * 4 + 0] = fmaf(a, fw.x, ft[o4 * 4 + 0]); ft[o4 * 4 + 1] = fmaf(a, fw.y, ft[o4 * 4 + 1]);
+                ft[o4 * 4 + 2] = fmaf(a, fw.z, ft[o4 * 4 + 2]); ft[o4 * 4 + 3] = fmaf(a, fw.w, ft[o4 * 4 + 3]);
+            }
+        }
+    }
+    float logit[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) logit[k] = s_ob[k];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float a = fmaxf(ft[j], 0.f);
+        const float4 wa = *reinterpret_cast<const float4*>(&s_ok[j][0]), wb = *reinterpret_cast<const float4*>(&s_ok[j][4]);
+        logit[0] = fmaf(a, wa.x, logit[0]); logit[1] = fmaf(a, wa.y, logit[1]); logit[2] = fmaf(a, wa.z, logit[2]);
+        logit[3] = fmaf(a, wa.w, logit[3]); logit[4] = fmaf(a, wb.x, logit[4]); logit[5] = fmaf(a, wb.y, logit[5]);
+        logit[6] = fmaf(a, wb.z, logit[6]); logit[7] = fmaf(a, wb.w, logit[7]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < nc) mx = fmaxf(mx, logit[k]);
+    float e[8], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = (k < nc) ? expf(logit[k] - mx) : 0.f; sum += e[k]; }
+    float bp = -1.f;
+    int bi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float pr = e[k] / sum;
+        if (k < nc) {
+            if (probs) probs[w * nc + k] = pr;
+            if (pr > bp) { bp = pr; bi = k; }          // first maximum (numpy argmax semantics)
+        }
+    }
+    if (labels) labels[w] = (uint8_t)bi;
+}
+
+template <int T>
+static int launch_heads_tail_thread_t(const HeadsDev& H, const float* d2, int64_t n_win, int64_t in_nwp, float* probs,
+                                      uint8_t* labels, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n_win + HT_THREADS - 1) / HT_THREADS);
+    heads_tail_thread_kernel<T><<<grid, HT_THREADS, 0, st>>>(H, d2, n_win, in_nwp, probs, labels);
+    return 1;
+}
+
 template <int T, bool D2_DONE>
 static int launch_heads_tail_t(const HeadsDev& H, const float* d1, int64_t n_win, int64_t in_nwp, float* probs,
                                uint8_t* labels, cudaStream_t st) {
@@ -306,7 +404,8 @@ int launch_heads(const HeadsDev& H, const float* act_in, int64_t n_win, int T, f
     if (n_win <= 0) return 0;
 #define NRV_HEADS_CASE(TT)                                                                        \
     case TT:                                                                                      \
-        return stage == 2   ? launch_heads_tail_t<TT, true>(H, act_in, n_win, in_nwp, probs, labels, st)   \
+        return stage == 2   ? (in_nwp ? launch_heads_tail_thread_t<TT>(H, act_in, n_win, in_nwp, probs, labels, st)     \
+                                      : launch_heads_tail_t<TT, true>(H, act_in, n_win, in_nwp, probs, labels, st)) \
                : stage == 1 ? launch_heads_tail_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st)  \
                             : launch_heads_t<TT, false>(H, act_in, n_win, in_nwp, probs, labels, st);
     switch (T) {   // W is read from the weights (feature.kernel.shape[0] / 6); the shipped files have 11
