@@ -30,7 +30,8 @@ using namespace tc;
 
 constexpr int G_TM = 128, G_KC = 64;
 constexpr int G_A_BYTES = G_TM * G_KC * 2;            // 16 KB (one of hi / lo)
-constexpr int G_THREADS = 192;
+constexpr int G_EPI_WARPS = 8;                        // 2 per TMEM lane quarter: column halves of the tile
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
 
 constexpr int G_A2_BYTES = 4 * G_A_BYTES;            // fused head: relu(Dense128) tile [128][128] as fp16 (hi, lo), 2 K-chunks each
 constexpr int G_W2_BYTES = 4 * 32 * 128;              // fused head: W2^T [32][128] as fp16 (hi, lo), 2 K-chunks each (4 x 4 KB)
@@ -42,7 +43,7 @@ struct GemmCfg {
     static constexpr int STAGES = (TN == 256 || FUSE2) ? 2 : 3;
     static constexpr int TMEM_COLS = FUSE2 ? 512 : 2 * TN;             // double-buffered accumulator (+ 32 columns for the fused head)
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (FUSE2 ? G_A2_BYTES + G_W2_BYTES : 0) + 1024 /*alignment slack*/ +
-                                   256 /*barriers*/;
+                                   256 /*barriers*/ + 768 /*FUSE2 biases*/;
 };
 
 struct GemmOut {
@@ -83,6 +84,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     uint64_t* a2_ready = tempty + 2;        // fused head: epilogue -> MMA warp ("A tile of the second dense is in smem")
     uint64_t* d2_ready = a2_ready + 1;      // fused head: MMA warp -> epilogue ("second accumulator complete")
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_ready + 1);
+    float* s_bias = reinterpret_cast<float*>(bars + 16);             // FUSE2: bias of the first dense [128] | b2 [32] (16-byte aligned)
     constexpr uint32_t D2_COL = 2 * G_TN;                            // TMEM columns of the fused head's accumulator
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,8 +96,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
-        mbar_init(a2_ready, 4); mbar_init(d2_ready, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], G_EPI_WARPS); }
+        mbar_init(a2_ready, G_EPI_WARPS); mbar_init(d2_ready, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -105,6 +107,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(part ? out.w2t_lo : out.w2t_hi) + row * 16 + c16);
             *reinterpret_cast<uint4*>(s_w2 + (part * 2 + (c16 >> 3)) * 4096 + sw128_offset(row, c16 & 7)) = v;
         }
+        if (threadIdx.x < 128) s_bias[threadIdx.x] = __ldg(out.bias + threadIdx.x);
+        if (threadIdx.x < 32) s_bias[128 + threadIdx.x] = __ldg(out.b2 + threadIdx.x);
         fence_proxy_async_smem();
     }
     tc_fence_before();
@@ -193,10 +197,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         if (FUSE2 && pending_head) issue_head();
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====================
+        const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t head_phase = 0;
+        const uint32_t sb = smem_u32(s_bias);
+        const uint32_t sa2 = smem_u32(s_a2);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t m0 = (tile / n_tiles_n) * G_TM;
             const int n0 = (int)((tile % n_tiles_n) * G_TN);
@@ -218,8 +225,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             }
             if (FUSE2) {
                 // (1) relu(acc + bias1) -> fp16 (hi, lo) A tile of the second dense, K index = column of this layer
-#pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+                for (int cbi = 0; cbi < 2; ++cbi) {
+                    const int cb = ch * 2 + cbi;
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
                     tmem_ld_wait();
@@ -227,36 +235,43 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     for (int g8 = 0; g8 < 4; ++g8) {
                         uint32_t ph[4], pl[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
+                        for (int e = 0; e < 4; e += 2) {
                             const int j = g8 * 8 + e * 2;
-                            const float x0 = fmaxf(__uint_as_float(v[j]) + __ldg(out.bias + cb * 32 + j), 0.f);
-                            const float x1 = fmaxf(__uint_as_float(v[j + 1]) + __ldg(out.bias + cb * 32 + j + 1), 0.f);
-                            __half h0, l0, h1, l1;
-                            split_f16(x0, h0, l0); split_f16(x1, h1, l1);
-                            ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            const float4 bq = ld_shared_f4(sb + (uint32_t)(cb * 32 + j) * 4);
+                            const float x0 = fmaxf(__uint_as_float(v[j]) + bq.x, 0.f), x1 = fmaxf(__uint_as_float(v[j + 1]) + bq.y, 0.f);
+                            const float x2 = fmaxf(__uint_as_float(v[j + 2]) + bq.z, 0.f), x3 = fmaxf(__uint_as_float(v[j + 3]) + bq.w, 0.f);
+                            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                            ph[e] = *reinterpret_cast<const uint32_t*>(&h01); ph[e + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            pl[e] = *reinterpret_cast<const uint32_t*>(&l01); pl[e + 1] = *reinterpret_cast<const uint32_t*>(&l23);
                         }
                         const uint32_t off = ((cb >> 1) * G_A_BYTES) + sw128_offset(q * 32 + lane, (cb & 1) * 4 + g8);
-                        *reinterpret_cast<uint4*>(s_a2 + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        *reinterpret_cast<uint4*>(s_a2 + 2 * G_A_BYTES + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        st_shared_v4(sa2 + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                        st_shared_v4(sa2 + 2 * G_A_BYTES + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(a2_ready); mbar_arrive(&tempty[acc]); }   // main accumulator is drained
-                // (2) second accumulator -> + b2, relu -> out[r][32]
+                // (2) second accumulator -> + b2, relu -> out[r][32]: 16 columns per warp
                 mbar_wait(d2_ready, head_phase);
                 head_phase ^= 1;
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + D2_COL, v);
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + D2_COL + (uint32_t)(ch * 16))
+                    : "memory");
                 tmem_ld_wait();
                 if (r < M) {
-                    float4* o = reinterpret_cast<float4*>(out.c + r * 32);
+                    float4* o = reinterpret_cast<float4*>(out.c + r * 32 + ch * 16);
 #pragma unroll
-                    for (int o4 = 0; o4 < 8; ++o4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(out.b2) + o4);
+                    for (int o4 = 0; o4 < 4; ++o4) {
+                        const float4 b = ld_shared_f4(sb + (uint32_t)(128 + ch * 16 + o4 * 4) * 4);
                         o[o4] = make_float4(fmaxf(__uint_as_float(v[4 * o4]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * o4 + 1]) + b.y, 0.f),
                                             fmaxf(__uint_as_float(v[4 * o4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * o4 + 3]) + b.w, 0.f));
                     }
@@ -266,7 +281,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 continue;
             }
 #pragma unroll 1
-            for (int cb = 0; cb < G_TN / 32; ++cb) {
+            for (int cbi = 0; cbi < G_TN / 64; ++cbi) {
+                const int cb = ch * (G_TN / 64) + cbi;
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_TN + cb * 32), v);
                 tmem_ld_wait();
