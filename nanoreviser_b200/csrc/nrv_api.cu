@@ -143,6 +143,27 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
     out->cnn.blob = upload(h, blob, &e); if (e) goto cuda_fail;
     out->cnn.dense_k = upload(h, std::vector<float>(w->sig_dense_k, w->sig_dense_k + 400 * 64), &e); if (e) goto cuda_fail;
     out->cnn.dense_b = upload(h, std::vector<float>(w->sig_dense_b, w->sig_dense_b + 64), &e); if (e) goto cuda_fail;
+    {   // tensor-core (mma.sync) B fragments of the 400 -> 64 dense, split fp16 (hi, lo)
+        std::vector<uint2> fh(25 * 8 * 32), fl(25 * 8 * 32);
+        auto split = [&](int k, int n, uint16_t& hi, uint16_t& lo) {
+            const float wv = w->sig_dense_k[(size_t)k * 64 + n];
+            const __half a = __float2half_rn(wv);
+            const __half b = __float2half_rn(wv - __half2float(a));
+            hi = __half_as_ushort(a); lo = __half_as_ushort(b);
+        };
+        for (int kt = 0; kt < 25; ++kt)
+            for (int nt = 0; nt < 8; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int n = nt * 8 + lane / 4, k0 = kt * 16 + (lane % 4) * 2;
+                    uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
+                    split(k0, n, h0, l0); split(k0 + 1, n, h1, l1); split(k0 + 8, n, h2, l2); split(k0 + 9, n, h3, l3);
+                    const size_t i = ((size_t)kt * 8 + nt) * 32 + lane;
+                    fh[i] = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                    fl[i] = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+                }
+        out->cnn.dfrag_hi = upload(h, fh, &e); if (e) goto cuda_fail;
+        out->cnn.dfrag_lo = upload(h, fl, &e); if (e) goto cuda_fail;
+    }
     // ---- LSTM layers ----
     for (int l = 0; l < 4; ++l) {
         LstmLayerDev& L = out->lstm[l];

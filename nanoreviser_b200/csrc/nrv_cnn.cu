@@ -5,6 +5,8 @@
 // The reference runs this inside TimeDistributed for each of the W timesteps of every window,
 // i.e. 11x redundantly; here it is computed once per base and the LSTM kernels index it by
 // (first base of window + t).
+#include <cuda_fp16.h>
+
 #include "nrv_common.cuh"
 
 namespace nrv {
@@ -12,14 +14,25 @@ namespace nrv {
 constexpr int CNN_TB = 32;          // bases per CTA
 constexpr int CNN_THREADS = 256;
 constexpr int WIN_LD = 52;          // 50 + zero halo on both sides ('same' padding)
-constexpr int FLAT_LD = 404;        // 400 + 4: rows 2 apart land in different banks
+constexpr int FLAT_LDH = 408;       // halves per row of the flattened tile: 816 B rows -> conflict-free ldmatrix
 
 struct CnnSmem {
     float win[CNN_TB][WIN_LD];
     float c1[CNN_TB][WIN_LD][NRV_CNN_CH];
-    float flat[CNN_TB][FLAT_LD];
+    __half fh[CNN_TB][FLAT_LDH];    // flatten(conv stack) as an fp16 (hi, lo) pair: A operand of the tensor-core dense
+    __half fl[CNN_TB][FLAT_LDH];
     float w[264];
 };
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// D(16x8, fp32) += A(16x16, fp16, row) . B(16x8, fp16, col)
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint2& b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
 
 __global__ void __launch_bounds__(CNN_THREADS, 2)
 cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
@@ -77,6 +90,7 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
     for (int i = tid; i < CNN_TB * NRV_SIG; i += CNN_THREADS) {
         const int b = i / NRV_SIG, p = i - b * NRV_SIG;
         const float x0 = s.win[b][p], x1 = s.win[b][p + 1], x2 = s.win[b][p + 2];
+        float o[NRV_CNN_CH];
 #pragma unroll
         for (int c = 0; c < NRV_CNN_CH; ++c) {
             float a = b1[c];
@@ -84,70 +98,103 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
             a = fmaf(x1, w1[8 + c], a);
             a = fmaf(x2, w1[16 + c], a);
             a = fmaxf(a, 0.f);
-            s.c1[b][p + 1][c] = fmaf(a, s1[c], t1[c]);
+            o[c] = fmaf(a, s1[c], t1[c]);
         }
+        *reinterpret_cast<float4*>(&s.c1[b][p + 1][0]) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(&s.c1[b][p + 1][4]) = make_float4(o[4], o[5], o[6], o[7]);
     }
     __syncthreads();
-    // ---- stage C: conv2 + relu + BN2 + Add(input) -> flat[b][pos*8 + ch] -----------------------
-    for (int i = tid; i < CNN_TB * NRV_SIG; i += CNN_THREADS) {
-        const int b = i / NRV_SIG, p = i - b * NRV_SIG;
-        float acc[NRV_CNN_CH];
+    // ---- stage C: conv2 + relu + BN2 + Add(input) -> flat[b][pos*8 + ch] as fp16 (hi, lo) ------
+    // Two positions per thread: every weight broadcast (LDS.128) feeds 8 FMAs and every input row is shared by the two
+    // outputs it touches (one position per thread was shared-memory-bound: 1 LDS per FMA).
+    for (int i = tid; i < CNN_TB * (NRV_SIG / 2); i += CNN_THREADS) {
+        const int b = i / (NRV_SIG / 2), p0 = (i - b * (NRV_SIG / 2)) * 2;
+        float in[4][NRV_CNN_CH];
 #pragma unroll
-        for (int c = 0; c < NRV_CNN_CH; ++c) acc[c] = b2[c];
+        for (int r = 0; r < 4; ++r) {
+            const float4 lo4 = *reinterpret_cast<const float4*>(&s.c1[b][p0 + r][0]);
+            const float4 hi4 = *reinterpret_cast<const float4*>(&s.c1[b][p0 + r][4]);
+            in[r][0] = lo4.x; in[r][1] = lo4.y; in[r][2] = lo4.z; in[r][3] = lo4.w;
+            in[r][4] = hi4.x; in[r][5] = hi4.y; in[r][6] = hi4.z; in[r][7] = hi4.w;
+        }
+        float acc[2][NRV_CNN_CH];
+#pragma unroll
+        for (int c = 0; c < NRV_CNN_CH; ++c) acc[0][c] = acc[1][c] = b2[c];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
 #pragma unroll
             for (int ci = 0; ci < NRV_CNN_CH; ++ci) {
-                const float xv = s.c1[b][p + k][ci];
+                const float4 wa = *reinterpret_cast<const float4*>(w2 + (k * 8 + ci) * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(w2 + (k * 8 + ci) * 8 + 4);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-                for (int co = 0; co < NRV_CNN_CH; ++co) acc[co] = fmaf(xv, w2[(k * 8 + ci) * 8 + co], acc[co]);
+                for (int co = 0; co < NRV_CNN_CH; ++co) {
+                    acc[0][co] = fmaf(in[k][ci], wv[co], acc[0][co]);
+                    acc[1][co] = fmaf(in[k + 1][ci], wv[co], acc[1][co]);
+                }
             }
         }
-        const float xin = s.win[b][p + 1];
 #pragma unroll
-        for (int c = 0; c < NRV_CNN_CH; ++c) {
-            float a = fmaxf(acc[c], 0.f);
-            s.flat[b][p * 8 + c] = fmaf(a, s2[c], t2[c]) + xin;
+        for (int j = 0; j < 2; ++j) {
+            const float xin = s.win[b][p0 + j + 1];
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int c = 0; c < NRV_CNN_CH; c += 2) {
+                const float y0 = fmaf(fmaxf(acc[j][c], 0.f), s2[c], t2[c]) + xin;
+                const float y1 = fmaf(fmaxf(acc[j][c + 1], 0.f), s2[c + 1], t2[c + 1]) + xin;
+                const __half2 h = __floats2half2_rn(y0, y1);
+                const float2 f = __half22float2(h);
+                const __half2 l = __floats2half2_rn(y0 - f.x, y1 - f.y);
+                ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h); pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            *reinterpret_cast<uint4*>(&s.fh[b][(p0 + j) * 8]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(&s.fl[b][(p0 + j) * 8]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
     }
     __syncthreads();
-    // ---- stage D: Dense(400 -> 64) -----------------------------------------------------------
+    // ---- stage D: Dense(400 -> 64) on the tensor cores (mma.sync m16n8k16, 3 split-fp16 passes, fp32 accumulate) ----
+    // warp w owns output columns [8w, 8w + 8) for both 16-row halves of the tile; B fragments come pre-packed from L2.
     {
-        const int tx = tid & 15, ty = tid >> 4;          // 16 column groups x 16 row pairs
-        const int r0 = ty * 2;
-        float acc0[4], acc1[4];
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(W.dense_b) + tx);
-        acc0[0] = acc1[0] = bb.x; acc0[1] = acc1[1] = bb.y; acc0[2] = acc1[2] = bb.z; acc0[3] = acc1[3] = bb.w;
-        const float4* Wd = reinterpret_cast<const float4*>(W.dense_k) + tx;
-#pragma unroll 8
-        for (int k = 0; k < 400; ++k) {
-            const float4 w = __ldg(Wd + k * 16);
-            const float a0 = s.flat[r0][k], a1 = s.flat[r0 + 1][k];
-            acc0[0] = fmaf(a0, w.x, acc0[0]); acc0[1] = fmaf(a0, w.y, acc0[1]);
-            acc0[2] = fmaf(a0, w.z, acc0[2]); acc0[3] = fmaf(a0, w.w, acc0[3]);
-            acc1[0] = fmaf(a1, w.x, acc1[0]); acc1[1] = fmaf(a1, w.y, acc1[1]);
-            acc1[2] = fmaf(a1, w.z, acc1[2]); acc1[3] = fmaf(a1, w.w, acc1[3]);
-        }
-        const int64_t ja = j0 + r0, jb = ja + 1;
-        if (ja < n_bases)
-            reinterpret_cast<float4*>(sig_feat + ja * NRV_SIGFEAT)[tx] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
-        if (jb < n_bases)
-            reinterpret_cast<float4*>(sig_feat + jb * NRV_SIGFEAT)[tx] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
-        if (sf_hi) {   // fp16 (hi, lo) copy: A operand of the tensor-core projection of total_rnn1's per-base part
+        const int warp = tid >> 5, lane = tid & 31;
+        float acc[2][4];
+        const float bias0 = __ldg(W.dense_b + warp * 8 + (lane & 3) * 2), bias1 = __ldg(W.dense_b + warp * 8 + (lane & 3) * 2 + 1);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (ja < n_bases) {
-                    const __half h = __float2half_rn(acc0[c]);
-                    sf_hi[ja * NRV_SIGFEAT + tx * 4 + c] = h;
-                    sf_lo[ja * NRV_SIGFEAT + tx * 4 + c] = __float2half_rn(acc0[c] - __half2float(h));
-                }
-                if (jb < n_bases) {
-                    const __half h = __float2half_rn(acc1[c]);
-                    sf_hi[jb * NRV_SIGFEAT + tx * 4 + c] = h;
-                    sf_lo[jb * NRV_SIGFEAT + tx * 4 + c] = __float2half_rn(acc1[c] - __half2float(h));
-                }
+        for (int mt = 0; mt < 2; ++mt) { acc[mt][0] = acc[mt][2] = bias0; acc[mt][1] = acc[mt][3] = bias1; }
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+        const uint32_t ah0 = (uint32_t)__cvta_generic_to_shared(&s.fh[lrow][lcol]);
+        const uint32_t al0 = (uint32_t)__cvta_generic_to_shared(&s.fl[lrow][lcol]);
+        const uint2* bh = W.dfrag_hi + warp * 32 + lane;
+        const uint2* bl = W.dfrag_lo + warp * 32 + lane;
+#pragma unroll 5
+        for (int kt = 0; kt < 25; ++kt) {
+            const uint2 b_hi = __ldg(bh + kt * 256), b_lo = __ldg(bl + kt * 256);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a_hi[4], a_lo[4];
+                ldmatrix_x4(ah0 + (uint32_t)(mt * 16 * FLAT_LDH + kt * 16) * 2, a_hi);
+                ldmatrix_x4(al0 + (uint32_t)(mt * 16 * FLAT_LDH + kt * 16) * 2, a_lo);
+                mma_16816(acc[mt], a_lo, b_hi);
+                mma_16816(acc[mt], a_hi, b_lo);
+                mma_16816(acc[mt], a_hi, b_hi);
             }
         }
+        const int col = warp * 8 + (lane & 3) * 2;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int64_t j = j0 + mt * 16 + hh * 8 + (lane >> 2);
+                if (j < n_bases) {
+                    const float y0 = acc[mt][hh * 2], y1 = acc[mt][hh * 2 + 1];
+                    *reinterpret_cast<float2*>(sig_feat + j * NRV_SIGFEAT + col) = make_float2(y0, y1);
+                    if (sf_hi) {   // fp16 (hi, lo) copy: A operand of the tensor-core projection of total_rnn1's per-base part
+                        const __half2 h = __floats2half2_rn(y0, y1);
+                        const float2 f = __half22float2(h);
+                        *reinterpret_cast<__half2*>(sf_hi + j * NRV_SIGFEAT + col) = h;
+                        *reinterpret_cast<__half2*>(sf_lo + j * NRV_SIGFEAT + col) = __floats2half2_rn(y0 - f.x, y1 - f.y);
+                    }
+                }
+            }
     }
 }
 
