@@ -369,3 +369,58 @@ def test_stage_timing_api(reviser_by_species, reads):
     assert set(ms) == set(nl) and {"read_stats", "cnn", "rec2", "heads", "decode"} <= set(ms)
     assert sum(nl.values()) <= rv.launch_count - n0 and nl["decode"] == 4 and nl["read_stats"] == 2
     assert all(v >= 0 for v in ms.values()) and ms["rec2"] > 0
+
+
+# --------------------------------------------------------------------------------------------------
+# cfg3 / cfg5 shapes (BASELINE.json configs[2], configs[4]): size-independent properties at full read lengths
+# --------------------------------------------------------------------------------------------------
+def _check_properties(out, b, W, orc):
+    assert out.status.tolist() == [0] * b.n_reads
+    woff = b.win_off(W)
+    np.testing.assert_allclose(out.p1.sum(1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(out.p2.sum(1), 1.0, atol=1e-5)
+    assert np.array_equal(out.y1, out.p1.argmax(1)) and np.array_equal(out.y2, out.p2.argmax(1))
+    for i in range(b.n_reads):
+        src = b.bases[b.base_off[i]:b.base_off[i + 1]].tobytes().decode()
+        seq = out.sequence(i)
+        M = len(src) - W
+        if M <= 0:
+            assert seq == src
+            continue
+        assert seq[:5] == src[:5] and seq[-6:] == src[-6:]                      # pass-through edges (D4)
+        y1 = out.y1[woff[i]:woff[i + 1]].astype(int); y2 = out.y2[woff[i]:woff[i + 1]].astype(int)
+        assert seq == src[:5] + orc.get_base_1(list(src[5:5 + M]), y1, y2 + 2) + src[5 + M:]
+
+
+def test_cfg3_ragged_lognormal_reads_human(reviser_by_species):
+    """cfg3 shape: human weights, LogNormal(9.0935, 0.9) read lengths clipped to [500, 300000] (N50 20 kb): a ragged batch
+    gives, read by read, the same bytes as the reads alone / in another order (independence of the length-balanced shards)."""
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import synth
+    rv = reviser_by_species("human")
+    lens = synth.read_lengths("cfg3", 24, seed=0x5EED)
+    assert lens.min() >= 500 and lens.max() <= 300_000 and len(set(lens.tolist())) > 10
+    b = synth.make_batch(lens, seed=3)
+    out = rv.revise_batch(b, want_labels=True, want_probs=True)
+    _check_properties(out, b, rv.window, orc)
+    order = [int(np.argmax(lens)), int(np.argmin(lens)), 7, 0]
+    sub = rv.revise_batch(synth.split_batch(b, order))
+    assert [sub.sequence(k) for k in range(len(order))] == [out.sequence(i) for i in order]
+
+
+def test_cfg5_long_reads_human(reviser_by_species):
+    """cfg5 shape: 100-300 kb reads (S up to 2.7 M samples: whole-read median/MAD, windows spanning many internal
+    chunks, no O(N*W*50) materialisation).  Properties + the 300 kb read alone == inside the batch."""
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import synth
+    rv = reviser_by_species("human")
+    b = synth.make_batch([300_000, 100_000, 173_211], seed=5)
+    out = rv.revise_batch(b, want_labels=True, want_probs=True)
+    _check_properties(out, b, rv.window, orc)
+    for i in range(3):        # exact whole-read statistics at cfg5 sizes
+        f = b.signal[b.sig_off[i]:b.sig_off[i + 1]].astype(np.float64)
+        sh = np.median(f)
+        shift, scale, *_ = rv.segment(synth.split_batch(b, [i]))
+        assert shift[0] == sh and scale[0] == np.median(np.abs(f - sh))
+    alone = rv.revise_batch(synth.split_batch(b, [0]))
+    assert alone.sequence(0) == out.sequence(0)
