@@ -130,7 +130,9 @@ def cpu_oracle_bases_per_sec(n_reads: int, read_len: int, faithful: bool, seed: 
             M = len(X)
             orc.get_base_1(bases[5:5 + M], P1.argmax(1), P2.argmax(1) + 2)
         else:
-            orc.revise_arrays(m1, m2, bases, starts, length, b.signal[s0:s1], b.ev_mean[b0:b1], b.ev_std[b0:b1])
+            res = orc.revise_arrays(m1, m2, bases, starts, length, b.signal[s0:s1], b.ev_mean[b0:b1], b.ev_std[b0:b1])
+            if i == 0:
+                cpu_oracle_bases_per_sec.last = (b, res["revised"])     # checker for the GPU result on the same read
         total += b1 - b0
     dt = time.perf_counter() - t0
     return total / dt, dt, total
@@ -295,16 +297,16 @@ def main():
         # algorithmic MACs per window and per model of each stage (both directions, 11 timesteps)
         if tc_path:
             macs = {"lstm0": 30_976, "proj1": 180_224, "rec1": 360_448, "proj2": 2_162_688, "rec2": 1_441_792,
-                    "proj3": 1_441_792, "rec3": 360_448, "heads_gemm": 180_224, "heads": 48_320}
-            names = {"proj2": "gemm_f16x3_kernel<256> (total_rnn1 input projection, tcgen05 3-pass split-fp16)",
+                    "proj3": 1_441_792, "rec3": 360_448, "heads_gemm": 225_280, "heads": 3_264}
+            names = {"proj2": "gemm_f16x3_pair_kernel (total_rnn1 input projection, tcgen05 cta_group::2, 3-pass split-fp16)",
                      "rec2": "lstm_rec_tc128_pair_kernel (total_rnn1 recurrence, tcgen05 cta_group::2)",
-                     "proj3": "gemm_f16x3_kernel<256> (total_rnn2 input projection, tcgen05)",
+                     "proj3": "gemm_f16x3_pair_kernel (total_rnn2 input projection, tcgen05 cta_group::2)",
                      "rec3": "lstm_rec_tc64_kernel (total_rnn2 recurrence, tcgen05)",
                      "proj1": "gemm_f16x3_kernel<256> (read_rnn11 input projection, tcgen05)",
                      "rec1": "lstm_fused_tc64_kernel (read_rnn11 projection+recurrence, tcgen05)",
                      "heads_gemm": "gemm_f16x3_kernel<128,FUSE2> (dense head 128->128->32, tcgen05)",
-                     "heads": "heads_tail_kernel (dense 32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
-                     "lstm0": "lstm_layer_kernel<0,6,16,...> (read_rnn1, fp32 SIMT)"}
+                     "heads": "heads_tail_thread_kernel (dense 32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
+                     "lstm0": "read_rnn1_kernel (read_rnn1, fp32 SIMT, one thread per window pair)"}
         else:
             macs = {"lstm0": 30_976, "rec1": 540_672, "rec2": 3_604_480, "rec3": 1_802_240, "heads": 228_544}
             names = {k: "lstm_layer_kernel (fp32 SIMT, fused projection+recurrence)" for k in macs}
@@ -366,6 +368,12 @@ def main():
             v, dt, nb = cpu_oracle_bases_per_sec(nreads, READ_LEN, False)
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": "%d synthetic cfg2 read(s) x %d bases (%.1f s), batched oracle (CNN once per base)" % (nreads, READ_LEN, dt)}
+            # the oracle as the checker: the CUDA path must give the same revised bytes on the read the CPU just timed
+            sb, want = cpu_oracle_bases_per_sec.last
+            got = rv.revise_batch(synth.split_batch(sb, [0])).sequence(0)
+            cpu["gpu_matches_oracle_on_sample"] = bool(got == want)
+            if got != want:
+                raise SystemExit("bench.py: CUDA result differs from the CPU oracle on the sampled read -- number withheld")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
