@@ -30,6 +30,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # the reference arm uses every host core; torchrun exports OMP_NUM_THREADS=1, which would pin the BLAS to one thread
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -363,7 +368,7 @@ def main():
         whole = {"achieved_tflops": FLOP_PER_BASE * value / world / 1e12, "frac_of_bf16_sustained":
                  FLOP_PER_BASE * value / world / 1e12 / peak}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # rank 0 at N = 1 only
             nreads = max(1, args.cpu_sample_bases // READ_LEN)
             v, dt, nb = cpu_oracle_bases_per_sec(nreads, READ_LEN, False)
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
