@@ -21,6 +21,8 @@ import time
 from concurrent.futures import ThreadPoolExecutor
 from optparse import OptionParser
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -58,6 +60,8 @@ def get_args(argv=None):
                          help='comma separated CUDA device ids; reads are sharded over them (no collectives)')
     optParser.add_option('--batch-bases', action='store', type="int", dest='batch_bases', default=2_000_000,
                          help='ragged batch budget (bases per GPU launch)')
+    optParser.add_option('--ingest', action='store', type="string", dest='ingest', default='native',
+                         help='fast5 reader: native (C++ threads, default) or python')
     (tmp_args, _) = optParser.parse_args(argv)
     if tmp_args.virsion:
         print("The virsion of NanoReviser : 1.0 ")
@@ -104,57 +108,81 @@ def _write_read(args, fn_sg, bases, qul=None):
 
 
 def run_worker(args, file_list, device, logger=None):
-    """One GPU: ingest with host threads, ragged batches by base budget, revise, write."""
-    from nanoreviser_b200 import api, engine, fast5, weights, workqueue
+    """One GPU: native multi-threaded ingest (C++, include/nrv.h nrv_ingest_fast5) slab by slab -> ragged batches by base
+    budget -> revise -> write.  Files the native reader does not cover or cannot read go through the Python reader, which
+    follows the reference branch by branch and produces its error messages."""
+    from nanoreviser_b200 import api, engine, fast5, synth, weights, workqueue
     m1 = weights.load_model_weights(args.model1_predict_dir)
     m2 = weights.load_model_weights(args.model2_predict_dir)
-    n_ok = n_fallback = n_failed = 0
+    counts = {'ok': 0, 'fallback': 0, 'failed': 0}
     failed = []
-    with engine.Reviser(m1, m2, device=device) as rv:
-        nthreads = max(1, min(int(args.thread), os.cpu_count() or 4, 32))
-        with ThreadPoolExecutor(max_workers=nthreads) as ex:
-            loaded = list(ex.map(lambda f: _ingest(args, f), file_list))
-        good = []
-        for fn_sg, r, err in loaded:
-            if r is None:
-                print('！！！[Error] fast5 file: ' + fn_sg.split('.')[0] + str(err))
-                failed.append(fn_sg)
-                n_failed += 1
-                if logger:
-                    logger.error('[!!! Error] Basecalling')
+    nthreads = max(1, min(int(args.thread), os.cpu_count() or 4, 32))
+    native = getattr(args, 'ingest', 'native') == 'native'
+    slab_files = 512
+
+    def emit(fn_sg, ok, seq_bytes, orig_bases):
+        try:
+            if ok:
+                seq = seq_bytes.decode() if isinstance(seq_bytes, (bytes, bytearray)) else seq_bytes
+                qul = 'I' * len(seq) if args.output_format == 'fastq' else None   # D6: provisional
+                _write_read(args, fn_sg, list(seq), qul)
+                counts['ok'] += 1
             else:
-                good.append((fn_sg, r))
-        lengths = [r.n_bases for _, r in good]
-        for batch in workqueue.make_batches(range(len(good)), lengths, int(args.batch_bases)):
-            reads = [good[i][1] for i in batch]
-            out = api.revise_reads(reads, reviser=rv)
-            for k, i in enumerate(batch):
-                fn_sg, r = good[i]
-                try:
-                    if out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT):
-                        seq = out.sequence(k)
-                        qul = 'I' * len(seq) if args.output_format == 'fastq' else None   # D6: provisional
-                        _write_read(args, fn_sg, list(seq), qul)
-                        n_ok += 1
-                    else:
-                        # fallback to the un-revised read (NanoReviser.py:146-154 / :172-181)
-                        if args.output_format == 'fasta':
-                            _write_read(args, fn_sg, [chr(c) for c in r.bases])
-                        else:
-                            seq, qul = fast5.extract_fastq(os.path.join(args.fast5_base_dir, fn_sg), None)
-                            _write_read(args, fn_sg, list(seq), list(qul))
-                        n_fallback += 1
+                # fallback to the un-revised read (NanoReviser.py:146-154 / :172-181)
+                if args.output_format == 'fasta':
+                    _write_read(args, fn_sg, [chr(c) for c in orig_bases])
+                else:
+                    seq, qul = fast5.extract_fastq(os.path.join(args.fast5_base_dir, fn_sg), None)
+                    _write_read(args, fn_sg, list(seq), list(qul))
+                counts['fallback'] += 1
+                failed.append(fn_sg)
+            if logger:
+                logger.info("Congratulations, NanoReviser is installed properly")
+            elif not args.test_mode:
+                print('[p:::] ' + fn_sg.split('.')[0] + '_out.' + args.output_format + ' was saved......')
+        except Exception as e:
+            print('[！！！Error] stroring : ' + fn_sg.split('.')[0] + ' ' + str(e))
+            failed.append(fn_sg)
+            if logger:
+                logger.error('[!!! Error] Basecalling')
+
+    with engine.Reviser(m1, m2, device=device) as rv:
+        for s0 in range(0, len(file_list), slab_files):
+            slab = file_list[s0:s0 + slab_files]
+            todo_python = list(slab)
+            if native:
+                paths = [os.path.join(args.fast5_base_dir, f) for f in slab]
+                batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
+                todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
+                lengths = np.diff(batch.base_off).tolist()
+                for idx in workqueue.make_batches(range(batch.n_reads), lengths, int(args.batch_bases)):
+                    sub = batch if len(idx) == batch.n_reads else synth.split_batch(batch, idx)
+                    out = rv.revise_batch(sub)
+                    for k, i in enumerate(idx):
+                        ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
+                        emit(slab[int(read_file[i])], ok, out.revised[out.out_off[k]:out.out_off[k + 1]].tobytes(),
+                             batch.bases[batch.base_off[i]:batch.base_off[i + 1]])
+            if todo_python:
+                with ThreadPoolExecutor(max_workers=nthreads) as ex:
+                    loaded = list(ex.map(lambda f: _ingest(args, f), todo_python))
+                good = []
+                for fn_sg, r, err in loaded:
+                    if r is None:
+                        print('！！！[Error] fast5 file: ' + fn_sg.split('.')[0] + str(err))
                         failed.append(fn_sg)
-                    if logger:
-                        logger.info("Congratulations, NanoReviser is installed properly")
-                    elif not args.test_mode:
-                        print('[p:::] ' + fn_sg.split('.')[0] + '_out.' + args.output_format + ' was saved......')
-                except Exception as e:
-                    print('[！！！Error] stroring : ' + fn_sg.split('.')[0] + ' ' + str(e))
-                    failed.append(fn_sg)
-                    if logger:
-                        logger.error('[!!! Error] Basecalling')
-    return n_ok, n_fallback, n_failed, failed
+                        counts['failed'] += 1
+                        if logger:
+                            logger.error('[!!! Error] Basecalling')
+                    else:
+                        good.append((fn_sg, r))
+                lengths = [r.n_bases for _, r in good]
+                for idx in workqueue.make_batches(range(len(good)), lengths, int(args.batch_bases)):
+                    out = api.revise_reads([good[i][1] for i in idx], reviser=rv)
+                    for k, i in enumerate(idx):
+                        fn_sg, r = good[i]
+                        ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
+                        emit(fn_sg, ok, out.sequence(k), r.bases)
+    return counts['ok'], counts['fallback'], counts['failed'], failed
 
 
 def _worker_entry(payload):

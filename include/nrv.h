@@ -171,6 +171,32 @@ int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r);
  * N must be a multiple of 256 and K a multiple of 64. */
 int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const float* Bt, const float* bias, float* C);
 
+/* ---- A1 at GPU rate: multi-threaded native fast5 ingest ----------------------------
+ * Replaces get_read_data(fast5_fn, basecall_group, basecall_subgroup) (nanorev_fast5_handeler.py:39-150) for a LIST of
+ * single-read fast5 files: own HDF5-subset reader + zlib inflate + event collapse (:84-118) on n_threads host threads
+ * (0 = all cores), packing the reads that succeed straight into the CSR batch above (signal = raw[a0:], NanoReviser.py:120).
+ * Host-only (no CUDA call).  Per-file status mirrors the exceptions of the reference; NRV_INGEST_UNSUPPORTED marks inputs
+ * outside the native subset (Albacore <= 0.0 event tables :65-72, float starts, non-deflate filters, multi-read files),
+ * which the caller must route through the Python reader (nanoreviser_b200/fast5.py) -- nothing is guessed. */
+#define NRV_INGEST_OK            0
+#define NRV_INGEST_OPEN_FAILED   1   /* "Error opening file. Likely a corrupted file." (:59-61) */
+#define NRV_INGEST_NO_EVENTS     2   /* "No events or corrupted events in file" (:76-77) */
+#define NRV_INGEST_TOO_SHORT     3   /* "Events is too short or there are too much zero moves" (:127-128) */
+#define NRV_INGEST_NO_SIGNAL     4   /* "No signal stored in the file" (:134-135) */
+#define NRV_INGEST_SIGNAL_SHORT  5   /* "Signal is shorter than the Events" (:142-143) */
+#define NRV_INGEST_CORRUPT       6   /* structurally invalid HDF5 inside the supported subset */
+#define NRV_INGEST_UNSUPPORTED   7   /* valid but outside the native subset: use the Python reader */
+
+typedef struct nrv_ingest nrv_ingest;   /* owns the packed host arrays */
+
+int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* basecall_group, const char* basecall_subgroup,
+                     int n_threads, nrv_ingest** out);
+/* Views into the result, valid until nrv_ingest_free: the batch of the reads that succeeded (in file order),
+ * file_status[n_files], read_file[n_reads] (index into paths of every packed read), a0[n_reads] (abs_event_start). */
+int nrv_ingest_view(const nrv_ingest* r, nrv_batch* batch, const int32_t** file_status, const int64_t** read_file,
+                    const int64_t** a0);
+void nrv_ingest_free(nrv_ingest* r);
+
 #ifdef __cplusplus
 }
 #endif

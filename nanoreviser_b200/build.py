@@ -16,7 +16,8 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libnrv.so")
 
-SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_api.cu"]
+SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_api.cu",
+           "nrv_ingest.cpp"]       # host-only C++ (native fast5 ingest); links zlib
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo"] + os.environ.get("NRV_EXTRA_NVCC", "").split() + [ "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -43,7 +44,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         if force or _stale(o, [s] + headers):
             cmd = [nvcc] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append((src, cmd))
@@ -60,9 +61,9 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
                     sys.stderr.write("[nvcc %s]\n%s\n" % (name, out))
                 if rc != 0:
                     raise RuntimeError("nvcc failed on %s" % name)
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(OBJ, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-lz"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)

@@ -57,7 +57,8 @@ class _Result(C.Structure):
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
            "nrv_stage_count", "nrv_stage_name", "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
-           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_debug_gemm")
+           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_debug_gemm",
+           "nrv_ingest_fast5", "nrv_ingest_view", "nrv_ingest_free")
 
 _lib = None
 
@@ -109,9 +110,55 @@ def load_library(path: Optional[str] = None):
     lib.nrv_revise_batch_device.restype = C.c_int
     lib.nrv_debug_gemm.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.nrv_debug_gemm.restype = C.c_int
+    lib.nrv_ingest_fast5.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.nrv_ingest_fast5.restype = C.c_int
+    lib.nrv_ingest_view.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.nrv_ingest_view.restype = C.c_int
+    lib.nrv_ingest_free.argtypes = [vp]
+    lib.nrv_ingest_free.restype = None
     if path is None:
         _lib = lib
     return lib
+
+
+INGEST_OK, INGEST_OPEN_FAILED, INGEST_NO_EVENTS, INGEST_TOO_SHORT, INGEST_NO_SIGNAL, INGEST_SIGNAL_SHORT, INGEST_CORRUPT, \
+    INGEST_UNSUPPORTED = range(8)
+
+
+def ingest_fast5(paths: Sequence[str], basecall_group: str = "Basecall_1D_000", basecall_subgroup: str = "BaseCalled_template",
+                 threads: int = 0):
+    """Native multi-threaded ``get_read_data`` over a list of single-read fast5 files (include/nrv.h: nrv_ingest_fast5).
+
+    -> ``(batch, file_status int32[n_files], read_file int64[n_reads], a0 int64[n_reads])``: ``batch`` holds the reads whose
+    status is 0, in file order; the arrays are copies owned by numpy.  Host-only: works without a GPU."""
+    lib = load_library()
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    h = C.c_void_p()
+    rc = lib.nrv_ingest_fast5(arr, n, basecall_group.encode(), basecall_subgroup.encode(), int(threads), C.byref(h))
+    if rc != 0:
+        raise NrvError("nrv_ingest_fast5 failed (%d)" % rc)
+    try:
+        cb = _Batch()
+        fs, rf, a0 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = lib.nrv_ingest_view(h, C.byref(cb), C.byref(fs), C.byref(rf), C.byref(a0))
+        if rc != 0:
+            raise NrvError("nrv_ingest_view failed (%d)" % rc)
+        R = int(cb.n_reads)
+
+        def view(ptr, count, dt):
+            if count == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+        sig_off = view(cb.sig_off, R + 1, np.int64)
+        base_off = view(cb.base_off, R + 1, np.int64)
+        nb, ns = int(base_off[-1]), int(sig_off[-1])
+        batch = Batch(view(cb.signal, ns, np.int16), sig_off, view(cb.starts, nb, np.int32), base_off,
+                      view(cb.bases, nb, np.uint8), view(cb.ev_mean, nb, np.float32), view(cb.ev_std, nb, np.float32),
+                      view(cb.last_dur, R, np.int32))
+        return batch, view(fs.value, n, np.int32), view(rf.value, R, np.int64), view(a0.value, R, np.int64)
+    finally:
+        lib.nrv_ingest_free(h)
 
 
 def _ptr(a) -> Optional[int]:
