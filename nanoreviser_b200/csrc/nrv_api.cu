@@ -69,6 +69,7 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
+    int trnn2_fused = 1;    // total_rnn2 as one fused CTA-pair kernel (h in TMEM); NRV_TRNN2=split selects GEMM + recurrence
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
@@ -440,7 +441,14 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
                     h->launches += n;
                 }
-                {   // total_rnn2: projection (K = 256), recurrence (u = 64)
+                if (h->trnn2_fused) {
+                    // total_rnn2: projection (K = 256) and recurrence (u = 64) fused on CTA pairs, h in tensor memory -- no zin
+                    StageTimer tm(h, ST_REC3);
+                    LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
+                    n = launch_lstm_fused_tc64_pair(M.lstm[3], a3h, a3l, io, nwp, nw, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn2) could not be launched");
+                    h->launches += n;
+                } else {   // total_rnn2: projection (K = 256), recurrence (u = 64)
                     {
                         StageTimer tm(h, ST_PROJ3);
                         n = launch_gemm_f16x3(a3h, a3l, M.lstm[3].pb_hi, M.lstm[3].pb_lo, R, 512, 256, zin, M.lstm[3].bias_tc, 1,
@@ -703,6 +711,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (ch && atoll(ch) > 0) h->chunk_windows = atoll(ch);
     const char* pa = getenv("NRV_PATH");
     if (pa && !strcmp(pa, "simt")) h->path = 0;
+    const char* t2 = getenv("NRV_TRNN2");
+    if (t2 && !strcmp(t2, "split")) h->trnn2_fused = 0;
     const char* r128 = getenv("NRV_REC128");
     if (r128 && !strcmp(r128, "single")) h->rec128_pair = 0;
     h->num_sms = prop.multiProcessorCount;

@@ -112,6 +112,8 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                            cudaStream_t st);
 int launch_read_rnn1(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
+int launch_lstm_fused_tc64_pair(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int64_t n_win,
+                                int T, cudaStream_t st);
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 

@@ -245,6 +245,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+// ---- A operand from TMEM (".ts" form), verified by tools/ts_probe: a 16-bit A tile lives in TMEM as lane = row,
+// 32-bit column c = the fp16 pair (k = 2c in the low half, k = 2c + 1 in the high half); one K = 16 step = 8 columns.
+// With cta_group::2 every CTA supplies its own 128 rows from its own TMEM at the same address.
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// this thread's lane, 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // ---- split-precision helpers ---------------------------------------------------------------------
 // x = hi + lo with hi, lo fp16 (22 significant bits); three fp16 MMAs  hi*hi + lo*hi + hi*lo  with fp32
 // accumulation reproduce an fp32 contraction to ~2^-22 relative.
