@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libnrv.so")
 
-SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_api.cu",
+SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_fused_pair.cu", "nrv_api.cu",
            "nrv_ingest.cpp"]       # host-only C++ (native fast5 ingest); links zlib
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo"] + os.environ.get("NRV_EXTRA_NVCC", "").split() + [ "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

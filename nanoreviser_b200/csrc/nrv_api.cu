@@ -69,7 +69,9 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
-    int trnn2_fused = 1;    // total_rnn2 as one fused CTA-pair kernel (h in TMEM); NRV_TRNN2=split selects GEMM + recurrence
+    int trnn2_fused = 2;    // total_rnn2: 2 = fused CTA-pair kernel with drained accumulator (nrv_fused_pair.cu); 1 = first fused version
+                            // (NRV_TRNN2=v1); 0 = GEMM + recurrence (NRV_TRNN2=split)
+    int trnn1_fused = 0;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu, NRV_TRNN1=fused); 0 = GEMM + recurrence
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
@@ -429,6 +431,14 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
                         h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
                     h->launches += 1;
+                    if (h->trnn1_fused) {
+                        delete tp;
+                        StageTimer tm(h, ST_REC2);
+                        LstmIo io; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
+                        n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
+                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn1) could not be launched");
+                        h->launches += n;
+                    } else {
                     n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, R, 1024, 192, zin, M.lstm[2].bias_tc,
                                           1, T, nwp, 512, 0, h->num_sms, h->stream);
                     if (n >= 0) h->launches += n;
@@ -440,8 +450,15 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                                        : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
                     h->launches += n;
+                    }
                 }
-                if (h->trnn2_fused) {
+                if (h->trnn2_fused == 2) {
+                    StageTimer tm(h, ST_REC3);
+                    LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
+                    n = launch_lstm_fused_pair64(M.lstm[3], a3h, a3l, io, nwp, T, h->num_sms, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn2) could not be launched");
+                    h->launches += n;
+                } else if (h->trnn2_fused) {
                     // total_rnn2: projection (K = 256) and recurrence (u = 64) fused on CTA pairs, h in tensor memory -- no zin
                     StageTimer tm(h, ST_REC3);
                     LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
@@ -713,6 +730,10 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (pa && !strcmp(pa, "simt")) h->path = 0;
     const char* t2 = getenv("NRV_TRNN2");
     if (t2 && !strcmp(t2, "split")) h->trnn2_fused = 0;
+    if (t2 && !strcmp(t2, "v1")) h->trnn2_fused = 1;
+    const char* t1 = getenv("NRV_TRNN1");
+    if (t1 && !strcmp(t1, "split")) h->trnn1_fused = 0;
+    if (t1 && !strcmp(t1, "fused")) h->trnn1_fused = 1;
     const char* r128 = getenv("NRV_REC128");
     if (r128 && !strcmp(r128, "single")) h->rec128_pair = 0;
     h->num_sms = prop.multiProcessorCount;
