@@ -71,7 +71,7 @@ struct nrv_handle {
     int num_sms = 148;
     int trnn2_fused = 2;    // total_rnn2: 2 = fused CTA-pair kernel with drained accumulator (nrv_fused_pair.cu); 1 = first fused version
                             // (NRV_TRNN2=v1); 0 = GEMM + recurrence (NRV_TRNN2=split)
-    int trnn1_fused = 0;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu, NRV_TRNN1=fused); 0 = GEMM + recurrence
+    int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().

@@ -23,9 +23,12 @@
 // projection MMAs of the next step (which need no h) start right then and run under the gate arithmetic; `h_ready`
 // releases the recurrent MMAs.  x_t is read exactly once; the tensor pipe only idles during the drain.
 //
-// total_rnn1's exchange goes through the layer's own output: each thread stores its 16 units of h_t to the activation
-// tensor (which the next layer needs anyway), fences, and arrives on the sibling CTA's `xfull` barrier; the sibling thread
-// that owns the same window reads the peer's 16 units back (L2) and tcgen05.st's them into its TMEM.  No shared memory.
+// total_rnn1's exchange: the thread that owns window w in pair p and the thread that owns w in pair 1-p (the "sibling" CTA)
+// swap their 16 units of h_t in two blocks of 8: st.async puts 2 x 16 B straight from registers into a 16 KB landing zone of
+// the sibling's shared memory and counts the bytes on the sibling WARP's mbarrier (no fences, no global round trip); the
+// receiver copies its 32 B into TMEM and releases the zone with a remote arrive.  Block 0 travels under the arithmetic of
+// block 1.  (First version: through the layer output in L2 with __threadfence + acquire.cluster -- 12 us per step.)
+// The landing zone costs one ring stage (3 x 16 KB instead of 4).
 #include <algorithm>
 
 #include "nrv_cell.cuh"
@@ -41,14 +44,17 @@ bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, i
 constexpr int FP_EPI_WARPS = 16;                      // 4 per TMEM lane quarter; 16 units (64 gate columns) per thread
 constexpr int FP_THREADS = 64 + 32 * FP_EPI_WARPS;    // warp 0: MMA issue (pair leader); warp 1: TMA producer; warps 2..17: epilogue
 constexpr int FP_TILE = 128 * 64 * 2;                 // 16 KB: [128 rows][64 halves], K-major, 128-byte swizzle
-constexpr int FP_STAGES = 4;
-constexpr uint32_t FP_H_COL = 256;                    // TMEM: accumulator [0, 256); h_hi [256, 256 + UT/2); h_lo [.., 256 + UT)
+constexpr int FP_XCH_BYTES = 16 * 1024;             // total_rnn1: landing zone of the sibling pair's h (one 8-unit block per thread, hi + lo)
+constexpr uint32_t FP_H_COL = 384;                    // TMEM: accumulator block 0 [0, 128); block 1 [128, 256) on even steps, [256, 384) on
+                                                      // odd steps; h_hi [384, 384 + UT/2); h_lo [.., 384 + UT)
 
 template <int KIN, int UT>
 struct FpCfg {
     static constexpr int KC = KIN / 64, RC = UT / 64, NP = UT / 64;
     static constexpr int W_BYTES = (KC + RC) * 2 * FP_TILE;
-    static constexpr size_t SMEM = (size_t)W_BYTES + FP_STAGES * FP_TILE + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+    static constexpr int STAGES = NP == 1 ? 4 : 3;                   // x ring depth (16 KB tiles)
+    static constexpr int XCH = NP == 1 ? 0 : FP_XCH_BYTES;
+    static constexpr size_t SMEM = (size_t)W_BYTES + STAGES * FP_TILE + XCH + 1024 /*bias*/ + 512 /*barriers*/ + 1024 /*alignment*/;
 };
 
 __device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
@@ -57,6 +63,15 @@ __device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+#ifdef NRV_TRACE
+// timeline of cluster 0 / direction 0 (debug builds: NRV_EXTRA_NVCC=-DNRV_TRACE): SM clock at key events of the MMA warp (role 0)
+// and of the first epilogue warp (role 1), printed by the 4th launch of each instantiation
+__device__ long long g_tr[2][2][128][8];
+__device__ int g_tr_launch[2];
+#define TR(role, step, ev) do { if (trace_on && (threadIdx.x & 31) == 0 && (step) < 128) g_tr[UT == 128][role][step][ev] = clock64() - tr_t0; } while (0)
+#else
+#define TR(role, step, ev) do { } while (0)
+#endif
 #ifdef NRV_HANG_DEBUG
 // bounded spin: report which barrier / role / step is stuck and trap (debug builds only: NRV_EXTRA_NVCC=-DNRV_HANG_DEBUG)
 template <bool CL>
@@ -84,26 +99,42 @@ __device__ __forceinline__ void fp_wait_dbg(uint64_t* bar, uint32_t parity, int 
 #define FP_WAIT(bar, parity, tag, g) mbar_wait(bar, parity)
 #define FP_WAIT_CL(bar, parity, tag, g) mbar_wait_cluster(bar, parity)
 #endif
-__device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
+// 2-D tile -> L2 only (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+// 16 bytes from registers into another CTA's shared memory; the bytes are counted on that CTA's mbarrier (complete_tx)
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, const uint4& v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(remote_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+                 : "memory");
 }
 
-// One 32-column block (8 units) of the cell with the bias read from shared memory unit by unit (keeps the 64 drained
-// accumulator registers + 16 cell states close to the 96-register budget of a 576-thread CTA: warps are allocated in fours, so 20 x 32 x 96).
-__device__ __forceinline__ void cell_block_bias(const uint32_t (&v)[32], uint32_t sbias, float* c8, uint4& phi, uint4& plo) {
-    float hv[8];
+// Units [J0, J1) of one 32-column block (8 units x gates i,f,c,o) of the cell; the bias is read from shared memory unit by
+// unit (keeps the 64 drained accumulator registers + 16 cell states close to the 96-register budget of a 576-thread CTA:
+// warps are allocated in fours, so 20 x 32 x 96 registers).
+template <int J0, int J1>
+__device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbias, float* c8, float* hv) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 b = ld_shared_f4(sbias + j * 16);
-        const float zi = b.x + __uint_as_float(v[4 * j + 0]), zf = b.y + __uint_as_float(v[4 * j + 1]);
-        const float zc = b.z + __uint_as_float(v[4 * j + 2]), zo = b.w + __uint_as_float(v[4 * j + 3]);
-        const float ig = hsig(zi), fg = hsig(zf), gg = tanh_fast(zc), og = hsig(zo);
+    for (int j = J0; j < J1; ++j) {
+        const float4 b = ld_shared_f4(sbias + j * 16);       // {0.2 b_i + 0.5, 0.2 b_f + 0.5, b_c, 0.2 b_o + 0.5}
+        const float ig = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 0]), b.x));
+        const float fg = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 1]), b.y));
+        const float gg = tanh_fast(b.z + __uint_as_float(v[4 * j + 2]));
+        const float og = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 3]), b.w));
         const float cn = fmaf(fg, c8[j], ig * gg);
         c8[j] = cn;
         hv[j] = og * tanh_fast(cn);
     }
+}
+// h = hi + lo as fp16 pairs (packed conversions, ALU pipe)
+__device__ __forceinline__ void pack_h8(const float* hv, uint4& phi, uint4& plo) {
     uint32_t ph[4], pl[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -123,24 +154,31 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                        const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                        __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int T) {
     using Cfg = FpCfg<KIN, UT>;
-    constexpr int KC = Cfg::KC, NP = Cfg::NP, CS = 2 * NP;
+    constexpr int KC = Cfg::KC, NP = Cfg::NP, CS = 2 * NP, FP_STAGES = Cfg::STAGES;
     constexpr int NT = 4 * UT;                              // gate columns per direction
     constexpr uint32_t H_HI = FP_H_COL, H_LO = FP_H_COL + UT / 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;                                    // [Wk chunk 0..KC-1 | Wr chunk 0..RC-1][hi | lo][128 rows][64]
     uint8_t* s_ring = smem + Cfg::W_BYTES;                  // [stage][128 rows][64]
-    float* s_bias = reinterpret_cast<float*>(s_ring + FP_STAGES * FP_TILE);    // [256]: this pair's gate columns
+    uint8_t* s_xch = s_ring + FP_STAGES * FP_TILE;          // NP == 2: [cg][hi | lo][128 rows] x 16 B, written by the sibling CTA (st.async)
+    float* s_bias = reinterpret_cast<float*>(s_xch + Cfg::XCH);               // [256]: this pair's gate columns
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-    uint64_t* full = bars;                                  // [4] pair leader's copy: 1 arrive + 32 KB tx (both CTAs' tiles)
-    uint64_t* empty = bars + FP_STAGES;                     // [4] both CTAs of the pair: multicast commit
+    uint64_t* full = bars;                                  // [STAGES] pair leader's copy: 1 arrive + 32 KB tx (both CTAs' tiles)
+    uint64_t* empty = bars + FP_STAGES;                     // [STAGES] both CTAs of the pair: multicast commit
     uint64_t* acc_ready = bars + 2 * FP_STAGES;             // both CTAs of the pair: multicast commit
     uint64_t* drained = acc_ready + 1;                      // pair leader's copy: 32 arrivals (16 epilogue warps x 2 CTAs)
-    uint64_t* h_ready = acc_ready + 2;                      // pair leader's copy: 32 arrivals
-    uint64_t* xfull = acc_ready + 3;                        // NP == 2: 16 arrivals from the sibling CTA (other pair, same windows)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 4);
+    uint64_t* hq = acc_ready + 2;                           // [4] pair leader's copy, 32 arrivals each: quarter (b, who) of h_t is in
+                                                            // TMEM in both CTAs; b = unit block 0/1, who = 0 own pair's units, 1 sibling's
+    uint64_t* xfull = acc_ready + 6;                        // NP == 2: [16] per epilogue warp: 1 arrive.expect_tx + 1 KB from the sibling warp
+    uint64_t* xfree = xfull + FP_EPI_WARPS;                 // NP == 2: [16] per epilogue warp: the sibling warp has read our block
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + FP_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef NRV_TRACE
+    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0;
+    const long long tr_t0 = clock64();
+#endif
     const uint32_t rank = cluster_ctarank();
     const uint32_t p = rank >> 1, r = rank & 1, leader = rank & ~1u;
     const int dir = blockIdx.y;
@@ -152,25 +190,30 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         for (int i = 0; i < FP_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_ready, 1);
         mbar_init(drained, 2 * FP_EPI_WARPS);
-        mbar_init(h_ready, 2 * FP_EPI_WARPS);
-        mbar_init(xfull, FP_EPI_WARPS);
+        for (int i = 0; i < 4; ++i) mbar_init(&hq[i], 2 * FP_EPI_WARPS);
+        for (int i = 0; i < FP_EPI_WARPS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo);
     }
     if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
-    if (threadIdx.x < 256) s_bias[threadIdx.x] = __ldg(bias + dir * NT + p * 256 + threadIdx.x);
-    {   // resident weights: this CTA's 128 gate columns (global rows dir*NT + p*256 + r*128 + row), all of K, hi and lo
-        const size_t grow0 = (size_t)dir * NT + p * 256 + r * 128;
+    if (threadIdx.x < 256) {       // hard_sigmoid(z + b) = sat(0.2 z + (0.2 b + 0.5)): the gates i, f, o keep the folded constant
+        const float b = __ldg(bias + dir * NT + p * 256 + threadIdx.x);
+        s_bias[threadIdx.x] = (threadIdx.x & 3) == 2 ? b : fmaf(0.2f, b, 0.5f);
+    }
+    {   // resident weights: this CTA's 128 gate columns, all of K, hi and lo.  Shared-memory row b*64 + j = gate column
+        // b*128 + r*64 + j of the pair: an N = 128 MMA on unit block b takes rows [b*64, +64) from each CTA of the pair
+        const size_t grow0 = (size_t)dir * NT + p * 256 + r * 64;
+        auto gcol = [](int row) { return (row >> 6) * 128 + (row & 63); };
         constexpr int CK = KIN / 8, CR = UT / 8;            // 16-byte chunks per row
         for (int i = threadIdx.x; i < 2 * 128 * CK; i += FP_THREADS) {
             const int c = i % CK, row = (i / CK) & 127, part = i / (CK * 128);
-            const __half* src = (part ? wk_lo : wk_hi) + (grow0 + row) * KIN;
+            const __half* src = (part ? wk_lo : wk_hi) + (grow0 + gcol(row)) * KIN;
             *reinterpret_cast<uint4*>(s_w + (size_t)((c >> 3) * 2 + part) * FP_TILE + sw128_offset(row, c & 7)) =
                 __ldg(reinterpret_cast<const uint4*>(src) + c);
         }
         for (int i = threadIdx.x; i < 2 * 128 * CR; i += FP_THREADS) {
             const int c = i % CR, row = (i / CR) & 127, part = i / (CR * 128);
-            const __half* src = (part ? wr_lo : wr_hi) + (grow0 + row) * UT;
+            const __half* src = (part ? wr_lo : wr_hi) + (grow0 + gcol(row)) * UT;
             *reinterpret_cast<uint4*>(s_w + (size_t)((KC + (c >> 3)) * 2 + part) * FP_TILE + sw128_offset(row, c & 7)) =
                 __ldg(reinterpret_cast<const uint4*>(src) + c);
         }
@@ -191,6 +234,10 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 for (int s = 0; s < T; ++s) {
                     const int t = dir ? (T - 1 - s) : s;
                     const int grow = (int)(t * nwp + wtile * 128);
+                    if (s + 1 < T) {                                       // next step's tiles -> L2 (the layer input comes from HBM: ring
+                        const int gnext = grow + (dir ? -1 : 1) * (int)nwp;   // loads then see L2 latency, which 3-4 stages cover)
+                        for (int i = 0; i < KC; ++i) { tma_prefetch_2d(&tm_x_lo, i * 64, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                    }
                     for (int i = 0; i < 2 * KC; ++i) {                     // (K-chunk, part): lo tile first, then hi
                         FP_WAIT(&empty[stage], phase ^ 1, 1, (uint32_t)s);
                         if (r == 0) mbar_arrive_expect_tx(&full[stage], 2 * FP_TILE);
@@ -204,7 +251,8 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     } else if (warp == 0) {
         // ===================== MMA issue (leader CTA of every pair) =====================
         if (r == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
+            constexpr uint32_t idesc = umma_idesc_f16_f32(256, 128);     // one MMA = 256 windows x one unit block (128 gate columns)
+            constexpr uint32_t BB = 64 * 128;                           // byte offset of block 1's weight rows inside a tile
             const uint16_t mask = (uint16_t)(3u << leader);
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
             int stage = 0; uint32_t phase = 0;
@@ -215,16 +263,20 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         FP_WAIT(drained, (g - 1) & 1, 2, g);
                         tc_fence_after();
                     }
-                    for (int kc = 0; kc < KC; ++kc) {
+                    const uint32_t d0 = tmem_base, d1 = tmem_base + 128 + (g & 1) * 128;      // block 1 alternates: never waits for a drain
+                    // projection K-chunk kc: x_lo . W_hi, then x_hi . W_lo and x_hi . W_hi (two ring tiles), both unit blocks
+                    auto proj = [&](int kc) {
                         const uint32_t wb_hi = w_base + (uint32_t)((kc * 2 + 0) * FP_TILE), wb_lo = w_base + (uint32_t)((kc * 2 + 1) * FP_TILE);
                         FP_WAIT(&full[stage], phase, 3, g);                   // x_lo(kc)
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t xa = ring_base + (uint32_t)(stage * FP_TILE);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16_ss_pair(tmem_base, umma_desc_k_sw128(xa + k * 32), umma_desc_k_sw128(wb_hi + k * 32), idesc,
-                                                 (kc | k) != 0);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_lo = umma_desc_k_sw128(xa + k * 32);
+                                umma_f16_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_hi + k * 32), idesc, (kc | k) != 0);
+                                umma_f16_ss_pair(d1, a_lo, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, (kc | k) != 0);
+                            }
                             umma_commit_mask(&empty[stage], mask);
                         }
                         __syncwarp();
@@ -236,42 +288,90 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_hi = umma_desc_k_sw128(xa + k * 32);
-                                umma_f16_ss_pair(tmem_base, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, 1);
-                                umma_f16_ss_pair(tmem_base, a_hi, umma_desc_k_sw128(wb_hi + k * 32), idesc, 1);
+                                umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, 1);
+                                umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_hi + k * 32), idesc, 1);
+                                umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, 1);
+                                umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, 1);
                             }
                             umma_commit_mask(&empty[stage], mask);
                         }
                         __syncwarp();
                         if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                    if (g > 0) {                                          // h of the previous step is in TMEM (both CTAs)
-                        FP_WAIT(h_ready, (g - 1) & 1, 5, g);
-                        tc_fence_after();
-                    }
-                    if (elect_one()) {
-                        if (s > 0) {
+                    };
+                    // recurrent quarter (b, who): the 32 units b*32.. of pair `who ? 1-p : p` = K-steps k0, k0 + 1 of h_{t-1} (TMEM)
+                    auto rec = [&](int b, int who) {
+                        if (g > 0) {
+                            FP_WAIT(&hq[b * 2 + who], (g - 1) & 1, 5, g);
+                            tc_fence_after();
+                        }
+                        if (s > 0 && elect_one()) {
+                            const int k0 = (int)(who ? 1 - p : p) * 4 + b * 2;
 #pragma unroll
-                            for (int k = 0; k < UT / 16; ++k) {
+                            for (int k = k0; k < k0 + 2; ++k) {
                                 const uint32_t wr = w_base + (uint32_t)(((KC + (k >> 2)) * 2) * FP_TILE) + (k & 3) * 32;
-                                const uint64_t b_hi = umma_desc_k_sw128(wr), b_lo = umma_desc_k_sw128(wr + FP_TILE);
-                                umma_f16_ts_pair(tmem_base, tmem_base + H_LO + k * 8, b_hi, idesc, 1);
-                                umma_f16_ts_pair(tmem_base, tmem_base + H_HI + k * 8, b_lo, idesc, 1);
-                                umma_f16_ts_pair(tmem_base, tmem_base + H_HI + k * 8, b_hi, idesc, 1);
+#pragma unroll
+                                for (int blk = 0; blk < 2; ++blk) {
+                                    const uint64_t b_hi = umma_desc_k_sw128(wr + blk * BB), b_lo = umma_desc_k_sw128(wr + FP_TILE + blk * BB);
+                                    const uint32_t d = blk ? d1 : d0;
+                                    umma_f16_ts_pair(d, tmem_base + H_LO + k * 8, b_hi, idesc, 1);
+                                    umma_f16_ts_pair(d, tmem_base + H_HI + k * 8, b_lo, idesc, 1);
+                                    umma_f16_ts_pair(d, tmem_base + H_HI + k * 8, b_hi, idesc, 1);
+                                }
                             }
                         }
-                        umma_commit_mask(acc_ready, mask);
-                    }
+                        __syncwarp();
+                    };
+                    // static interleave: the epilogue delivers h_t in quarters (own block 0, sibling's block 0, own block 1, sibling's
+                    // block 1); each quarter's 6 recurrent MMAs are queued as soon as it lands, projection chunks fill the gaps
+                    TR(0, g, 0);
+                    proj(0); proj(1);
+                    TR(0, g, 1);
+                    rec(0, 0);
+                    TR(0, g, 2);
+                    proj(2);
+                    if constexpr (NP == 2) rec(0, 1);
+                    TR(0, g, 3);
+                    if constexpr (KC > 3) proj(3);
+                    TR(0, g, 4);
+                    rec(1, 0);
+                    TR(0, g, 5);
+                    if constexpr (NP == 2) rec(1, 1);
+                    if (elect_one()) umma_commit_mask(acc_ready, mask);
+                    TR(0, g, 6);
                     __syncwarp();
                 }
         }
     } else {
         // ===================== epilogue: warps 2..17; TMEM lane quarter = warp % 4; 64-column group = (warp - 2) / 4 =====================
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;                   // units p*64 + cg*16 .. +16
+        const int cg = (warp - 2) >> 2;                   // pair-local units b*32 + cg*8 .. +8 for block b = 0, 1
         const int row = q * 32 + lane;
-        const uint32_t sb = smem_u32(s_bias) + (uint32_t)(cg * 64) * 4;
+        const uint32_t sb = smem_u32(s_bias) + (uint32_t)(cg * 32) * 4;   // block b at + b*512 B
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t own_col = p * 32 + cg * 8;         // this thread's 16 units inside the h_hi / h_lo column ranges
+        const uint32_t own_col = p * 32 + cg * 4;         // this thread's units inside the h_hi / h_lo column ranges (block b at + b*16)
+        const int ew = warp - 2;                           // epilogue warp index = index of its exchange barriers
+        const uint32_t peer_col = (1 - p) * 32 + cg * 4;
+        const uint32_t xsrc = smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + row) * 16;       // our landing slots (hi; lo at + 2 KB)
+        const uint32_t sib = NP == 2 ? (rank ^ 2u) : rank;   // sibling CTA: other pair, same windows
+        const uint32_t xdst = mapa_u32(xsrc, sib), xbar = mapa_u32(smem_u32(&xfull[ew]), sib);
+        if (NP == 2 && lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                   // phase 0
+        // receive exchange phase k: the sibling warp's 8 units x (hi, lo) of our rows -> TMEM columns of the other pair's units
+        auto xch_recv = [&](uint32_t k) {
+            FP_WAIT(&xfull[ew], k & 1, 7, k);
+            if (lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                          // arm the next phase
+            uint4 a, b2;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(xsrc) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b2.x), "=r"(b2.y), "=r"(b2.z), "=r"(b2.w) : "r"(xsrc + 128 * 16) : "memory");
+            tmem_st_32x4(lane_addr + H_HI + peer_col + (k & 1) * 16, a);
+            tmem_st_32x4(lane_addr + H_LO + peer_col + (k & 1) * 16, b2);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_remote(&xfree[ew], sib);
+                mbar_arrive_remote(&hq[(k & 1) * 2 + 1], leader);
+            }
+        };
         uint32_t g = 0;
         for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
             const int64_t wtile = min(tp * 2 + (int64_t)r, ntw - 1);     // odd tile count: the last peer repeats the last tile
@@ -283,51 +383,70 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 const int t = dir ? (T - 1 - s) : s;
                 FP_WAIT(acc_ready, g & 1, 6, g);
                 tc_fence_after();
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(lane_addr + (uint32_t)(cg * 64), v0);
-                tmem_ld_32x32(lane_addr + (uint32_t)(cg * 64 + 32), v1);
+                if (warp == 2) TR(1, g, 0);
+                uint32_t v0[32];
+                tmem_ld_32x32(lane_addr + (uint32_t)(cg * 32), v0);
                 tmem_ld_wait();
-                tc_fence_before();                        // our tcgen05.ld precede the next step's MMAs
+                tc_fence_before();                        // our tcgen05.ld of block 0 precede the next step's MMAs into it
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(drained, leader);
-                uint4 phi0, plo0, phi1, plo1;
-                cell_block_bias(v0, sb, &c[0], phi0, plo0);
-                cell_block_bias(v1, sb + 128, &c[8], phi1, plo1);
-                tmem_st_32x4(lane_addr + H_HI + own_col, phi0);
-                tmem_st_32x4(lane_addr + H_HI + own_col + 4, phi1);
-                tmem_st_32x4(lane_addr + H_LO + own_col, plo0);
-                tmem_st_32x4(lane_addr + H_LO + own_col + 4, plo1);
+                if (warp == 2) TR(1, g, 1);
                 const int64_t orow = ((int64_t)t * nwp + w) * out_ld + dir * UT;     // padded rows are written too (finite, never read as windows)
-                {
-                    __half* oh = out_hi + orow + p * 64 + cg * 16;
-                    __half* ol = out_lo + orow + p * 64 + cg * 16;
-                    *reinterpret_cast<uint4*>(oh) = phi0; *reinterpret_cast<uint4*>(oh + 8) = phi1;
-                    *reinterpret_cast<uint4*>(ol) = plo0; *reinterpret_cast<uint4*>(ol + 8) = plo1;
-                }
-                if constexpr (NP == 2) {
-                    // exchange through the layer output: publish our 16 units, fetch the sibling pair's 16 units of the same window
-                    __threadfence();
+                __half* oh = out_hi + orow + p * 64 + cg * 8;
+                __half* ol = out_lo + orow + p * 64 + cg * 8;
+                // own block b: h -> TMEM (A operand of the next step), -> layer output, -> sibling CTA; then signal the quarter
+                auto publish = [&](int b, const float* hv) {
+                    uint4 phi, plo;
+                    pack_h8(hv, phi, plo);
+                    tmem_st_32x4(lane_addr + H_HI + own_col + b * 16, phi);
+                    tmem_st_32x4(lane_addr + H_LO + own_col + b * 16, plo);
+                    *reinterpret_cast<uint4*>(oh + b * 32) = phi;
+                    *reinterpret_cast<uint4*>(ol + b * 32) = plo;
+                    if constexpr (NP == 2) {
+                        // our block goes straight from registers into the sibling's landing zone (st.async, bytes counted on ITS
+                        // per-warp mbarrier -- no fences) once the sibling has read what we sent last
+                        const uint32_t k = 2 * g + b;
+                        if (k > 0) FP_WAIT(&xfree[ew], (k - 1) & 1, 8, k);
+                        st_async_v4(xdst, phi, xbar);
+                        st_async_v4(xdst + 128 * 16, plo, xbar);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();                    // our tcgen05.st of h precede the recurrent MMAs that read it
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(xfull, rank ^ 2u);
-                    FP_WAIT_CL(xfull, g & 1, 7, g);
-                    const __half* ph = out_hi + orow + (1 - p) * 64 + cg * 16;
-                    const __half* pl = out_lo + orow + (1 - p) * 64 + cg * 16;
-                    const uint4 a0 = ld_cg_u4(ph), a1 = ld_cg_u4(ph + 8), b0 = ld_cg_u4(pl), b1 = ld_cg_u4(pl + 8);
-                    const uint32_t peer_col = (1 - p) * 32 + cg * 8;
-                    tmem_st_32x4(lane_addr + H_HI + peer_col, a0);
-                    tmem_st_32x4(lane_addr + H_HI + peer_col + 4, a1);
-                    tmem_st_32x4(lane_addr + H_LO + peer_col, b0);
-                    tmem_st_32x4(lane_addr + H_LO + peer_col + 4, b1);
-                }
-                tmem_st_wait();
-                tc_fence_before();                        // our tcgen05.st of h precede the recurrent MMAs of the next step
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(h_ready, leader);
+                    if (lane == 0) mbar_arrive_remote(&hq[b * 2], leader);
+                };
+                float hv[8];
+                cell_units<0, 8>(v0, sb, &c[0], hv);
+                uint32_t v1[32];                          // block 1 stayed in TMEM: only 32 accumulator registers are live at a time;
+                tmem_ld_32x32(lane_addr + (uint32_t)(128 + (g & 1) * 128 + cg * 32), v1);   // its load flies under block 0's publication
+                publish(0, hv);
+                if (warp == 2) TR(1, g, 2);
+                tmem_ld_wait();
+                cell_units<0, 4>(v1, sb + 512, &c[8], hv);
+                if (warp == 2) TR(1, g, 3);
+                if constexpr (NP == 2) xch_recv(2 * g);   // sibling's block 0: arrived during the first half of our block 1
+                if (warp == 2) TR(1, g, 4);
+                cell_units<4, 8>(v1, sb + 512, &c[8], hv);
+                publish(1, hv);
+                if (warp == 2) TR(1, g, 5);
+                if constexpr (NP == 2) xch_recv(2 * g + 1);
+                if (warp == 2) TR(1, g, 6);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+#ifdef NRV_TRACE
+    if (trace_on && threadIdx.x == 0 && atomicAdd(&g_tr_launch[UT == 128], 1) == 3) {
+        for (int st = 0; st < 40; ++st) {
+            printf("TR%d step %2d mma:", UT, st);
+            for (int e = 0; e < 7; ++e) printf(" %7lld", g_tr[UT == 128][0][st][e]);
+            printf("  epi:");
+            for (int e = 0; e < 7; ++e) printf(" %7lld", g_tr[UT == 128][1][st][e]);
+            printf("\n");
+        }
+    }
+#endif
     cluster_sync_all();            // the leaders' MMAs read their peers' shared memory: nobody leaves early
     if (warp == 0) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }

@@ -4,7 +4,7 @@ for cfg in "$@"; do
   [ "$cfg" = "-" ] && cfg="NRV_DUMMY=1"
   echo "=== $cfg"
   env $cfg NRV_VERBOSE=1 timeout 240 python -m pytest tests/test_gpu_parity.py -x -q -k "revise_unitest or window_chunking or predict_windows" 2>&1 | tail -4
-  env $cfg timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err || tail -5 gpurun_out/bench_quick.err
+  env $cfg timeout 90 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err || tail -5 gpurun_out/bench_quick.err
   python - <<'P'
 import json
 try:
