@@ -300,6 +300,9 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         tc_path = stage_ms.get("proj2", 0.0) > 0.0
         # algorithmic MACs per window and per model of each stage (both directions, 11 timesteps)
+        # which kernels ran for total_rnn1 / total_rnn2 (library defaults: both fused; NRV_TRNN1 / NRV_TRNN2 = split select GEMM + recurrence)
+        fused1 = tc_path and os.environ.get("NRV_TRNN1", "fused") != "split"
+        fused2 = tc_path and stage_ms.get("proj3", 0.0) == 0.0
         if tc_path:
             macs = {"lstm0": 30_976, "proj1": 180_224, "rec1": 360_448, "proj2": 2_162_688, "rec2": 1_441_792,
                     "proj3": 1_441_792, "rec3": 360_448, "heads_gemm": 225_280, "heads": 3_264}
@@ -312,6 +315,16 @@ def main():
                      "heads_gemm": "gemm_f16x3_kernel<128,FUSE2> (dense head 128->128->32, tcgen05)",
                      "heads": "heads_tail_thread_kernel (dense 32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
                      "lstm0": "read_rnn1_kernel (read_rnn1, fp32 SIMT, one thread per window pair)"}
+            if fused1:      # stage proj2 holds only the CNN-feature gather (no MACs); rec2 is the whole layer
+                macs.pop("proj2")
+                macs["rec2"] = 3_604_480
+                names["rec2"] = ("lstm_fused_pair_kernel<192,128> (total_rnn1 projection+recurrence fused, tcgen05 cta_group::2, "
+                                 "cluster of 4, h in TMEM, 3-pass split-fp16)")
+            if fused2:
+                macs.pop("proj3")
+                macs["rec3"] = 1_802_240
+                names["rec3"] = ("lstm_fused_pair_kernel<256,64> (total_rnn2 projection+recurrence fused, tcgen05 cta_group::2, "
+                                 "h in TMEM, 3-pass split-fp16)")
         else:
             macs = {"lstm0": 30_976, "rec1": 540_672, "rec2": 3_604_480, "rec3": 1_802_240, "heads": 228_544}
             names = {k: "lstm_layer_kernel (fp32 SIMT, fused projection+recurrence)" for k in macs}
@@ -321,6 +334,10 @@ def main():
         abytes = {"lstm0": 11 * (6 + 32) * 4, "rec1": 11 * (32 + 128) * 4, "proj2": 11 * (192 + 1024) * 4,
                   "rec2": 11 * (1024 + 256) * 4, "proj3": 11 * (256 + 512) * 4, "rec3": 11 * (512 + 128) * 4,
                   "heads_gemm": 11 * (128 + 32) * 4, "heads": 11 * 32 * 4 + 32} if tc_path else {}
+        if fused1:          # reads x = [read_rnn11 | CNN features] (192), writes h (256): no pre-activations
+            abytes["rec2"] = 11 * (192 + 256) * 4
+        if fused2:
+            abytes["rec3"] = 11 * (256 + 128) * 4
         hbm_peak = float(peaks.get("hbm_gbs"))
         traffic_db = {}
         tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
@@ -346,12 +363,18 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peak_src,
                     "launches": kernels[dom]["launches"], "avg_launch_ms": kernels[dom]["avg_launch_ms"],
                     "flops_per_launch": kernels[dom]["flops_per_launch"],
-                    "traffic": traffic_db.get(dom, {}).get("dram_bytes_per_launch"),
+                    # measured DRAM bytes per launch (ncu --set full) -- only if the capture is of the kernel that ran
+                    "traffic": (traffic_db.get(dom, {}).get("dram_bytes_per_launch")
+                                if kernels[dom]["kernel"].startswith(str(traffic_db.get(dom, {}).get("kernel", "?")).split()[0].split("<")[0])
+                                else None),
                     "share_of_step": kernels[dom]["share_of_step"],
                     "hbm": {"achieved": kernels[dom].get("hbm_achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
                             "frac": kernels[dom].get("hbm_frac"), "bytes_per_launch": kernels[dom].get("hbm_bytes_per_launch")},
-                    "note": "algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay "
-                            "fp32-equivalent, and is HBM-bound on the fp32 pre-activations (see traffic)",
+                    "note": ("algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay fp32-equivalent "
+                             "(effective tensor ceiling = peak / 3) and runs under the 1000 W power cap; fused layers move only "
+                             "x and h through HBM (see traffic)") if (fused1 or fused2) else
+                            ("algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay "
+                             "fp32-equivalent, and is HBM-bound on the fp32 pre-activations (see traffic)"),
                     "all_model_kernels": kernels}
         # K1 (segmentation) and K4 (decode) are the HBM-bound kernels of SURVEY.md section 8(d)
         n_samp = int(slabs[0].sig_off[-1])

@@ -67,7 +67,9 @@ __device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
 // timeline of cluster 0 / direction 0 (debug builds: NRV_EXTRA_NVCC=-DNRV_TRACE): SM clock at key events of the MMA warp (role 0)
 // and of the first epilogue warp (role 1), printed by the 4th launch of each instantiation
 __device__ long long g_tr[2][2][128][8];
+__device__ unsigned long long g_tr_cl[2][2][64][3];     // [inst][dir][cluster]: globaltimer at start / end, SM id
 __device__ int g_tr_launch[2];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TR(role, step, ev) do { if (trace_on && (threadIdx.x & 31) == 0 && (step) < 128) g_tr[UT == 128][role][step][ev] = clock64() - tr_t0; } while (0)
 #else
 #define TR(role, step, ev) do { } while (0)
@@ -178,6 +180,11 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #ifdef NRV_TRACE
     const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0;
     const long long tr_t0 = clock64();
+    if (threadIdx.x == 0 && cluster_ctarank() == 0 && blockIdx.x / (2 * Cfg::NP) < 64) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_tr_cl[UT == 128][blockIdx.y][blockIdx.x / (2 * Cfg::NP)][0] = gtimer();
+        g_tr_cl[UT == 128][blockIdx.y][blockIdx.x / (2 * Cfg::NP)][2] = smid;
+    }
 #endif
     const uint32_t rank = cluster_ctarank();
     const uint32_t p = rank >> 1, r = rank & 1, leader = rank & ~1u;
@@ -437,7 +444,14 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     tc_fence_before();
     __syncthreads();
 #ifdef NRV_TRACE
+    if (threadIdx.x == 0 && cluster_ctarank() == 0 && blockIdx.x / (2 * Cfg::NP) < 64) g_tr_cl[UT == 128][blockIdx.y][blockIdx.x / (2 * Cfg::NP)][1] = gtimer();
     if (trace_on && threadIdx.x == 0 && atomicAdd(&g_tr_launch[UT == 128], 1) == 3) {
+        // clusters of the PREVIOUS launch of this instantiation (all finished): start / end relative to the first start
+        unsigned long long t0 = ~0ull;
+        for (int d = 0; d < 2; ++d) for (int c = 0; c < (int)(gridDim.x / (2 * Cfg::NP)); ++c) if (g_tr_cl[UT == 128][d][c][0] < t0 && !(d == 0 && c == 0)) t0 = g_tr_cl[UT == 128][d][c][0];
+        for (int d = 0; d < 2; ++d) for (int c = 0; c < (int)(gridDim.x / (2 * Cfg::NP)) && c < 64; ++c)
+            printf("CL%d dir %d cluster %2d sm %3llu start %8lld end %8lld\n", UT, d, c, g_tr_cl[UT == 128][d][c][2],
+                   (long long)(g_tr_cl[UT == 128][d][c][0] - t0), (long long)(g_tr_cl[UT == 128][d][c][1] - t0));
         for (int st = 0; st < 40; ++st) {
             printf("TR%d step %2d mma:", UT, st);
             for (int e = 0; e < 7; ++e) printf(" %7lld", g_tr[UT == 128][0][st][e]);
