@@ -120,12 +120,14 @@ def run_worker(args, file_list, device, logger=None):
     native = getattr(args, 'ingest', 'native') == 'native'
     slab_files = 512
 
-    def emit(fn_sg, ok, seq_bytes, orig_bases):
+    fastq = args.output_format == 'fastq'
+
+    def emit(fn_sg, ok, seq_bytes, orig_bases, qul=None):
         try:
             if ok:
                 seq = seq_bytes.decode() if isinstance(seq_bytes, (bytes, bytearray)) else seq_bytes
-                qul = 'I' * len(seq) if args.output_format == 'fastq' else None   # D6: provisional
-                _write_read(args, fn_sg, list(seq), qul)
+                # D6': qualities of the two-model path come from the softmax outputs (include/nrv.h nrv_result.revised_qual)
+                _write_read(args, fn_sg, list(seq), list(qul) if fastq else None)
                 counts['ok'] += 1
             else:
                 # fallback to the un-revised read (NanoReviser.py:146-154 / :172-181)
@@ -155,13 +157,23 @@ def run_worker(args, file_list, device, logger=None):
                 batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
                 todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
                 lengths = np.diff(batch.base_off).tolist()
+                if fastq and batch.n_reads:
+                    # the native reader does not extract the basecaller's Fastq dataset: attach its Phred scores here
+                    # (bases that pass through unrevised keep them; reads where it is missing use Phred 40)
+                    def phred(i):
+                        b0, b1 = int(batch.base_off[i]), int(batch.base_off[i + 1])
+                        q = fast5.basecall_phred(paths[int(read_file[i])], batch.bases[b0:b1], args.basecall_group,
+                                                 args.basecall_subgroup)
+                        return q if q is not None else np.full(b1 - b0, 40, np.uint8)
+                    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+                        batch.qual = np.concatenate(list(ex.map(phred, range(batch.n_reads))))
                 for idx in workqueue.make_batches(range(batch.n_reads), lengths, int(args.batch_bases)):
                     sub = batch if len(idx) == batch.n_reads else synth.split_batch(batch, idx)
-                    out = rv.revise_batch(sub)
+                    out = rv.revise_batch(sub, want_qual=fastq)
                     for k, i in enumerate(idx):
                         ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
                         emit(slab[int(read_file[i])], ok, out.revised[out.out_off[k]:out.out_off[k + 1]].tobytes(),
-                             batch.bases[batch.base_off[i]:batch.base_off[i + 1]])
+                             batch.bases[batch.base_off[i]:batch.base_off[i + 1]], out.quality(k) if fastq else None)
             if todo_python:
                 with ThreadPoolExecutor(max_workers=nthreads) as ex:
                     loaded = list(ex.map(lambda f: _ingest(args, f), todo_python))
@@ -177,11 +189,17 @@ def run_worker(args, file_list, device, logger=None):
                         good.append((fn_sg, r))
                 lengths = [r.n_bases for _, r in good]
                 for idx in workqueue.make_batches(range(len(good)), lengths, int(args.batch_bases)):
-                    out = api.revise_reads([good[i][1] for i in idx], reviser=rv)
+                    if fastq:
+                        for i in idx:
+                            fn_sg, r = good[i]
+                            q = fast5.basecall_phred(os.path.join(args.fast5_base_dir, fn_sg), r.bases, args.basecall_group,
+                                                     args.basecall_subgroup)
+                            r.qual = q if q is not None else np.full(r.n_bases, 40, np.uint8)
+                    out = api.revise_reads([good[i][1] for i in idx], reviser=rv, want_qual=fastq)
                     for k, i in enumerate(idx):
                         fn_sg, r = good[i]
                         ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
-                        emit(fn_sg, ok, out.sequence(k), r.bases)
+                        emit(fn_sg, ok, out.sequence(k), r.bases, out.quality(k) if fastq else None)
     return counts['ok'], counts['fallback'], counts['failed'], failed
 
 

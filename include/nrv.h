@@ -92,6 +92,10 @@ typedef struct {
     const float*   ev_mean;
     const float*   ev_std;
     const int32_t* last_dur;  /* [n_reads] */
+    const uint8_t* qual;      /* optional (may be NULL), [total_bases]: the basecaller's Phred score (0..93, i.e. the Fastq
+                                 quality character minus 33) of every base; only read when nrv_result.revised_qual is set:
+                                 bases that pass through unrevised keep it (NULL: Phred 40).  The reference copies the
+                                 basecaller's qualities in its per-read fallback (NanoReviser.py:172-181) */
 } nrv_batch;
 
 /* Outputs.  Every pointer except revised/out_off/status is optional (NULL = not wanted).
@@ -105,6 +109,11 @@ typedef struct {
     uint8_t* y2;              /* [n_windows] argmax of model2 (class 0..4 == label-1) */
     float*   p1;              /* [n_windows][6] softmax of model1 */
     float*   p2;              /* [n_windows][5] softmax of model2 */
+    uint8_t* revised_qual;    /* optional (may be NULL), [revised_cap]: Phred+33 quality character of every byte of `revised`
+                                 (-F fastq, NanoReviser.py:158-181 / prep_read_fastq output_handeler.py:48-62).  The reference
+                                 defines no qualities for the two-model path; definition D6' (DESIGN.md): symbols emitted because
+                                 of the models carry min over both models of floor(-10 log10(1 - p_argmax)) capped at 60, the
+                                 leading label symbol that of model1, bases that pass through keep nrv_batch.qual */
 } nrv_result;
 
 typedef struct nrv_handle nrv_handle;

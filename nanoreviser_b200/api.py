@@ -163,10 +163,11 @@ def prep_read_fastq(fast5_fn, read_fastq_fn, bases, qul):
 
 # ---- the NN path of provide_fasta, batched ------------------------------------------------------------
 def revise_reads(reads: Sequence[ReadArrays], reviser: Optional[engine.Reviser] = None, want_labels=False,
-                 want_probs=False) -> engine.ReviseResult:
-    """get_read_data outputs of many reads -> revised sequences (one ragged GPU batch)."""
+                 want_probs=False, want_qual=False) -> engine.ReviseResult:
+    """get_read_data outputs of many reads -> revised sequences (one ragged GPU batch); ``want_qual`` adds the
+    fastq quality string of every revised read (``ReviseResult.quality(i)``, definition D6')."""
     r = _rev(reviser)
-    return r.revise_batch(engine.pack_batch(reads), want_labels=want_labels, want_probs=want_probs)
+    return r.revise_batch(engine.pack_batch(reads), want_labels=want_labels, want_probs=want_probs, want_qual=want_qual)
 
 
 def out_filename(output_dir: str, fast5_fn_sg: str, fmt: str) -> str:

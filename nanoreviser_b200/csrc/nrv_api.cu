@@ -64,7 +64,7 @@ struct nrv_handle {
     int64_t chunk_windows = 148 * 4 * 64;
     // inputs / per-batch arenas
     Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
-        d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag,
+        d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag, d_wq[2], d_qual_in, d_revq,
         d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin;
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
@@ -633,12 +633,15 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
                                      h->stream);
     float* probs[2] = {nullptr, nullptr};
     uint8_t* labels[2];
+    const bool want_q = r->revised_qual != nullptr;      // -F fastq: per-window Phred scores need the softmax outputs
     if (host_io) {
-        if (r->p1) { CU(h, h->d_probs[0].ensure((size_t)o.n_win * 6 * 4 + 16)); probs[0] = h->d_probs[0].as<float>(); }
-        if (r->p2) { CU(h, h->d_probs[1].ensure((size_t)o.n_win * 5 * 4 + 16)); probs[1] = h->d_probs[1].as<float>(); }
+        if (r->p1 || want_q) { CU(h, h->d_probs[0].ensure((size_t)o.n_win * 6 * 4 + 16)); probs[0] = h->d_probs[0].as<float>(); }
+        if (r->p2 || want_q) { CU(h, h->d_probs[1].ensure((size_t)o.n_win * 5 * 4 + 16)); probs[1] = h->d_probs[1].as<float>(); }
         for (int mi = 0; mi < 2; ++mi) { CU(h, h->d_y[mi].ensure((size_t)o.n_win + 16)); labels[mi] = h->d_y[mi].as<uint8_t>(); }
     } else {
         probs[0] = r->p1; probs[1] = r->p2;
+        if (want_q && !probs[0]) { CU(h, h->d_probs[0].ensure((size_t)o.n_win * 6 * 4 + 16)); probs[0] = h->d_probs[0].as<float>(); }
+        if (want_q && !probs[1]) { CU(h, h->d_probs[1].ensure((size_t)o.n_win * 5 * 4 + 16)); probs[1] = h->d_probs[1].as<float>(); }
         uint8_t* user[2] = {r->y1, r->y2};
         for (int mi = 0; mi < 2; ++mi) {
             if (user[mi]) labels[mi] = user[mi];
@@ -655,19 +658,43 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
     CU(h, h->d_flag.ensure(16));
     CU(h, cudaMemsetAsync(h->d_flag.p, 0, 4, h->stream));
     uint8_t* d_rev; int64_t* d_outoff;
+    uint8_t* d_revq = nullptr;
+    const uint8_t* d_qual_in = nullptr;
+    uint8_t* wq[2] = {nullptr, nullptr};
     if (host_io) {
         CU(h, h->d_revised.ensure((size_t)r->revised_cap + 16));
         CU(h, h->d_outoff.ensure((size_t)(o.n_reads + 1) * 8));
         d_rev = h->d_revised.as<uint8_t>(); d_outoff = h->d_outoff.as<int64_t>();
+        if (want_q) {
+            CU(h, h->d_revq.ensure((size_t)r->revised_cap + 16));
+            d_revq = h->d_revq.as<uint8_t>();
+            if (b->qual) {
+                CU(h, h->d_qual_in.ensure((size_t)o.n_bases + 16));
+                CU(h, cudaMemcpyAsync(h->d_qual_in.p, b->qual, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
+                d_qual_in = h->d_qual_in.as<uint8_t>();
+            }
+        }
     } else {
         d_rev = r->revised; d_outoff = r->out_off;
+        d_revq = r->revised_qual; d_qual_in = b->qual;
     }
     {
         StageTimer tm(h, ST_DECODE);
-        h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
-                                     h->d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
-                                     h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, h->d_flag.as<int>(),
-                                     h->stream);
+        if (want_q) {
+            for (int mi = 0; mi < 2; ++mi) {
+                CU(h, h->d_wq[mi].ensure((size_t)o.n_win + 16));
+                wq[mi] = h->d_wq[mi].as<uint8_t>();
+                const int n = launch_window_phred(probs[mi], labels[mi], mi == 0 ? 6 : 5, o.n_win, wq[mi], h->stream);
+                if (n < 0) return fail(h, NRV_E_CUDA, "window_phred kernel could not be launched");
+                h->launches += n;
+            }
+        }
+        const int n = launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
+                                    h->d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
+                                    h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, h->d_flag.as<int>(),
+                                    h->stream, wq[0], wq[1], d_qual_in, d_revq);
+        if (n < 0) return fail(h, NRV_E_INVALID, "decode: qualities requested without per-window scores");
+        h->launches += n;
     }
     CU(h, cudaGetLastError());
     if (!host_io) {
@@ -687,6 +714,7 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
     if (*h->h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
     const int64_t total = r->out_off[o.n_reads];
     CU(h, cudaMemcpyAsync(r->revised, d_rev, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    if (want_q) CU(h, cudaMemcpyAsync(r->revised_qual, d_revq, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return NRV_OK;
 }
@@ -749,7 +777,7 @@ void nrv_destroy(nrv_handle* h) {
     Arena* arenas[] = {&h->d_signal, &h->d_starts, &h->d_bases, &h->d_evm, &h->d_evs, &h->d_lastdur, &h->d_off, &h->d_shift,
                        &h->d_scale, &h->d_status, &h->d_base_read, &h->d_win_base, &h->d_x, &h->d_sigfeat[0],
                        &h->d_sigfeat[1], &h->d_act[0], &h->d_act[1], &h->d_act[2], &h->d_act[3], &h->d_probs[0],
-                       &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff,
+                       &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff, &h->d_wq[0], &h->d_wq[1], &h->d_qual_in, &h->d_revq,
                        &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
                        &h->d_sfl[1], &h->d_a1[0], &h->d_a1[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_a4[0],
                        &h->d_a4[1], &h->d_zin};

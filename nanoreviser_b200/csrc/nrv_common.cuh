@@ -133,7 +133,10 @@ int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int
 int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,
                   const uint8_t* bases, const uint8_t* y1, const uint8_t* y2, const int32_t* status,
                   int64_t n_reads, int64_t n_bases, int window, int32_t* counts_tmp, int64_t* tile_tmp,
-                  uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st);
+                  uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st,
+                  const uint8_t* q1 = nullptr, const uint8_t* q2 = nullptr, const uint8_t* qual_in = nullptr,
+                  uint8_t* revised_qual = nullptr);
+int launch_window_phred(const float* probs, const uint8_t* labels, int n_class, int64_t n_win, uint8_t* q, cudaStream_t st);
 int64_t decode_tile_count(int64_t n_bases);
 
 }  // namespace nrv

@@ -2,6 +2,8 @@
 // pass-through edges of composition D4, see include/nrv.h / DESIGN.md):
 //   every base of every read emits 0..3 characters -> tile sums -> scan of tile sums -> scatter.
 // Integer / byte work only; HBM-bound (reads 1 B base + 2 B labels, writes <= 2 B per base).
+#include <math.h>
+
 #include "nrv_common.cuh"
 
 namespace nrv {
@@ -18,15 +20,36 @@ __device__ __forceinline__ uint8_t label_char(int l) {
     return (l < 4) ? (uint8_t)(lo >> (8 * l)) : (l == 4 ? 'G' : 'A');
 }
 
-struct Emit { int n; uint8_t c[3]; };
+struct Emit { int n; uint8_t c[3]; uint8_t q[3]; };
+
+// Quality definition D6' (include/nrv.h nrv_result.revised_qual; oracle/nanorev_oracle.py get_qual_1): Phred of a window and
+// model = #{k in 1..60 : 1 - p_argmax <= 10^(-k/10)} (fp32), i.e. floor(-10 log10(1 - p)) capped at 60, from a threshold table
+constexpr int PHRED_MAX = 60;
+constexpr int PHRED_PASS = 40;
+struct PhredTable { float t[PHRED_MAX]; };      // kernel parameter (constant bank): no per-device symbol to initialise
+
+__global__ void window_phred_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ labels, int nc, int64_t n_win,
+                                    uint8_t* __restrict__ q, const PhredTable tab) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    const float e = 1.0f - probs[w * nc + labels[w]];
+    int cnt = 0;
+#pragma unroll 4
+    for (int k = 0; k < PHRED_MAX; ++k) cnt += (e <= tab.t[k]) ? 1 : 0;
+    q[w] = (uint8_t)cnt;
+}
 
 __device__ __forceinline__ Emit emit_for_base(int64_t j, const int64_t* __restrict__ base_off,
                                               const int64_t* __restrict__ win_off,
                                               const int32_t* __restrict__ base_read,
                                               const uint8_t* __restrict__ bases, const uint8_t* __restrict__ y1,
                                               const uint8_t* __restrict__ y2, const int32_t* __restrict__ status,
-                                              int window, int* read_out, int64_t* idx_in_read) {
+                                              int window, int* read_out, int64_t* idx_in_read,
+                                              const uint8_t* __restrict__ q1 = nullptr, const uint8_t* __restrict__ q2 = nullptr,
+                                              const uint8_t* __restrict__ qual_in = nullptr, bool want_q = false) {
     Emit e; e.n = 0;
+    // quality of a base that passes through: the basecaller's, when known (capped at Phred 93), else Phred 40
+    const uint8_t qpass = want_q ? (qual_in ? (uint8_t)min((int)qual_in[j], 93) : (uint8_t)PHRED_PASS) : (uint8_t)0;
     const int r = base_read[j];
     const int64_t i = j - base_off[r];
     const int64_t N = base_off[r + 1] - base_off[r];
@@ -35,22 +58,24 @@ __device__ __forceinline__ Emit emit_for_base(int64_t j, const int64_t* __restri
     *read_out = r; *idx_in_read = i;
     const uint8_t base = bases[j];
     const bool ok = (status == nullptr) || (status[r] == NRV_READ_OK);
-    if (!ok || M <= 0 || i < bef || i >= bef + M) { e.c[e.n++] = base; return e; }   // pass-through
+    if (!ok || M <= 0 || i < bef || i >= bef + M) { e.q[e.n] = qpass; e.c[e.n++] = base; return e; }   // pass-through
     const int64_t w = win_off[r] + (i - bef);
+    const uint8_t qa = want_q ? q1[w] : (uint8_t)0;
+    const uint8_t qm = want_q ? (uint8_t)min((int)qa, (int)q2[w]) : (uint8_t)0;
     const int l1 = y1[w];                               // label space 0..5
     const int l2 = (int)y2[w] + 1;                      // class k of model2 == label k+1
     if (i == bef) {                                     // output_handeler.py:107: leading label_to_base[y_pre[0]]
         const uint8_t lead = label_char(l1);
-        if (lead != '-') e.c[e.n++] = lead;
+        if (lead != '-') { e.q[e.n] = qa; e.c[e.n++] = lead; }
     }
     if (l1 == l2 && l1 >= 2) {                          // both models agree on a base
-        e.c[e.n++] = label_char(l1);
+        e.q[e.n] = qm; e.c[e.n++] = label_char(l1);
     } else if (l1 == 0 && l2 >= 2) {                    // 'D': a base is missing after this one -> insert
-        if (base != '-') e.c[e.n++] = base;
-        e.c[e.n++] = label_char(l2);
+        if (base != '-') { e.q[e.n] = qpass; e.c[e.n++] = base; }
+        e.q[e.n] = qm; e.c[e.n++] = label_char(l2);
     } else if (l1 == 1 && l2 == 1) {                    // both say '-': this base is an insertion -> drop
     } else {
-        if (base != '-') e.c[e.n++] = base;
+        if (base != '-') { e.q[e.n] = qpass; e.c[e.n++] = base; }
     }
     return e;
 }
@@ -123,7 +148,8 @@ decode_scatter_kernel(const int64_t* __restrict__ base_off, const int64_t* __res
                       const uint8_t* __restrict__ y1, const uint8_t* __restrict__ y2,
                       const int32_t* __restrict__ status, int64_t n_bases, int window,
                       const int64_t* __restrict__ tile_off, uint8_t* __restrict__ revised, int64_t revised_cap,
-                      int64_t* __restrict__ out_off) {
+                      int64_t* __restrict__ out_off, const uint8_t* __restrict__ q1, const uint8_t* __restrict__ q2,
+                      const uint8_t* __restrict__ qual_in, uint8_t* __restrict__ revised_qual) {
     __shared__ int warp_sum[DEC_THREADS / 32];
     const int64_t j0 = (int64_t)blockIdx.x * DEC_TILE + (int64_t)threadIdx.x * DEC_PER;
     Emit em[DEC_PER];
@@ -135,7 +161,8 @@ decode_scatter_kernel(const int64_t* __restrict__ base_off, const int64_t* __res
         const int64_t j = j0 + k;
         em[k].n = 0; rd[k] = -1; ii[k] = -1;
         if (j < n_bases) {
-            em[k] = emit_for_base(j, base_off, win_off, base_read, bases, y1, y2, status, window, &rd[k], &ii[k]);
+            em[k] = emit_for_base(j, base_off, win_off, base_read, bases, y1, y2, status, window, &rd[k], &ii[k], q1, q2, qual_in,
+                                  revised_qual != nullptr);
             cnt += em[k].n;
         }
     }
@@ -155,7 +182,10 @@ decode_scatter_kernel(const int64_t* __restrict__ base_off, const int64_t* __res
     for (int k = 0; k < DEC_PER; ++k) {
         if (rd[k] >= 0 && ii[k] == 0) out_off[rd[k]] = pos;      // first base of a read
         for (int c = 0; c < em[k].n; ++c) {
-            if (pos < revised_cap) revised[pos] = em[k].c[c];
+            if (pos < revised_cap) {
+                revised[pos] = em[k].c[c];
+                if (revised_qual) revised_qual[pos] = (uint8_t)(em[k].q[c] + 33);      // Phred+33
+            }
             ++pos;
         }
     }
@@ -175,8 +205,10 @@ __global__ void decode_fix_empty_kernel(const int64_t* __restrict__ base_off, in
 int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,
                   const uint8_t* bases, const uint8_t* y1, const uint8_t* y2, const int32_t* status,
                   int64_t n_reads, int64_t n_bases, int window, int32_t* counts_tmp, int64_t* tile_tmp,
-                  uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st) {
+                  uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st,
+                  const uint8_t* q1, const uint8_t* q2, const uint8_t* qual_in, uint8_t* revised_qual) {
     const int64_t n_tiles = decode_tile_count(n_bases);
+    if (revised_qual && (!q1 || !q2)) return -1;
     int n = 0;
     if (n_tiles > 0) {
         decode_count_kernel<<<(unsigned)n_tiles, DEC_THREADS, 0, st>>>(base_off, win_off, base_read, bases, y1, y2,
@@ -188,7 +220,7 @@ int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t
     if (n_tiles > 0) {
         decode_scatter_kernel<<<(unsigned)n_tiles, DEC_THREADS, 0, st>>>(base_off, win_off, base_read, bases, y1, y2,
                                                                         status, n_bases, window, tile_tmp, revised,
-                                                                        revised_cap, out_off);
+                                                                        revised_cap, out_off, q1, q2, qual_in, revised_qual);
         ++n;
     }
     if (n_reads > 0) {
@@ -196,6 +228,15 @@ int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t
         ++n;
     }
     return n;
+}
+
+// Phred score of every window of one model from its softmax output and argmax labels (see window_phred_kernel)
+int launch_window_phred(const float* probs, const uint8_t* labels, int n_class, int64_t n_win, uint8_t* q, cudaStream_t st) {
+    if (n_win <= 0) return 0;
+    PhredTable tab;
+    for (int k = 1; k <= PHRED_MAX; ++k) tab.t[k - 1] = (float)pow(10.0, -k / 10.0);
+    window_phred_kernel<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(probs, labels, n_class, n_win, q, tab);
+    return 1;
 }
 
 }  // namespace nrv

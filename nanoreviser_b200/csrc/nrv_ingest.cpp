@@ -541,6 +541,7 @@ int nrv_ingest_view(const nrv_ingest* r, nrv_batch* batch, const int32_t** file_
     batch->starts = r->starts.data(); batch->base_off = r->base_off.data();
     batch->bases = r->bases.data(); batch->ev_mean = r->ev_mean.data(); batch->ev_std = r->ev_std.data();
     batch->last_dur = r->last_dur.data();
+    batch->qual = nullptr;              // the native reader does not extract the Fastq dataset (callers attach qualities themselves)
     if (file_status) *file_status = r->file_status.data();
     if (read_file) *read_file = r->read_file.data();
     if (a0) *a0 = r->a0.data();

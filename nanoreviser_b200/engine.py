@@ -46,13 +46,13 @@ class _ModelWeights(C.Structure):
 class _Batch(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("signal", C.c_void_p), ("sig_off", C.c_void_p),
                 ("starts", C.c_void_p), ("base_off", C.c_void_p), ("bases", C.c_void_p),
-                ("ev_mean", C.c_void_p), ("ev_std", C.c_void_p), ("last_dur", C.c_void_p)]
+                ("ev_mean", C.c_void_p), ("ev_std", C.c_void_p), ("last_dur", C.c_void_p), ("qual", C.c_void_p)]
 
 
 class _Result(C.Structure):
     _fields_ = [("revised", C.c_void_p), ("revised_cap", C.c_int64), ("out_off", C.c_void_p),
                 ("status", C.c_void_p), ("y1", C.c_void_p), ("y2", C.c_void_p),
-                ("p1", C.c_void_p), ("p2", C.c_void_p)]
+                ("p1", C.c_void_p), ("p2", C.c_void_p), ("revised_qual", C.c_void_p)]
 
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
@@ -209,6 +209,7 @@ class Batch:
     ev_mean: np.ndarray     # float32 [sum N]
     ev_std: np.ndarray      # float32 [sum N]
     last_dur: np.ndarray    # int32 [R]
+    qual: Optional[np.ndarray] = None   # uint8 [sum N], optional: basecaller Phred scores (Fastq quality char - 33)
 
     @property
     def n_reads(self) -> int:
@@ -255,7 +256,10 @@ def pack_batch(reads: Sequence) -> Batch:
         evm[s:e] = r.ev_mean
         evs[s:e] = r.ev_std
         last[i] = int(r.last_dur)
-    return Batch(signal, sig_off, starts, base_off, bases, evm, evs, last)
+    qual = None
+    if R and all(getattr(r, "qual", None) is not None for r in reads):
+        qual = np.concatenate([np.asarray(r.qual, dtype=np.uint8) for r in reads])
+    return Batch(signal, sig_off, starts, base_off, bases, evm, evs, last, qual)
 
 
 @dataclass
@@ -267,9 +271,16 @@ class ReviseResult:
     y2: Optional[np.ndarray] = None
     p1: Optional[np.ndarray] = None
     p2: Optional[np.ndarray] = None
+    revised_qual: Optional[np.ndarray] = None   # uint8 Phred+33 characters parallel to ``revised`` (want_qual)
 
     def sequence(self, i: int) -> str:
         return self.revised[self.out_off[i]:self.out_off[i + 1]].tobytes().decode("ascii")
+
+    def quality(self, i: int) -> str:
+        """Fastq quality string of read ``i`` (definition D6', include/nrv.h nrv_result.revised_qual)."""
+        if self.revised_qual is None:
+            raise ValueError("revise_batch was called without want_qual")
+        return self.revised_qual[self.out_off[i]:self.out_off[i + 1]].tobytes().decode("ascii")
 
     def sequences(self) -> List[str]:
         return [self.sequence(i) for i in range(len(self.status))]
@@ -354,6 +365,12 @@ class Reviser:
         for k, a in arrs.items():
             keep.append(a)
             setattr(cb, k, a.ctypes.data)
+        if getattr(b, "qual", None) is not None:
+            q = np.ascontiguousarray(b.qual, dtype=np.uint8)
+            if q.shape[0] != arrs["bases"].shape[0]:
+                raise ValueError("Batch.qual must hold one Phred score per base")
+            keep.append(q)
+            cb.qual = q.ctypes.data
         return cb
 
     # -- stage-level entry points -------------------------------------------------------------
@@ -415,7 +432,7 @@ class Reviser:
 
     # -- the whole path -----------------------------------------------------------------------
     def revise_batch(self, b: Batch, want_labels: bool = False, want_probs: bool = False,
-                     out: Optional[ReviseResult] = None) -> ReviseResult:
+                     out: Optional[ReviseResult] = None, want_qual: bool = False) -> ReviseResult:
         keep: list = []
         cb = self._cbatch(b, keep)
         R, N = b.n_reads, b.n_bases
@@ -427,10 +444,13 @@ class Reviser:
                 out.y1 = np.empty(nw, np.uint8); out.y2 = np.empty(nw, np.uint8)
             if want_probs:
                 out.p1 = np.empty((nw, 6), np.float32); out.p2 = np.empty((nw, 5), np.float32)
+            if want_qual:
+                out.revised_qual = np.empty(cap, np.uint8)
         cr = _Result()
         cr.revised = _ptr(out.revised); cr.revised_cap = int(out.revised.shape[0])
         cr.out_off = _ptr(out.out_off); cr.status = _ptr(out.status)
         cr.y1 = _ptr(out.y1); cr.y2 = _ptr(out.y2); cr.p1 = _ptr(out.p1); cr.p2 = _ptr(out.p2)
+        cr.revised_qual = _ptr(out.revised_qual)
         self._check(self._lib.nrv_revise_batch(self._h, C.byref(cb), C.byref(cr)), "nrv_revise_batch")
         return out
 
@@ -449,7 +469,8 @@ class Reviser:
         cr = _Result()
         cr.revised = int(dres["revised"]); cr.revised_cap = int(revised_cap)
         cr.out_off = int(dres["out_off"]); cr.status = int(dres["status"])
-        for k in ("y1", "y2", "p1", "p2"):
+        cb.qual = int(dptr["qual"]) if dptr.get("qual") else None
+        for k in ("y1", "y2", "p1", "p2", "revised_qual"):
             v = dres.get(k)
             setattr(cr, k, int(v) if v else None)
         self._check(self._lib.nrv_revise_batch_device(self._h, C.byref(cb), C.byref(cr)), "nrv_revise_batch_device")

@@ -28,6 +28,7 @@ class ReadArrays:
     signal: np.ndarray      # int16[S_total] (whole raw signal; the hot path uses signal[a0:])
     ev_mean: np.ndarray     # float32[N]
     ev_std: np.ndarray      # float32[N]
+    qual: "np.ndarray | None" = None   # uint8[N] optional: basecaller Phred scores (see basecall_phred)
 
     @property
     def n_bases(self) -> int:
@@ -125,6 +126,26 @@ def get_read_data(fast5_fn, basecall_group, basecall_subgroup):
     r = read_fast5_arrays(fast5_fn, basecall_group, basecall_subgroup)
     bases = [chr(c) for c in r.bases]
     return r.a0, r.starts, r.length, bases, r.signal, list(r.ev_mean), list(r.ev_std)
+
+
+def basecall_phred(fast5_fn, bases, basecall_group="Basecall_1D_000", basecall_subgroup="BaseCalled_template"):
+    """Phred scores (uint8, quality character - 33) of the event-collapsed ``bases`` of a read, taken from the
+    basecaller's Fastq dataset: the collapsed call is the Fastq sequence without its first and last two bases
+    (``bases == Fastq_seq[2:-2]``, the Albacore known answer of SURVEY.md section 8(c)).  Returns None when the
+    dataset is missing or does not line up -- the revision path then uses its constant pass-through quality."""
+    try:
+        f = h5mini.File(fast5_fn, "r")
+        fastq = f["/Analyses/" + basecall_group + "/" + basecall_subgroup + "/Fastq"][()]
+        f.close()
+        lines = bytes(fastq).decode("utf8").split("\n")
+        seq, qul = lines[1], lines[3]
+    except Exception:
+        return None
+    b = bytes(bytearray(np.asarray(bases, dtype=np.uint8))).decode("ascii") if not isinstance(bases, str) else bases
+    if len(seq) != len(qul) or len(seq) != len(b) + 4 or seq[2:-2] != b:
+        return None
+    q = np.frombuffer(qul[2:-2].encode("ascii"), dtype=np.uint8).astype(np.int16) - 33
+    return np.clip(q, 0, 93).astype(np.uint8)
 
 
 def extract_fastq(fast5_fn, out_fasta_fn=None, basecall_group="Basecall_1D_000",

@@ -94,5 +94,8 @@ def split_batch(b: Batch, idx: Sequence[int]) -> Batch:
         sig.append(b.signal[s0:s1]); st.append(b.starts[b0:b1]); ba.append(b.bases[b0:b1])
         em.append(b.ev_mean[b0:b1]); es.append(b.ev_std[b0:b1])
     cat = lambda parts, dt: (np.concatenate(parts).astype(dt, copy=False) if parts else np.zeros(0, dt))
+    qual = None
+    if getattr(b, "qual", None) is not None:
+        qual = cat([b.qual[int(b.base_off[i]):int(b.base_off[i + 1])] for i in idx], np.uint8)
     return Batch(cat(sig, np.int16), sig_off, cat(st, np.int32), base_off, cat(ba, np.uint8), cat(em, np.float32),
-                 cat(es, np.float32), np.asarray(b.last_dur)[idx].astype(np.int32))
+                 cat(es, np.float32), np.asarray(b.last_dur)[idx].astype(np.int32), qual)

@@ -322,6 +322,71 @@ def get_base_1(event_bases, y_pre, y_pre2):
 
 
 # --------------------------------------------------------------------------------------
+# D6': fastq qualities of the NN path.  The reference has NO definition
+# for them (-F fastq only exists on the Guppy path, output_handeler.py:86-102, and in the per-read
+# fallback that copies the basecaller's Fastq[7:-7], NanoReviser.py:172-181); this is the builder's
+# definition, restated here so that the CUDA path can be checked byte for byte:
+#   * Phred of a window and model: Q(p) = #{k in 1..60 : float32(1) - p <= float32(10**(-k/10))} with
+#     p = the softmax value of the argmax class as float32 (i.e. floor(-10 log10(1-p)) capped at 60,
+#     evaluated with a threshold table so that it is exact and portable);
+#   * every symbol get_base_1 emits BECAUSE of the models (agreed base, inserted base) gets
+#     min(Q1, Q2) of its window, the leading label symbol gets Q1 of window 0;
+#   * every base that passes through (edges, disagreement, kept base before an insertion, failed
+#     read) keeps the basecaller's quality when it is known, else Phred 40 (the former constant 'I').
+# Output characters are Phred + 33.
+# --------------------------------------------------------------------------------------
+PHRED_MAX = 60
+PHRED_PASS = 40
+PHRED_THRESH = np.array([10.0 ** (-k / 10.0) for k in range(1, PHRED_MAX + 1)]).astype(np.float32)
+
+
+def phred_of_prob(p):
+    """p: float32 array of argmax-class probabilities -> uint8 Phred 0..60."""
+    e = np.float32(1.0) - np.asarray(p, dtype=np.float32)
+    return (e[..., None] <= PHRED_THRESH).sum(axis=-1).astype(np.uint8)
+
+
+def get_qual_1(event_bases, y_pre, y_pre2, q1, q2, pass_q):
+    """Phred values parallel to get_base_1(event_bases, y_pre, y_pre2): same branches, same order
+    (output_handeler.py:104-122), one value per emitted symbol, dropped where get_base_1 drops '-'."""
+    res = []
+    lead = label_to_base[int(y_pre[0])]
+    if lead != '-':
+        res.append(int(q1[0]))
+    y_pre2 = np.asarray(y_pre2) - 1
+    for k, (y_tmp, y_tmp2, base) in enumerate(zip(y_pre, y_pre2, event_bases)):
+        y_tmp = label_to_base.get(int(y_tmp), 0)
+        y_tmp2 = label_to_base.get(int(y_tmp2), 0)
+        qm = min(int(q1[k]), int(q2[k]))
+        if y_tmp == y_tmp2 and y_tmp in ['A', 'T', 'C', 'G']:
+            res.append(qm)
+        elif y_tmp == 'D' and y_tmp2 in ['A', 'T', 'C', 'G']:
+            if base != '-':
+                res.append(int(pass_q[k]))
+            res.append(qm)
+        elif y_tmp == '-' and y_tmp2 == '-':
+            continue
+        else:
+            if base != '-':
+                res.append(int(pass_q[k]))
+    return res
+
+
+def revise_quality(bases, y1, y2, p1max, p2max, window, qual_in=None, revised_ok=True):
+    """Quality string (Phred+33) of the whole revised read under composition D4; p1max / p2max are the
+    float32 argmax probabilities of the N-W windows; qual_in the basecaller's Phred values per base or None."""
+    N = len(bases)
+    pass_q = np.full(N, PHRED_PASS, dtype=np.int64) if qual_in is None else np.minimum(np.asarray(qual_in, dtype=np.int64), 93)
+    M = N - window
+    if not revised_ok or M <= 0:
+        return ''.join(chr(int(q) + 33) for q in pass_q)
+    q1, q2 = phred_of_prob(p1max), phred_of_prob(p2max)
+    core = get_qual_1(bases[SET_BEF:SET_BEF + M], y1, np.asarray(y2) + 2, q1, q2, pass_q[SET_BEF:SET_BEF + M])
+    allq = list(pass_q[:SET_BEF]) + core + list(pass_q[SET_BEF + M:])
+    return ''.join(chr(int(q) + 33) for q in allq)
+
+
+# --------------------------------------------------------------------------------------
 # A11: writers   (output_handeler.py:26-62; file names NanoReviser.py:137,163)
 # --------------------------------------------------------------------------------------
 def fasta_text(fast5_fn, bases):

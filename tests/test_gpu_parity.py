@@ -250,6 +250,44 @@ def test_revise_unitest_set_matches_goldens(reviser_by_species, reads, golden_di
     assert n_same / n_lab >= 0.9999
 
 
+@pytest.mark.parametrize("with_basecall_qual", [True, False])
+def test_fastq_qualities_byte_exact(reviser_by_species, reads, fast5_files, with_basecall_qual):
+    """D6' (include/nrv.h nrv_result.revised_qual): byte work, so the bar is bit-exact -- the CUDA decode must give the
+    oracle's quality string when the oracle is fed the labels and the float32 softmax values the GPU returned."""
+    import copy
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import api, fast5
+    rv = reviser_by_species("ecoli")
+    rs = [copy.copy(r) for r in reads]
+    for r, fn in zip(rs, fast5_files):
+        r.qual = fast5.basecall_phred(fn, r.bases) if with_basecall_qual else None
+        assert (r.qual is not None) == with_basecall_qual and (r.qual is None or len(r.qual) == r.n_bases)
+    out = api.revise_reads(rs, reviser=rv, want_labels=True, want_probs=True, want_qual=True)
+    plain = api.revise_reads(rs, reviser=rv)
+    W = rv.window
+    w0 = 0
+    for k, r in enumerate(rs):
+        M = r.n_bases - W
+        p1, p2 = out.p1[w0:w0 + M], out.p2[w0:w0 + M]
+        y1, y2 = out.y1[w0:w0 + M], out.y2[w0:w0 + M]
+        src = list(r.bases.tobytes().decode())
+        want = orc.revise_quality(src, y1.astype(int), y2.astype(int), p1[np.arange(M), y1], p2[np.arange(M), y2], W, qual_in=r.qual)
+        assert out.sequence(k) == plain.sequence(k)                  # asking for qualities does not change the sequence
+        assert len(out.quality(k)) == len(out.sequence(k))
+        assert out.quality(k) == want, "quality string of read %d" % k
+        w0 += M
+    # a read that fails (too short for a window) passes through with its own qualities
+    short = copy.copy(rs[0])
+    n = 8
+    short.starts, short.length, short.bases = short.starts[:n], short.length[:n].copy(), short.bases[:n]
+    short.ev_mean, short.ev_std = short.ev_mean[:n], short.ev_std[:n]
+    short.qual = None if short.qual is None else short.qual[:n]
+    short.length[-1] = 5.0
+    o2 = api.revise_reads([short], reviser=rv, want_qual=True)
+    assert o2.sequence(0) == short.bases.tobytes().decode()
+    assert o2.quality(0) == ("".join(chr(33 + int(v)) for v in short.qual) if with_basecall_qual else "I" * n)
+
+
 def test_batch_invariance_and_determinism(reviser_by_species, reads):
     """Reads are independent: a ragged batch gives the same bytes as one read at a time, in any order."""
     from nanoreviser_b200 import api
@@ -350,12 +388,29 @@ def test_cli_fasta_bytes_match_goldens(tmp_path, golden_dir, monkeypatch):
     for k, f in enumerate(files):
         out_fn = out_dir + f.split(".")[0] + "_out.fasta"
         assert open(out_fn, "rb").read() == gold["r%d_fasta" % k].tobytes(), f
-    # fastq mode writes the same sequence (qualities on the NN path are a documented builder decision, D6)
+    # fastq mode writes the same sequence in the reference's layout (output_handeler.py:48-62: no newline before '+', none at
+    # the end) with the qualities of definition D6' (softmax-derived where the models decided, the basecaller's elsewhere)
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import fast5
     args = cli.get_args(["-d", os.path.join(golden_dir, "fast5") + "/", "-o", out_dir, "-F", "fastq", "-S", "ecoli"])
     cli.main(args)
-    txt = open(out_dir + files[0].split(".")[0] + "_out.fastq").read()
-    seq = gold["r0_revised"].tobytes().decode()
-    assert txt.startswith("@" + files[0] + "\n" + seq + "+\n") and len(txt.split("+\n")[1]) == len(seq)
+    for k, f in enumerate(files):
+        txt = open(out_dir + f.split(".")[0] + "_out.fastq").read()
+        seq = gold["r%d_revised" % k].tobytes().decode()
+        head = "@" + f + "\n" + seq + "+\n"
+        assert txt.startswith(head)
+        ql = txt[len(head):]
+        assert len(ql) == len(seq) and "\n" not in ql
+        r = fast5.read_fast5_arrays(os.path.join(golden_dir, "fast5", f))
+        bq = fast5.basecall_phred(os.path.join(golden_dir, "fast5", f), r.bases)
+        assert ql[:5] == "".join(chr(33 + int(v)) for v in bq[:5])          # pass-through edge keeps the basecaller's quality
+        # against the oracle's definition on the oracle's own float32 probabilities: equal up to +-1 Phred where the GPU's
+        # probability (tolerance 1e-3, measured 1e-4) falls on the other side of a threshold
+        p1, p2 = gold["r%d_P1_f64" % k].astype(np.float32), gold["r%d_P2_f64" % k].astype(np.float32)
+        want = orc.revise_quality(list(r.bases.tobytes().decode()), p1.argmax(1), p2.argmax(1), p1.max(1), p2.max(1), 11, qual_in=bq)
+        d = np.abs(np.frombuffer(ql.encode(), np.uint8).astype(int) - np.frombuffer(want.encode(), np.uint8).astype(int))
+        print('fastq quality vs fp32-oracle probabilities: read %d max |dQ| %d, exact %.4f, within 1: %.4f' % (k, d.max(), (d == 0).mean(), (d <= 1).mean()))
+        assert (d <= 1).mean() >= 0.99 and (d == 0).mean() >= 0.95, (k, d.max(), (d == 0).mean())
 
 
 def test_stage_timing_api(reviser_by_species, reads):
