@@ -55,6 +55,9 @@ const char* const kStageNames[ST_COUNT] = {"read_stats", "base_features", "cnn",
 struct nrv_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;       // side stream: read_rnn1 of the NEXT (chunk, model) runs under the fused layers of the current one
+    cudaEvent_t ev_a1_free = nullptr, ev_l0_done = nullptr;
+    int overlap_l0 = 1;                   // NRV_OVERLAP=0 keeps everything on one stream
     std::string err;
     bool sticky = false;
     int window = 11;
@@ -69,8 +72,7 @@ struct nrv_handle {
     PinnedArena h_off, h_flag;
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
-    int trnn2_fused = 2;    // total_rnn2: 2 = fused CTA-pair kernel with drained accumulator (nrv_fused_pair.cu); 1 = first fused version
-                            // (NRV_TRNN2=v1); 0 = GEMM + recurrence (NRV_TRNN2=split)
+    int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
     int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
@@ -298,8 +300,8 @@ cuda_fail:
 }
 
 struct StageTimer {
-    nrv_handle* h; int stage; int64_t launches0; nrv_handle::EvPair* ev = nullptr;
-    StageTimer(nrv_handle* h_, int s) : h(h_), stage(s), launches0(h_->launches) {
+    nrv_handle* h; int stage; int64_t launches0; nrv_handle::EvPair* ev = nullptr; cudaStream_t st;
+    StageTimer(nrv_handle* h_, int s, cudaStream_t st_ = nullptr) : h(h_), stage(s), launches0(h_->launches), st(st_ ? st_ : h_->stream) {
         if (!h->timing) return;
         if (h->ev_used == h->ev_pool.size()) {
             if (h->ev_pool.size() >= 8192) h->fold_events();
@@ -311,11 +313,11 @@ struct StageTimer {
         }
         ev = &h->ev_pool[h->ev_used++];
         ev->stage = stage;
-        cudaEventRecord(ev->a, h->stream);
+        cudaEventRecord(ev->a, st);
     }
     ~StageTimer() {
         h->stage_launches[stage] += h->launches - launches0;
-        if (ev) cudaEventRecord(ev->b, h->stream);
+        if (ev) cudaEventRecord(ev->b, st);
     }
 };
 
@@ -375,6 +377,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
         CU(h, h->d_a3[0].ensure((size_t)rows * 256 * 2)); CU(h, h->d_a3[1].ensure((size_t)rows * 256 * 2));
         CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
     }
+    bool l0_prefetched = false;      // read_rnn1 of the current iteration was already launched on the side stream
     for (int64_t c0 = 0; c0 < n_win; c0 += CH) {
         const int64_t nw = std::min(CH, n_win - c0);
         for (int mi = 0; mi < 2; ++mi) {
@@ -409,14 +412,26 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 __half *a4h = h->d_a4[0].as<__half>(), *a4l = h->d_a4[1].as<__half>();
                 float* zin = h->d_zin.as<float>();
                 int n;
-                {   // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand
-                    StageTimer tm(h, ST_L0);
-                    LstmIo io; io.base_in = x; io.win_base = win_base + c0; io.out_hi = a1h; io.out_lo = a1l; io.out_ld = 64;
-                    io.out_nwp = nwp;
-                    n = launch_read_rnn1(M.lstm[0], io, nw, T, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
-                    h->launches += n;
+                // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand.
+                // The cluster-of-4 kernel of total_rnn1 can only use 128 of the 148 SMs (32 co-resident clusters) and read_rnn1 is a
+                // grid of small CTAs, so the read_rnn1 of the NEXT (chunk, model) is launched on a side stream as soon as read_rnn11 of
+                // this one has consumed a1: it runs on the idle SMs under the fused layers.
+                auto launch_l0 = [&](int64_t c0_, int mi_, cudaStream_t st) -> int {
+                    const int64_t nw_ = std::min(CH, n_win - c0_);
+                    StageTimer tm(h, ST_L0, st);
+                    LstmIo io; io.base_in = x; io.win_base = win_base + c0_; io.out_hi = a1h; io.out_lo = a1l; io.out_ld = 64;
+                    io.out_nwp = (nw_ + 127) / 128 * 128;
+                    const int k = launch_read_rnn1(h->m[mi_].lstm[0], io, nw_, T, st);
+                    if (k > 0) h->launches += k;
+                    return k;
+                };
+                const bool overlap = h->overlap_l0 && h->stream2 && h->trnn1_fused;
+                if (!overlap || !l0_prefetched) {
+                    if (launch_l0(c0, mi, h->stream) < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
+                } else {
+                    CU(h, cudaStreamWaitEvent(h->stream, h->ev_l0_done, 0));     // launched during the previous iteration
                 }
+                l0_prefetched = false;
                 {   // read_rnn11: projection (K = 32 -> 64, bias as the weight row of a constant-1 column) and recurrence
                     // (u = 64) fused in one tcgen05 kernel -- no zin round trip for this layer
                     StageTimer tm(h, ST_REC1);
@@ -431,6 +446,20 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
                         h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
                     h->launches += 1;
+                    if (overlap) {
+                        // next iteration in launch order: the other model of this chunk, or model 1 of the next chunk.  The side stream has the
+                        // lowest priority and becomes eligible together with the cluster kernel (after the gather): the cluster kernel takes
+                        // its 128 SMs first, read_rnn1 gets the rest
+                        const int mi_n = mi == 0 ? 1 : 0;
+                        const int64_t c0_n = mi == 0 ? c0 : c0 + CH;
+                        if (c0_n < n_win) {
+                            CU(h, cudaEventRecord(h->ev_a1_free, h->stream));
+                            CU(h, cudaStreamWaitEvent(h->stream2, h->ev_a1_free, 0));
+                            if (launch_l0(c0_n, mi_n, h->stream2) < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
+                            CU(h, cudaEventRecord(h->ev_l0_done, h->stream2));
+                            l0_prefetched = true;
+                        }
+                    }
                     if (h->trnn1_fused) {
                         delete tp;
                         StageTimer tm(h, ST_REC2);
@@ -452,17 +481,10 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     h->launches += n;
                     }
                 }
-                if (h->trnn2_fused == 2) {
+                if (h->trnn2_fused) {
                     StageTimer tm(h, ST_REC3);
                     LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
                     n = launch_lstm_fused_pair64(M.lstm[3], a3h, a3l, io, nwp, T, h->num_sms, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn2) could not be launched");
-                    h->launches += n;
-                } else if (h->trnn2_fused) {
-                    // total_rnn2: projection (K = 256) and recurrence (u = 64) fused on CTA pairs, h in tensor memory -- no zin
-                    StageTimer tm(h, ST_REC3);
-                    LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
-                    n = launch_lstm_fused_tc64_pair(M.lstm[3], a3h, a3l, io, nwp, nw, T, h->stream);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn2) could not be launched");
                     h->launches += n;
                 } else {   // total_rnn2: projection (K = 256), recurrence (u = 64)
@@ -743,7 +765,12 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     h->device = device;
     h->window = m1->window;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_a1_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_l0_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_create_error = std::string("nrv_create: ") + cudaGetErrorString(e);
         delete h;
@@ -758,7 +785,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (pa && !strcmp(pa, "simt")) h->path = 0;
     const char* t2 = getenv("NRV_TRNN2");
     if (t2 && !strcmp(t2, "split")) h->trnn2_fused = 0;
-    if (t2 && !strcmp(t2, "v1")) h->trnn2_fused = 1;
+    const char* ov = getenv("NRV_OVERLAP");
+    if (ov && !strcmp(ov, "0")) h->overlap_l0 = 0;
     const char* t1 = getenv("NRV_TRNN1");
     if (t1 && !strcmp(t1, "split")) h->trnn1_fused = 0;
     if (t1 && !strcmp(t1, "fused")) h->trnn1_fused = 1;
@@ -784,6 +812,9 @@ void nrv_destroy(nrv_handle* h) {
     for (Arena* a : arenas) a->release();
     h->h_off.release(); h->h_flag.release();
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (h->ev_a1_free) cudaEventDestroy(h->ev_a1_free);
+    if (h->ev_l0_done) cudaEventDestroy(h->ev_l0_done);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

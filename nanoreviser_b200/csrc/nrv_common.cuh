@@ -112,8 +112,6 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t n_win,
 int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                            cudaStream_t st);
 int launch_read_rnn1(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
-int launch_lstm_fused_tc64_pair(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int64_t n_win,
-                                int T, cudaStream_t st);
 // nrv_fused_pair.cu: projection + recurrence of total_rnn2 (cluster of 2) / total_rnn1 (cluster of 4), drained accumulator, h in TMEM
 int launch_lstm_fused_pair64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
                              cudaStream_t st);

@@ -279,6 +279,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         if (elect_one()) {
                             const uint32_t xa = ring_base + (uint32_t)(stage * FP_TILE);
 #pragma unroll
+#ifdef NRV_FP_SKIP_XLO     // precision experiment only: drop the x_lo . W_hi pass of the projection (NP mask: 1 = total_rnn2, 2 = total_rnn1)
+                            if (!((NRV_FP_SKIP_XLO) & NP))
+#endif
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_lo = umma_desc_k_sw128(xa + k * 32);
                                 umma_f16_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_hi + k * 32), idesc, (kc | k) != 0);
@@ -295,9 +298,14 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_hi = umma_desc_k_sw128(xa + k * 32);
-                                umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, 1);
+#ifdef NRV_FP_SKIP_XLO
+                                const uint32_t acc0 = ((NRV_FP_SKIP_XLO) & NP) ? (uint32_t)((kc | k) != 0) : 1u;
+#else
+                                const uint32_t acc0 = 1u;
+#endif
+                                umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_hi + k * 32), idesc, 1);
-                                umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, 1);
+                                umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, 1);
                             }
                             umma_commit_mask(&empty[stage], mask);

@@ -435,219 +435,6 @@ int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __ha
 }
 
 // ============================================================================================================
-// total_rnn2 (lstmmodel.py:51: Bidirectional(LSTM(64)) on the 256-wide output of total_rnn1) FUSED on CTA pairs:
-// input projection AND recurrence in one persistent kernel -- the fp32 pre-activations (zin: 2 x 22.5 KB per window,
-// written by a GEMM and read back by the recurrence) never exist.
-//   * tcgen05 cta_group::2: one MMA covers M = 256 windows (128 per CTA) x N = 256 gate columns and takes half of the B
-//     operand from each CTA, so [Wk ; Wr]^T (K = 256 + 64, hi + lo = 327 KB per direction) is RESIDENT: 160 KB per SM.
-//   * that leaves 64 KB of shared memory: a 2-stage TMA ring of x_t K-chunks ([128 rows][64] hi + lo = 32 KB).  There is
-//     no room for the h tile -- so h_{t-1} (the A operand of the recurrent MMAs) lives in TENSOR MEMORY: the epilogue
-//     threads own one TMEM lane = one window each and tcgen05.st their new h (fp16 hi / lo pairs, 32 + 32 columns) next
-//     to the 256-column accumulator; the recurrent MMAs use the A-from-TMEM form of tcgen05.mma (tools/ts_probe).
-//   * per step: 48 projection MMAs (x_t . Wk, A from the ring) + 12 recurrent MMAs (h . Wr, A from TMEM) into one
-//     accumulator, commit -> 8 epilogue warps: + bias (shared memory), gates, c (registers), h -> TMEM and -> HBM
-//     (fp16 pair, the operand of the dense head).
-// ============================================================================================================
-constexpr int RQ_THREADS = 352;                       // warp 0: MMA issue (leader); warp 1: TMA producer; warp 2: idle; warps 3..10: epilogue
-constexpr int RQ_W_BYTES = (4 + 1) * 2 * 128 * 64 * 2;   // 160 KB: [Wk chunk 0..3 | Wr][hi | lo][128 rows][64]
-constexpr int RQ_X_STAGE = 2 * 128 * 64 * 2;          // 32 KB: x_t chunk hi + lo
-constexpr int RQ_XS = 2;
-constexpr size_t RQ_SMEM = (size_t)RQ_W_BYTES + RQ_XS * RQ_X_STAGE + 1024 /*bias*/ + 128 /*barriers*/ + 1024 /*alignment*/;
-constexpr uint32_t RQ_H_HI_COL = 256, RQ_H_LO_COL = 288;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RQ_THREADS, 1)
-lstm_fused_tc64_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
-                            const __half* __restrict__ wr_lo, const float* __restrict__ bias,
-                            const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                            __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int64_t n_win, int T) {
-    constexpr int U = 64, N = 256, KIN = 256;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_w = smem;                                   // [chunk 0..4][part][128 rows][64]
-    uint8_t* s_x = smem + RQ_W_BYTES;                      // [stage][part][128 rows][64]
-    float* s_bias = reinterpret_cast<float*>(s_x + RQ_XS * RQ_X_STAGE);     // [256] this direction, column = unit*4 + gate
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + N);
-    uint64_t* full = bars;                                 // [2] leader's copy: 1 arrive + 64 KB tx (both CTAs' chunks)
-    uint64_t* empty = bars + 2;                            // [2] both CTAs: multicast commit
-    uint64_t* acc_ready = bars + 4;                        // both CTAs: multicast commit
-    uint64_t* h_ready = bars + 5;                          // leader's copy: 16 arrivals (8 epilogue warps x 2 CTAs)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int dir = blockIdx.y;
-    const int64_t ntw = nwp >> 7;
-    const int64_t n_pairs = (ntw + 1) >> 1;
-    const int64_t cl0 = blockIdx.x >> 1, cl_stride = gridDim.x >> 1;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < RQ_XS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(acc_ready, 1);
-        mbar_init(h_ready, 16);
-        fence_mbar_init();
-        tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo);
-    }
-    if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
-    if (threadIdx.x < N) s_bias[threadIdx.x] = __ldg(bias + dir * N + threadIdx.x);
-    {   // resident weights: this CTA's 128 gate columns (global rows dir*256 + rank*128 + row), all of K, hi and lo
-        for (int i = threadIdx.x; i < 2 * 128 * (KIN / 8); i += RQ_THREADS) {          // Wk: 32 16-byte chunks per row
-            const int c = i & 31, row = (i >> 5) & 127, part = i >> 12;
-            const __half* src = (part ? wk_lo : wk_hi) + ((size_t)dir * N + rank * 128 + row) * KIN;
-            *reinterpret_cast<uint4*>(s_w + ((size_t)((c >> 3) * 2 + part)) * (128 * 128) + sw128_offset(row, c & 7)) =
-                __ldg(reinterpret_cast<const uint4*>(src) + c);
-        }
-        for (int i = threadIdx.x; i < 2 * 128 * 8; i += RQ_THREADS) {                  // Wr: 8 chunks per row
-            const int c = i & 7, row = (i >> 3) & 127, part = i >> 10;
-            const __half* src = (part ? wr_lo : wr_hi) + ((size_t)dir * N + rank * 128 + row) * U;
-            *reinterpret_cast<uint4*>(s_w + ((size_t)(4 * 2 + part)) * (128 * 128) + sw128_offset(row, c)) =
-                __ldg(reinterpret_cast<const uint4*>(src) + c);
-        }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 1) {
-        // ===================== TMA producer (both CTAs): x_t K-chunks of this CTA's 128 windows, in consumption order =====================
-        if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
-            for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
-                const int64_t wtile = min(tp * 2 + (int64_t)rank, ntw - 1);
-                for (int s = 0; s < T; ++s) {
-                    const int t = dir ? (T - 1 - s) : s;
-                    const int grow = (int)(t * nwp + wtile * 128);
-                    for (int kc = 0; kc < KIN / 64; ++kc) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* st = s_x + (size_t)stage * RQ_X_STAGE;
-                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * RQ_X_STAGE);
-                        tma_load_2d_pair(st, &tm_x_hi, &full[stage], 0, kc * 64, grow);
-                        tma_load_2d_pair(st + RQ_X_STAGE / 2, &tm_x_lo, &full[stage], 0, kc * 64, grow);
-                        if (++stage == RQ_XS) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 0) {
-        // ===================== MMA issue (leader CTA) =====================
-        if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16_f32(256, 256);
-            const uint32_t w_base = smem_u32(s_w);
-            int stage = 0; uint32_t phase = 0;
-            uint32_t g = 0;                                               // running step count over all tiles
-            for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride)
-                for (int s = 0; s < T; ++s, ++g) {
-                    if (g > 0) {                                          // epilogue of the previous step: accumulator drained, h in TMEM
-                        mbar_wait(h_ready, (g - 1) & 1);
-                        tc_fence_after();
-                    }
-                    for (int kc = 0; kc < KIN / 64; ++kc) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t xa = smem_u32(s_x + (size_t)stage * RQ_X_STAGE);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t a_hi = umma_desc_k_sw128(xa + k * 32), a_lo = umma_desc_k_sw128(xa + RQ_X_STAGE / 2 + k * 32);
-                                const uint64_t b_hi = umma_desc_k_sw128(w_base + (uint32_t)((kc * 2 + 0) * (128 * 128)) + k * 32);
-                                const uint64_t b_lo = umma_desc_k_sw128(w_base + (uint32_t)((kc * 2 + 1) * (128 * 128)) + k * 32);
-                                umma_f16_ss_pair(tmem_base, a_lo, b_hi, idesc, (kc | k) != 0);
-                                umma_f16_ss_pair(tmem_base, a_hi, b_lo, idesc, 1);
-                                umma_f16_ss_pair(tmem_base, a_hi, b_hi, idesc, 1);
-                            }
-                            umma_commit_pair(&empty[stage]);
-                        }
-                        __syncwarp();
-                        if (++stage == RQ_XS) { stage = 0; phase ^= 1; }
-                    }
-                    if (elect_one()) {
-                        if (s > 0) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t b_hi = umma_desc_k_sw128(w_base + (uint32_t)((4 * 2 + 0) * (128 * 128)) + k * 32);
-                                const uint64_t b_lo = umma_desc_k_sw128(w_base + (uint32_t)((4 * 2 + 1) * (128 * 128)) + k * 32);
-                                umma_f16_ts_pair(tmem_base, tmem_base + RQ_H_LO_COL + k * 8, b_hi, idesc, 1);
-                                umma_f16_ts_pair(tmem_base, tmem_base + RQ_H_HI_COL + k * 8, b_lo, idesc, 1);
-                                umma_f16_ts_pair(tmem_base, tmem_base + RQ_H_HI_COL + k * 8, b_hi, idesc, 1);
-                            }
-                        }
-                        umma_commit_pair(acc_ready);
-                    }
-                    __syncwarp();
-                }
-        }
-    } else if (warp >= 3) {
-        // ===================== epilogue: warps 3..10; TMEM lane quarter = warp % 4; column half = (warp - 3) / 4 =====================
-        const int q = warp & 3;
-        const int ch = (warp - 3) >> 2;                   // units ch*32 .. +32 (4 blocks of 32 gate columns)
-        const int row = q * 32 + lane;
-        const uint32_t sb = smem_u32(s_bias);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t g = 0;
-        for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
-            const int64_t wtile = min(tp * 2 + (int64_t)rank, ntw - 1);
-            const int64_t w = wtile * 128 + row;
-            float c[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) c[j] = 0.f;
-            for (int s = 0; s < T; ++s, ++g) {
-                const int t = dir ? (T - 1 - s) : s;
-                mbar_wait(acc_ready, g & 1);
-                tc_fence_after();
-                __half* oh = out_hi + ((int64_t)t * nwp + w) * out_ld + dir * U + ch * 32;
-                __half* ol = out_lo + ((int64_t)t * nwp + w) * out_ld + dir * U + ch * 32;
-#pragma unroll
-                for (int cbi = 0; cbi < 4; ++cbi) {
-                    const int cb = ch * 4 + cbi;
-                    uint32_t v[32];
-                    tmem_ld_32x32(lane_addr + (uint32_t)(cb * 32), v);
-                    float4 zb[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) zb[j] = ld_shared_f4(sb + (uint32_t)(cb * 32 + j * 4) * 4);
-                    tmem_ld_wait();
-                    uint4 phi, plo;
-                    lstm_cell_block(v, true, zb, &c[cbi * 8], phi, plo);
-                    tmem_st_32x4(lane_addr + RQ_H_HI_COL + (uint32_t)(cb * 4), phi);
-                    tmem_st_32x4(lane_addr + RQ_H_LO_COL + (uint32_t)(cb * 4), plo);
-                    if (w < n_win || true) {           // padded rows are written too (finite garbage, never read back as windows)
-                        *reinterpret_cast<uint4*>(oh + cbi * 8) = phi;
-                        *reinterpret_cast<uint4*>(ol + cbi * 8) = plo;
-                    }
-                }
-                tmem_st_wait();
-                tc_fence_before();           // our tcgen05.ld / st of this step precede the next step's MMAs
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(h_ready, 0);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
-}
-
-int launch_lstm_fused_tc64_pair(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int64_t n_win,
-                                int T, cudaStream_t st) {
-    if (nwp <= 0) return 0;
-    if (L.u != 64 || L.in_a != 256 || !L.rt_hi || !L.pb_hi || !L.bias_tc || !io.out_hi || !io.out_lo || (nwp & 127) || (io.out_ld & 7)) return -1;
-    CUtensorMap txh, txl;
-    if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, 256, 128) || !make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, 256, 128)) return -2;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(lstm_fused_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_SMEM) != cudaSuccess) return -3;
-        attr = true;
-    }
-    const int64_t n_pairs = ((nwp >> 7) + 1) / 2;
-    dim3 grid((unsigned)(2 * std::min<int64_t>(n_pairs, 37)), 2);
-    lstm_fused_tc64_pair_kernel<<<grid, RQ_THREADS, RQ_SMEM, st>>>(L.pb_hi, L.pb_lo, L.rt_hi, L.rt_lo, L.bias_tc, txh, txl, io.out_hi, io.out_lo,
-                                                                    io.out_ld, nwp, n_win, T);
-    return 1;
-}
-
-// ============================================================================================================
 // u = 128 variant (total_rnn1, lstmmodel.py:49): N = 512 gate columns, K = 128.
 // Wr^T as an fp16 (hi, lo) pair is 2 x 128 KB -- more than one SM's shared memory -- so the hi half stays
 // resident (128 KB, used by the lo*hi and hi*hi passes) and the lo half (used only by the hi*lo pass) is
