@@ -128,11 +128,19 @@ __device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbi
         const float4 b = ld_shared_f4(sbias + j * 16);       // {0.2 b_i + 0.5, 0.2 b_f + 0.5, b_c, 0.2 b_o + 0.5}
         const float ig = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 0]), b.x));
         const float fg = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 1]), b.y));
+#if defined(NRV_TANH_NR) && NRV_TANH_NR >= 1
+        const float gg = tanh_fast_nr(b.z + __uint_as_float(v[4 * j + 2]));
+#else
         const float gg = tanh_fast(b.z + __uint_as_float(v[4 * j + 2]));
+#endif
         const float og = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 3]), b.w));
         const float cn = fmaf(fg, c8[j], ig * gg);
         c8[j] = cn;
+#if defined(NRV_TANH_NR) && NRV_TANH_NR >= 2
+        hv[j] = og * tanh_fast_nr(cn);
+#else
         hv[j] = og * tanh_fast(cn);
+#endif
     }
 }
 // h = hi + lo as fp16 pairs (packed conversions, ALU pipe)
