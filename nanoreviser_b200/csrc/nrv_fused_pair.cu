@@ -52,8 +52,12 @@ template <int KIN, int UT>
 struct FpCfg {
     static constexpr int KC = KIN / 64, RC = UT / 64, NP = UT / 64;
     static constexpr int W_BYTES = (KC + RC) * 2 * FP_TILE;
-    static constexpr int STAGES = NP == 1 ? 4 : 3;                   // x ring depth (16 KB tiles)
-    static constexpr int XCH = NP == 1 ? 0 : FP_XCH_BYTES;
+#ifndef NRV_FP_XCH_DMA
+#define NRV_FP_XCH_DMA 0      // total_rnn1 exchange: 0 = st.async from registers (3-stage x ring); 1 = staged in local shared memory and pushed by the
+                              // bulk-copy engine (2-stage x ring).  Measured equal (53.2 vs 54.4 ms per step; 11.7k vs 11.0k clocks per step)
+#endif
+    static constexpr int STAGES = NP == 1 ? 4 : (NRV_FP_XCH_DMA ? 2 : 3);      // x ring depth (16 KB tiles)
+    static constexpr int XCH = NP == 1 ? 0 : (NRV_FP_XCH_DMA ? 2 : 1) * FP_XCH_BYTES;   // landing zone (+ outgoing staging)
     static constexpr size_t SMEM = (size_t)W_BYTES + STAGES * FP_TILE + XCH + 1024 /*bias*/ + 512 /*barriers*/ + 1024 /*alignment*/;
 };
 
@@ -110,6 +114,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(cta));
     return r;
+}
+// bulk copy (DMA) from this CTA's shared memory into another CTA's; the bytes are counted on that CTA's mbarrier (complete_tx)
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(remote_dst),
+                 "r"(local_src), "r"(bytes), "r"(remote_bar)
+                 : "memory");
 }
 // 16 bytes from registers into another CTA's shared memory; the bytes are counted on that CTA's mbarrier (complete_tx)
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, const uint4& v, uint32_t remote_bar) {
@@ -377,6 +387,10 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const uint32_t xsrc = smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + row) * 16;       // our landing slots (hi; lo at + 2 KB)
         const uint32_t sib = NP == 2 ? (rank ^ 2u) : rank;   // sibling CTA: other pair, same windows
         const uint32_t xdst = mapa_u32(xsrc, sib), xbar = mapa_u32(smem_u32(&xfull[ew]), sib);
+        // outgoing staging (DMA variant): same layout as the landing zone, 16 KB behind it; a warp's 32 slots are 512 contiguous bytes
+        const uint32_t xout = xsrc + FP_XCH_BYTES;
+        const uint32_t xout_w = smem_u32(s_xch) + FP_XCH_BYTES + (uint32_t)((cg * 2) * 128 + q * 32) * 16;
+        const uint32_t xdst_w = mapa_u32(smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + q * 32) * 16, sib);
         if (NP == 2 && lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                   // phase 0
         // receive exchange phase k: the sibling warp's 8 units x (hi, lo) of our rows -> TMEM columns of the other pair's units
         auto xch_recv = [&](uint32_t k) {
@@ -426,12 +440,30 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     *reinterpret_cast<uint4*>(oh + b * 32) = phi;
                     *reinterpret_cast<uint4*>(ol + b * 32) = plo;
                     if constexpr (NP == 2) {
+                        const uint32_t k = 2 * g + b;
+#if NRV_FP_XCH_DMA
+                        // exchange: our block is staged in local shared memory and one lane hands it to the bulk-copy engine (2 x 512 B
+                        // into the sibling's landing zone, bytes counted on ITS per-warp mbarrier): no warp waits for the ~20 B/clock
+                        // DSMEM path (st.async from registers stalled every warp for 1,500-2,700 clocks per block)
+                        if (lane == 0) tma_store_wait_read();             // the previous block's copies have read the staging slots
+                        __syncwarp();
+                        st_shared_v4(xout, phi);
+                        st_shared_v4(xout + 128 * 16, plo);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (k > 0) FP_WAIT(&xfree[ew], (k - 1) & 1, 8, k);             // sibling has read what we sent last
+                            bulk_copy_to_cluster(xdst_w, xout_w, 512, xbar);
+                            bulk_copy_to_cluster(xdst_w + 128 * 16, xout_w + 128 * 16, 512, xbar);
+                            tma_store_commit();
+                        }
+#else
                         // our block goes straight from registers into the sibling's landing zone (st.async, bytes counted on ITS
                         // per-warp mbarrier -- no fences) once the sibling has read what we sent last
-                        const uint32_t k = 2 * g + b;
                         if (k > 0) FP_WAIT(&xfree[ew], (k - 1) & 1, 8, k);
                         st_async_v4(xdst, phi, xbar);
                         st_async_v4(xdst + 128 * 16, plo, xbar);
+#endif
                     }
                     tmem_st_wait();
                     tc_fence_before();                    // our tcgen05.st of h precede the recurrent MMAs that read it
@@ -456,6 +488,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 if (warp == 2) TR(1, g, 6);
             }
         }
+#if NRV_FP_XCH_DMA
+        if (NP == 2 && lane == 0) tma_store_wait_all();       // our last bulk copies are complete before this CTA retires
+#endif
     }
     tc_fence_before();
     __syncthreads();
