@@ -53,7 +53,7 @@ struct FpCfg {
     static constexpr int KC = KIN / 64, RC = UT / 64, NP = UT / 64;
     static constexpr int W_BYTES = (KC + RC) * 2 * FP_TILE;
 #ifndef NRV_FP_XCH_DMA
-#define NRV_FP_XCH_DMA 0      // total_rnn1 exchange: 0 = st.async from registers (3-stage x ring); 1 = staged in local shared memory and pushed by the
+#define NRV_FP_XCH_DMA 2      // total_rnn1 exchange: 0 = st.async from registers (3-stage x ring); 1 = staged in local shared memory and pushed by the
                               // bulk-copy engine (2-stage x ring).  Measured equal (53.2 vs 54.4 ms per step; 11.7k vs 11.0k clocks per step)
 #endif
     static constexpr int STAGES = NP == 1 ? 4 : (NRV_FP_XCH_DMA ? 2 : 3);      // x ring depth (16 KB tiles)
@@ -152,6 +152,19 @@ __device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbi
         hv[j] = og * tanh_fast(cn);
 #endif
     }
+}
+// 4 units of h = hi + lo as fp16 pairs
+__device__ __forceinline__ void pack_h4(const float* hv, uint2& phi, uint2& plo) {
+    uint32_t ph[2], pl[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(hv[2 * p] - hf.x, hv[2 * p + 1] - hf.y);
+        ph[p] = half2_bits(hi); pl[p] = half2_bits(lo);
+    }
+    phi = make_uint2(ph[0], ph[1]);
+    plo = make_uint2(pl[0], pl[1]);
 }
 // h = hi + lo as fp16 pairs (packed conversions, ALU pipe)
 __device__ __forceinline__ void pack_h8(const float* hv, uint4& phi, uint4& plo) {
@@ -391,14 +404,27 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const uint32_t xout = xsrc + FP_XCH_BYTES;
         const uint32_t xout_w = smem_u32(s_xch) + FP_XCH_BYTES + (uint32_t)((cg * 2) * 128 + q * 32) * 16;
         const uint32_t xdst_w = mapa_u32(smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + q * 32) * 16, sib);
+        // variant 2 addresses: slot (part, half) of this lane at x2src + (part*2 + half) * 128 * 8; per-warp chunk of 256 B
+        const uint32_t x2src = smem_u32(s_xch) + (uint32_t)((cg * 4) * 128 + row) * 8;
+        const uint32_t x2out = x2src + FP_XCH_BYTES;
+        const uint32_t x2out_w = smem_u32(s_xch) + FP_XCH_BYTES + (uint32_t)((cg * 4) * 128 + q * 32) * 8;
+        const uint32_t x2dst_w = mapa_u32(smem_u32(s_xch) + (uint32_t)((cg * 4) * 128 + q * 32) * 8, sib);
         if (NP == 2 && lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                   // phase 0
         // receive exchange phase k: the sibling warp's 8 units x (hi, lo) of our rows -> TMEM columns of the other pair's units
         auto xch_recv = [&](uint32_t k) {
             FP_WAIT(&xfull[ew], k & 1, 7, k);
             if (lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                          // arm the next phase
             uint4 a, b2;
+#if NRV_FP_XCH_DMA == 2
+            // layout [cg][part][half][row] x 8 B: a warp's half of a part is 256 contiguous bytes (one bulk copy)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(x2src) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a.z), "=r"(a.w) : "r"(x2src + 128 * 8) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b2.x), "=r"(b2.y) : "r"(x2src + 256 * 8) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b2.z), "=r"(b2.w) : "r"(x2src + 384 * 8) : "memory");
+#else
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(xsrc) : "memory");
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b2.x), "=r"(b2.y), "=r"(b2.z), "=r"(b2.w) : "r"(xsrc + 128 * 16) : "memory");
+#endif
             tmem_st_32x4(lane_addr + H_HI + peer_col + (k & 1) * 16, a);
             tmem_st_32x4(lane_addr + H_LO + peer_col + (k & 1) * 16, b2);
             tmem_st_wait();
@@ -470,6 +496,61 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&hq[b * 2], leader);
                 };
+#if NRV_FP_XCH_DMA == 2
+                // exchange in halves of 4 units, each handed to the bulk-copy engine as soon as it exists (2 x 256 B per warp): the DSMEM
+                // traffic is spread over the arithmetic instead of arriving as a 16 KB burst at the end of a block
+                uint32_t ph[4], pl[4];
+                auto send_half = [&](int half, const float* hv4, uint32_t wait_k) {      // wait_k != 0: first half of exchange phase wait_k
+                    uint2 hi2, lo2;
+                    pack_h4(hv4, hi2, lo2);
+                    ph[half * 2] = hi2.x; ph[half * 2 + 1] = hi2.y; pl[half * 2] = lo2.x; pl[half * 2 + 1] = lo2.y;
+                    if constexpr (NP == 2) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(x2out + (0 * 2 + half) * 128 * 8), "r"(hi2.x), "r"(hi2.y) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(x2out + (1 * 2 + half) * 128 * 8), "r"(lo2.x), "r"(lo2.y) : "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (wait_k) FP_WAIT(&xfree[ew], (wait_k - 1) & 1, 8, wait_k);
+                            bulk_copy_to_cluster(x2dst_w + (0 * 2 + half) * 128 * 8, x2out_w + (0 * 2 + half) * 128 * 8, 256, xbar);
+                            bulk_copy_to_cluster(x2dst_w + (1 * 2 + half) * 128 * 8, x2out_w + (1 * 2 + half) * 128 * 8, 256, xbar);
+                            tma_store_commit();
+                        }
+                    }
+                };
+                auto publish2 = [&](int b) {
+                    const uint4 phi = make_uint4(ph[0], ph[1], ph[2], ph[3]), plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    tmem_st_32x4(lane_addr + H_HI + own_col + b * 16, phi);
+                    tmem_st_32x4(lane_addr + H_LO + own_col + b * 16, plo);
+                    *reinterpret_cast<uint4*>(oh + b * 32) = phi;
+                    *reinterpret_cast<uint4*>(ol + b * 32) = plo;
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&hq[b * 2], leader);
+                };
+                float hv[8];
+                cell_units<0, 4>(v0, sb, &c[0], hv);
+                send_half(0, hv, 2 * g);                  // phase 2g: the sibling has consumed phase 2g-1 (wait_k = 0 for the very first)
+                cell_units<4, 8>(v0, sb, &c[0], hv);
+                send_half(1, hv + 4, 0);
+                uint32_t v1[32];
+                tmem_ld_32x32(lane_addr + (uint32_t)(128 + (g & 1) * 128 + cg * 32), v1);
+                publish2(0);
+                if (warp == 2) TR(1, g, 2);
+                tmem_ld_wait();
+                cell_units<0, 4>(v1, sb + 512, &c[8], hv);
+                if (warp == 2) TR(1, g, 3);
+                if constexpr (NP == 2) xch_recv(2 * g);
+                if (warp == 2) TR(1, g, 4);
+                send_half(0, hv, 2 * g + 1);              // phase 2g+1 after the sibling has consumed phase 2g
+                cell_units<4, 8>(v1, sb + 512, &c[8], hv);
+                send_half(1, hv + 4, 0);
+                publish2(1);
+                if (warp == 2) TR(1, g, 5);
+                if constexpr (NP == 2) xch_recv(2 * g + 1);
+#else
                 float hv[8];
                 cell_units<0, 8>(v0, sb, &c[0], hv);
                 uint32_t v1[32];                          // block 1 stayed in TMEM: only 32 accumulator registers are live at a time;
@@ -485,6 +566,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 publish(1, hv);
                 if (warp == 2) TR(1, g, 5);
                 if constexpr (NP == 2) xch_recv(2 * g + 1);
+#endif
                 if (warp == 2) TR(1, g, 6);
             }
         }
