@@ -27,7 +27,7 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
         if m and cur:
             line_of[int(m.group(1), 16)] = cur
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
 ia, isamp, isrc = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Source")

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one kernel): headline metrics, stall reasons, top stalled SASS lines.  usage: ncu_top.py rep [n]"""
-import collections, csv, io, re, subprocess, sys
+import os, collections, csv, io, re, subprocess, sys
 rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + os.environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
 for k in ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -11,7 +11,7 @@ for k in ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.s
           "lts__t_bytes.sum.per_second", "l1tex__data_bank_conflicts_pipe_lsu.sum"]:
     if k in hdr:
         print("%-75s %s %s" % (k, vals[hdr.index(k)], rows[1][hdr.index(k)]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
