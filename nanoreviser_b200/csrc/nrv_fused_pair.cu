@@ -16,19 +16,21 @@
 // MEMORY: every epilogue thread owns one TMEM lane (= one window) and tcgen05.st's its new h (fp16 hi / lo pairs) next to
 // the 256-column accumulator; the recurrent MMAs use the A-from-TMEM (.ts) form (layout pinned by tools/ts_probe).
 //
-// Pipeline (one accumulator, drained fast):
-//     tensor core :  rec(s) | ............ proj(s+1): 3 x KIN/16 MMAs ............ | rec(s+1) | proj(s+2) ...
-//     epilogue    :         | drain | gates, c, h -> TMEM + HBM (+ exchange)       |          | drain | ...
-// 16 epilogue warps: each thread tcgen05.ld's its 64 accumulator columns into registers and signals `drained`; the
-// projection MMAs of the next step (which need no h) start right then and run under the gate arithmetic; `h_ready`
-// releases the recurrent MMAs.  x_t is read exactly once; the tensor pipe only idles during the drain.
+// Pipeline.  The accumulator is two unit blocks of 128 columns (N = 128 MMAs); block 1 alternates between two TMEM regions, so
+// only block 0 is ever waited for (`drained`: 32 registers per thread, right after the commit).  The epilogue (16 warps, one
+// TMEM lane = one window per thread, 2 x 8 units) delivers h_t in QUARTERS (own block 0, sibling's block 0, own block 1,
+// sibling's block 1: four mbarriers) and the MMA warp interleaves statically
+//     proj kc0, kc1 | rec(q0) | proj kc2 | rec(q0') | [proj kc3] | rec(q1) | rec(q1') | commit
+// so that only the 12 MMAs of the last quarter stand between the end of the epilogue and the next accumulator.  x_t is read
+// exactly once (TMA ring, next step prefetched into L2 by the producer warp).
 //
 // total_rnn1's exchange: the thread that owns window w in pair p and the thread that owns w in pair 1-p (the "sibling" CTA)
-// swap their 16 units of h_t in two blocks of 8: st.async puts 2 x 16 B straight from registers into a 16 KB landing zone of
-// the sibling's shared memory and counts the bytes on the sibling WARP's mbarrier (no fences, no global round trip); the
-// receiver copies its 32 B into TMEM and releases the zone with a remote arrive.  Block 0 travels under the arithmetic of
-// block 1.  (First version: through the layer output in L2 with __threadfence + acquire.cluster -- 12 us per step.)
-// The landing zone costs one ring stage (3 x 16 KB instead of 4).
+// swap their 16 units of h_t in four halves of 4 units.  A warp stages a half (fp16 hi / lo, 2 x 256 B) in local shared memory
+// and one lane hands it to the bulk-copy engine (cp.async.bulk.shared::cluster into a 16 KB landing zone of the sibling, bytes
+// counted on the sibling WARP's mbarrier): no fences, no global round trip, nobody stalls on the ~20 B/clock DSMEM path, and the
+// traffic is spread over the gate arithmetic.  The receiver copies its 32 B into TMEM and releases the zone with a remote
+// arrive (`xfree`), which gates the sender's next phase.  Landing zone + staging cost two ring stages (2 x 16 KB instead of 4).
+// History of the exchange (L2 round trip, st.async bursts, whole-block copies, a dedicated sender warp): DESIGN.md section 4.
 #include <algorithm>
 
 #include "nrv_cell.cuh"
@@ -52,12 +54,8 @@ template <int KIN, int UT>
 struct FpCfg {
     static constexpr int KC = KIN / 64, RC = UT / 64, NP = UT / 64;
     static constexpr int W_BYTES = (KC + RC) * 2 * FP_TILE;
-#ifndef NRV_FP_XCH_DMA
-#define NRV_FP_XCH_DMA 2      // total_rnn1 exchange: 0 = st.async from registers (3-stage x ring); 1 = staged in local shared memory and pushed by the
-                              // bulk-copy engine (2-stage x ring).  Measured equal (53.2 vs 54.4 ms per step; 11.7k vs 11.0k clocks per step)
-#endif
-    static constexpr int STAGES = NP == 1 ? 4 : (NRV_FP_XCH_DMA ? 2 : 3);      // x ring depth (16 KB tiles)
-    static constexpr int XCH = NP == 1 ? 0 : (NRV_FP_XCH_DMA ? 2 : 1) * FP_XCH_BYTES;   // landing zone (+ outgoing staging)
+    static constexpr int STAGES = NP == 1 ? 4 : 2;                   // x ring depth (16 KB tiles)
+    static constexpr int XCH = NP == 1 ? 0 : 2 * FP_XCH_BYTES;       // total_rnn1: landing zone + outgoing staging of the h exchange
     static constexpr size_t SMEM = (size_t)W_BYTES + STAGES * FP_TILE + XCH + 1024 /*bias*/ + 512 /*barriers*/ + 1024 /*alignment*/;
 };
 
@@ -100,10 +98,8 @@ __device__ __forceinline__ void fp_wait_dbg(uint64_t* bar, uint32_t parity, int 
     }
 }
 #define FP_WAIT(bar, parity, tag, g) fp_wait_dbg<false>(bar, parity, tag, g)
-#define FP_WAIT_CL(bar, parity, tag, g) fp_wait_dbg<true>(bar, parity, tag, g)
 #else
 #define FP_WAIT(bar, parity, tag, g) mbar_wait(bar, parity)
-#define FP_WAIT_CL(bar, parity, tag, g) mbar_wait_cluster(bar, parity)
 #endif
 // 2-D tile -> L2 only (no shared-memory destination)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
@@ -119,12 +115,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
 __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(remote_dst),
                  "r"(local_src), "r"(bytes), "r"(remote_bar)
-                 : "memory");
-}
-// 16 bytes from registers into another CTA's shared memory; the bytes are counted on that CTA's mbarrier (complete_tx)
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, const uint4& v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(remote_addr),
-                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                  : "memory");
 }
 
@@ -165,19 +155,6 @@ __device__ __forceinline__ void pack_h4(const float* hv, uint2& phi, uint2& plo)
     }
     phi = make_uint2(ph[0], ph[1]);
     plo = make_uint2(pl[0], pl[1]);
-}
-// h = hi + lo as fp16 pairs (packed conversions, ALU pipe)
-__device__ __forceinline__ void pack_h8(const float* hv, uint4& phi, uint4& plo) {
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
-        const float2 hf = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(hv[2 * p] - hf.x, hv[2 * p + 1] - hf.y);
-        ph[p] = half2_bits(hi); pl[p] = half2_bits(lo);
-    }
-    phi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
 template <int KIN, int UT>
@@ -397,14 +374,10 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const uint32_t own_col = p * 32 + cg * 4;         // this thread's units inside the h_hi / h_lo column ranges (block b at + b*16)
         const int ew = warp - 2;                           // epilogue warp index = index of its exchange barriers
         const uint32_t peer_col = (1 - p) * 32 + cg * 4;
-        const uint32_t xsrc = smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + row) * 16;       // our landing slots (hi; lo at + 2 KB)
         const uint32_t sib = NP == 2 ? (rank ^ 2u) : rank;   // sibling CTA: other pair, same windows
-        const uint32_t xdst = mapa_u32(xsrc, sib), xbar = mapa_u32(smem_u32(&xfull[ew]), sib);
-        // outgoing staging (DMA variant): same layout as the landing zone, 16 KB behind it; a warp's 32 slots are 512 contiguous bytes
-        const uint32_t xout = xsrc + FP_XCH_BYTES;
-        const uint32_t xout_w = smem_u32(s_xch) + FP_XCH_BYTES + (uint32_t)((cg * 2) * 128 + q * 32) * 16;
-        const uint32_t xdst_w = mapa_u32(smem_u32(s_xch) + (uint32_t)((cg * 2) * 128 + q * 32) * 16, sib);
-        // variant 2 addresses: slot (part, half) of this lane at x2src + (part*2 + half) * 128 * 8; per-warp chunk of 256 B
+        const uint32_t xbar = mapa_u32(smem_u32(&xfull[ew]), sib);
+        // landing zone / staging layout [cg][part][half][row] x 8 B: slot (part, half) of this lane at x2src + (part*2 + half) * 128 * 8;
+        // a warp's half of a part is 256 contiguous bytes (one bulk copy)
         const uint32_t x2src = smem_u32(s_xch) + (uint32_t)((cg * 4) * 128 + row) * 8;
         const uint32_t x2out = x2src + FP_XCH_BYTES;
         const uint32_t x2out_w = smem_u32(s_xch) + FP_XCH_BYTES + (uint32_t)((cg * 4) * 128 + q * 32) * 8;
@@ -415,16 +388,10 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
             FP_WAIT(&xfull[ew], k & 1, 7, k);
             if (lane == 0) mbar_arrive_expect_tx(&xfull[ew], 1024);                          // arm the next phase
             uint4 a, b2;
-#if NRV_FP_XCH_DMA == 2
-            // layout [cg][part][half][row] x 8 B: a warp's half of a part is 256 contiguous bytes (one bulk copy)
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(x2src) : "memory");
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a.z), "=r"(a.w) : "r"(x2src + 128 * 8) : "memory");
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b2.x), "=r"(b2.y) : "r"(x2src + 256 * 8) : "memory");
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b2.z), "=r"(b2.w) : "r"(x2src + 384 * 8) : "memory");
-#else
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(xsrc) : "memory");
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b2.x), "=r"(b2.y), "=r"(b2.z), "=r"(b2.w) : "r"(xsrc + 128 * 16) : "memory");
-#endif
             tmem_st_32x4(lane_addr + H_HI + peer_col + (k & 1) * 16, a);
             tmem_st_32x4(lane_addr + H_LO + peer_col + (k & 1) * 16, b2);
             tmem_st_wait();
@@ -457,46 +424,6 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 const int64_t orow = ((int64_t)t * nwp + w) * out_ld + dir * UT;     // padded rows are written too (finite, never read as windows)
                 __half* oh = out_hi + orow + p * 64 + cg * 8;
                 __half* ol = out_lo + orow + p * 64 + cg * 8;
-                // own block b: h -> TMEM (A operand of the next step), -> layer output, -> sibling CTA; then signal the quarter
-                auto publish = [&](int b, const float* hv) {
-                    uint4 phi, plo;
-                    pack_h8(hv, phi, plo);
-                    tmem_st_32x4(lane_addr + H_HI + own_col + b * 16, phi);
-                    tmem_st_32x4(lane_addr + H_LO + own_col + b * 16, plo);
-                    *reinterpret_cast<uint4*>(oh + b * 32) = phi;
-                    *reinterpret_cast<uint4*>(ol + b * 32) = plo;
-                    if constexpr (NP == 2) {
-                        const uint32_t k = 2 * g + b;
-#if NRV_FP_XCH_DMA
-                        // exchange: our block is staged in local shared memory and one lane hands it to the bulk-copy engine (2 x 512 B
-                        // into the sibling's landing zone, bytes counted on ITS per-warp mbarrier): no warp waits for the ~20 B/clock
-                        // DSMEM path (st.async from registers stalled every warp for 1,500-2,700 clocks per block)
-                        if (lane == 0) tma_store_wait_read();             // the previous block's copies have read the staging slots
-                        __syncwarp();
-                        st_shared_v4(xout, phi);
-                        st_shared_v4(xout + 128 * 16, plo);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (k > 0) FP_WAIT(&xfree[ew], (k - 1) & 1, 8, k);             // sibling has read what we sent last
-                            bulk_copy_to_cluster(xdst_w, xout_w, 512, xbar);
-                            bulk_copy_to_cluster(xdst_w + 128 * 16, xout_w + 128 * 16, 512, xbar);
-                            tma_store_commit();
-                        }
-#else
-                        // our block goes straight from registers into the sibling's landing zone (st.async, bytes counted on ITS
-                        // per-warp mbarrier -- no fences) once the sibling has read what we sent last
-                        if (k > 0) FP_WAIT(&xfree[ew], (k - 1) & 1, 8, k);
-                        st_async_v4(xdst, phi, xbar);
-                        st_async_v4(xdst + 128 * 16, plo, xbar);
-#endif
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();                    // our tcgen05.st of h precede the recurrent MMAs that read it
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(&hq[b * 2], leader);
-                };
-#if NRV_FP_XCH_DMA == 2
                 // exchange in halves of 4 units, each handed to the bulk-copy engine as soon as it exists (2 x 256 B per warp): the DSMEM
                 // traffic is spread over the arithmetic instead of arriving as a 16 KB burst at the end of a block
                 uint32_t ph[4], pl[4];
@@ -550,29 +477,10 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 publish2(1);
                 if (warp == 2) TR(1, g, 5);
                 if constexpr (NP == 2) xch_recv(2 * g + 1);
-#else
-                float hv[8];
-                cell_units<0, 8>(v0, sb, &c[0], hv);
-                uint32_t v1[32];                          // block 1 stayed in TMEM: only 32 accumulator registers are live at a time;
-                tmem_ld_32x32(lane_addr + (uint32_t)(128 + (g & 1) * 128 + cg * 32), v1);   // its load flies under block 0's publication
-                publish(0, hv);
-                if (warp == 2) TR(1, g, 2);
-                tmem_ld_wait();
-                cell_units<0, 4>(v1, sb + 512, &c[8], hv);
-                if (warp == 2) TR(1, g, 3);
-                if constexpr (NP == 2) xch_recv(2 * g);   // sibling's block 0: arrived during the first half of our block 1
-                if (warp == 2) TR(1, g, 4);
-                cell_units<4, 8>(v1, sb + 512, &c[8], hv);
-                publish(1, hv);
-                if (warp == 2) TR(1, g, 5);
-                if constexpr (NP == 2) xch_recv(2 * g + 1);
-#endif
                 if (warp == 2) TR(1, g, 6);
             }
         }
-#if NRV_FP_XCH_DMA
         if (NP == 2 && lane == 0) tma_store_wait_all();       // our last bulk copies are complete before this CTA retires
-#endif
     }
     tc_fence_before();
     __syncthreads();

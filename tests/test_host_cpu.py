@@ -164,3 +164,25 @@ def test_no_cpu_fallback_without_device(weights_by_species):
     for mod in ("engine", "api", "fast5", "weights", "synth", "workqueue", "h5mini", "build"):
         src = open(os.path.join(ROOT, "nanoreviser_b200", mod + ".py")).read()
         assert "import oracle" not in src and "from oracle" not in src, mod
+
+
+def test_basecall_phred_and_qual_plumbing(fast5_files, reads):
+    """Basecaller qualities for the fastq path (D6'): the Fastq dataset lines up with the event-collapsed bases
+    (bases == Fastq_seq[2:-2]) on every fixture; Batch.qual travels through pack_batch / split_batch."""
+    import copy
+    from nanoreviser_b200 import engine, fast5, synth
+    rs = []
+    for fn, r in zip(fast5_files, reads):
+        q = fast5.basecall_phred(fn, r.bases)
+        assert q is not None and q.dtype == np.uint8 and q.shape == (r.n_bases,) and q.max() <= 93
+        seq, qul = fast5.extract_fastq(fn)                           # the reference's own trimmed view (Fastq[7:-7])
+        assert bytes(q[5:-5] + 33).decode() == qul                   # [2:-2] of the call vs [7:-7]: 5 more on each side
+        assert fast5.basecall_phred(fn, r.bases[:-1]) is None        # does not line up -> caller falls back to Phred 40
+        rr = copy.copy(r)
+        rr.qual = q
+        rs.append(rr)
+    b = engine.pack_batch(rs)
+    assert b.qual is not None and b.qual.shape[0] == b.n_bases
+    sub = synth.split_batch(b, [3, 1])
+    assert np.array_equal(sub.qual, np.concatenate([rs[3].qual, rs[1].qual]))
+    assert engine.pack_batch(reads).qual is None                    # all-or-nothing: no qualities unless every read has them
