@@ -375,7 +375,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
         }
         CU(h, h->d_a2[0].ensure((size_t)rows * 192 * 2)); CU(h, h->d_a2[1].ensure((size_t)rows * 192 * 2));
         CU(h, h->d_a3[0].ensure((size_t)rows * 256 * 2)); CU(h, h->d_a3[1].ensure((size_t)rows * 256 * 2));
-        CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
+        // fp32 gate pre-activations exist only on the split (GEMM + recurrence) paths; the fused layer kernels never materialise them
+        if (!h->trnn1_fused || !h->trnn2_fused) CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
     }
     bool l0_prefetched = false;      // read_rnn1 of the current iteration was already launched on the side stream
     for (int64_t c0 = 0; c0 < n_win; c0 += CH) {
@@ -440,46 +441,41 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (read_rnn11) could not be launched");
                     h->launches += n;
                 }
-                {   // total_rnn1: gather CNN features, projection (K = 192), recurrence (u = 128)
-                    StageTimer* tp = new StageTimer(h, ST_PROJ2);
-                    const int64_t items = nw * T * 8;
-                    gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
-                        h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
-                    h->launches += 1;
-                    if (overlap) {
-                        // next iteration in launch order: the other model of this chunk, or model 1 of the next chunk.  The side stream has the
-                        // lowest priority and becomes eligible together with the cluster kernel (after the gather): the cluster kernel takes
-                        // its 128 SMs first, read_rnn1 gets the rest
-                        const int mi_n = mi == 0 ? 1 : 0;
-                        const int64_t c0_n = mi == 0 ? c0 : c0 + CH;
-                        if (c0_n < n_win) {
-                            CU(h, cudaEventRecord(h->ev_a1_free, h->stream));
-                            CU(h, cudaStreamWaitEvent(h->stream2, h->ev_a1_free, 0));
-                            if (launch_l0(c0_n, mi_n, h->stream2) < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
-                            CU(h, cudaEventRecord(h->ev_l0_done, h->stream2));
-                            l0_prefetched = true;
+                {   // total_rnn1 (K = 192, u = 128): gather the CNN features, then the fused layer kernel (or projection GEMM + recurrence)
+                    {
+                        StageTimer tm(h, ST_PROJ2);
+                        const int64_t items = nw * T * 8;
+                        gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
+                            h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
+                        h->launches += 1;
+                        if (overlap) {
+                            // next iteration in launch order: the other model of this chunk, or model 1 of the next chunk.  The side stream has the
+                            // lowest priority and becomes eligible together with the cluster kernel (after the gather): the cluster kernel takes
+                            // its 128 SMs first, read_rnn1 gets the rest
+                            const int mi_n = mi == 0 ? 1 : 0;
+                            const int64_t c0_n = mi == 0 ? c0 : c0 + CH;
+                            if (c0_n < n_win) {
+                                CU(h, cudaEventRecord(h->ev_a1_free, h->stream));
+                                CU(h, cudaStreamWaitEvent(h->stream2, h->ev_a1_free, 0));
+                                if (launch_l0(c0_n, mi_n, h->stream2) < 0) return fail(h, NRV_E_CUDA, "read_rnn1 kernel could not be launched");
+                                CU(h, cudaEventRecord(h->ev_l0_done, h->stream2));
+                                l0_prefetched = true;
+                            }
+                        }
+                        if (!h->trnn1_fused) {
+                            n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, R, 1024, 192, zin, M.lstm[2].bias_tc,
+                                                  1, T, nwp, 512, 0, h->num_sms, h->stream);
+                            if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
+                            h->launches += n;
                         }
                     }
-                    if (h->trnn1_fused) {
-                        delete tp;
-                        StageTimer tm(h, ST_REC2);
-                        LstmIo io; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                        n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
-                        if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn1) could not be launched");
-                        h->launches += n;
-                    } else {
-                    n = launch_gemm_f16x3(a2h, a2l, M.lstm[2].pb_hi, M.lstm[2].pb_lo, R, 1024, 192, zin, M.lstm[2].bias_tc,
-                                          1, T, nwp, 512, 0, h->num_sms, h->stream);
-                    if (n >= 0) h->launches += n;
-                    delete tp;
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 projection (total_rnn1) could not be launched");
                     StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
-                                       : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
-                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 recurrence (total_rnn1) could not be launched");
+                    if (h->trnn1_fused) n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
+                    else n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
+                                            : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
+                    if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 layer kernel (total_rnn1) could not be launched");
                     h->launches += n;
-                    }
                 }
                 if (h->trnn2_fused) {
                     StageTimer tm(h, ST_REC3);
