@@ -360,9 +360,11 @@ def main():
         # read_rnn1 (lstm0) of the next (chunk, model) runs on a low-priority side stream UNDER the fused total_rnn1 kernel (on the
         # SMs its clusters of 4 cannot use): its event time is its stretched duration there, not exclusive time
         overlapped = fused1 and os.environ.get("NRV_OVERLAP", "1") != "0"
-        if overlapped and "lstm0" in kernels:
-            kernels["lstm0"]["overlapped_with"] = "rec2"
-        dom = max((k for k in kernels if not (overlapped and k == "lstm0")), key=lambda k: stage_ms[k])
+        side = ("lstm0", "heads") if overlapped else ()          # read_rnn1 under rec2; heads tail under the next iteration's kernels
+        for k in side:
+            if k in kernels:
+                kernels[k]["overlapped_with"] = "rec2" if k == "lstm0" else "rec1 (next chunk)"
+        dom = max((k for k in kernels if k not in side), key=lambda k: stage_ms[k])
         roofline = {"bound": "tensor", "kernel": kernels[dom]["kernel"], "stage": dom, "achieved": kernels[dom]["achieved"],
                     "peak": peak, "unit": "TFLOP/s", "frac": kernels[dom]["frac"],
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peak_src,
@@ -419,8 +421,9 @@ def main():
                         "d2h_bytes_per_step": d2h // max(args.steps, 1)},
                 "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "whole_path": whole,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "stage_note": ("lstm0 (read_rnn1) is launched on a low-priority side stream and runs under rec2 (fused total_rnn1, "
-                               "128 of 148 SMs): its time overlaps rec2, the stage times do not add up to ms_per_step") if overlapped else None,
+                "stage_note": ("lstm0 (read_rnn1) and heads (heads tail) are launched on a low-priority side stream: read_rnn1 of the next "
+                               "chunk runs under rec2 (fused total_rnn1, 128 of 148 SMs), the heads tail under the next chunk's persistent "
+                               "kernels; their times overlap other stages, the stage times do not add up to ms_per_step") if overlapped else None,
                 "device_vs_host_path_identical": same}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -56,7 +56,7 @@ struct nrv_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;       // side stream: read_rnn1 of the NEXT (chunk, model) runs under the fused layers of the current one
-    cudaEvent_t ev_a1_free = nullptr, ev_l0_done = nullptr;
+    cudaEvent_t ev_a1_free = nullptr, ev_l0_done = nullptr, ev_hg_done = nullptr, ev_tail_done = nullptr;
     int overlap_l0 = 1;                   // NRV_OVERLAP=0 keeps everything on one stream
     std::string err;
     bool sticky = false;
@@ -379,6 +379,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
         if (!h->trnn1_fused || !h->trnn2_fused) CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
     }
     bool l0_prefetched = false;      // read_rnn1 of the current iteration was already launched on the side stream
+    bool tail_pending = false;       // a heads tail is (possibly) still running on the side stream
     for (int64_t c0 = 0; c0 < n_win; c0 += CH) {
         const int64_t nw = std::min(CH, n_win - c0);
         for (int mi = 0; mi < 2; ++mi) {
@@ -498,6 +499,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     h->launches += n;
                 }
                 {   // heads: relu(Dense(128 -> 128)) as a tcgen05 GEMM with relu(Dense(128 -> 32)) fused into its epilogue
+                    if (tail_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_tail_done, 0));   // the side-stream tail has read d_act[3]
                     StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
                                           M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2t_hi, M.heads.d2t_lo,
@@ -510,14 +512,29 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 heads_nwp = nwp;
             }
             {
-                StageTimer tm(h, ST_HEADS);
-                int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
-                                     labels[mi] ? labels[mi] + c0 : nullptr, heads_stage, heads_nwp, h->stream);
-                if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
-                h->launches += n;
+                // heads tail (small CTAs, 33 us): on the side stream it runs under the next iteration's persistent kernels (they leave
+                // room for small CTAs on every SM) instead of between them
+                const bool side = h->path != 0 && h->overlap_l0 && h->stream2 && h->trnn1_fused;
+                cudaStream_t st = side ? h->stream2 : h->stream;
+                if (side) {
+                    CU(h, cudaEventRecord(h->ev_hg_done, h->stream));
+                    CU(h, cudaStreamWaitEvent(h->stream2, h->ev_hg_done, 0));
+                }
+                {
+                    StageTimer tm(h, ST_HEADS, st);
+                    int n = launch_heads(M.heads, heads_in, nw, T, probs[mi] ? probs[mi] + c0 * M.n_class : nullptr,
+                                         labels[mi] ? labels[mi] + c0 : nullptr, heads_stage, heads_nwp, st);
+                    if (n < 0) return fail(h, NRV_E_INVALID, "unsupported window length");
+                    h->launches += n;
+                }
+                if (side) {
+                    CU(h, cudaEventRecord(h->ev_tail_done, h->stream2));
+                    tail_pending = true;
+                }
             }
         }
     }
+    if (tail_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_tail_done, 0));     // labels / probabilities of the last chunk
     CU(h, cudaGetLastError());
     return NRV_OK;
 }
@@ -767,6 +784,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_a1_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_l0_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_hg_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_tail_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_create_error = std::string("nrv_create: ") + cudaGetErrorString(e);
         delete h;
@@ -810,6 +829,8 @@ void nrv_destroy(nrv_handle* h) {
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (h->ev_a1_free) cudaEventDestroy(h->ev_a1_free);
     if (h->ev_l0_done) cudaEventDestroy(h->ev_l0_done);
+    if (h->ev_hg_done) cudaEventDestroy(h->ev_hg_done);
+    if (h->ev_tail_done) cudaEventDestroy(h->ev_tail_done);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
