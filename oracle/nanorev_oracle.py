@@ -82,12 +82,22 @@ def get_base_label(base):
 # --------------------------------------------------------------------------------------
 # A1: events -> bases   (nanorev_fast5_handeler.py:39-150)
 # --------------------------------------------------------------------------------------
+def _loose_version(v):
+    """distutils.version.LooseVersion(v).version (the reference's comparison, fast5_handeler.py:65-68): the string is cut into
+    runs of digits / runs of letters, dots dropped, digit runs become ints; compared as lists."""
+    import re
+    if isinstance(v, (bytes, np.bytes_)):
+        v = bytes(v).decode()
+    parts = [x for x in re.split(r'(\d+|[a-z]+|\.)', str(v)) if x and x != '.']
+    return [int(x) if x.isdigit() else x for x in parts]
+
+
 def get_read_data(fast5_fn, basecall_group='Basecall_1D_000', basecall_subgroup='BaseCalled_template'):
     f = h5mini.File(fast5_fn, 'r')
     grp = f['/Analyses/' + basecall_group]
     version = grp.attrs['version'] if 'version' in grp.attrs else b'0.0'
     called = f['/Analyses/' + basecall_group + '/' + basecall_subgroup + '/Events'][()]
-    if bytes(version).decode() in ('0.0', '0', ''):   # :65-73 legacy tables
+    if _loose_version(version) <= _loose_version('0.0'):   # :65-73 legacy tables (LooseVersion(v) <= LooseVersion('0.0'))
         raw_attrs = dict(list(f['/Raw/Reads/'].values())[0].attrs.items())
         called['start'] = called['start'] * 4000 - raw_attrs['start_time']
         called['length'] = called['length'] * 4000

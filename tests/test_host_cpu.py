@@ -186,3 +186,38 @@ def test_basecall_phred_and_qual_plumbing(fast5_files, reads):
     sub = synth.split_batch(b, [3, 1])
     assert np.array_equal(sub.qual, np.concatenate([rs[3].qual, rs[1].qual]))
     assert engine.pack_batch(reads).qual is None                    # all-or-nothing: no qualities unless every read has them
+
+
+def test_legacy_version_gate_follows_the_reference(fast5_files, tmp_path):
+    """SURVEY.md section 8(f) rank 3 (legacy event tables): a file whose Basecall group says version <= 0.0 takes the reference's
+    rescaling branch (start*4000 - start_time, fast5_handeler.py:65-72).  The fixture's integer sample starts then wrap around and
+    the reference's own length check (:142-143) rejects the read -- in the oracle, in the Python reader, and the native reader
+    declines the file (NRV_INGEST_UNSUPPORTED) so that the CLI sends it through the Python reader."""
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import engine, fast5, h5mini
+    # the version gate itself, against distutils' LooseVersion semantics restated in the oracle
+    for v, legacy in (("0.0", True), ("0", True), ("00.00", True), ("0.0.0", False), ("0.0.1", False), ("1.0", False), ("2.0.2", False),
+                      ("0.0a", False), (b"0.0", True)):
+        assert (orc._loose_version(v) <= orc._loose_version("0.0")) == legacy, v
+        assert fast5._version_le_zero(v) == legacy, v
+    raw = bytearray(open(fast5_files[0], "rb").read())
+    hits = [i for i in range(len(raw) - 5) if raw[i:i + 5] == b"2.0.2"]
+    patched = None
+    for off in hits:                                   # the vlen string of /Analyses/Basecall_1D_000 attrs['version'] lives in a global heap
+        b = bytearray(raw)
+        b[off:off + 5] = b"00.00"
+        p = str(tmp_path / ("legacy_%d.fast5" % off))
+        open(p, "wb").write(b)
+        f = h5mini.File(p, "r")
+        v = f["/Analyses/Basecall_1D_000"].attrs["version"]
+        f.close()
+        if bytes(v) == b"00.00":
+            patched = p
+    assert patched is not None
+    with pytest.raises(RuntimeError, match="Signal is shorter than the Events"):
+        orc.get_read_data(patched)
+    with pytest.raises(RuntimeError, match="Signal is shorter than the Events"):
+        fast5.read_fast5_arrays(patched)
+    if os.path.exists(engine.LIB_PATH):
+        _, st, _, _ = engine.ingest_fast5([patched, fast5_files[0]], "Basecall_1D_000", "BaseCalled_template", 1)
+        assert st[0] != engine.INGEST_OK and st[1] == engine.INGEST_OK
