@@ -253,17 +253,17 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     uint8_t* s_h = smem + 4 * RF_W_BYTES;                 // [hi | lo][128 rows][64]
     uint8_t* s_x = s_h + 2 * RF_H_BYTES;                  // [stage][hi | lo][128 rows][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + RF_XS * 2 * RF_H_BYTES);
-    uint64_t* h_ready = bars;                             // count RF_EPI_WARPS (one arrive per epilogue warp)
-    uint64_t* acc_ready = bars + 1;                       // count 2 (commit + "h store left smem"); step 0: see below
-    uint64_t* xfull = bars + 2;                           // [RF_XS]
-    uint64_t* xempty = bars + 2 + RF_XS;                  // [RF_XS] count 1 (commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * RF_XS);
+    uint64_t* h_half = bars;                              // [2] count RF_EPI_WARPS: units 0-31 / 32-63 of h_t are in the shared-memory tile
+    uint64_t* acc_ready = bars + 2;                       // count 2 (commit + "h store left smem"); step 0: see below
+    uint64_t* xfull = bars + 3;                           // [RF_XS]
+    uint64_t* xempty = bars + 3 + RF_XS;                  // [RF_XS] count 1 (commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * RF_XS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
 
     if (threadIdx.x == 0) {
-        mbar_init(h_ready, RF_EPI_WARPS);
+        mbar_init(&h_half[0], RF_EPI_WARPS); mbar_init(&h_half[1], RF_EPI_WARPS);
         mbar_init(acc_ready, 2);
         for (int i = 0; i < RF_XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
         fence_mbar_init();
@@ -336,7 +336,29 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
             if (T > 1) proj(g + 1);
             for (int s = 1; s <= T; ++s) {
                 const int t_prev = dir ? (T - s) : (s - 1);
-                mbar_wait(h_ready, (g + (uint32_t)s - 1) & 1);
+                const uint32_t ha = smem_u32(s_h);
+                const uint32_t d = tmem_base + ((g + (uint32_t)s) & 1) * N;
+                // recurrent product in two halves of K: the epilogue delivers units 0-31 first (h_half[0]), so K-steps 0, 1 run on the
+                // tensor core while it is still busy with units 32-63
+                auto rec_half = [&](int hf) {
+#pragma unroll
+                    for (int k = 2 * hf; k < 2 * hf + 2; ++k) {
+                        const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
+                        const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
+#if NRV_REC_PASSES >= 3
+                        umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
+#endif
+#if NRV_REC_PASSES >= 2
+                        umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+#endif
+                        umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                    }
+                };
+                mbar_wait(&h_half[0], (g + (uint32_t)s - 1) & 1);
+                tc_fence_after();
+                if (s < T && elect_one()) rec_half(0);
+                __syncwarp();
+                mbar_wait(&h_half[1], (g + (uint32_t)s - 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const int grow = (int)(t_prev * nwp + wtile * 128);
@@ -344,20 +366,7 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     tma_store_2d(&tm_out_lo, s_h + RF_H_BYTES, dir * U, grow);
                     tma_store_commit();
                     if (s < T) {
-                        const uint32_t ha = smem_u32(s_h);
-                        const uint32_t d = tmem_base + ((g + (uint32_t)s) & 1) * N;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
-                            const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
-#if NRV_REC_PASSES >= 3
-                            umma_f16_ss(d, a_lo, b_hi, idesc, 1);            // accumulate onto the projection of this step
-#endif
-#if NRV_REC_PASSES >= 2
-                            umma_f16_ss(d, a_hi, b_lo, idesc, 1);
-#endif
-                            umma_f16_ss(d, a_hi, b_hi, idesc, 1);
-                        }
+                        rec_half(1);
                         umma_commit(acc_ready);
                     }
                 }
@@ -380,7 +389,8 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         // scheduler it issued at ~0.5 IPC (ncu) -- the epilogue, not the tensor core, set the step time
         constexpr int NB = 8 / (RF_EPI_WARPS / 4);        // 32-column blocks per warp
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;                  // units cg*8*NB .. +8*NB
+        const int cg = (warp - 2) >> 2;                  // block cb: units cb*32 + cg*8 .. +8 (K-steps 2*cb, 2*cb + 1 of the recurrent product)
+        static_assert(NB == 2, "unit blocks of 32: 16 epilogue warps");
         const int row = q * 32 + lane;
         const float4 zero4[8] = {};
         const uint32_t sh_base = smem_u32(s_h);
@@ -395,18 +405,18 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #pragma unroll
                 for (int cb = 0; cb < NB; ++cb) {
                     uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * N + (uint32_t)((cg * NB + cb) * 32), v);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * N + (uint32_t)((cb * 4 + cg) * 32), v);
                     tmem_ld_wait();
                     uint4 phi, plo;
                     lstm_cell_block(v, true, zero4, &c[cb * 8], phi, plo);
-                    const uint32_t off = sw128_offset(row, cg * NB + cb);
+                    const uint32_t off = sw128_offset(row, cb * 4 + cg);
                     st_shared_v4(sh_base + off, phi);
                     st_shared_v4(sh_base + RF_H_BYTES + off, plo);
+                    if (cb == NB - 1) tc_fence_before();      // all our tcgen05.ld of this step precede the next accumulator's MMAs
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&h_half[cb]);
                 }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(h_ready);
             }
         }
     }
