@@ -64,7 +64,8 @@ struct nrv_handle {
     ModelDev m[2];
     std::vector<void*> weight_allocs;
     int64_t launches = 0;
-    int64_t chunk_windows = 148 * 4 * 64;
+    int64_t chunk_windows = 148 * 1024;   // 592 tile pairs: 37 rounds on the 16 clusters per direction of total_rnn1, 16 on the 37 of total_rnn2,
+                                          // 8 on the 148 CTAs of read_rnn11 -- all exact (NRV_CHUNK_WINDOWS; 37,888 measured 4 % slower)
     // inputs / per-batch arenas
     Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag, d_wq[2], d_qual_in, d_revq,
