@@ -32,7 +32,10 @@ for r in data:
     vals = []
     for k, _ in want:
         v, u = r[col[k]], units[col[k]]
-        if k.startswith("dram__bytes"):
+        if k == "gpu__time_duration.sum":      # ncu picks the unit per report: always print microseconds
+            vals.append("%.1f" % (float(v.replace(",", "")) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3,
+                                                                 "s": 1e6, "second": 1e6}.get(u, 1)))
+        elif k.startswith("dram__bytes"):
             vals.append("%.3f GB" % (to_bytes(v, u) / 1e9))
         else:
             try:
@@ -40,8 +43,7 @@ for r in data:
             except ValueError:
                 vals.append(v)
     t_us = float(r[col["gpu__time_duration.sum"]].replace(",", ""))
-    if units[col["gpu__time_duration.sum"]] in ("ms", "msecond"):
-        t_us *= 1e3
+    t_us *= {"ns": 1e-3, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(units[col["gpu__time_duration.sum"]], 1)
     tot = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
         to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
     lines.append("| %s | %s | %.0f |" % (name, " | ".join(vals), tot / t_us / 1e3))
