@@ -221,3 +221,32 @@ def test_legacy_version_gate_follows_the_reference(fast5_files, tmp_path):
     if os.path.exists(engine.LIB_PATH):
         _, st, _, _ = engine.ingest_fast5([patched, fast5_files[0]], "Basecall_1D_000", "BaseCalled_template", 1)
         assert st[0] != engine.INGEST_OK and st[1] == engine.INGEST_OK
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """include/nrv.h is plain C (a reference maintainer binds it with ctypes / cgo-style FFI): compile it with gcc and compare every
+    field offset and struct size of nrv_batch / nrv_result / nrv_model_weights with the ctypes mirrors in engine.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from nanoreviser_b200 import engine
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"nrv_batch": engine._Batch, "nrv_result": engine._Result, "nrv_model_weights": engine._ModelWeights,
+               "nrv_lstm_dir": engine._LstmDir}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "nrv.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "abi")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", exe], check=True)
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname + ".sizeof"]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
