@@ -157,9 +157,10 @@ def run_worker(args, file_list, device, logger=None):
                 batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
                 todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
                 lengths = np.diff(batch.base_off).tolist()
-                if fastq and batch.n_reads:
-                    # the native reader does not extract the basecaller's Fastq dataset: attach its Phred scores here
-                    # (bases that pass through unrevised keep them; reads where it is missing use Phred 40)
+                if fastq and batch.n_reads and batch.qual is None:
+                    # the native reader attaches the basecaller's Phred scores when EVERY read of the slab has a Fastq dataset that
+                    # lines up; otherwise they are fetched per file here (bases that pass through unrevised keep them; reads where
+                    # the dataset is missing use Phred 40)
                     def phred(i):
                         b0, b1 = int(batch.base_off[i]), int(batch.base_off[i + 1])
                         q = fast5.basecall_phred(paths[int(read_file[i])], batch.bases[b0:b1], args.basecall_group,

@@ -242,6 +242,7 @@ struct ReadOut {
     std::vector<uint8_t> bases;
     std::vector<float> ev_mean, ev_std;
     std::vector<int16_t> signal;       // raw[a0:]
+    std::vector<uint8_t> qual;         // basecaller Phred scores of the bases (empty when the Fastq dataset is absent / does not line up)
 };
 
 double load_real(const uint8_t* p, const Member& m) {
@@ -448,6 +449,44 @@ void read_one(const char* path, const std::string& group, const std::string& sub
         } else {
             throw Fail{NRV_INGEST_UNSUPPORTED};
         }
+        // ---- basecaller qualities for -F fastq (best effort, never fails the read): the event-collapsed call is the Fastq sequence
+        //      without its first and last two bases (bases == Fastq_seq[2:-2]); qualities are Phred = character - 33, capped at 93 ----
+        try {
+            uint64_t qaddr;
+            if (h.resolve(gaddr, subgroup + "/Fastq", &qaddr)) {
+                Dtype qdt; uint64_t qdata = UNDEF; std::vector<uint64_t> qdims; bool filtered = false;
+                for (const Msg& m : h.object_header(qaddr)) {
+                    if (m.type == 0x0001) parse_dataspace(h.b, m.off, qdims);
+                    else if (m.type == 0x0003) qdt = parse_dtype(h.b, m.off, nullptr);
+                    else if (m.type == 0x0008) {
+                        if (h.b.u8(m.off) == 3 && h.b.u8(m.off + 1) == 1) qdata = h.b.u64(m.off + 2);            // contiguous
+                        else if (h.b.u8(m.off) == 3 && h.b.u8(m.off + 1) == 0) qdata = m.off + 4;                 // compact: u16 size, data
+                    } else if (m.type == 0x000B) filtered = true;
+                }
+                if (qdt.cls == 3 && qdims.empty() && qdata != UNDEF && !filtered) {
+                    h.b.need(qdata, qdt.size);
+                    const char* t = (const char*)h.b.p + qdata;
+                    const size_t n = strnlen(t, qdt.size);
+                    // lines: @name \n sequence \n + \n qualities
+                    const char* l1 = (const char*)memchr(t, '\n', n);
+                    const char* l2 = l1 ? (const char*)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - t)) : nullptr;
+                    const char* l3 = l2 ? (const char*)memchr(l2 + 1, '\n', n - (size_t)(l2 + 1 - t)) : nullptr;
+                    if (l3) {
+                        const char* seq = l1 + 1; const size_t nseq = (size_t)(l2 - seq);
+                        const char* ql = l3 + 1;
+                        const char* l4 = (const char*)memchr(ql, '\n', n - (size_t)(ql - t));
+                        const size_t nq = l4 ? (size_t)(l4 - ql) : n - (size_t)(ql - t);
+                        if (nseq == nq && nseq == nb + 4 && !memcmp(seq + 2, out.bases.data(), nb)) {
+                            out.qual.resize(nb);
+                            for (size_t i = 0; i < nb; ++i) {
+                                const int q = (int)(uint8_t)ql[i + 2] - 33;
+                                out.qual[i] = (uint8_t)std::min(std::max(q, 0), 93);
+                            }
+                        }
+                    }
+                }
+            }
+        } catch (...) { out.qual.clear(); }
         // ---- per-read outputs in the C-ABI layout ----
         out.a0 = a0;
         out.last_dur = last_dur;
@@ -480,6 +519,7 @@ struct nrv_ingest {
     std::vector<int32_t> starts, last_dur;
     std::vector<uint8_t> bases;
     std::vector<float> ev_mean, ev_std;
+    std::vector<uint8_t> qual;             // [n_bases] basecaller Phred scores, or empty when any packed read has none
 };
 
 extern "C" {
@@ -516,10 +556,15 @@ int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* grou
     r->signal.resize((size_t)ns); r->starts.resize((size_t)nb); r->bases.resize((size_t)nb);
     r->ev_mean.resize((size_t)nb); r->ev_std.resize((size_t)nb);
     r->last_dur.reserve((size_t)nr); r->a0.reserve((size_t)nr); r->read_file.reserve((size_t)nr);
+    bool all_qual = nr > 0;
+    for (int64_t i = 0; i < n_files; ++i)
+        if (per[(size_t)i].status == NRV_INGEST_OK && per[(size_t)i].qual.size() != per[(size_t)i].starts.size()) all_qual = false;
+    if (all_qual) r->qual.resize((size_t)nb);
     int64_t so = 0, bo = 0;
     for (int64_t i = 0; i < n_files; ++i) {
         ReadOut& p = per[(size_t)i];
         if (p.status != NRV_INGEST_OK) continue;
+        if (all_qual) memcpy(r->qual.data() + bo, p.qual.data(), p.qual.size());
         memcpy(r->signal.data() + so, p.signal.data(), p.signal.size() * 2);
         memcpy(r->starts.data() + bo, p.starts.data(), p.starts.size() * 4);
         memcpy(r->bases.data() + bo, p.bases.data(), p.bases.size());
@@ -541,7 +586,7 @@ int nrv_ingest_view(const nrv_ingest* r, nrv_batch* batch, const int32_t** file_
     batch->starts = r->starts.data(); batch->base_off = r->base_off.data();
     batch->bases = r->bases.data(); batch->ev_mean = r->ev_mean.data(); batch->ev_std = r->ev_std.data();
     batch->last_dur = r->last_dur.data();
-    batch->qual = nullptr;              // the native reader does not extract the Fastq dataset (callers attach qualities themselves)
+    batch->qual = r->qual.empty() ? nullptr : r->qual.data();   // all-or-nothing: NULL unless every packed read has its qualities
     if (file_status) *file_status = r->file_status.data();
     if (read_file) *read_file = r->read_file.data();
     if (a0) *a0 = r->a0.data();

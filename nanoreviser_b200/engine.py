@@ -155,7 +155,7 @@ def ingest_fast5(paths: Sequence[str], basecall_group: str = "Basecall_1D_000", 
         nb, ns = int(base_off[-1]), int(sig_off[-1])
         batch = Batch(view(cb.signal, ns, np.int16), sig_off, view(cb.starts, nb, np.int32), base_off,
                       view(cb.bases, nb, np.uint8), view(cb.ev_mean, nb, np.float32), view(cb.ev_std, nb, np.float32),
-                      view(cb.last_dur, R, np.int32))
+                      view(cb.last_dur, R, np.int32), view(cb.qual, nb, np.uint8) if cb.qual else None)
         return batch, view(fs.value, n, np.int32), view(rf.value, R, np.int64), view(a0.value, R, np.int64)
     finally:
         lib.nrv_ingest_free(h)

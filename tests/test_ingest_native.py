@@ -96,3 +96,15 @@ def test_native_ingest_random_corruption_never_crashes(lib_built, fast5_files, t
         paths.append(fn)
     batch, status, read_file, _ = engine.ingest_fast5(paths, threads=4)
     assert len(status) == 40 and batch.n_reads == int((status == 0).sum())
+
+
+def test_native_reader_extracts_basecall_qualities(fast5_files):
+    """-F fastq: the native reader returns the basecaller's Phred scores of the event-collapsed bases (Fastq quality - 33 of
+    Fastq_seq[2:-2]) exactly as the Python reader does; all-or-nothing per slab."""
+    from nanoreviser_b200 import engine, fast5
+    batch, st, rf, _ = engine.ingest_fast5(list(fast5_files), "Basecall_1D_000", "BaseCalled_template", 2)
+    assert list(st) == [engine.INGEST_OK] * len(fast5_files) and batch.qual is not None and batch.qual.shape[0] == batch.n_bases
+    for k, i in enumerate(rf):
+        b0, b1 = int(batch.base_off[k]), int(batch.base_off[k + 1])
+        want = fast5.basecall_phred(fast5_files[int(i)], batch.bases[b0:b1])
+        assert np.array_equal(batch.qual[b0:b1], want)
