@@ -201,7 +201,10 @@ typedef struct nrv_ingest nrv_ingest;   /* owns the packed host arrays */
 int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* basecall_group, const char* basecall_subgroup,
                      int n_threads, nrv_ingest** out);
 /* Views into the result, valid until nrv_ingest_free: the batch of the reads that succeeded (in file order),
- * file_status[n_files], read_file[n_reads] (index into paths of every packed read), a0[n_reads] (abs_event_start). */
+ * file_status[n_files], read_file[n_reads] (index into paths of every packed read), a0[n_reads] (abs_event_start).
+ * batch->qual holds the basecaller's Phred scores of the event-collapsed bases (the Fastq dataset next to Events: the call is
+ * Fastq_seq[2:-2]; extract_fastq, nanorev_fast5_handeler.py:152-171, reads the same dataset) when EVERY packed read has a
+ * Fastq dataset that lines up, else NULL. */
 int nrv_ingest_view(const nrv_ingest* r, nrv_batch* batch, const int32_t** file_status, const int64_t** read_file,
                     const int64_t** a0);
 void nrv_ingest_free(nrv_ingest* r);
