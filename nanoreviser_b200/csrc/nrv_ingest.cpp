@@ -69,7 +69,10 @@ struct H5 {
             while (p + 8 <= end && out.size() < nmsg) {
                 const uint16_t t = b.u16(p), sz = b.u16(p + 2);
                 b.need(p + 8, sz);
-                if (t == 0x0010) blocks.push_back({b.u64(p + 8), b.u64(p + 16)});
+                if (t == 0x0010) {
+                    if (blocks.size() > 64) throw Fail{NRV_INGEST_CORRUPT};
+                    blocks.push_back({b.u64(p + 8), b.u64(p + 16)});
+                }
                 out.push_back({t, p + 8, sz});
                 p += 8 + sz;
             }
@@ -85,16 +88,17 @@ struct H5 {
             b.need(heap, 32);
             if (memcmp(b.p + heap, "HEAP", 4)) throw Fail{NRV_INGEST_CORRUPT};
             const uint64_t dseg = b.u64(heap + 24);
-            walk_group(btree, dseg, out, 0);
+            size_t budget = 1 << 16;                      // nodes visited: a cyclic tree fails instead of exploding
+            walk_group(btree, dseg, out, 0, budget);
         }
     }
-    void walk_group(uint64_t node, uint64_t dseg, std::vector<std::pair<std::string, uint64_t>>& out, int depth) const {
-        if (depth > 16) throw Fail{NRV_INGEST_CORRUPT};
+    void walk_group(uint64_t node, uint64_t dseg, std::vector<std::pair<std::string, uint64_t>>& out, int depth, size_t& budget) const {
+        if (depth > 16 || budget-- == 0) throw Fail{NRV_INGEST_CORRUPT};
         b.need(node, 8);
         if (!memcmp(b.p + node, "TREE", 4)) {
             const uint16_t used = b.u16(node + 6);
             uint64_t p = node + 24;
-            for (int i = 0; i < used; ++i, p += 16) walk_group(b.u64(p + 8), dseg, out, depth + 1);
+            for (int i = 0; i < used; ++i, p += 16) walk_group(b.u64(p + 8), dseg, out, depth + 1, budget);
         } else if (!memcmp(b.p + node, "SNOD", 4)) {
             const uint16_t n = b.u16(node + 6);
             for (int i = 0; i < n; ++i) {
@@ -332,7 +336,12 @@ void read_one(const char* path, const std::string& group, const std::string& sub
         if (!m_mean.present || !m_start.present || !m_stdv.present || !m_state.present || !m_move.present) throw Fail{NRV_INGEST_NO_EVENTS};
         if (m_start.cls != 0) throw Fail{NRV_INGEST_UNSUPPORTED};                          // float starts: legacy tables
         if (m_state.cls != 3 || m_state.size < 3) throw Fail{NRV_INGEST_UNSUPPORTED};
+        // every member the collapse reads must lie inside one record (a corrupt compound type must not send the loops below
+        // past the file buffer)
+        for (const Member* mm : {&m_mean, &m_start, &m_stdv, &m_state, &m_move})
+            if ((uint64_t)mm->offset + mm->size > itemsize) throw Fail{NRV_INGEST_CORRUPT};
         const uint64_t E = dims[0];
+        if (E > h.b.n / itemsize) throw Fail{NRV_INGEST_CORRUPT};                          // E * itemsize cannot wrap below
         h.b.need(ev_addr, E * itemsize);
         const uint8_t* ev = h.b.p + ev_addr;
         // ---- collapse events to bases (:84-118), forward order ----
@@ -394,6 +403,7 @@ void read_one(const char* path, const std::string& group, const std::string& sub
         }
         if (sdims.size() != 1 || sdt.cls != 0 || sdt.size != 2 || !sdt.is_signed) throw Fail{NRV_INGEST_UNSUPPORTED};
         const uint64_t S = sdims[0];
+        if (S > ((uint64_t)1 << 34) || S / 1100 > h.b.n) throw Fail{NRV_INGEST_CORRUPT};      // deflate expands at most ~1032x
         if ((int64_t)S < start[nb - 1] + last_dur) throw Fail{NRV_INGEST_SIGNAL_SHORT};   // :142-143
         const int64_t a0 = start[0];
         if (a0 < 0 || (uint64_t)a0 > S) throw Fail{NRV_INGEST_SIGNAL_SHORT};
@@ -408,13 +418,19 @@ void read_one(const char* path, const std::string& group, const std::string& sub
             const uint64_t btree = h.b.u64(lay_off + 3);
             const uint32_t cdim = h.b.u32(lay_off + 11), esize = h.b.u32(lay_off + 15);
             if (esize != 2) throw Fail{NRV_INGEST_UNSUPPORTED};
+            if (cdim == 0 || cdim > (1u << 28)) throw Fail{NRV_INGEST_CORRUPT};
             for (int f : filters) if (f != 1) throw Fail{NRV_INGEST_UNSUPPORTED};         // deflate only (no VBZ 32020)
             if (filters.size() > 1) throw Fail{NRV_INGEST_UNSUPPORTED};
             if (btree != UNDEF) {
                 // chunk B-tree v1 (node type 1): keys {u32 size, u32 filter mask, ndims x u64 offsets}, children = chunk addresses
-                std::vector<uint64_t> stack{btree};
+                // bounded walk: a corrupt (cyclic) tree cannot loop or grow the stack without limit
+                std::vector<std::pair<uint64_t, int>> stack{{btree, 0}};
+                size_t visited = 0;
                 while (!stack.empty()) {
-                    const uint64_t node = stack.back(); stack.pop_back();
+                    const uint64_t node = stack.back().first;
+                    const int depth = stack.back().second;
+                    stack.pop_back();
+                    if (depth > 16 || ++visited > 65536) throw Fail{NRV_INGEST_CORRUPT};
                     h.b.need(node, 24);
                     if (memcmp(h.b.p + node, "TREE", 4) || h.b.u8(node + 4) != 1) throw Fail{NRV_INGEST_CORRUPT};
                     const int level = h.b.u8(node + 5), used = h.b.u16(node + 6);
@@ -423,7 +439,7 @@ void read_one(const char* path, const std::string& group, const std::string& sub
                     for (int i = 0; i < used; ++i, p += keysz + 8) {
                         const uint32_t csize = h.b.u32(p), fmask = h.b.u32(p + 4);
                         const uint64_t off0 = h.b.u64(p + 8), childaddr = h.b.u64(p + keysz);
-                        if (level > 0) { stack.push_back(childaddr); continue; }
+                        if (level > 0) { stack.push_back({childaddr, depth + 1}); continue; }
                         if (off0 >= S) continue;
                         h.b.need(childaddr, csize);
                         const uint64_t room = (S - off0) * 2;

@@ -108,3 +108,65 @@ def test_native_reader_extracts_basecall_qualities(fast5_files):
         b0, b1 = int(batch.base_off[k]), int(batch.base_off[k + 1])
         want = fast5.basecall_phred(fast5_files[int(i)], batch.bases[b0:b1])
         assert np.array_equal(batch.qual[b0:b1], want)
+
+
+def _patched(data: bytes, pos: int, new: bytes) -> bytes:
+    return data[:pos] + new + data[pos + len(new):]
+
+
+def test_native_ingest_targeted_corruptions(lib_built, fast5_files, tmp_path):
+    """File-supplied sizes and offsets are never trusted (round-1 advisor findings): a record count whose byte size wraps in
+    64 bits, compound member offsets beyond the record, and a cyclic chunk B-tree must each yield a per-file status -- the
+    worker neither crashes nor hangs, and the other files of the slab are still packed."""
+    import struct
+    from nanoreviser_b200 import h5mini
+    engine = lib_built
+    good = fast5_files[0]
+    data = open(good, "rb").read()
+    n_events = len(h5mini.File(good)["/Analyses/Basecall_1D_000/BaseCalled_template/Events"][()])
+    cases = {}
+    # (1) Events dataspace: every 8-byte occurrence of the event count -> 2^61 + 1  (E * itemsize wraps to a tiny range)
+    d = data
+    pos, hits = 0, 0
+    needle = struct.pack("<Q", n_events)
+    while True:
+        pos = d.find(needle, pos)
+        if pos < 0:
+            break
+        d = _patched(d, pos, struct.pack("<Q", (1 << 61) + 1))
+        pos += 8
+        hits += 1
+    assert hits >= 1
+    cases["wrap"] = d
+    # (2) compound members: offset of `move` / `start` / `model_state` far beyond the record
+    for name in (b"move", b"start", b"model_state"):
+        key = name + b"\x00" * (8 - len(name) % 8 if len(name) % 8 else 8)
+        pos = data.find(key)
+        assert pos > 0, name
+        cases["member_" + name.decode()] = _patched(data, pos + len(key), struct.pack("<I", 0x7FFFFFF0))
+    # (3) chunk B-tree of the signal: make the leaf an internal node whose first child is itself
+    pos = 0
+    trees = []
+    while True:
+        pos = data.find(b"TREE", pos)
+        if pos < 0:
+            break
+        if data[pos + 4] == 1:           # node type 1 = raw-data chunks
+            trees.append(pos)
+        pos += 4
+    assert trees
+    t = trees[0]
+    d = _patched(data, t + 5, b"\x01")                                   # level 1: children are nodes
+    keysz = 8 + 8 * 2
+    d = _patched(d, t + 24 + keysz, struct.pack("<Q", t))                # first child -> the node itself
+    cases["cycle"] = d
+    paths = [good]
+    for k, v in cases.items():
+        fn = str(tmp_path / (k + ".fast5"))
+        open(fn, "wb").write(v)
+        paths.append(fn)
+    paths.append(fast5_files[1])
+    batch, status, read_file, _ = engine.ingest_fast5(paths, threads=2)
+    assert status[0] == engine.INGEST_OK and status[-1] == engine.INGEST_OK
+    assert all(s != engine.INGEST_OK for s in status[1:-1]), dict(zip(["good"] + list(cases) + ["good2"], status.tolist()))
+    assert read_file.tolist() == [0, len(paths) - 1]
