@@ -84,9 +84,11 @@ struct nrv_handle {
     struct EvPair { cudaEvent_t a, b; int stage; };
     std::vector<EvPair> ev_pool;
     size_t ev_used = 0;
+    int timers_open = 0;                  // live StageTimer scopes (they nest): the pool is never folded under them
     void fold_events() {
-        if (ev_used == 0) return;
+        if (ev_used == 0 || timers_open > 0) return;
         cudaStreamSynchronize(stream);
+        if (stream2) cudaStreamSynchronize(stream2);      // side-stream stages (read_rnn1, heads tail) record there
         for (size_t i = 0; i < ev_used; ++i) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b) == cudaSuccess) stage_ms[ev_pool[i].stage] += ms;
@@ -300,25 +302,29 @@ cuda_fail:
     return fail(h, NRV_E_CUDA, std::string("weight upload: ") + cudaGetErrorString(e));
 }
 
+// Scoped stage timer.  Scopes nest (ST_PROJ2 encloses launch_l0's ST_L0) and the pool is a std::vector that grows under
+// them, so a timer keeps the INDEX of its event pair, never a pointer; a full pool is folded only when no timer is open.
 struct StageTimer {
-    nrv_handle* h; int stage; int64_t launches0; nrv_handle::EvPair* ev = nullptr; cudaStream_t st;
+    nrv_handle* h; int stage; int64_t launches0; ptrdiff_t slot = -1; cudaStream_t st;
     StageTimer(nrv_handle* h_, int s, cudaStream_t st_ = nullptr) : h(h_), stage(s), launches0(h_->launches), st(st_ ? st_ : h_->stream) {
         if (!h->timing) return;
         if (h->ev_used == h->ev_pool.size()) {
-            if (h->ev_pool.size() >= 8192) h->fold_events();
-            else {
+            if (h->ev_pool.size() >= 8192 && h->timers_open == 0) h->fold_events();
+            if (h->ev_used == h->ev_pool.size()) {
                 nrv_handle::EvPair p; p.stage = 0;
-                if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+                if (cudaEventCreate(&p.a) != cudaSuccess) return;
+                if (cudaEventCreate(&p.b) != cudaSuccess) { cudaEventDestroy(p.a); return; }
                 h->ev_pool.push_back(p);
             }
         }
-        ev = &h->ev_pool[h->ev_used++];
-        ev->stage = stage;
-        cudaEventRecord(ev->a, st);
+        slot = (ptrdiff_t)h->ev_used++;
+        h->ev_pool[slot].stage = stage;
+        cudaEventRecord(h->ev_pool[slot].a, st);
+        ++h->timers_open;
     }
     ~StageTimer() {
         h->stage_launches[stage] += h->launches - launches0;
-        if (ev) cudaEventRecord(ev->b, st);
+        if (slot >= 0) { cudaEventRecord(h->ev_pool[slot].b, st); --h->timers_open; }
     }
 };
 

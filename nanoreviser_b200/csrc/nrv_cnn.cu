@@ -34,6 +34,8 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
+__device__ __forceinline__ float clamp_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
 __global__ void __launch_bounds__(CNN_THREADS, 2)
 cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
            const int32_t* __restrict__ starts, const int32_t* __restrict__ base_read,
@@ -140,8 +142,9 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
             uint32_t ph[4], pl[4];
 #pragma unroll
             for (int c = 0; c < NRV_CNN_CH; c += 2) {
-                const float y0 = fmaf(fmaxf(acc[j][c], 0.f), s2[c], t2[c]) + xin;
-                const float y1 = fmaf(fmaxf(acc[j][c + 1], 0.f), s2[c + 1], t2[c + 1]) + xin;
+                // clamped to the fp16 range: an outlier spike on a quiet read (tiny MAD) must saturate, not become inf - inf = NaN
+                const float y0 = clamp_f16(fmaf(fmaxf(acc[j][c], 0.f), s2[c], t2[c]) + xin);
+                const float y1 = clamp_f16(fmaf(fmaxf(acc[j][c + 1], 0.f), s2[c + 1], t2[c + 1]) + xin);
                 const __half2 h = __floats2half2_rn(y0, y1);
                 const float2 f = __half22float2(h);
                 const __half2 l = __floats2half2_rn(y0 - f.x, y1 - f.y);
@@ -188,10 +191,11 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
                     const float y0 = acc[mt][hh * 2], y1 = acc[mt][hh * 2 + 1];
                     *reinterpret_cast<float2*>(sig_feat + j * NRV_SIGFEAT + col) = make_float2(y0, y1);
                     if (sf_hi) {   // fp16 (hi, lo) copy: A operand of the tensor-core projection of total_rnn1's per-base part
-                        const __half2 h = __floats2half2_rn(y0, y1);
+                        const float c0 = clamp_f16(y0), c1 = clamp_f16(y1);
+                        const __half2 h = __floats2half2_rn(c0, c1);
                         const float2 f = __half22float2(h);
                         *reinterpret_cast<__half2*>(sf_hi + j * NRV_SIGFEAT + col) = h;
-                        *reinterpret_cast<__half2*>(sf_lo + j * NRV_SIGFEAT + col) = __floats2half2_rn(y0 - f.x, y1 - f.y);
+                        *reinterpret_cast<__half2*>(sf_lo + j * NRV_SIGFEAT + col) = __floats2half2_rn(c0 - f.x, c1 - f.y);
                     }
                 }
             }
@@ -203,11 +207,8 @@ int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, co
                const double* shift, const double* scale, const float* explicit_win, int64_t n_bases,
                float* sig_feat1, float* sig_feat2, __half* const sf_hi[2], __half* const sf_lo[2], cudaStream_t st) {
     if (n_bases <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CnnSmem));
-        attr_set = true;
-    }
+    static PerDevice attr_set;
+    if (attr_set.first()) cudaFuncSetAttribute(cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CnnSmem));
     const unsigned grid = (unsigned)((n_bases + CNN_TB - 1) / CNN_TB);
     int n = 0;
     if (m1 && sig_feat1) {

@@ -16,6 +16,16 @@
 
 namespace nrv {
 
+// cudaFuncSetAttribute / cluster occupancy are PER DEVICE: a process may hold one nrv_handle per GPU, so "done once" state of
+// a launcher is kept per device ordinal (the launchers run on the handle's device: every entry point calls cudaSetDevice).
+constexpr int NRV_MAX_DEVICES = 64;
+struct PerDevice {
+    int v[NRV_MAX_DEVICES] = {0};
+    int& cur() { int d = 0; cudaGetDevice(&d); return v[d & (NRV_MAX_DEVICES - 1)]; }
+    // true exactly once per device
+    bool first() { int& x = cur(); if (x) return false; x = 1; return true; }
+};
+
 // ---- packed device weights of one model ---------------------------------------------------
 struct LstmLayerDev {
     int in_a, in_b, u, k, k_pad;       // K = in_a + in_b + u (x_t rows, then h rows); k_pad = roundup(K, 16)

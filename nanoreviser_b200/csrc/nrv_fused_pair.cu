@@ -514,7 +514,8 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     CUtensorMap txh, txl;
     if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, KIN, 128) || !make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, KIN, 128)) return -2;
     auto kern = lstm_fused_pair_kernel<KIN, UT>;
-    static int max_clusters = 0;                  // co-resident clusters on this device (per template instance)
+    static PerDevice per_dev;                     // co-resident clusters on the current device (per template instance)
+    int& max_clusters = per_dev.cur();
     if (!max_clusters) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e == cudaSuccess && CS > 2) e = cudaSuccess;

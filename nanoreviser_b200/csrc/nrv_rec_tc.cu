@@ -214,11 +214,8 @@ int launch_lstm_rec_tc64(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, i
     if (!make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
         !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
         return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_rec_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
-        attr = true;
-    }
+    static PerDevice attr;
+    if (attr.first()) cudaFuncSetAttribute(lstm_rec_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
     dim3 grid((unsigned)(((nwp >> 7) + 1) / 2), 2);
     lstm_rec_tc64_kernel<<<grid, RT_THREADS, RT_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, tmh, tml, nwp, T);
     return 1;
@@ -434,11 +431,8 @@ int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __ha
         !make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
         !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
         return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_fused_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        attr = true;
-    }
+    static PerDevice attr;
+    if (attr.first()) cudaFuncSetAttribute(lstm_fused_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
     dim3 grid((unsigned)std::min<int64_t>(nwp >> 7, 74), 2);       // persistent: 148 CTAs, weights loaded once each
     lstm_fused_tc64_kernel<<<grid, RF_THREADS, RF_SMEM, st>>>(L.pb_hi, L.pb_lo, L.rt_hi, L.rt_lo, txh, txl, tmh, tml, nwp, T);
     return 1;
@@ -655,11 +649,8 @@ int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t nwp, 
         !make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
         !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
         return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_rec_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM);
-        attr = true;
-    }
+    static PerDevice attr;
+    if (attr.first()) cudaFuncSetAttribute(lstm_rec_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM);
     dim3 grid((unsigned)(nwp >> 7), 2);
     lstm_rec_tc128_kernel<<<grid, R2_THREADS, R2_SMEM, st>>>(L.rt_hi, tm, io.zin, tmh, tml, nwp, T);
     return 1;
@@ -908,11 +899,8 @@ int launch_lstm_rec_tc128_pair(const LstmLayerDev& L, const LstmIo& io, int64_t 
     if (!make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
         !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
         return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_rec_tc128_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM);
-        attr = true;
-    }
+    static PerDevice attr;
+    if (attr.first()) cudaFuncSetAttribute(lstm_rec_tc128_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RP_SMEM);
     const int64_t n_pairs = ((nwp >> 7) + 1) / 2;
     dim3 grid((unsigned)(2 * std::min<int64_t>(n_pairs, 37)), 2);   // persistent: 74 clusters = 148 CTAs, weights loaded once each
     lstm_rec_tc128_pair_kernel<<<grid, RP_THREADS, RP_SMEM, st>>>(L.rt_hi, L.rt_lo, io.zin, tmh, tml, nwp, T);

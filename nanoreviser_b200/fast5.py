@@ -73,7 +73,11 @@ def collapse_events(ev_start, ev_mean, ev_stdv, ev_state, ev_move):
     # int(start_l) truncates (legacy float starts), as fast5_handeler.py:93
     st = st.astype(np.int64) if st.dtype.kind != "f" else np.trunc(st).astype(np.int64)
     start = st + np.where(two & (rank == 1), 2, 0)
-    states = np.frombuffer(np.ascontiguousarray(ev_state).tobytes(), dtype=np.uint8).reshape(-1, 5)
+    ev_state = np.ascontiguousarray(ev_state)
+    width = ev_state.dtype.itemsize                 # k-mer width of the basecaller's model (5 for Albacore r9.4; any width >= 3:
+    if width < 3:                                   # the reference indexes characters 1 and 2 whatever the length, :98-109)
+        raise RuntimeError("model_state is narrower than 3 characters")
+    states = np.frombuffer(ev_state.tobytes(), dtype=np.uint8).reshape(-1, width)
     col = np.where(two & (rank == 0), 1, 2)
     bases = states[src, col]
     return start, bases, np.asarray(ev_mean)[src].astype(np.float32), np.asarray(ev_stdv)[src].astype(np.float32)
