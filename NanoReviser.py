@@ -111,7 +111,7 @@ def run_worker(args, file_list, device, logger=None):
     """One GPU: native multi-threaded ingest (C++, include/nrv.h nrv_ingest_fast5) slab by slab -> ragged batches by base
     budget -> revise -> write.  Files the native reader does not cover or cannot read go through the Python reader, which
     follows the reference branch by branch and produces its error messages."""
-    from nanoreviser_b200 import api, engine, fast5, synth, weights, workqueue
+    from nanoreviser_b200 import api, engine, fast5, weights, workqueue
     m1 = weights.load_model_weights(args.model1_predict_dir)
     m2 = weights.load_model_weights(args.model2_predict_dir)
     counts = {'ok': 0, 'fallback': 0, 'failed': 0}
@@ -169,7 +169,7 @@ def run_worker(args, file_list, device, logger=None):
                     with ThreadPoolExecutor(max_workers=nthreads) as ex:
                         batch.qual = np.concatenate(list(ex.map(phred, range(batch.n_reads))))
                 for idx in workqueue.make_batches(range(batch.n_reads), lengths, int(args.batch_bases)):
-                    sub = batch if len(idx) == batch.n_reads else synth.split_batch(batch, idx)
+                    sub = batch if len(idx) == batch.n_reads else engine.split_batch(batch, idx)
                     out = rv.revise_batch(sub, want_qual=fastq)
                     for k, i in enumerate(idx):
                         ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)

@@ -405,7 +405,7 @@ def main():
                    "sample": "%d synthetic cfg2 read(s) x %d bases (%.1f s), batched oracle (CNN once per base)" % (nreads, READ_LEN, dt)}
             # the oracle as the checker: the CUDA path must give the same revised bytes on the read the CPU just timed
             sb, want = cpu_oracle_bases_per_sec.last
-            got = rv.revise_batch(synth.split_batch(sb, [0])).sequence(0)
+            got = rv.revise_batch(engine.split_batch(sb, [0])).sequence(0)
             cpu["gpu_matches_oracle_on_sample"] = bool(got == want)
             if got != want:
                 raise SystemExit("bench.py: CUDA result differs from the CPU oracle on the sampled read -- number withheld")

@@ -171,8 +171,20 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
  * are inside; returns after the results are in the caller's buffers. */
 int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r);
 
-/* Same, but the bulk arrays of `b` and the outputs of `r` are DEVICE pointers (sig_off/base_off stay
- * host).  Enqueues on nrv_stream(h) and returns without synchronising. */
+/* The same call split in two so that a host thread can keep TWO batches in flight (the reference gets its concurrency from a
+ * multiprocessing.Pool of provide_fasta workers, NanoReviser.py:203-223; here one host thread per GPU pipelines instead):
+ * nrv_submit_batch stages the offsets, enqueues the H2D copies on a copy stream and K1..K4 on nrv_stream(h), and returns a
+ * ticket without waiting; nrv_wait_batch(ticket) copies the results out (D2H on the copy stream) and returns when they are in
+ * the buffers of the nrv_result given at submit time.  Submitting batch i+1 before waiting for batch i puts the H2D of i+1
+ * and the D2H of i under the kernels of the other batch.  At most 2 tickets may be outstanding (a third submit fails with
+ * NRV_E_INVALID); the batch's and the result's host arrays must stay valid until nrv_wait_batch returns (use pinned memory for
+ * truly asynchronous copies).  nrv_revise_batch == submit + wait. */
+int nrv_submit_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, int64_t* ticket);
+int nrv_wait_batch(nrv_handle* h, int64_t ticket);
+
+/* Same as nrv_revise_batch, but the bulk arrays of `b` and the outputs of `r` are DEVICE pointers (sig_off/base_off stay
+ * host).  Enqueues on nrv_stream(h) and returns without synchronising: the offsets go through a ring of pinned staging
+ * slots guarded by events, so consecutive calls never drain the stream. */
 int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r);
 
 /* Diagnostic entry point (tests only): C[M][N] = A[M][K] . Bt[N][K]^T (+ bias[N]) through the split-fp16

@@ -12,6 +12,7 @@ using namespace nrv;
 namespace {
 
 std::string g_create_error;
+constexpr int NRV_SLOTS = 2;
 
 struct Arena {
     void* p = nullptr;
@@ -67,10 +68,30 @@ struct nrv_handle {
     int64_t chunk_windows = 148 * 1024;   // 592 tile pairs: 37 rounds on the 16 clusters per direction of total_rnn1, 16 on the 37 of total_rnn2,
                                           // 8 on the 148 CTAs of read_rnn11 -- all exact (NRV_CHUNK_WINDOWS; 37,888 measured 4 % slower)
     // inputs / per-batch arenas
-    Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_shift, d_scale, d_status, d_base_read,
-        d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_revised, d_outoff, d_flag, d_wq[2], d_qual_in, d_revq,
+    // Per-batch I/O lives in a ring of NRV_SLOTS slots so that two batches can be in flight: the H2D copies of batch i+1 (copy
+    // stream) run under the kernels of batch i (main stream) and the D2H of batch i under the kernels of batch i+1.  Everything
+    // BETWEEN input and output (features, activations, labels) is shared: the kernels of consecutive batches are serialised on
+    // the main stream anyway.
+    struct IoSlot {
+        Arena d_signal, d_starts, d_bases, d_evm, d_evs, d_lastdur, d_off, d_qual_in;      // inputs
+        Arena d_status, d_revised, d_outoff, d_revq, d_flag;                               // outputs
+        PinnedArena h_off, h_flag;
+        cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr;
+        // the ticket that owns the slot (0 = free) and what nrv_wait needs to finish it
+        int64_t ticket = 0;
+        nrv_result res = {};
+        int64_t n_reads = 0;
+        bool want_q = false;
+    };
+    IoSlot slot[NRV_SLOTS];
+    int64_t next_ticket = 1;
+    int cur = 0;                          // slot of the batch being enqueued
+    cudaStream_t copy_stream = nullptr;
+    Arena d_shift, d_scale, d_base_read,
+        d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_wq[2],
         d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin;
-    PinnedArena h_off, h_flag;
+    IoSlot& io() { return slot[cur]; }
+    int in_flight() const { int n = 0; for (const IoSlot& s : slot) n += s.ticket != 0; return n; }
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
     int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
@@ -552,13 +573,15 @@ struct Offsets {
 };
 
 // host offsets -> pinned staging -> device; also derives the window CSR.
-int stage_offsets(nrv_handle* h, int64_t R, const int64_t* sig_off, const int64_t* base_off, Offsets* o) {
+int stage_offsets(nrv_handle* h, int64_t R, const int64_t* sig_off, const int64_t* base_off, Offsets* o, cudaStream_t st) {
     const size_t n = (size_t)R + 1;
-    CU(h, h->h_off.ensure(3 * n * sizeof(int64_t)));
-    CU(h, h->d_off.ensure(3 * n * sizeof(int64_t)));
-    // the previous batch's async upload from this staging buffer must be done before it is overwritten
-    CU(h, cudaStreamSynchronize(h->stream));
-    int64_t* hs = h->h_off.as<int64_t>();
+    nrv_handle::IoSlot& S = h->io();
+    // the upload that last used this slot's pinned staging buffer must be done before it is overwritten: wait for THAT copy
+    // (an event recorded right after it, NRV_SLOTS batches ago) -- not for the stream, which would drain the batch in flight
+    CU(h, cudaEventSynchronize(S.ev_h2d));
+    CU(h, S.h_off.ensure(3 * n * sizeof(int64_t)));
+    CU(h, S.d_off.ensure(3 * n * sizeof(int64_t)));
+    int64_t* hs = S.h_off.as<int64_t>();
     int64_t* hb = hs + n;
     int64_t* hw = hb + n;
     for (size_t i = 0; i < n; ++i) { hs[i] = sig_off ? sig_off[i] : 0; hb[i] = base_off[i]; }
@@ -569,9 +592,10 @@ int stage_offsets(nrv_handle* h, int64_t R, const int64_t* sig_off, const int64_
         hw[r + 1] = hw[r] + std::max<int64_t>(N - h->window, 0);
     }
     if (hb[0] != 0 || hs[0] != 0) return fail(h, NRV_E_INVALID, "offsets must start at 0");
-    CU(h, cudaMemcpyAsync(h->d_off.p, hs, 3 * n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(S.d_off.p, hs, 3 * n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(S.ev_h2d, st));
     o->n_reads = R; o->n_samples = hs[R]; o->n_bases = hb[R]; o->n_win = hw[R];
-    o->d_sig_off = h->d_off.as<int64_t>();
+    o->d_sig_off = S.d_off.as<int64_t>();
     o->d_base_off = o->d_sig_off + n;
     o->d_win_off = o->d_base_off + n;
     if (o->n_bases >= (int64_t)INT32_MAX || o->n_samples >= ((int64_t)1 << 40))
@@ -593,21 +617,22 @@ struct DevBatch {
     const int32_t* last_dur;
 };
 
-int upload_batch(nrv_handle* h, const nrv_batch* b, const Offsets& o, DevBatch* d) {
-    CU(h, h->d_signal.ensure((size_t)o.n_samples * 2 + 64));
-    CU(h, h->d_starts.ensure((size_t)o.n_bases * 4 + 16));
-    CU(h, h->d_bases.ensure((size_t)o.n_bases + 16));
-    CU(h, h->d_evm.ensure((size_t)o.n_bases * 4 + 16));
-    CU(h, h->d_evs.ensure((size_t)o.n_bases * 4 + 16));
-    CU(h, h->d_lastdur.ensure((size_t)o.n_reads * 4 + 16));
-    CU(h, cudaMemcpyAsync(h->d_signal.p, b->signal, (size_t)o.n_samples * 2, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_starts.p, b->starts, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_bases.p, b->bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_evm.p, b->ev_mean, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_evs.p, b->ev_std, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_lastdur.p, b->last_dur, (size_t)o.n_reads * 4, cudaMemcpyHostToDevice, h->stream));
-    d->signal = h->d_signal.as<int16_t>(); d->starts = h->d_starts.as<int32_t>(); d->bases = h->d_bases.as<uint8_t>();
-    d->evm = h->d_evm.as<float>(); d->evs = h->d_evs.as<float>(); d->last_dur = h->d_lastdur.as<int32_t>();
+int upload_batch(nrv_handle* h, const nrv_batch* b, const Offsets& o, DevBatch* d, cudaStream_t st) {
+    nrv_handle::IoSlot& S = h->io();
+    CU(h, S.d_signal.ensure((size_t)o.n_samples * 2 + 64));
+    CU(h, S.d_starts.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, S.d_bases.ensure((size_t)o.n_bases + 16));
+    CU(h, S.d_evm.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, S.d_evs.ensure((size_t)o.n_bases * 4 + 16));
+    CU(h, S.d_lastdur.ensure((size_t)o.n_reads * 4 + 16));
+    CU(h, cudaMemcpyAsync(S.d_signal.p, b->signal, (size_t)o.n_samples * 2, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(S.d_starts.p, b->starts, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(S.d_bases.p, b->bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(S.d_evm.p, b->ev_mean, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(S.d_evs.p, b->ev_std, (size_t)o.n_bases * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(S.d_lastdur.p, b->last_dur, (size_t)o.n_reads * 4, cudaMemcpyHostToDevice, st));
+    d->signal = S.d_signal.as<int16_t>(); d->starts = S.d_starts.as<int32_t>(); d->bases = S.d_bases.as<uint8_t>();
+    d->evm = S.d_evm.as<float>(); d->evs = S.d_evs.as<float>(); d->last_dur = S.d_lastdur.as<int32_t>();
     return NRV_OK;
 }
 
@@ -615,13 +640,13 @@ int upload_batch(nrv_handle* h, const nrv_batch* b, const Offsets& o, DevBatch* 
 int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x, double* seg_mean, double* seg_std) {
     CU(h, h->d_shift.ensure((size_t)o.n_reads * 8 + 16));
     CU(h, h->d_scale.ensure((size_t)o.n_reads * 8 + 16));
-    CU(h, h->d_status.ensure((size_t)o.n_reads * 4 + 16));
+    CU(h, h->io().d_status.ensure((size_t)o.n_reads * 4 + 16));
     CU(h, h->d_base_read.ensure((size_t)o.n_bases * 4 + 16));
     if (want_x) CU(h, h->d_x.ensure((size_t)o.n_bases * 6 * 4 + 16));
     {
         StageTimer tm(h, ST_STATS);
         h->launches += launch_read_stats(d.signal, o.d_sig_off, o.d_base_off, d.starts, d.last_dur, h->window, o.n_reads,
-                                         h->d_shift.as<double>(), h->d_scale.as<double>(), h->d_status.as<int32_t>(),
+                                         h->d_shift.as<double>(), h->d_scale.as<double>(), h->io().d_status.as<int32_t>(),
                                          h->stream);
         h->launches += launch_base_read_map(o.d_base_off, o.n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
     }
@@ -636,22 +661,51 @@ int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x,
     return NRV_OK;
 }
 
-int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) {
+// Pick the slot for a new batch.  Sync entry points (nrv_segment, nrv_decode, nrv_predict_windows) need an idle handle.
+int begin_batch(nrv_handle* h, bool need_idle) {
+    if (need_idle && h->in_flight()) return fail(h, NRV_E_INVALID, "call nrv_wait on the batches in flight first");
+    int c = -1;
+    for (int k = 0; k < NRV_SLOTS; ++k) {
+        const int cand = (h->cur + 1 + k) % NRV_SLOTS;
+        if (h->slot[cand].ticket == 0) { c = cand; break; }
+    }
+    if (c < 0) return fail(h, NRV_E_INVALID, "too many batches in flight (nrv_wait the oldest ticket first)");
+    h->cur = c;
+    return NRV_OK;
+}
+
+// Enqueue one batch: H2D (host_io: on the copy stream, so that it runs under the previous batch's kernels), K1..K4 on the main
+// stream.  host_io: the results stay in the slot's device arenas until finish_batch() copies them out.
+int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) {
     int rc = check_batch(h, b);
     if (rc) return rc;
     if (!r || !r->revised || !r->out_off || !r->status) return fail(h, NRV_E_INVALID, "result needs revised/out_off/status");
     CU(h, cudaSetDevice(h->device));
+    rc = begin_batch(h, false);
+    if (rc) return rc;
+    nrv_handle::IoSlot& S = h->io();
+    cudaStream_t up = host_io ? h->copy_stream : h->stream;
     Offsets o;
-    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o);
+    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o, up);
     if (rc) return rc;
     if (r->revised_cap < o.n_bases) return fail(h, NRV_E_CAPACITY, "revised_cap smaller than the number of bases");
     DevBatch d;
+    const bool want_q = r->revised_qual != nullptr;      // -F fastq: per-window Phred scores need the softmax outputs
+    const uint8_t* d_qual_in = nullptr;
     if (host_io) {
-        rc = upload_batch(h, b, o, &d);
+        rc = upload_batch(h, b, o, &d, up);
         if (rc) return rc;
+        if (want_q && b->qual) {
+            CU(h, S.d_qual_in.ensure((size_t)o.n_bases + 16));
+            CU(h, cudaMemcpyAsync(S.d_qual_in.p, b->qual, (size_t)o.n_bases, cudaMemcpyHostToDevice, up));
+            d_qual_in = S.d_qual_in.as<uint8_t>();
+        }
+        CU(h, cudaEventRecord(S.ev_h2d, up));
+        CU(h, cudaStreamWaitEvent(h->stream, S.ev_h2d, 0));
     } else {
         d.signal = b->signal; d.starts = b->starts; d.bases = b->bases; d.evm = b->ev_mean; d.evs = b->ev_std;
         d.last_dur = b->last_dur;
+        d_qual_in = b->qual;
     }
     rc = run_segment(h, d, o, true, nullptr, nullptr);
     if (rc) return rc;
@@ -675,7 +729,6 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
                                      h->stream);
     float* probs[2] = {nullptr, nullptr};
     uint8_t* labels[2];
-    const bool want_q = r->revised_qual != nullptr;      // -F fastq: per-window Phred scores need the softmax outputs
     if (host_io) {
         if (r->p1 || want_q) { CU(h, h->d_probs[0].ensure((size_t)o.n_win * 6 * 4 + 16)); probs[0] = h->d_probs[0].as<float>(); }
         if (r->p2 || want_q) { CU(h, h->d_probs[1].ensure((size_t)o.n_win * 5 * 4 + 16)); probs[1] = h->d_probs[1].as<float>(); }
@@ -697,28 +750,22 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
     const int64_t n_tiles = decode_tile_count(o.n_bases);
     CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
     CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
-    CU(h, h->d_flag.ensure(16));
-    CU(h, cudaMemsetAsync(h->d_flag.p, 0, 4, h->stream));
+    CU(h, S.d_flag.ensure(16));
+    CU(h, cudaMemsetAsync(S.d_flag.p, 0, 4, h->stream));
     uint8_t* d_rev; int64_t* d_outoff;
     uint8_t* d_revq = nullptr;
-    const uint8_t* d_qual_in = nullptr;
     uint8_t* wq[2] = {nullptr, nullptr};
     if (host_io) {
-        CU(h, h->d_revised.ensure((size_t)r->revised_cap + 16));
-        CU(h, h->d_outoff.ensure((size_t)(o.n_reads + 1) * 8));
-        d_rev = h->d_revised.as<uint8_t>(); d_outoff = h->d_outoff.as<int64_t>();
+        CU(h, S.d_revised.ensure((size_t)r->revised_cap + 16));
+        CU(h, S.d_outoff.ensure((size_t)(o.n_reads + 1) * 8));
+        d_rev = S.d_revised.as<uint8_t>(); d_outoff = S.d_outoff.as<int64_t>();
         if (want_q) {
-            CU(h, h->d_revq.ensure((size_t)r->revised_cap + 16));
-            d_revq = h->d_revq.as<uint8_t>();
-            if (b->qual) {
-                CU(h, h->d_qual_in.ensure((size_t)o.n_bases + 16));
-                CU(h, cudaMemcpyAsync(h->d_qual_in.p, b->qual, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
-                d_qual_in = h->d_qual_in.as<uint8_t>();
-            }
+            CU(h, S.d_revq.ensure((size_t)r->revised_cap + 16));
+            d_revq = S.d_revq.as<uint8_t>();
         }
     } else {
         d_rev = r->revised; d_outoff = r->out_off;
-        d_revq = r->revised_qual; d_qual_in = b->qual;
+        d_revq = r->revised_qual;
     }
     {
         StageTimer tm(h, ST_DECODE);
@@ -732,32 +779,48 @@ int revise_impl(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io) 
             }
         }
         const int n = launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
-                                    h->d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
-                                    h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, h->d_flag.as<int>(),
+                                    S.d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
+                                    h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, S.d_flag.as<int>(),
                                     h->stream, wq[0], wq[1], d_qual_in, d_revq);
         if (n < 0) return fail(h, NRV_E_INVALID, "decode: qualities requested without per-window scores");
         h->launches += n;
     }
     CU(h, cudaGetLastError());
     if (!host_io) {
-        CU(h, cudaMemcpyAsync(r->status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(r->status, S.d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToDevice, h->stream));
         return NRV_OK;
     }
-    // ---- D2H ---------------------------------------------------------------------------------------
-    CU(h, h->h_flag.ensure(16));
-    CU(h, cudaMemcpyAsync(r->out_off, d_outoff, (size_t)(o.n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(r->status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(h->h_flag.p, h->d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    // labels / probabilities (diagnostics) live in arenas the next batch overwrites: copied out in stream order, now
     if (r->y1) CU(h, cudaMemcpyAsync(r->y1, labels[0], (size_t)o.n_win, cudaMemcpyDeviceToHost, h->stream));
     if (r->y2) CU(h, cudaMemcpyAsync(r->y2, labels[1], (size_t)o.n_win, cudaMemcpyDeviceToHost, h->stream));
     if (r->p1) CU(h, cudaMemcpyAsync(r->p1, probs[0], (size_t)o.n_win * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
     if (r->p2) CU(h, cudaMemcpyAsync(r->p2, probs[1], (size_t)o.n_win * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    if (*h->h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
-    const int64_t total = r->out_off[o.n_reads];
-    CU(h, cudaMemcpyAsync(r->revised, d_rev, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
-    if (want_q) CU(h, cudaMemcpyAsync(r->revised_qual, d_revq, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventRecord(S.ev_compute, h->stream));
+    S.ticket = h->next_ticket++;
+    S.res = *r;
+    S.n_reads = o.n_reads;
+    S.want_q = want_q;
+    return NRV_OK;
+}
+
+// D2H of a host-I/O batch on the copy stream (under the kernels of the batch enqueued after it); blocks until the results are
+// in the caller's buffers.
+int finish_batch(nrv_handle* h, nrv_handle::IoSlot& S) {
+    const nrv_result& r = S.res;
+    const int64_t R = S.n_reads;
+    S.ticket = 0;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, S.h_flag.ensure(16));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, S.ev_compute, 0));
+    CU(h, cudaMemcpyAsync(r.out_off, S.d_outoff.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaMemcpyAsync(r.status, S.d_status.p, (size_t)R * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaMemcpyAsync(S.h_flag.p, S.d_flag.p, 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaStreamSynchronize(h->copy_stream));
+    if (*S.h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
+    const int64_t total = r.out_off[R];
+    CU(h, cudaMemcpyAsync(r.revised, S.d_revised.p, (size_t)total, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (S.want_q) CU(h, cudaMemcpyAsync(r.revised_qual, S.d_revq.p, (size_t)total, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaStreamSynchronize(h->copy_stream));
     return NRV_OK;
 }
 
@@ -789,6 +852,11 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < NRV_SLOTS && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&h->slot[k].ev_h2d, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slot[k].ev_compute, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_a1_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_l0_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_hg_done, cudaEventDisableTiming);
@@ -823,16 +891,25 @@ void nrv_destroy(nrv_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (void* p : h->weight_allocs) cudaFree(p);
-    Arena* arenas[] = {&h->d_signal, &h->d_starts, &h->d_bases, &h->d_evm, &h->d_evs, &h->d_lastdur, &h->d_off, &h->d_shift,
-                       &h->d_scale, &h->d_status, &h->d_base_read, &h->d_win_base, &h->d_x, &h->d_sigfeat[0],
+    Arena* arenas[] = {&h->d_shift, &h->d_scale, &h->d_base_read, &h->d_win_base, &h->d_x, &h->d_sigfeat[0],
                        &h->d_sigfeat[1], &h->d_act[0], &h->d_act[1], &h->d_act[2], &h->d_act[3], &h->d_probs[0],
-                       &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_revised, &h->d_outoff, &h->d_wq[0], &h->d_wq[1], &h->d_qual_in, &h->d_revq,
-                       &h->d_flag, &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
+                       &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_wq[0], &h->d_wq[1],
+                       &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
                        &h->d_sfl[1], &h->d_a1[0], &h->d_a1[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_a4[0],
                        &h->d_a4[1], &h->d_zin};
     for (Arena* a : arenas) a->release();
-    h->h_off.release(); h->h_flag.release();
+    for (nrv_handle::IoSlot& S : h->slot) {
+        Arena* io[] = {&S.d_signal, &S.d_starts, &S.d_bases, &S.d_evm, &S.d_evs, &S.d_lastdur, &S.d_off, &S.d_qual_in,
+                       &S.d_status, &S.d_revised, &S.d_outoff, &S.d_revq, &S.d_flag};
+        for (Arena* a : io) a->release();
+        S.h_off.release(); S.h_flag.release();
+        if (S.ev_h2d) cudaEventDestroy(S.ev_h2d);
+        if (S.ev_compute) cudaEventDestroy(S.ev_compute);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (h->ev_a1_free) cudaEventDestroy(h->ev_a1_free);
     if (h->ev_l0_done) cudaEventDestroy(h->ev_l0_done);
@@ -877,11 +954,13 @@ int nrv_segment(nrv_handle* h, const nrv_batch* b, double* shift, double* scale,
     int rc = check_batch(h, b);
     if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
+    rc = begin_batch(h, true);
+    if (rc) return rc;
     Offsets o;
-    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o);
+    rc = stage_offsets(h, b->n_reads, b->sig_off, b->base_off, &o, h->stream);
     if (rc) return rc;
     DevBatch d;
-    rc = upload_batch(h, b, o, &d);
+    rc = upload_batch(h, b, o, &d, h->stream);
     if (rc) return rc;
     if (seg_mean) CU(h, h->d_segmean.ensure((size_t)o.n_bases * 8 + 16));
     if (seg_std) CU(h, h->d_segstd.ensure((size_t)o.n_bases * 8 + 16));
@@ -897,7 +976,7 @@ int nrv_segment(nrv_handle* h, const nrv_batch* b, double* shift, double* scale,
     }
     if (shift) CU(h, cudaMemcpyAsync(shift, h->d_shift.p, (size_t)o.n_reads * 8, cudaMemcpyDeviceToHost, h->stream));
     if (scale) CU(h, cudaMemcpyAsync(scale, h->d_scale.p, (size_t)o.n_reads * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (status) CU(h, cudaMemcpyAsync(status, h->d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(status, h->io().d_status.p, (size_t)o.n_reads * 4, cudaMemcpyDeviceToHost, h->stream));
     if (seg_mean) CU(h, cudaMemcpyAsync(seg_mean, h->d_segmean.p, (size_t)o.n_bases * 8, cudaMemcpyDeviceToHost, h->stream));
     if (seg_std) CU(h, cudaMemcpyAsync(seg_std, h->d_segstd.p, (size_t)o.n_bases * 8, cudaMemcpyDeviceToHost, h->stream));
     if (x) CU(h, cudaMemcpyAsync(x, h->d_x.p, (size_t)o.n_bases * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -912,6 +991,7 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     if (n < 0 || (n > 0 && (!S || !X))) return fail(h, NRV_E_INVALID, "bad arguments");
     if (n == 0) return NRV_OK;
     CU(h, cudaSetDevice(h->device));
+    if (h->in_flight()) return fail(h, NRV_E_INVALID, "call nrv_wait on the batches in flight first");
     const int W = h->window;
     const int64_t nb = n * W;
     if (nb >= (int64_t)INT32_MAX) return fail(h, NRV_E_INVALID, "too many windows in one call");
@@ -952,41 +1032,44 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
     if (h->sticky) return NRV_E_CUDA;
     if (n_reads < 0 || !base_off || !revised || !out_off) return fail(h, NRV_E_INVALID, "bad arguments");
     CU(h, cudaSetDevice(h->device));
+    int rc = begin_batch(h, true);
+    if (rc) return rc;
+    nrv_handle::IoSlot& S = h->io();
     Offsets o;
-    int rc = stage_offsets(h, n_reads, nullptr, base_off, &o);
+    rc = stage_offsets(h, n_reads, nullptr, base_off, &o, h->stream);
     if (rc) return rc;
     if (o.n_bases > 0 && !bases) return fail(h, NRV_E_INVALID, "bases is NULL");
     if (o.n_win > 0 && (!y1 || !y2)) return fail(h, NRV_E_INVALID, "labels are NULL");
     if (revised_cap < o.n_bases) return fail(h, NRV_E_CAPACITY, "revised_cap smaller than the number of bases");
-    CU(h, h->d_bases.ensure((size_t)o.n_bases + 16));
+    CU(h, S.d_bases.ensure((size_t)o.n_bases + 16));
     CU(h, h->d_y[0].ensure((size_t)o.n_win + 16));
     CU(h, h->d_y[1].ensure((size_t)o.n_win + 16));
-    CU(h, h->d_status.ensure((size_t)n_reads * 4 + 16));
+    CU(h, S.d_status.ensure((size_t)n_reads * 4 + 16));
     CU(h, h->d_base_read.ensure((size_t)o.n_bases * 4 + 16));
     const int64_t n_tiles = decode_tile_count(o.n_bases);
     CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
     CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
-    CU(h, h->d_flag.ensure(16));
-    CU(h, h->h_flag.ensure(16));
-    CU(h, h->d_revised.ensure((size_t)revised_cap + 16));
-    CU(h, h->d_outoff.ensure((size_t)(n_reads + 1) * 8));
-    CU(h, cudaMemsetAsync(h->d_flag.p, 0, 4, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_bases.p, bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
+    CU(h, S.d_flag.ensure(16));
+    CU(h, S.h_flag.ensure(16));
+    CU(h, S.d_revised.ensure((size_t)revised_cap + 16));
+    CU(h, S.d_outoff.ensure((size_t)(n_reads + 1) * 8));
+    CU(h, cudaMemsetAsync(S.d_flag.p, 0, 4, h->stream));
+    CU(h, cudaMemcpyAsync(S.d_bases.p, bases, (size_t)o.n_bases, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_y[0].p, y1, (size_t)o.n_win, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_y[1].p, y2, (size_t)o.n_win, cudaMemcpyHostToDevice, h->stream));
-    if (status) CU(h, cudaMemcpyAsync(h->d_status.p, status, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
-    else CU(h, cudaMemsetAsync(h->d_status.p, 0, (size_t)n_reads * 4 + 16, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(S.d_status.p, status, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
+    else CU(h, cudaMemsetAsync(S.d_status.p, 0, (size_t)n_reads * 4 + 16, h->stream));
     h->launches += launch_base_read_map(o.d_base_off, n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
-    h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), h->d_bases.as<uint8_t>(),
-                                 h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), h->d_status.as<int32_t>(), n_reads,
+    h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), S.d_bases.as<uint8_t>(),
+                                 h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), S.d_status.as<int32_t>(), n_reads,
                                  o.n_bases, h->window, h->d_counts.as<int32_t>(), h->d_tiles.as<int64_t>(),
-                                 h->d_revised.as<uint8_t>(), revised_cap, h->d_outoff.as<int64_t>(), h->d_flag.as<int>(),
+                                 S.d_revised.as<uint8_t>(), revised_cap, S.d_outoff.as<int64_t>(), S.d_flag.as<int>(),
                                  h->stream);
-    CU(h, cudaMemcpyAsync(out_off, h->d_outoff.p, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(h->h_flag.p, h->d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(out_off, S.d_outoff.p, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(S.h_flag.p, S.d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (*h->h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
-    CU(h, cudaMemcpyAsync(revised, h->d_revised.p, (size_t)out_off[n_reads], cudaMemcpyDeviceToHost, h->stream));
+    if (*S.h_flag.as<int>()) return fail(h, NRV_E_CAPACITY, "revised_cap too small for the revised sequences");
+    CU(h, cudaMemcpyAsync(revised, S.d_revised.p, (size_t)out_off[n_reads], cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaGetLastError());
     return NRV_OK;
@@ -1023,7 +1106,28 @@ int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const
     return rc;
 }
 
-int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return revise_impl(h, b, r, true); }
-int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return revise_impl(h, b, r, false); }
+int nrv_submit_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, int64_t* ticket) {
+    if (!h || !ticket) return NRV_E_INVALID;
+    *ticket = 0;
+    const int rc = enqueue_batch(h, b, r, true);
+    if (rc == NRV_OK) *ticket = h->io().ticket;
+    return rc;
+}
+
+int nrv_wait_batch(nrv_handle* h, int64_t ticket) {
+    if (!h) return NRV_E_INVALID;
+    if (h->sticky) return NRV_E_CUDA;
+    for (nrv_handle::IoSlot& S : h->slot)
+        if (ticket != 0 && S.ticket == ticket) return finish_batch(h, S);
+    return fail(h, NRV_E_INVALID, "unknown ticket (already waited for?)");
+}
+
+int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r) {
+    int64_t t = 0;
+    const int rc = nrv_submit_batch(h, b, r, &t);
+    return rc != NRV_OK ? rc : nrv_wait_batch(h, t);
+}
+
+int nrv_revise_batch_device(nrv_handle* h, const nrv_batch* b, nrv_result* r) { return enqueue_batch(h, b, r, false); }
 
 }  // extern "C"

@@ -546,7 +546,7 @@ int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
     GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2};
     // CTA-pair kernel (B resident, 8 epilogue warps) unless NRV_GEMM=single: proj2 36.7 -> 30.8 ms, proj3 21.3 -> 17.9 ms per step
-    static const bool use_pair = !(getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "single"));
+    const bool use_pair = !(getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "single"));
     if (mode == 1 && use_pair && N % 256 == 0 && n_per_dir % 256 == 0 && M % G_TM == 0 && K <= 256) {
         CUtensorMap ta_hi, ta_lo;
         if (!make_tmap_f16_k64(&ta_hi, a_hi, M, K, G_TM) || !make_tmap_f16_k64(&ta_lo, a_lo, M, K, G_TM)) return -2;

@@ -57,7 +57,8 @@ class _Result(C.Structure):
 
 EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_launch_count",
            "nrv_stage_count", "nrv_stage_name", "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
-           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_debug_gemm",
+           "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_submit_batch",
+           "nrv_wait_batch", "nrv_debug_gemm",
            "nrv_ingest_fast5", "nrv_ingest_view", "nrv_ingest_free")
 
 _lib = None
@@ -108,6 +109,10 @@ def load_library(path: Optional[str] = None):
     lib.nrv_revise_batch.restype = C.c_int
     lib.nrv_revise_batch_device.argtypes = [vp, C.POINTER(_Batch), C.POINTER(_Result)]
     lib.nrv_revise_batch_device.restype = C.c_int
+    lib.nrv_submit_batch.argtypes = [vp, C.POINTER(_Batch), C.POINTER(_Result), C.POINTER(C.c_int64)]
+    lib.nrv_submit_batch.restype = C.c_int
+    lib.nrv_wait_batch.argtypes = [vp, C.c_int64]
+    lib.nrv_wait_batch.restype = C.c_int
     lib.nrv_debug_gemm.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.nrv_debug_gemm.restype = C.c_int
     lib.nrv_ingest_fast5.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
@@ -260,6 +265,28 @@ def pack_batch(reads: Sequence) -> Batch:
     if R and all(getattr(r, "qual", None) is not None for r in reads):
         qual = np.concatenate([np.asarray(r.qual, dtype=np.uint8) for r in reads])
     return Batch(signal, sig_off, starts, base_off, bases, evm, evs, last, qual)
+
+
+def split_batch(b: Batch, idx: Sequence[int]) -> Batch:
+    """Sub-batch with the given reads (in the given order)."""
+    idx = list(idx)
+    R = len(idx)
+    sig_off = np.zeros(R + 1, dtype=np.int64)
+    base_off = np.zeros(R + 1, dtype=np.int64)
+    sig, st, ba, em, es = [], [], [], [], []
+    for k, i in enumerate(idx):
+        s0, s1 = int(b.sig_off[i]), int(b.sig_off[i + 1])
+        b0, b1 = int(b.base_off[i]), int(b.base_off[i + 1])
+        sig_off[k + 1] = sig_off[k] + (s1 - s0)
+        base_off[k + 1] = base_off[k] + (b1 - b0)
+        sig.append(b.signal[s0:s1]); st.append(b.starts[b0:b1]); ba.append(b.bases[b0:b1])
+        em.append(b.ev_mean[b0:b1]); es.append(b.ev_std[b0:b1])
+    cat = lambda parts, dt: (np.concatenate(parts).astype(dt, copy=False) if parts else np.zeros(0, dt))
+    qual = None
+    if getattr(b, "qual", None) is not None:
+        qual = cat([b.qual[int(b.base_off[i]):int(b.base_off[i + 1])] for i in idx], np.uint8)
+    return Batch(cat(sig, np.int16), sig_off, cat(st, np.int32), base_off, cat(ba, np.uint8), cat(em, np.float32),
+                 cat(es, np.float32), np.asarray(b.last_dur)[idx].astype(np.int32), qual)
 
 
 @dataclass
@@ -433,7 +460,15 @@ class Reviser:
     # -- the whole path -----------------------------------------------------------------------
     def revise_batch(self, b: Batch, want_labels: bool = False, want_probs: bool = False,
                      out: Optional[ReviseResult] = None, want_qual: bool = False) -> ReviseResult:
-        keep: list = []
+        """nrv_revise_batch: submit + wait."""
+        return self.wait(self.submit(b, want_labels, want_probs, out, want_qual))
+
+    def submit(self, b: Batch, want_labels: bool = False, want_probs: bool = False,
+               out: Optional[ReviseResult] = None, want_qual: bool = False):
+        """nrv_submit_batch: enqueue one host batch (H2D on the copy stream, kernels on the main stream) and return a pending
+        object for :meth:`wait`.  Up to two batches may be in flight: submit batch i+1, then wait for batch i -- the copies of
+        one run under the kernels of the other.  The arrays of ``b`` must stay alive (and unmodified) until ``wait``."""
+        keep: list = [b]
         cb = self._cbatch(b, keep)
         R, N = b.n_reads, b.n_bases
         nw = b.n_windows(self.window)
@@ -451,7 +486,14 @@ class Reviser:
         cr.out_off = _ptr(out.out_off); cr.status = _ptr(out.status)
         cr.y1 = _ptr(out.y1); cr.y2 = _ptr(out.y2); cr.p1 = _ptr(out.p1); cr.p2 = _ptr(out.p2)
         cr.revised_qual = _ptr(out.revised_qual)
-        self._check(self._lib.nrv_revise_batch(self._h, C.byref(cb), C.byref(cr)), "nrv_revise_batch")
+        ticket = C.c_int64(0)
+        self._check(self._lib.nrv_submit_batch(self._h, C.byref(cb), C.byref(cr), C.byref(ticket)), "nrv_submit_batch")
+        return (int(ticket.value), out, keep)
+
+    def wait(self, pending) -> ReviseResult:
+        """nrv_wait_batch: block until the batch's results are in its ReviseResult (D2H on the copy stream)."""
+        ticket, out, _keep = pending
+        self._check(self._lib.nrv_wait_batch(self._h, ticket), "nrv_wait_batch")
         return out
 
     def revise_batch_device(self, n_reads: int, sig_off: np.ndarray, base_off: np.ndarray, dptr: dict, dres: dict,

@@ -79,23 +79,4 @@ def make_batch(lengths: Sequence[int], seed: int = 0, first_id: int = 0) -> Batc
                  last_dur=np.array([p[5] for p in parts], dtype=np.int32))
 
 
-def split_batch(b: Batch, idx: Sequence[int]) -> Batch:
-    """Sub-batch with the given reads (in the given order)."""
-    idx = list(idx)
-    R = len(idx)
-    sig_off = np.zeros(R + 1, dtype=np.int64)
-    base_off = np.zeros(R + 1, dtype=np.int64)
-    sig, st, ba, em, es = [], [], [], [], []
-    for k, i in enumerate(idx):
-        s0, s1 = int(b.sig_off[i]), int(b.sig_off[i + 1])
-        b0, b1 = int(b.base_off[i]), int(b.base_off[i + 1])
-        sig_off[k + 1] = sig_off[k] + (s1 - s0)
-        base_off[k + 1] = base_off[k] + (b1 - b0)
-        sig.append(b.signal[s0:s1]); st.append(b.starts[b0:b1]); ba.append(b.bases[b0:b1])
-        em.append(b.ev_mean[b0:b1]); es.append(b.ev_std[b0:b1])
-    cat = lambda parts, dt: (np.concatenate(parts).astype(dt, copy=False) if parts else np.zeros(0, dt))
-    qual = None
-    if getattr(b, "qual", None) is not None:
-        qual = cat([b.qual[int(b.base_off[i]):int(b.base_off[i + 1])] for i in idx], np.uint8)
-    return Batch(cat(sig, np.int16), sig_off, cat(st, np.int32), base_off, cat(ba, np.uint8), cat(em, np.float32),
-                 cat(es, np.float32), np.asarray(b.last_dur)[idx].astype(np.int32), qual)
+from .engine import split_batch  # noqa: E402,F401  (moved to engine.py; kept importable from here for the tests)

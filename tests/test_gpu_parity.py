@@ -479,3 +479,70 @@ def test_cfg5_long_reads_human(reviser_by_species):
         assert shift[0] == sh and scale[0] == np.median(np.abs(f - sh))
     alone = rv.revise_batch(synth.split_batch(b, [0]))
     assert alone.sequence(0) == out.sequence(0)
+
+
+# --------------------------------------------------------------------------------------------------
+# round 2: two batches in flight (nrv_submit_batch / nrv_wait_batch) and the non-default kernel paths
+# --------------------------------------------------------------------------------------------------
+def test_two_batches_in_flight_give_the_same_bytes(reviser_by_species, reads):
+    """submit(A), submit(B), wait(A), wait(B): copies of one batch run under the kernels of the other; every byte equals the
+    synchronous call; a third outstanding ticket is refused; sync entry points refuse to run under batches in flight."""
+    from nanoreviser_b200 import engine
+    rv = reviser_by_species("ecoli")
+    A = engine.pack_batch(reads[:2])
+    B = engine.pack_batch(reads[2:])
+    ra = rv.revise_batch(A, want_labels=True, want_qual=True)
+    rb = rv.revise_batch(B, want_labels=True)
+    for rounds in range(3):
+        pa = rv.submit(A, want_labels=True, want_qual=True)
+        pb = rv.submit(B, want_labels=True)
+        with pytest.raises(engine.NrvError):
+            rv.submit(A)
+        with pytest.raises(engine.NrvError):
+            rv.segment(A)
+        oa = rv.wait(pa)
+        ob = rv.wait(pb)
+        assert oa.sequences() == ra.sequences() and ob.sequences() == rb.sequences()
+        assert np.array_equal(oa.y1, ra.y1) and np.array_equal(ob.y2, rb.y2)
+        assert [oa.quality(i) for i in range(2)] == [ra.quality(i) for i in range(2)]
+        assert np.array_equal(oa.status, ra.status) and np.array_equal(ob.out_off, rb.out_off)
+    with pytest.raises(engine.NrvError):
+        rv.wait(pa)                                      # a ticket can be waited for once
+    # waiting in the other order is legal too
+    pa = rv.submit(A); pb = rv.submit(B)
+    assert rv.wait(pb).sequences() == rb.sequences() and rv.wait(pa).sequences() == ra.sequences()
+    shift, *_ = rv.segment(A)                            # idle again
+    assert len(shift) == 2
+
+
+@pytest.mark.parametrize("env", [
+    {"NRV_PATH": "simt"},                                 # fp32 SIMT everywhere (lstm_layer_kernel, heads_kernel)
+    {"NRV_TRNN1": "split"},                               # total_rnn1 = pair GEMM + lstm_rec_tc128_pair_kernel
+    {"NRV_TRNN1": "split", "NRV_REC128": "single"},       # ... + lstm_rec_tc128_kernel
+    {"NRV_TRNN2": "split"},                               # total_rnn2 = pair GEMM + lstm_rec_tc64_kernel
+    {"NRV_TRNN1": "split", "NRV_TRNN2": "split", "NRV_GEMM": "single"},   # gemm_f16x3_kernel<256> projections
+    {"NRV_OVERLAP": "0"},                                 # everything on one stream
+], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_non_default_kernel_paths_match_goldens(weights_by_species, reads, golden_dir, monkeypatch, env):
+    """Every kernel variant that an environment switch can select is held to the same bar as the default path on the
+    unitest set (ecoli): max |dP| <= 1e-3 against the fp64 oracle goldens, labels >= 99.99 %, identical sequences.
+    The fp32 SIMT path doubles as an on-GPU cross-check of the tensor-core kernels by independent code."""
+    from nanoreviser_b200 import api, engine
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m1, m2 = weights_by_species("ecoli")
+    gold = np.load(os.path.join(golden_dir, "forward_ecoli.npz"))
+    sel = [0, 4] if env.get("NRV_PATH") == "simt" else [0, 1, 2, 3, 4]
+    with engine.Reviser(m1, m2) as rv:
+        out = api.revise_reads([reads[i] for i in sel], reviser=rv, want_labels=True, want_probs=True)
+    w0 = 0
+    n_lab = n_same = 0
+    for k, i in enumerate(sel):
+        M = reads[i].n_bases - m1.window
+        assert np.abs(out.p1[w0:w0 + M] - gold["r%d_P1_f64" % i]).max() <= P_TOL
+        assert np.abs(out.p2[w0:w0 + M] - gold["r%d_P2_f64" % i]).max() <= P_TOL
+        n_same += int((out.y1[w0:w0 + M] == gold["r%d_y1_f64" % i]).sum() + (out.y2[w0:w0 + M] == gold["r%d_y2_f64" % i]).sum())
+        n_lab += 2 * M
+        assert out.sequence(k) == gold["r%d_revised" % i].tobytes().decode()
+        w0 += M
+    assert n_same / n_lab >= 0.9999
