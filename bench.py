@@ -1,12 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- revised bases/s of the revision-inference hot path on N B200s (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads-per-step R]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg5]
 
 A *step* is one pass of the whole hot path (K1 segmentation -> K2 CNN -> K3 Bi-LSTM x2 models + heads
--> K4 decode) over one ragged slab of synthetic reads of BASELINE.json's configs[1] shape ("ecoli
-model, synthetic 100k reads x 10 kb (4 kHz signal), 1xB200"): R reads x 10,000 bases per step, i.e.
-the steady state of the 100k-read job (a full 1e9-base pass would not fit the bench budget).
+-> K4 decode) over one JOB of synthetic reads that is sharded over the N ranks by the host work queue
+INSIDE the timed region: ``workqueue.lpt_partition`` (length-balanced shards from the list of read lengths,
+identical on every rank, no communication) -> ``workqueue.make_batches`` (ragged batches under a base budget)
+-> one library call per batch.  A job holds N x 1.28 M bases, i.e. per-GPU work is fixed ("weak").
+
+  N = 1 (default config cfg2): BASELINE.json configs[1], "ecoli model, synthetic 100k reads x 10 kb (4 kHz
+          signal), 1xB200": 128 reads x 10,000 bases per step -- the steady state of the 100k-read job.
+  N > 1 (default config cfg3): configs[2], "human model, synthetic 1M reads N50 20 kb, read-sharded over
+          2/4/8 B200": lengths ~ LogNormal(9.0935, 0.9) clipped to [500, 300000], ~96 reads per GPU and step.
+  --config cfg5: configs[4], ragged 100-300 kb reads, human model (4 x 1.28 M bases per GPU and step so that
+          LPT has enough reads to balance).
 
   value : whole-job revised bases/s, inputs already resident in HBM (nrv_revise_batch_device),
           timed with CUDA events on the library's stream, max over ranks.
@@ -110,11 +118,52 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_bases_per_sec(n_reads: int, read_len: int, faithful: bool, seed: int = 99):
+BUDGET = 1_280_000          # bases per GPU and step (= 128 cfg2 reads)
+JOBS = 2                    # distinct jobs, alternated, so that no step finds its inputs in L2
+
+
+def job_config(cfg: str, world: int, reads_per_step: int):
+    """-> (species default, bases per rank and step, batch base budget)"""
+    if cfg == "cfg2":
+        return "ecoli", reads_per_step * READ_LEN, reads_per_step * READ_LEN
+    if cfg == "cfg3":
+        return "human", BUDGET, int(BUDGET * 1.25)
+    if cfg == "cfg5":
+        return "human", 4 * BUDGET, int(BUDGET * 1.25)
+    raise ValueError(cfg)
+
+
+def job_lengths(cfg: str, world: int, per_rank_bases: int, job: int):
+    """Read lengths of job `job` (a pure function of (cfg, world, job): every rank derives the same list) and the global
+    read id of its first read."""
+    from nanoreviser_b200 import synth
+    first = 1_000_000 * job
+    if cfg == "cfg2":
+        n = world * per_rank_bases // READ_LEN
+        return np.full(n, READ_LEN, dtype=np.int64), first
+    target = world * per_rank_bases
+    est = {"cfg3": 13_300, "cfg5": 200_000}[cfg]
+    L = synth.read_lengths(cfg, int(target / est * 1.3) + 64, first_id=first)
+    n = int(np.searchsorted(np.cumsum(L), target)) + 1
+    return L[:n].copy(), first
+
+
+def plan_step(lengths, rank: int, world: int, batch_budget: int):
+    """The host work queue of one step: length-balanced shard of this rank, cut into ragged batches (ranges of the shard's
+    reads, which are kept in ascending read order so that a batch is a contiguous slice of the shard's CSR arrays)."""
+    from nanoreviser_b200 import workqueue
+    parts = workqueue.lpt_partition(lengths, world)
+    mine = parts[rank]
+    pos = {r: k for k, r in enumerate(mine)}
+    batches = [(pos[b[0]], pos[b[-1]] + 1) for b in workqueue.make_batches(mine, lengths, batch_budget)]
+    return parts, mine, batches
+
+
+def cpu_oracle_bases_per_sec(n_reads: int, read_len: int, faithful: bool, seed: int = 99, species: str = "ecoli"):
     """Time the CPU oracle on a bounded sample of the same workload.  Returns (bases/s, seconds, bases)."""
     from nanoreviser_b200 import synth, weights
     from oracle import nanorev_oracle as orc
-    m1, m2 = weights.load_species("ecoli", os.path.join(ROOT, "model"))
+    m1, m2 = weights.load_species(species, os.path.join(ROOT, "model"))
     b = synth.make_batch([read_len] * n_reads, seed=seed)
     t0 = time.perf_counter()
     total = 0
@@ -143,25 +192,41 @@ def cpu_oracle_bases_per_sec(n_reads: int, read_len: int, faithful: bool, seed: 
     return total / dt, dt, total
 
 
+def workload_config(cfg: str, species: str, world: int, per_rank: int, batch_budget: int, reads_per_job: int, n_win_rank: int):
+    what = {"cfg2": "cfg2: %s model, synthetic 10 kb reads (4 kHz signal)" % species,
+            "cfg3": "cfg3: %s model, synthetic reads N50 20 kb (LogNormal(9.0935, 0.9) clipped to [500, 300000]), read-sharded "
+                    "over the ranks" % species,
+            "cfg5": "cfg5: %s model, long-read stress, ragged 100-300 kb reads, read-sharded over the ranks" % species}[cfg]
+    return {"workload": "%s; one job of %d reads (%d bases per GPU) per step, sharded by the host work queue "
+                        "(lpt_partition -> make_batches, inside the timed region)" % (what, reads_per_job, per_rank),
+            "reads_per_step": int(reads_per_job), "bases_per_step": int(world * per_rank), "bases_per_gpu_per_step": int(per_rank),
+            "batch_base_budget": int(batch_budget),
+            "l2": "two alternating jobs; per-step activations (%.1f GB per GPU) exceed the 126 MB L2" % (n_win_rank * 11 * 544 * 4 / 1e9)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    cfg = args.config or ("cfg2" if world == 1 else "cfg3")
+    species_d, per_rank, batch_budget = job_config(cfg, world, args.reads_per_step)
+    species = args.species or species_d
+    L, _ = job_lengths(cfg, world, per_rank, 0)
     n = max(1, args.ref_reads)
     vals = []
     for _ in range(max(1, args.warmup > 0)):
-        cpu_oracle_bases_per_sec(1, 1000, True)
-    t_all = time.perf_counter()
+        cpu_oracle_bases_per_sec(1, 1000, True, species=species)
     for _ in range(args.steps):
-        v, dt, nb = cpu_oracle_bases_per_sec(n, args.ref_read_len, True)
+        v, dt, nb = cpu_oracle_bases_per_sec(n, args.ref_read_len, True, species=species)
         vals.append((v, dt, nb))
     v = sum(x[2] for x in vals) / sum(x[1] for x in vals)
-    sample = "%d synthetic cfg2-shape read(s) x %d bases per step, %d steps" % (n, args.ref_read_len, args.steps)
+    sample = "%d synthetic read(s) x %d bases of the step's job per step, %d steps" % (n, args.ref_read_len, args.steps)
+    n_win_rank = max(per_rank - 11 * (len(L) // world), 0)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: ecoli model, synthetic 10 kb reads (4 kHz signal); bounded CPU sample of the slab",
-                       "reads_per_step": n, "bases_per_step": n * args.ref_read_len},
+            "config": workload_config(cfg, species, world, per_rank, batch_budget, len(L), n_win_rank),
+            "sample_bases_per_step": n * args.ref_read_len,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "oracle port of the reference algorithm (numpy fp32 + OpenBLAS, per-read python "
                                      "segmentation, per-window CNN recompute); Keras 2.2.4/TF 1.12 not installable"},
@@ -176,10 +241,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=128)
-    ap.add_argument("--species", default="ecoli")
+    ap.add_argument("--config", default=None, choices=["cfg2", "cfg3", "cfg5"],
+                    help="default: cfg2 on one GPU, cfg3 (read-sharded) on several")
+    ap.add_argument("--reads-per-step", type=int, default=128, help="cfg2: reads per GPU and step")
+    ap.add_argument("--species", default=None)
     ap.add_argument("--ref-reads", type=int, default=1)
-    ap.add_argument("--ref-read-len", type=int, default=4000)
+    ap.add_argument("--ref-read-len", type=int, default=READ_LEN)
     ap.add_argument("--cpu-sample-bases", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,7 +262,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from nanoreviser_b200 import engine, synth, weights
+    from nanoreviser_b200 import engine, synth, weights, workqueue
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -204,32 +271,51 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks, peak_src = load_peaks()
 
-    m1, m2 = weights.load_species(args.species, os.path.join(ROOT, "model"))
+    cfg = args.config or ("cfg2" if world == 1 else "cfg3")
+    species_d, per_rank, batch_budget = job_config(cfg, world, args.reads_per_step)
+    species = args.species or species_d
+    m1, m2 = weights.load_species(species, os.path.join(ROOT, "model"))
     rv = engine.Reviser(m1, m2, device=local_rank)
     W = rv.window
-    R = args.reads_per_step
-    # two distinct slabs per rank, alternated, so that no step re-reads the previous step's inputs from L2
-    slabs = [synth.make_batch([READ_LEN] * R, seed=1000 + 17 * rank + s) for s in range(2)]
-    n_bases = slabs[0].n_bases
-    n_win = slabs[0].n_windows(W)
-    cap = 2 * n_bases + R + 16
+    dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(rv.stream, device=local_rank)
 
-    # ---- device-resident copies (torch only as the allocator / stream plumbing) ---------------------
-    dev = torch.device("cuda", local_rank)
-    dslabs = []
-    for b in slabs:
-        t = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in ("signal", "starts", "bases", "ev_mean", "ev_std", "last_dur")}
-        dslabs.append(t)
+    # ---- the jobs: lengths are the job description (known to every rank); each rank generates only its shard's reads -------
+    jobs = []
+    for j in range(JOBS):
+        L, first = job_lengths(cfg, world, per_rank, j)
+        parts, mine, batches = plan_step(L, rank, world, batch_budget)          # also recomputed inside the timed region
+        shard = synth.make_batch([int(L[i]) for i in mine], seed=1000 + j, ids=[first + i for i in mine])
+        pin = engine.Batch(**{k: torch.from_numpy(np.ascontiguousarray(getattr(shard, k))).pin_memory().numpy() for k in
+                              ("signal", "sig_off", "starts", "base_off", "bases", "ev_mean", "ev_std", "last_dur")})
+        dten = {k: torch.from_numpy(getattr(shard, k)).to(dev) for k in ("signal", "starts", "bases", "ev_mean", "ev_std", "last_dur")}
+        jobs.append({"L": L, "mine": mine, "shard": pin, "dev": dten, "imbalance": workqueue.imbalance(L, parts),
+                     "n_batches": len(batches)})
+    max_reads = max(j["shard"].n_reads for j in jobs)
+    max_bases = max(j["shard"].n_bases for j in jobs)
+    cap = 2 * max_bases + max_reads + 16
     d_rev = torch.empty(cap, dtype=torch.uint8, device=dev)
-    d_off = torch.empty(R + 1, dtype=torch.int64, device=dev)
-    d_status = torch.empty(R, dtype=torch.int32, device=dev)
-    dres = {"revised": d_rev.data_ptr(), "out_off": d_off.data_ptr(), "status": d_status.data_ptr()}
+    d_off = torch.empty(max_reads + 1, dtype=torch.int64, device=dev)
+    d_status = torch.empty(max_reads, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
+    esz = {"signal": 2, "starts": 4, "bases": 1, "ev_mean": 4, "ev_std": 4, "last_dur": 4}
 
     def step_device(i):
-        b, t = slabs[i & 1], dslabs[i & 1]
-        rv.revise_batch_device(R, b.sig_off, b.base_off, {k: v.data_ptr() for k, v in t.items()}, dres, cap)
+        """one step, inputs resident in HBM: work queue on the host, one asynchronous library call per batch"""
+        job = jobs[i % JOBS]
+        _, mine, batches = plan_step(job["L"], rank, world, batch_budget)
+        sh, t = job["shard"], job["dev"]
+        nb = 0
+        for r0, r1 in batches:
+            s0, b0 = int(sh.sig_off[r0]), int(sh.base_off[r0])
+            dptr = {"signal": t["signal"].data_ptr() + 2 * s0, "last_dur": t["last_dur"].data_ptr() + 4 * r0}
+            for k in ("starts", "bases", "ev_mean", "ev_std"):
+                dptr[k] = t[k].data_ptr() + esz[k] * b0
+            n = int(sh.base_off[r1]) - b0
+            dres = {"revised": d_rev.data_ptr() + 2 * b0 + r0, "out_off": d_off.data_ptr(), "status": d_status.data_ptr() + 4 * r0}
+            rv.revise_batch_device(r1 - r0, sh.sig_off[r0:r1 + 1] - s0, sh.base_off[r0:r1 + 1] - b0, dptr, dres, 2 * n + (r1 - r0) + 16)
+            nb += n
+        return nb
 
     def barrier():
         if world > 1:
@@ -246,11 +332,12 @@ def main():
     rv.set_stage_timing(True)
     launches0 = rv.launch_count
     barrier()
+    my_bases = 0
     with torch.cuda.stream(stream):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(args.steps):
-            step_device(i)
+            my_bases += step_device(i)
         e1.record(stream)
     rv.synchronize()
     barrier()
@@ -259,42 +346,72 @@ def main():
     stage_ms = rv.stage_ms()
     stage_launches = rv.stage_launches()
     rv.set_stage_timing(False)
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * n_bases * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers through nrv_revise_batch (H2D + kernels + D2H inside the timed region) -----
-    pinned = []
-    for b in slabs:
-        pb = engine.Batch(**{k: torch.from_numpy(getattr(b, k)).pin_memory().numpy() for k in
-                             ("signal", "sig_off", "starts", "base_off", "bases", "ev_mean", "ev_std", "last_dur")})
-        pinned.append(pb)
-    out = engine.ReviseResult(torch.empty(cap, dtype=torch.uint8).pin_memory().numpy(),
-                              torch.empty(R + 1, dtype=torch.int64).pin_memory().numpy(),
-                              torch.empty(R, dtype=torch.int32).pin_memory().numpy())
-    for i in range(max(1, min(args.warmup, 2))):
-        rv.revise_batch(pinned[i & 1], out=out)
+    def gather(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    rank_ms = gather(ms)
+    rank_bases = gather(my_bases)
+    ms_max = max(rank_ms)
+    total_bases = sum(rank_bases)
+    value = total_bases / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the public call (submit / wait: two batches in flight; H2D + kernels + D2H inside) -------
+    outs = [engine.ReviseResult(torch.empty(cap, dtype=torch.uint8).pin_memory().numpy(),
+                                torch.empty(max_reads + 1, dtype=torch.int64).pin_memory().numpy(),
+                                torch.empty(max_reads, dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
+
+    def run_host(steps):
+        """-> (bases, h2d bytes, d2h bytes); keeps two batches in flight"""
+        pend = []
+        nb = h2d = d2h = 0
+        k = 0
+        for i in range(steps):
+            job = jobs[i % JOBS]
+            _, mine, batches = plan_step(job["L"], rank, world, batch_budget)
+            for r0, r1 in batches:
+                sub = engine.slice_batch(job["shard"], r0, r1)
+                if len(pend) == 2:
+                    o = rv.wait(pend.pop(0))
+                    d2h += int(o.out_off[o.n_reads_done]) + 8 * (o.n_reads_done + 1) + 4 * o.n_reads_done
+                out = outs[k & 1]; k += 1
+                out.n_reads_done = sub.n_reads
+                pend.append(rv.submit(sub, out=out))
+                nb += sub.n_bases
+                h2d += sub.h2d_bytes()
+        for p in pend:
+            o = rv.wait(p)
+            d2h += int(o.out_off[o.n_reads_done]) + 8 * (o.n_reads_done + 1) + 4 * o.n_reads_done
+        return nb, h2d, d2h
+
+    run_host(max(1, min(args.warmup, 2)))
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
-    for i in range(args.steps):
-        rv.revise_batch(pinned[i & 1], out=out)
-        d2h += int(out.out_off[-1]) + out.out_off.nbytes + out.status.nbytes
+    e2e_bases, h2d, d2h = run_host(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_bases * args.steps / float(t_e.item())
-    # sanity: the device-resident and the host path produce the same bytes
-    chk = rv.revise_batch(pinned[(args.steps - 1) & 1])
+    e2e_value = sum(gather(e2e_bases)) / max(gather(e2e_s))
+    h2d_all, d2h_all = sum(gather(h2d)), sum(gather(d2h))
+    # sanity: the device-resident and the host path produce the same bytes (last batch of the last step)
+    job = jobs[(args.steps - 1) % JOBS]
+    r0, r1 = plan_step(job["L"], rank, world, batch_budget)[2][-1]
+    chk = rv.revise_batch(engine.slice_batch(job["shard"], r0, r1))
     torch.cuda.synchronize()
-    same = bool(np.array_equal(d_off.cpu().numpy(), chk.out_off)) and \
-        bool(np.array_equal(d_rev.cpu().numpy()[:chk.out_off[-1]], chk.revised[:chk.out_off[-1]]))
+    b0 = int(job["shard"].base_off[r0])
+    got_off = d_off.cpu().numpy()[:r1 - r0 + 1]
+    got_rev = d_rev.cpu().numpy()[2 * b0 + r0:2 * b0 + r0 + int(chk.out_off[-1])]
+    same = bool(np.array_equal(got_off, chk.out_off)) and bool(np.array_equal(got_rev, chk.revised[:chk.out_off[-1]]))
 
+    n_bases = int(round(total_bases / world / args.steps))            # per GPU and step
+    n_reads_rank = int(round(sum(j["shard"].n_reads for j in jobs) / JOBS))
+    n_win = max(n_bases - W * n_reads_rank, 0)
+    n_samp = int(round(sum(int(j["shard"].sig_off[-1]) for j in jobs) / JOBS))
     if rank == 0:
         # ---- roofline: per model kernel, algorithmic FLOPs (SURVEY.md section 8(d)) / CUDA-event time ----------
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
@@ -384,11 +501,10 @@ def main():
                              "fp32-equivalent, and is HBM-bound on the fp32 pre-activations (see traffic)"),
                     "all_model_kernels": kernels}
         # K1 (segmentation) and K4 (decode) are the HBM-bound kernels of SURVEY.md section 8(d)
-        n_samp = int(slabs[0].sig_off[-1])
         hbm_kernels = {}
         for k, nbytes in (("read_stats", 2 * n_samp * 2),                       # median pass + MAD pass over int16
                           ("base_features", 2 * n_samp + n_bases * (4 + 1 + 8 + 24)),   # samples, starts, base, ev_mean/std, 6 features
-                          ("decode", n_bases * (2 + 1 + 2) + 8 * R)):
+                          ("decode", n_bases * (2 + 1 + 2) + 8 * n_reads_rank)):
             t_ms = stage_ms.get(k, 0.0)
             if t_ms > 0:
                 gbs = nbytes * args.steps / (t_ms * 1e-3) / 1e9
@@ -400,9 +516,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:        # rank 0 at N = 1 only
             nreads = max(1, args.cpu_sample_bases // READ_LEN)
-            v, dt, nb = cpu_oracle_bases_per_sec(nreads, READ_LEN, False)
+            v, dt, nb = cpu_oracle_bases_per_sec(nreads, READ_LEN, False, species=species)
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": "%d synthetic cfg2 read(s) x %d bases (%.1f s), batched oracle (CNN once per base)" % (nreads, READ_LEN, dt)}
+                   "sample": "%d synthetic read(s) x %d bases, %s weights (%.1f s), batched oracle (CNN once per base)" % (nreads, READ_LEN, species, dt)}
             # the oracle as the checker: the CUDA path must give the same revised bytes on the read the CPU just timed
             sb, want = cpu_oracle_bases_per_sec.last
             got = rv.revise_batch(engine.split_batch(sb, [0])).sequence(0)
@@ -411,14 +527,19 @@ def main():
                 raise SystemExit("bench.py: CUDA result differs from the CPU oracle on the sampled read -- number withheld")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "cfg2: %s model, synthetic 10 kb reads (4 kHz signal), slab of %d reads "
-                                       "(%d bases) per step per GPU" % (args.species, R, n_bases),
-                           "reads_per_step": R, "bases_per_step": n_bases, "windows_per_step": n_win,
-                           "l2": "two alternating slabs; per-step activations (%.1f GB) exceed the 126 MB L2" %
-                                 (n_win * 11 * 544 * 4 / 1e9)},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": slabs[0].h2d_bytes(),
-                        "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16x3/f32acc", "data": "synthetic",
+                "dtype_note": "tensor-core products are three fp16 passes (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo) with fp32 accumulation; "
+                              "segmentation statistics in fp64, indices / decode in integers",
+                "config": workload_config(cfg, species, world, per_rank, batch_budget,
+                                          int(round(sum(len(j["L"]) for j in jobs) / JOBS)), n_win),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all // max(args.steps, 1)),
+                        "d2h_bytes_per_step": int(d2h_all // max(args.steps, 1)),
+                        "api": "Reviser.submit / Reviser.wait (nrv_submit_batch / nrv_wait_batch): pinned host buffers, two batches in flight"},
+                "work_queue": {"partition": "lpt_partition + make_batches inside the timed region, every step",
+                               "imbalance_max_over_mean": max(j["imbalance"] for j in jobs),
+                               "batches_per_rank_per_step": [j["n_batches"] for j in jobs],
+                               "rank_ms": rank_ms, "rank_bases": rank_bases,
+                               "tail_ms": ms_max - min(rank_ms)},
                 "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "whole_path": whole,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_note": ("lstm0 (read_rnn1) and heads (heads tail) are launched on a low-priority side stream: read_rnn1 of the next "

@@ -267,6 +267,14 @@ def pack_batch(reads: Sequence) -> Batch:
     return Batch(signal, sig_off, starts, base_off, bases, evm, evs, last, qual)
 
 
+def slice_batch(b: Batch, r0: int, r1: int) -> Batch:
+    """Reads [r0, r1) of a batch as VIEWS of its arrays (no copy; only the two offset arrays are rebased)."""
+    s0, s1 = int(b.sig_off[r0]), int(b.sig_off[r1])
+    b0, b1 = int(b.base_off[r0]), int(b.base_off[r1])
+    return Batch(b.signal[s0:s1], b.sig_off[r0:r1 + 1] - s0, b.starts[b0:b1], b.base_off[r0:r1 + 1] - b0, b.bases[b0:b1],
+                 b.ev_mean[b0:b1], b.ev_std[b0:b1], b.last_dur[r0:r1], None if b.qual is None else b.qual[b0:b1])
+
+
 def split_batch(b: Batch, idx: Sequence[int]) -> Batch:
     """Sub-batch with the given reads (in the given order)."""
     idx = list(idx)

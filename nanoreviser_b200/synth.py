@@ -65,9 +65,10 @@ def make_read(n_bases: int, seed: int, read_id: int):
     return signal, starts.astype(np.int32), bases, ev_mean, ev_std, last_dur
 
 
-def make_batch(lengths: Sequence[int], seed: int = 0, first_id: int = 0) -> Batch:
+def make_batch(lengths: Sequence[int], seed: int = 0, first_id: int = 0, ids: Sequence[int] = None) -> Batch:
+    """``ids``: explicit read ids (a shard of a larger job); default ``first_id + i``."""
     R = len(lengths)
-    parts = [make_read(int(n), seed, first_id + i) for i, n in enumerate(lengths)]
+    parts = [make_read(int(n), seed, int(ids[i]) if ids is not None else first_id + i) for i, n in enumerate(lengths)]
     sig_off = np.zeros(R + 1, dtype=np.int64)
     base_off = np.zeros(R + 1, dtype=np.int64)
     for i, p in enumerate(parts):
