@@ -57,11 +57,15 @@ def get_args(argv=None):
                          default='./model/human/human_win13_50ep_model2.h5', help='model dirs for model2')
     optParser.add_option("-v", "--virsion", action="store_true", dest="virsion", help="version of NanoReviser")
     optParser.add_option('--devices', action='store', type="string", dest='devices', default='0',
-                         help='comma separated CUDA device ids; reads are sharded over them (no collectives)')
+                         help='CUDA device ids, e.g. 0,1,2 or 0-7; reads are sharded over them (one worker process per GPU, no collectives)')
     optParser.add_option('--batch-bases', action='store', type="int", dest='batch_bases', default=2_000_000,
                          help='ragged batch budget (bases per GPU launch)')
     optParser.add_option('--ingest', action='store', type="string", dest='ingest', default='native',
                          help='fast5 reader: native (C++ threads, default) or python')
+    optParser.add_option('--slab-files', action='store', type="int", dest='slab_files', default=512,
+                         help='fast5 files per ingest slab (the ingest thread works one slab ahead of the GPU)')
+    optParser.add_option('--quiet', action='store_true', dest='quiet', default=False,
+                         help='do not print one line per saved read')
     (tmp_args, _) = optParser.parse_args(argv)
     if tmp_args.virsion:
         print("The virsion of NanoReviser : 1.0 ")
@@ -108,99 +112,148 @@ def _write_read(args, fn_sg, bases, qul=None):
 
 
 def run_worker(args, file_list, device, logger=None):
-    """One GPU: native multi-threaded ingest (C++, include/nrv.h nrv_ingest_fast5) slab by slab -> ragged batches by base
-    budget -> revise -> write.  Files the native reader does not cover or cannot read go through the Python reader, which
-    follows the reference branch by branch and produces its error messages."""
+    """One GPU, one pipeline (the reference fans single reads out to a multiprocessing.Pool, NanoReviser.py:203-223):
+
+        ingest thread   native multi-threaded reader (C++, include/nrv.h nrv_ingest_fast5) slab by slab; files it does not
+                        cover or cannot read go through the Python reader, which follows the reference branch by branch and
+                        produces its error messages                                             -> bounded queue
+        this thread     ragged batches by base budget (workqueue.make_batches), two batches in flight on the GPU
+                        (Reviser.submit / wait: copies of one batch run under the kernels of the other)
+        writer threads  per-read output files (prep_read_fasta / prep_read_fastq), fallback to the un-revised read on a
+                        per-read failure (NanoReviser.py:146-154)."""
+    import queue
+    import threading
     from nanoreviser_b200 import api, engine, fast5, weights, workqueue
     m1 = weights.load_model_weights(args.model1_predict_dir)
     m2 = weights.load_model_weights(args.model2_predict_dir)
     counts = {'ok': 0, 'fallback': 0, 'failed': 0}
     failed = []
+    lock = threading.Lock()
     nthreads = max(1, min(int(args.thread), os.cpu_count() or 4, 32))
     native = getattr(args, 'ingest', 'native') == 'native'
-    slab_files = 512
-
+    slab_files = int(getattr(args, 'slab_files', 512))
     fastq = args.output_format == 'fastq'
 
-    def emit(fn_sg, ok, seq_bytes, orig_bases, qul=None):
+    def emit(fn_sg, ok, seq, orig_bases, qul=None):
         try:
             if ok:
-                seq = seq_bytes.decode() if isinstance(seq_bytes, (bytes, bytearray)) else seq_bytes
                 # D6': qualities of the two-model path come from the softmax outputs (include/nrv.h nrv_result.revised_qual)
-                _write_read(args, fn_sg, list(seq), list(qul) if fastq else None)
-                counts['ok'] += 1
+                _write_read(args, fn_sg, seq, qul if fastq else None)
+                with lock:
+                    counts['ok'] += 1
             else:
                 # fallback to the un-revised read (NanoReviser.py:146-154 / :172-181)
                 if args.output_format == 'fasta':
-                    _write_read(args, fn_sg, [chr(c) for c in orig_bases])
+                    _write_read(args, fn_sg, orig_bases.tobytes().decode('ascii'))
                 else:
                     seq, qul = fast5.extract_fastq(os.path.join(args.fast5_base_dir, fn_sg), None)
-                    _write_read(args, fn_sg, list(seq), list(qul))
-                counts['fallback'] += 1
-                failed.append(fn_sg)
+                    _write_read(args, fn_sg, seq, qul)
+                with lock:
+                    counts['fallback'] += 1
+                    failed.append(fn_sg)
             if logger:
                 logger.info("Congratulations, NanoReviser is installed properly")
-            elif not args.test_mode:
+            elif not args.test_mode and not getattr(args, 'quiet', False):
                 print('[p:::] ' + fn_sg.split('.')[0] + '_out.' + args.output_format + ' was saved......')
         except Exception as e:
             print('[！！！Error] stroring : ' + fn_sg.split('.')[0] + ' ' + str(e))
-            failed.append(fn_sg)
+            with lock:
+                failed.append(fn_sg)
             if logger:
                 logger.error('[!!! Error] Basecalling')
 
-    with engine.Reviser(m1, m2, device=device) as rv:
-        for s0 in range(0, len(file_list), slab_files):
-            slab = file_list[s0:s0 + slab_files]
-            todo_python = list(slab)
-            if native:
-                paths = [os.path.join(args.fast5_base_dir, f) for f in slab]
-                batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
-                todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
-                lengths = np.diff(batch.base_off).tolist()
-                if fastq and batch.n_reads and batch.qual is None:
-                    # the native reader attaches the basecaller's Phred scores when EVERY read of the slab has a Fastq dataset that
-                    # lines up; otherwise they are fetched per file here (bases that pass through unrevised keep them; reads where
-                    # the dataset is missing use Phred 40)
-                    def phred(i):
-                        b0, b1 = int(batch.base_off[i]), int(batch.base_off[i + 1])
-                        q = fast5.basecall_phred(paths[int(read_file[i])], batch.bases[b0:b1], args.basecall_group,
-                                                 args.basecall_subgroup)
-                        return q if q is not None else np.full(b1 - b0, 40, np.uint8)
-                    with ThreadPoolExecutor(max_workers=nthreads) as ex:
-                        batch.qual = np.concatenate(list(ex.map(phred, range(batch.n_reads))))
-                for idx in workqueue.make_batches(range(batch.n_reads), lengths, int(args.batch_bases)):
-                    sub = batch if len(idx) == batch.n_reads else engine.split_batch(batch, idx)
-                    out = rv.revise_batch(sub, want_qual=fastq)
-                    for k, i in enumerate(idx):
-                        ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
-                        emit(slab[int(read_file[i])], ok, out.revised[out.out_off[k]:out.out_off[k + 1]].tobytes(),
-                             batch.bases[batch.base_off[i]:batch.base_off[i + 1]], out.quality(k) if fastq else None)
-            if todo_python:
+    def load_slab(slab):
+        """-> list of (Batch, names): the natively read files of the slab, then the ones the Python reader had to take"""
+        units = []
+        todo_python = list(slab)
+        if native:
+            paths = [os.path.join(args.fast5_base_dir, f) for f in slab]
+            batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
+            todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
+            if fastq and batch.n_reads and batch.qual is None:
+                # the native reader attaches the basecaller's Phred scores when EVERY read of the slab has a Fastq dataset that
+                # lines up; otherwise they are fetched per file here (bases that pass through unrevised keep them; reads where
+                # the dataset is missing use Phred 40)
+                def phred(i):
+                    b0, b1 = int(batch.base_off[i]), int(batch.base_off[i + 1])
+                    q = fast5.basecall_phred(paths[int(read_file[i])], batch.bases[b0:b1], args.basecall_group,
+                                             args.basecall_subgroup)
+                    return q if q is not None else np.full(b1 - b0, 40, np.uint8)
                 with ThreadPoolExecutor(max_workers=nthreads) as ex:
-                    loaded = list(ex.map(lambda f: _ingest(args, f), todo_python))
-                good = []
-                for fn_sg, r, err in loaded:
-                    if r is None:
-                        print('！！！[Error] fast5 file: ' + fn_sg.split('.')[0] + str(err))
+                    batch.qual = np.concatenate(list(ex.map(phred, range(batch.n_reads))))
+            if batch.n_reads:
+                units.append((batch, [slab[int(i)] for i in read_file]))
+        if todo_python:
+            with ThreadPoolExecutor(max_workers=nthreads) as ex:
+                loaded = list(ex.map(lambda f: _ingest(args, f), todo_python))
+            good = []
+            for fn_sg, r, err in loaded:
+                if r is None:
+                    print('！！！[Error] fast5 file: ' + fn_sg.split('.')[0] + str(err))
+                    with lock:
                         failed.append(fn_sg)
                         counts['failed'] += 1
-                        if logger:
-                            logger.error('[!!! Error] Basecalling')
-                    else:
-                        good.append((fn_sg, r))
-                lengths = [r.n_bases for _, r in good]
-                for idx in workqueue.make_batches(range(len(good)), lengths, int(args.batch_bases)):
+                    if logger:
+                        logger.error('[!!! Error] Basecalling')
+                else:
                     if fastq:
-                        for i in idx:
-                            fn_sg, r = good[i]
-                            q = fast5.basecall_phred(os.path.join(args.fast5_base_dir, fn_sg), r.bases, args.basecall_group,
-                                                     args.basecall_subgroup)
-                            r.qual = q if q is not None else np.full(r.n_bases, 40, np.uint8)
-                    out = api.revise_reads([good[i][1] for i in idx], reviser=rv, want_qual=fastq)
-                    for k, i in enumerate(idx):
-                        fn_sg, r = good[i]
-                        ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
-                        emit(fn_sg, ok, out.sequence(k), r.bases, out.quality(k) if fastq else None)
+                        q = fast5.basecall_phred(os.path.join(args.fast5_base_dir, fn_sg), r.bases, args.basecall_group,
+                                                 args.basecall_subgroup)
+                        r.qual = q if q is not None else np.full(r.n_bases, 40, np.uint8)
+                    good.append((fn_sg, r))
+            if good:
+                units.append((engine.pack_batch([r for _, r in good]), [f for f, _ in good]))
+        return units
+
+    q_in = queue.Queue(maxsize=2)
+
+    def ingest_loop():
+        try:
+            for s0 in range(0, len(file_list), slab_files):
+                q_in.put(load_slab(file_list[s0:s0 + slab_files]))
+        except BaseException as e:                     # surfaces in the GPU thread
+            q_in.put(e)
+        q_in.put(None)
+
+    def write_batch(names, sub, out):
+        for k, fn_sg in enumerate(names):
+            ok = out.status[k] in (engine.NRV_READ_OK, engine.NRV_READ_TOO_SHORT)
+            emit(fn_sg, ok, out.sequence(k), sub.bases[sub.base_off[k]:sub.base_off[k + 1]], out.quality(k) if fastq else None)
+
+    t_ingest = threading.Thread(target=ingest_loop, name='nrv-ingest', daemon=True)
+    t_ingest.start()
+    writers = ThreadPoolExecutor(max_workers=max(2, min(8, nthreads)))
+    pending_writes = []
+    with engine.Reviser(m1, m2, device=device) as rv:
+        in_flight = []
+
+        def drain_one():
+            pend, names, sub = in_flight.pop(0)
+            out = rv.wait(pend)
+            pending_writes.append(writers.submit(write_batch, names, sub, out))
+            while len(pending_writes) > 8:             # bound the memory held by finished batches
+                pending_writes.pop(0).result()
+
+        while True:
+            units = q_in.get()
+            if units is None:
+                break
+            if isinstance(units, BaseException):
+                raise units
+            for batch, names in units:
+                lengths = np.diff(batch.base_off).tolist()
+                for idx in workqueue.make_batches(range(batch.n_reads), lengths, int(args.batch_bases)):
+                    # make_batches keeps the order: a batch is a contiguous range of the slab -> views, no copies
+                    sub = batch if len(idx) == batch.n_reads else engine.slice_batch(batch, idx[0], idx[-1] + 1)
+                    if len(in_flight) == 2:
+                        drain_one()
+                    in_flight.append((rv.submit(sub, want_qual=fastq), [names[i] for i in idx], sub))
+        while in_flight:
+            drain_one()
+    for f in pending_writes:
+        f.result()
+    writers.shutdown(wait=True)
+    t_ingest.join()
     return counts['ok'], counts['fallback'], counts['failed'], failed
 
 
@@ -222,7 +275,13 @@ def main(ar_args):
         raise RuntimeError('！！！[Error] model file: Please check the dir of models file!!')
     os.makedirs(ar_args.output_dir, exist_ok=True)
     fast5_fns = [f for f in sorted(os.listdir(ar_args.fast5_base_dir)) if not f.startswith('.')]
-    devices = [int(d) for d in str(ar_args.devices).split(',') if d != '']
+    devices = []
+    for d in str(ar_args.devices).split(','):          # "0,1,2" or "0-7"
+        if '-' in d:
+            a, b = d.split('-')
+            devices += list(range(int(a), int(b) + 1))
+        elif d != '':
+            devices.append(int(d))
     start_time = time.time()
     if len(devices) <= 1:
         res = [run_worker(ar_args, fast5_fns, devices[0] if devices else 0, logger)]
