@@ -1,5 +1,6 @@
 // C-ABI of libnrv.so (include/nrv.h): handle, grow-only device arenas, weight re-packing, and the
 // orchestration of K1..K4 on one CUDA stream.  No allocation on the hot path after warm-up.
+#include <cuda_fp8.h>
 #include <math.h>
 #include <string.h>
 
@@ -96,6 +97,7 @@ struct nrv_handle {
     int num_sms = 148;
     int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
     int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
+    int f8_rnn2 = 1;        // total_rnn2's projection correction passes in e4m3 (kind::f8f6f4); NRV_F8=0 keeps them fp16
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
@@ -282,6 +284,52 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.pb_hi = upload(h, bh, &e); if (e) goto cuda_fail;
             L.pb_lo = upload(h, bl, &e); if (e) goto cuda_fail;
             L.bias_tc = upload(h, bias_tc, &e); if (e) goto cuda_fail;
+            if (l == 3) {
+                // total_rnn2 with e4m3 correction passes (nrv_fused_pair.cu, F8): power-of-two operand scales so that every pass
+                // accumulates 2^S z.  b = floor(log2(448 / max|W|)) puts the largest weight just below the e4m3 maximum:
+                //   W_hi8 = e4m3(W_hi 2^b),  x_lo8 = e4m3(x_lo 2^19)          => S = 19 + b
+                //   W_hi16 = fp16(W 2^(S-12)),  x_hi16 = fp16(x) 2^12          (|W| 2^(S-12) <= 448 * 128 < 65504)
+                //   W_lo8 = e4m3(W_lo 2^(S-8)),  x_hi8 = e4m3(x 2^8)           (|W_lo| <= 2^-11 |W|  =>  <= 448)
+                // The 8-bit copies of one row are interleaved in groups of 4 inputs (LstmLayerDev::f8_wk8) exactly like the 8-bit copies
+                // of the activations, so both correction passes are ONE K-contiguous e4m3 product of twice the length.
+                double wmax = 1e-30;
+                for (float v : bt) wmax = std::max(wmax, (double)fabsf(v));
+                for (int d = 0; d < 2; ++d)
+                    for (size_t i = 0; i < (size_t)u * 4 * u; ++i) wmax = std::max(wmax, (double)fabsf(w->lstm[l][d].recurrent[i]));
+                const int bexp = (int)floor(log2(448.0 / wmax));
+                const int S = 19 + bexp;
+                const double sq = ldexp(1.0, S - 12), s_hi8 = ldexp(1.0, S - 19), s_lo8 = ldexp(1.0, S - 8);
+                auto e4m3 = [](double v) { return (uint8_t)__nv_cvt_float_to_fp8((float)v, __NV_SATFINITE, __NV_E4M3); };
+                // row-major [rows][K] fp32 values (already in the kernel's row order) -> fp16(W sq) and the interleaved 8-bit row
+                auto split8 = [&](const std::vector<float>& src, size_t rows, int K, std::vector<__half>& h16, std::vector<uint8_t>& q8) {
+                    h16.resize(rows * K); q8.resize(rows * 2 * K);
+                    for (size_t r = 0; r < rows; ++r)
+                        for (int k = 0; k < K; ++k) {
+                            const double wv = (double)src[r * K + k];
+                            const __half hs = __float2half_rn((float)(wv * sq));
+                            const double hi = (double)__half2float(hs) / sq;
+                            h16[r * K + k] = hs;
+                            uint8_t* g = &q8[r * 2 * K + (size_t)(k >> 2) * 8 + (k & 3)];
+                            g[0] = e4m3(hi * s_hi8);
+                            g[4] = e4m3((wv - hi) * s_lo8);
+                        }
+                };
+                std::vector<__half> fh, rh;
+                std::vector<uint8_t> f8, r8;
+                split8(bt, (size_t)2 * 4 * u, kin, fh, f8);
+                std::vector<float> rt((size_t)2 * 4 * u * u);
+                for (int d = 0; d < 2; ++d)
+                    for (int g = 0; g < 4; ++g)
+                        for (int j = 0; j < u; ++j)
+                            for (int k = 0; k < u; ++k)
+                                rt[((size_t)d * 4 * u + j * 4 + g) * u + k] = w->lstm[l][d].recurrent[(size_t)k * 4 * u + g * u + j];
+                split8(rt, (size_t)2 * 4 * u, u, rh, r8);
+                L.f8_wk_hi = upload(h, fh, &e); if (e) goto cuda_fail;
+                L.f8_wk8 = upload(h, f8, &e); if (e) goto cuda_fail;
+                L.f8_wr_hi = upload(h, rh, &e); if (e) goto cuda_fail;
+                L.f8_wr8 = upload(h, r8, &e); if (e) goto cuda_fail;
+                L.f8_acc_scale = (float)ldexp(1.0, -S);
+            }
         }
     }
     // ---- heads ----
@@ -442,6 +490,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 __half *a4h = h->d_a4[0].as<__half>(), *a4l = h->d_a4[1].as<__half>();
                 float* zin = h->d_zin.as<float>();
                 int n;
+                const int f8 = h->f8_rnn2 && h->trnn1_fused && h->trnn2_fused;
                 // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand.
                 // The cluster-of-4 kernel of total_rnn1 can only use 128 of the 148 SMs (32 co-resident clusters) and read_rnn1 is a
                 // grid of small CTAs, so the read_rnn1 of the NEXT (chunk, model) is launched on a side stream as soon as read_rnn11 of
@@ -500,6 +549,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     }
                     StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
+                    io.out_f8 = f8 != 0;       // total_rnn2 runs its correction passes in e4m3: a3h = fp16(h) 2^12, a3l = the 8-bit copies
                     if (h->trnn1_fused) n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
                     else n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
                                             : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
@@ -509,7 +559,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 if (h->trnn2_fused) {
                     StageTimer tm(h, ST_REC3);
                     LstmIo io; io.out_hi = a4h; io.out_lo = a4l; io.out_ld = 128;
-                    n = launch_lstm_fused_pair64(M.lstm[3], a3h, a3l, io, nwp, T, h->num_sms, h->stream);
+                    n = launch_lstm_fused_pair64(M.lstm[3], a3h, a3l, io, nwp, T, h->num_sms, h->stream, f8);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 fused layer (total_rnn2) could not be launched");
                     h->launches += n;
                 } else {   // total_rnn2: projection (K = 256), recurrence (u = 64)
@@ -531,7 +581,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
                                           M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2t_hi, M.heads.d2t_lo,
-                                          M.heads.d2b);
+                                          M.heads.d2b, f8 ? 4096.f : 1.f);     // an F8 total_rnn2 writes h 2^12
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
                     h->launches += n;
                 }
@@ -880,6 +930,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     const char* t1 = getenv("NRV_TRNN1");
     if (t1 && !strcmp(t1, "split")) h->trnn1_fused = 0;
     if (t1 && !strcmp(t1, "fused")) h->trnn1_fused = 1;
+    const char* f8e = getenv("NRV_F8");
+    if (f8e && !strcmp(f8e, "0")) h->f8_rnn2 = 0;
     const char* r128 = getenv("NRV_REC128");
     if (r128 && !strcmp(r128, "single")) h->rec128_pair = 0;
     h->num_sms = prop.multiProcessorCount;

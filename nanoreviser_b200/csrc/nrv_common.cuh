@@ -41,6 +41,13 @@ struct LstmLayerDev {
     float* bias_tc;
     // tensor-core recurrence operand: Wr^T [2 dirs][4u][u] fp16 (hi, lo), row = unit*4 + gate (layers 1..3)
     __half* rt_hi; __half* rt_lo;
+    // total_rnn2 with e4m3 correction passes (nrv_fused_pair.cu, F8): operands with power-of-two scales, accumulator = 2^S z.
+    //   f8_wk_hi = fp16(Wk 2^(S-12)) [2*4u][in] (rows as pb_hi),  f8_wr_hi = fp16(Wr 2^(S-12)) [2*4u][u] (rows as rt_hi)
+    //   f8_wk8 / f8_wr8: the 8-bit copies for the two correction passes, [rows][2 in] / [rows][2 u] bytes, interleaved in groups
+    //   of 4 inputs: bytes 8g..8g+3 = e4m3(W_hi 2^(S-19)) (meets x_lo 2^19), bytes 8g+4..8g+7 = e4m3(W_lo 2^(S-8)) (meets x_hi 2^8)
+    __half* f8_wk_hi = nullptr; uint8_t* f8_wk8 = nullptr;
+    __half* f8_wr_hi = nullptr; uint8_t* f8_wr8 = nullptr;
+    float f8_acc_scale = 1.f;                                                // 2^-S
 };
 
 struct LstmIo {
@@ -54,6 +61,8 @@ struct LstmIo {
     __half* out_lo = nullptr;
     int out_ld = 0;
     int64_t out_nwp = 0;               // != 0: time-major padded rows, row(t, w) = t*out_nwp + w
+    bool out_f8 = false;               // fused total_rnn1 feeding an F8 total_rnn2: out_hi = fp16(h) 2^12 and out_lo holds, per 4 units,
+                                       // the 8 bytes {e4m3(h_lo 2^19) x 4, e4m3(h 2^8) x 4} (same bytes per row as the fp16 lo part)
 };
 
 struct CnnDev {
@@ -113,7 +122,8 @@ int launch_lstm_layer(int layer, int variant, const LstmLayerDev& L, const LstmI
 // nrv_gemm.cu: C[M][N] = A[M][K] . B[N][K]^T (+bias) with split-fp16 operands on tcgen05 (see file header)
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st, const __half* w2t_hi = nullptr, const __half* w2t_lo = nullptr, const float* b2 = nullptr);
+                      cudaStream_t st, const __half* w2t_hi = nullptr, const __half* w2t_lo = nullptr, const float* b2 = nullptr,
+                      float in_scale = 1.f);      // mode 2: the A operand carries this power-of-two scale (undone in the epilogue)
 int launch_split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // nrv_rec_tc.cu: tcgen05 recurrence (u = 64) consuming the projection GEMM's zin
@@ -124,7 +134,7 @@ int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __ha
 int launch_read_rnn1(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);
 // nrv_fused_pair.cu: projection + recurrence of total_rnn2 (cluster of 2) / total_rnn1 (cluster of 4), drained accumulator, h in TMEM
 int launch_lstm_fused_pair64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
-                             cudaStream_t st);
+                             cudaStream_t st, int f8 = 0);
 int launch_lstm_fused_pair128(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
                               cudaStream_t st);
 int launch_lstm_rec_tc128(const LstmLayerDev& L, const LstmIo& io, int64_t n_win, int T, cudaStream_t st);

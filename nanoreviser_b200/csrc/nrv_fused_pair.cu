@@ -33,6 +33,8 @@
 // History of the exchange (L2 round trip, st.async bursts, whole-block copies, a dedicated sender warp): DESIGN.md section 4.
 #include <algorithm>
 
+#include <cuda_fp8.h>
+
 #include "nrv_cell.cuh"
 #include "nrv_common.cuh"
 #include "nrv_tc.cuh"
@@ -42,6 +44,7 @@ namespace nrv {
 using namespace tc;
 
 bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);   // nrv_gemm.cu
+bool make_tmap_u8_k128(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);    // nrv_gemm.cu
 
 constexpr int FP_EPI_WARPS = 16;                      // 4 per TMEM lane quarter; 16 units (64 gate columns) per thread
 constexpr int FP_THREADS = 64 + 32 * FP_EPI_WARPS;    // warp 0: MMA issue (pair leader); warp 1: TMA producer; warps 2..17: epilogue
@@ -121,19 +124,20 @@ __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t remote_dst, uint32
 // Units [J0, J1) of one 32-column block (8 units x gates i,f,c,o) of the cell; the bias is read from shared memory unit by
 // unit (keeps the 64 drained accumulator registers + 16 cell states close to the 96-register budget of a 576-thread CTA:
 // warps are allocated in fours, so 20 x 32 x 96 registers).
+// `zs` = scale of the accumulator (1 for the fp16 x 3 kernels; 2^-S when the operands carry power-of-two scales, see F8), `zs02` = 0.2 zs
 template <int J0, int J1>
-__device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbias, float* c8, float* hv) {
+__device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbias, float* c8, float* hv, float zs, float zs02) {
 #pragma unroll
     for (int j = J0; j < J1; ++j) {
         const float4 b = ld_shared_f4(sbias + j * 16);       // {0.2 b_i + 0.5, 0.2 b_f + 0.5, b_c, 0.2 b_o + 0.5}
-        const float ig = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 0]), b.x));
-        const float fg = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 1]), b.y));
+        const float ig = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 0]), b.x));
+        const float fg = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 1]), b.y));
 #if defined(NRV_TANH_NR) && NRV_TANH_NR >= 1
-        const float gg = tanh_fast_nr(b.z + __uint_as_float(v[4 * j + 2]));
+        const float gg = tanh_fast_nr(fmaf(zs, __uint_as_float(v[4 * j + 2]), b.z));
 #else
-        const float gg = tanh_fast(b.z + __uint_as_float(v[4 * j + 2]));
+        const float gg = tanh_fast(fmaf(zs, __uint_as_float(v[4 * j + 2]), b.z));
 #endif
-        const float og = __saturatef(fmaf(0.2f, __uint_as_float(v[4 * j + 3]), b.w));
+        const float og = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 3]), b.w));
         const float cn = fmaf(fg, c8[j], ig * gg);
         c8[j] = cn;
 #if defined(NRV_TANH_NR) && NRV_TANH_NR >= 2
@@ -157,16 +161,79 @@ __device__ __forceinline__ void pack_h4(const float* hv, uint2& phi, uint2& plo)
     plo = make_uint2(pl[0], pl[1]);
 }
 
-template <int KIN, int UT>
+// ---- 8-bit copies of activations for a layer that runs its correction passes in e4m3 (F8 below) ----
+// An activation x in [-1, 1] is handed over as  hi16 = fp16(x) 2^12  and, per group of 4 units, 8 bytes
+// {e4m3(x_lo 2^19) x 4, e4m3(x 2^8) x 4}: as many bytes per row as the fp16 lo part they replace.
+constexpr float F8_XS = 4096.f;                  // 2^12: scale of the fp16 hi part of an activation
+constexpr float F8_XLO = 524288.f;               // 2^19: scale of the e4m3 copy of the lo part
+__device__ __forceinline__ uint32_t e4m3x2_f32(float a, float b) {
+    return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ uint32_t e4m3x2_h2(__half2 v) {
+    return (uint32_t)__nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(v), __NV_SATFINITE, __NV_E4M3);
+}
+// 4 units of h for the kernel's OWN fp16 x 3 recurrence (hi2, lo2 as pack_h4) and for an F8 consumer (hs2 = fp16(h) 2^12, q2 = 8-bit copies)
+__device__ __forceinline__ void pack_h4_out8(const float* hv, uint2& phi, uint2& plo, uint2& phs, uint2& pq) {
+    uint32_t ph[2], pl[2], ps[2], l8[2], h8[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
+        const float2 hf = __half22float2(hi);
+        const float l0 = hv[2 * p] - hf.x, l1 = hv[2 * p + 1] - hf.y;
+        ph[p] = half2_bits(hi);
+        pl[p] = half2_bits(__floats2half2_rn(l0, l1));
+        ps[p] = half2_bits(__hmul2(hi, __float2half2_rn(F8_XS)));          // exact: a power of two, |h| < 1
+        l8[p] = e4m3x2_f32(l0 * F8_XLO, l1 * F8_XLO);
+        h8[p] = e4m3x2_h2(__hmul2(hi, __float2half2_rn(256.f)));
+    }
+    phi = make_uint2(ph[0], ph[1]);
+    plo = make_uint2(pl[0], pl[1]);
+    phs = make_uint2(ps[0], ps[1]);
+    pq = make_uint2(l8[0] | (l8[1] << 16), h8[0] | (h8[1] << 16));
+}
+// 4 units of h of an F8 layer: hs2 = fp16(h 2^12) and q2 = 8-bit copies (the operands of its own recurrence), ls2 = the fp16 lo
+// part at the same scale 2^12 (the layer's output is the pair hs2, ls2: the consumer undoes the scale)
+__device__ __forceinline__ void pack_h4_f8(const float* hv, uint2& phs, uint2& pls, uint2& pq) {
+    uint32_t ps[2], pl[2], l8[2], h8[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const __half2 hs = __floats2half2_rn(hv[2 * p] * F8_XS, hv[2 * p + 1] * F8_XS);
+        const float2 hf = __half22float2(hs);
+        const float l0 = fmaf(hv[2 * p], F8_XS, -hf.x), l1 = fmaf(hv[2 * p + 1], F8_XS, -hf.y);     // lo 2^12, exact
+        ps[p] = half2_bits(hs);
+        pl[p] = half2_bits(__floats2half2_rn(l0, l1));
+        l8[p] = e4m3x2_f32(l0 * 128.f, l1 * 128.f);                          // lo 2^19
+        h8[p] = e4m3x2_h2(__hmul2(hs, __float2half2_rn(0.0625f)));           // h 2^8
+    }
+    phs = make_uint2(ps[0], ps[1]);
+    pls = make_uint2(pl[0], pl[1]);
+    pq = make_uint2(l8[0] | (l8[1] << 16), h8[0] | (h8[1] << 16));
+}
+
+// F8 (total_rnn2): the two correction passes of every product (projection AND recurrence) run in e4m3 (tcgen05 kind::f8f6f4:
+// K = 32 bytes per instruction, twice the fp16 rate) on 8-bit copies of the operands: the producing epilogue writes
+// {e4m3(x_lo 2^19) x 4, e4m3(x 2^8) x 4} per group of 4 units in place of the fp16 lo part, pack_model lays the weights out the
+// same way ({e4m3(W_hi 2^(S-19)) x 4, e4m3(W_lo 2^(S-8)) x 4}), so x_lo . W_hi + x_hi . W_lo is ONE K-contiguous e4m3 product over
+// a 128-byte tile per 64 units: 2 instructions (1 fp16 + 1 e4m3) per K-step of 16 units instead of 3.  All operands carry power-of-two
+// scales chosen per layer so that every pass accumulates 2^S z into the same fp32 accumulator:
+//     fp16(x) 2^12 . fp16(W 2^(S-12))  +  e4m3(x_lo 2^19) . e4m3(W_hi 2^(S-19))  +  e4m3(x 2^8) . e4m3(W_lo 2^(S-8))
+// and the epilogue folds 2^-S into the gate constants (free).  In the F8 kernel `wk_lo`, `wr_lo`, `tm_x_lo` and the h_lo columns of TMEM
+// hold those 8-bit copies (same bytes per row / tile / column as the fp16 lo parts they replace), `wk_hi` / `wr_hi` the scaled fp16
+// weights.  OUT8: the CONSUMER is an F8 layer -- out_hi / out_lo receive that format instead of the plain fp16 pair.
+// Precision: tests/precision_study.py (max |dP| 1.1e-4 with total_rnn2 in this form) and DESIGN.md section 4.
+template <int KIN, int UT, bool F8, bool OUT8>
 __global__ void __launch_bounds__(FP_THREADS, 1)
 lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
                        const __half* __restrict__ wr_lo, const float* __restrict__ bias,
                        const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int T) {
+                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int T, float acc_scale) {
+    static_assert(!F8 || UT == 64, "F8 is built for total_rnn2 (no exchange of 8-bit copies yet)");
+    static_assert(!(F8 && OUT8), "an F8 layer's own output is the scaled fp16 pair");
     using Cfg = FpCfg<KIN, UT>;
     constexpr int KC = Cfg::KC, NP = Cfg::NP, CS = 2 * NP, FP_STAGES = Cfg::STAGES;
     constexpr int NT = 4 * UT;                              // gate columns per direction
-    constexpr uint32_t H_HI = FP_H_COL, H_LO = FP_H_COL + UT / 2;
+    constexpr uint32_t H_HI = FP_H_COL, H_LO = FP_H_COL + UT / 2;      // F8: the H_LO columns hold the 8-bit copies of h
+    constexpr int XLO_W = F8 ? 128 : 64;                    // elements per 128-byte row of a lo tile (bytes / halves)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;                                    // [Wk chunk 0..KC-1 | Wr chunk 0..RC-1][hi | lo][128 rows][64]
@@ -220,6 +287,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const size_t grow0 = (size_t)dir * NT + p * 256 + r * 64;
         auto gcol = [](int row) { return (row >> 6) * 128 + (row & 63); };
         constexpr int CK = KIN / 8, CR = UT / 8;            // 16-byte chunks per row
+        // (F8: the lo parts are the interleaved 8-bit copies -- as many bytes per row as the fp16 lo part, same tiles)
         for (int i = threadIdx.x; i < 2 * 128 * CK; i += FP_THREADS) {
             const int c = i % CK, row = (i / CK) & 127, part = i / (CK * 128);
             const __half* src = (part ? wk_lo : wk_hi) + (grow0 + gcol(row)) * KIN;
@@ -251,13 +319,13 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     const int grow = (int)(t * nwp + wtile * 128);
                     if (s + 1 < T) {                                       // next step's tiles -> L2 (the layer input comes from HBM: ring
                         const int gnext = grow + (dir ? -1 : 1) * (int)nwp;   // loads then see L2 latency, which 3-4 stages cover)
-                        for (int i = 0; i < KC; ++i) { tma_prefetch_2d(&tm_x_lo, i * 64, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                        for (int i = 0; i < KC; ++i) { tma_prefetch_2d(&tm_x_lo, i * XLO_W, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
                     }
-                    for (int i = 0; i < 2 * KC; ++i) {                     // (K-chunk, part): lo tile first, then hi
+                    for (int i = 0; i < 2 * KC; ++i) {                     // (K-chunk, part): lo tile (F8: the 8-bit copies) first, then hi
                         FP_WAIT(&empty[stage], phase ^ 1, 1, (uint32_t)s);
                         if (r == 0) mbar_arrive_expect_tx(&full[stage], 2 * FP_TILE);
                         tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_x_hi : &tm_x_lo, &full[stage], leader,
-                                         (i >> 1) * 64, grow);
+                                         (i >> 1) * ((i & 1) ? 64 : XLO_W), grow);
                         if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -279,7 +347,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         tc_fence_after();
                     }
                     const uint32_t d0 = tmem_base, d1 = tmem_base + 128 + (g & 1) * 128;      // block 1 alternates: never waits for a drain
-                    // projection K-chunk kc: x_lo . W_hi, then x_hi . W_lo and x_hi . W_hi (two ring tiles), both unit blocks
+                    // projection K-chunk kc: x_lo . W_hi, then x_hi . W_lo and x_hi . W_hi (two ring tiles), both unit blocks.
+                    // F8: the lo tile is the 8-bit copies of the chunk's 64 units: 4 e4m3 MMAs (K = 32 bytes each) against the 8-bit
+                    // weight tile are both correction passes; then the fp16 main pass on the hi tile
                     auto proj = [&](int kc) {
                         const uint32_t wb_hi = w_base + (uint32_t)((kc * 2 + 0) * FP_TILE), wb_lo = w_base + (uint32_t)((kc * 2 + 1) * FP_TILE);
                         FP_WAIT(&full[stage], phase, 3, g);                   // x_lo(kc)
@@ -292,8 +362,13 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #endif
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_lo = umma_desc_k_sw128(xa + k * 32);
-                                umma_f16_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_hi + k * 32), idesc, (kc | k) != 0);
-                                umma_f16_ss_pair(d1, a_lo, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, (kc | k) != 0);
+                                if constexpr (F8) {
+                                    umma_f8_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_lo + k * 32), idesc, (kc | k) != 0);
+                                    umma_f8_ss_pair(d1, a_lo, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, (kc | k) != 0);
+                                } else {
+                                    umma_f16_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_hi + k * 32), idesc, (kc | k) != 0);
+                                    umma_f16_ss_pair(d1, a_lo, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, (kc | k) != 0);
+                                }
                             }
                             umma_commit_mask(&empty[stage], mask);
                         }
@@ -311,9 +386,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #else
                                 const uint32_t acc0 = 1u;
 #endif
-                                umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, acc0);
+                                if constexpr (!F8) umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_hi + k * 32), idesc, 1);
-                                umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, acc0);
+                                if constexpr (!F8) umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, 1);
                             }
                             umma_commit_mask(&empty[stage], mask);
@@ -321,7 +396,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         __syncwarp();
                         if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
                     };
-                    // recurrent quarter (b, who): the 32 units b*32.. of pair `who ? 1-p : p` = K-steps k0, k0 + 1 of h_{t-1} (TMEM)
+                    // recurrent quarter (b, who): the 32 units b*32.. of pair `who ? 1-p : p` = K-steps k0, k0 + 1 of h_{t-1} (TMEM).
+                    // F8: the 8 H_LO columns of a K-step are the 32 bytes of 8-bit copies of its 16 units = one e4m3 MMA (layout pinned by
+                    // tools/ts_probe/ts_probe8.cu: column c = bytes 4c .. 4c + 3)
                     auto rec = [&](int b, int who) {
                         if (g > 0) {
                             FP_WAIT(&hq[b * 2 + who], (g - 1) & 1, 5, g);
@@ -336,8 +413,12 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                                 for (int blk = 0; blk < 2; ++blk) {
                                     const uint64_t b_hi = umma_desc_k_sw128(wr + blk * BB), b_lo = umma_desc_k_sw128(wr + FP_TILE + blk * BB);
                                     const uint32_t d = blk ? d1 : d0;
-                                    umma_f16_ts_pair(d, tmem_base + H_LO + k * 8, b_hi, idesc, 1);
-                                    umma_f16_ts_pair(d, tmem_base + H_HI + k * 8, b_lo, idesc, 1);
+                                    if constexpr (F8) {
+                                        umma_f8_ts_pair(d, tmem_base + H_LO + k * 8, b_lo, idesc, 1);
+                                    } else {
+                                        umma_f16_ts_pair(d, tmem_base + H_LO + k * 8, b_hi, idesc, 1);
+                                        umma_f16_ts_pair(d, tmem_base + H_HI + k * 8, b_lo, idesc, 1);
+                                    }
                                     umma_f16_ts_pair(d, tmem_base + H_HI + k * 8, b_hi, idesc, 1);
                                 }
                             }
@@ -402,6 +483,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 mbar_arrive_remote(&hq[(k & 1) * 2 + 1], leader);
             }
         };
+        const float zs02 = 0.2f * acc_scale;
         uint32_t g = 0;
         for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
             const int64_t wtile = min(tp * 2 + (int64_t)r, ntw - 1);     // odd tile count: the last peer repeats the last tile
@@ -426,10 +508,23 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 __half* ol = out_lo + orow + p * 64 + cg * 8;
                 // exchange in halves of 4 units, each handed to the bulk-copy engine as soon as it exists (2 x 256 B per warp): the DSMEM
                 // traffic is spread over the arithmetic instead of arriving as a 16 KB burst at the end of a block
+                // ph / pl: the operands of this kernel's own recurrence (TMEM, exchange); gh / gl: what goes to global memory --
+                // the same registers unless the consumer wants the F8 format (OUT8) or this layer is F8 itself (output = scaled fp16 pair)
                 uint32_t ph[4], pl[4];
-                auto send_half = [&](int half, const float* hv4, uint32_t wait_k) {      // wait_k != 0: first half of exchange phase wait_k
+                uint32_t gh[(OUT8 || F8) ? 4 : 1], gl[(OUT8 || F8) ? 4 : 1];
+                auto send_half = [&](int b, int half, const float* hv4, uint32_t wait_k) {      // wait_k != 0: first half of exchange phase wait_k
                     uint2 hi2, lo2;
-                    pack_h4(hv4, hi2, lo2);
+                    if constexpr (F8) {
+                        uint2 ls2;
+                        pack_h4_f8(hv4, hi2, ls2, lo2);          // TMEM: fp16(h 2^12) + 8-bit copies; global: fp16 pair at scale 2^12
+                        gl[half * 2] = ls2.x; gl[half * 2 + 1] = ls2.y;
+                    } else if constexpr (OUT8) {
+                        uint2 hs2, q2;
+                        pack_h4_out8(hv4, hi2, lo2, hs2, q2);
+                        gh[half * 2] = hs2.x; gh[half * 2 + 1] = hs2.y; gl[half * 2] = q2.x; gl[half * 2 + 1] = q2.y;
+                    } else {
+                        pack_h4(hv4, hi2, lo2);
+                    }
                     ph[half * 2] = hi2.x; ph[half * 2 + 1] = hi2.y; pl[half * 2] = lo2.x; pl[half * 2 + 1] = lo2.y;
                     if constexpr (NP == 2) {
                         if (lane == 0) tma_store_wait_read();
@@ -450,30 +545,38 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     const uint4 phi = make_uint4(ph[0], ph[1], ph[2], ph[3]), plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     tmem_st_32x4(lane_addr + H_HI + own_col + b * 16, phi);
                     tmem_st_32x4(lane_addr + H_LO + own_col + b * 16, plo);
-                    *reinterpret_cast<uint4*>(oh + b * 32) = phi;
-                    *reinterpret_cast<uint4*>(ol + b * 32) = plo;
+                    if constexpr (OUT8) {
+                        *reinterpret_cast<uint4*>(oh + b * 32) = make_uint4(gh[0], gh[1], gh[2], gh[3]);
+                        *reinterpret_cast<uint4*>(ol + b * 32) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
+                    } else if constexpr (F8) {
+                        *reinterpret_cast<uint4*>(oh + b * 32) = phi;
+                        *reinterpret_cast<uint4*>(ol + b * 32) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
+                    } else {
+                        *reinterpret_cast<uint4*>(oh + b * 32) = phi;
+                        *reinterpret_cast<uint4*>(ol + b * 32) = plo;
+                    }
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&hq[b * 2], leader);
                 };
                 float hv[8];
-                cell_units<0, 4>(v0, sb, &c[0], hv);
-                send_half(0, hv, 2 * g);                  // phase 2g: the sibling has consumed phase 2g-1 (wait_k = 0 for the very first)
-                cell_units<4, 8>(v0, sb, &c[0], hv);
-                send_half(1, hv + 4, 0);
+                cell_units<0, 4>(v0, sb, &c[0], hv, acc_scale, zs02);
+                send_half(0, 0, hv, 2 * g);                  // phase 2g: the sibling has consumed phase 2g-1 (wait_k = 0 for the very first)
+                cell_units<4, 8>(v0, sb, &c[0], hv, acc_scale, zs02);
+                send_half(0, 1, hv + 4, 0);
                 uint32_t v1[32];
                 tmem_ld_32x32(lane_addr + (uint32_t)(128 + (g & 1) * 128 + cg * 32), v1);
                 publish2(0);
                 if (warp == 2) TR(1, g, 2);
                 tmem_ld_wait();
-                cell_units<0, 4>(v1, sb + 512, &c[8], hv);
+                cell_units<0, 4>(v1, sb + 512, &c[8], hv, acc_scale, zs02);
                 if (warp == 2) TR(1, g, 3);
                 if constexpr (NP == 2) xch_recv(2 * g);
                 if (warp == 2) TR(1, g, 4);
-                send_half(0, hv, 2 * g + 1);              // phase 2g+1 after the sibling has consumed phase 2g
-                cell_units<4, 8>(v1, sb + 512, &c[8], hv);
-                send_half(1, hv + 4, 0);
+                send_half(1, 0, hv, 2 * g + 1);              // phase 2g+1 after the sibling has consumed phase 2g
+                cell_units<4, 8>(v1, sb + 512, &c[8], hv, acc_scale, zs02);
+                send_half(1, 1, hv + 4, 0);
                 publish2(1);
                 if (warp == 2) TR(1, g, 5);
                 if constexpr (NP == 2) xch_recv(2 * g + 1);
@@ -506,19 +609,23 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     if (warp == 0) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
-template <int KIN, int UT>
+template <int KIN, int UT, bool F8, bool OUT8>
 static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                                int num_sms, cudaStream_t st) {
     using Cfg = FpCfg<KIN, UT>;
     constexpr int CS = 2 * Cfg::NP;
     CUtensorMap txh, txl;
-    if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, KIN, 128) || !make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, KIN, 128)) return -2;
-    auto kern = lstm_fused_pair_kernel<KIN, UT>;
+    if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, KIN, 128)) return -2;
+    if (F8) {   // x_lo = the producing layer's 8-bit copies: rows of 2 KIN bytes, 128-byte boxes (= the 64 units of an fp16 K-chunk)
+        if (!make_tmap_u8_k128(&txl, x_lo, (int64_t)T * nwp, 2 * KIN, 128)) return -2;
+    } else {
+        if (!make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, KIN, 128)) return -2;
+    }
+    auto kern = lstm_fused_pair_kernel<KIN, UT, F8, OUT8>;
     static PerDevice per_dev;                     // co-resident clusters on the current device (per template instance)
     int& max_clusters = per_dev.cur();
     if (!max_clusters) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        if (e == cudaSuccess && CS > 2) e = cudaSuccess;
         if (e != cudaSuccess) { fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: smem attribute: %s\n", KIN, UT, cudaGetErrorString(e)); return -3; }
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3(CS * 64, 2); qc.blockDim = dim3(FP_THREADS); qc.dynamicSmemBytes = Cfg::SMEM;
@@ -531,7 +638,7 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
             cudaGetLastError(); n = num_sms / CS;
         }
         max_clusters = n;
-        if (getenv("NRV_VERBOSE")) fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: cluster %d, %d co-resident clusters\n", KIN, UT, CS, n);
+        if (getenv("NRV_VERBOSE")) fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d,%d>: cluster %d, %d co-resident clusters\n", KIN, UT, (int)F8, CS, n);
     }
     const int64_t n_pairs = ((nwp >> 7) + 1) / 2;
     const int per_dir = std::max(1, max_clusters / 2);
@@ -542,8 +649,12 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     cfg.stream = st;
     cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CS; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const __half*)L.pb_hi, (const __half*)L.pb_lo, (const __half*)L.rt_hi,
-                                             (const __half*)L.rt_lo, (const float*)L.bias_tc, txh, txl, io.out_hi, io.out_lo, io.out_ld, nwp, T);
+    const __half* wk_hi = F8 ? (const __half*)L.f8_wk_hi : (const __half*)L.pb_hi;
+    const __half* wk_lo = F8 ? reinterpret_cast<const __half*>(L.f8_wk8) : (const __half*)L.pb_lo;
+    const __half* wr_hi = F8 ? (const __half*)L.f8_wr_hi : (const __half*)L.rt_hi;
+    const __half* wr_lo = F8 ? reinterpret_cast<const __half*>(L.f8_wr8) : (const __half*)L.rt_lo;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wk_hi, wk_lo, wr_hi, wr_lo, (const float*)L.bias_tc, txh, txl, io.out_hi, io.out_lo,
+                                             io.out_ld, nwp, T, F8 ? L.f8_acc_scale : 1.0f);
     if (e != cudaSuccess) {
         fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: launch (grid %u x 2, cluster %d, %zu B smem): %s\n", KIN, UT, cfg.gridDim.x, CS,
                 (size_t)Cfg::SMEM, cudaGetErrorString(e));
@@ -552,19 +663,24 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     return 1;
 }
 
-// total_rnn2: x = total_rnn1's output (K = 256), 64 units
+// total_rnn2: x = total_rnn1's output (K = 256), 64 units.  f8 != 0: x_hi is fp16(h) 2^12 and x_lo the 8-bit copies (see F8 above)
 int launch_lstm_fused_pair64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
-                             cudaStream_t st) {
+                             cudaStream_t st, int f8) {
     if (nwp <= 0) return 0;
     if (L.u != 64 || L.in_a != 256 || !L.rt_hi || !L.pb_hi || !L.bias_tc || !io.out_hi || !io.out_lo || (nwp & 127) || (io.out_ld & 7)) return -1;
-    return launch_fused_pair_t<256, 64>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (f8) {
+        if (!L.f8_wk_hi || !L.f8_wk8 || !L.f8_wr_hi || !L.f8_wr8) return -1;
+        return launch_fused_pair_t<256, 64, true, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    }
+    return launch_fused_pair_t<256, 64, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
 }
 // total_rnn1: x = [read_rnn11 | CNN features] (K = 192), 128 units, cluster of 4
 int launch_lstm_fused_pair128(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
                               cudaStream_t st) {
     if (nwp <= 0) return 0;
     if (L.u != 128 || !L.rt_hi || !L.pb_hi || !L.bias_tc || !io.out_hi || !io.out_lo || (nwp & 127) || (io.out_ld & 7)) return -1;
-    return launch_fused_pair_t<192, 128>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (io.out_f8) return launch_fused_pair_t<192, 128, false, true>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    return launch_fused_pair_t<192, 128, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
 }
 
 }  // namespace nrv

@@ -61,6 +61,7 @@ struct GemmOut {
     const __half* w2t_hi;   // W2^T [32][128]
     const __half* w2t_lo;
     const float* b2;
+    float inv_in_scale;     // mode 2: 1 / (power-of-two scale of the A operand), applied to the accumulator before the bias
 };
 
 template <int G_TN, bool FUSE2>
@@ -238,8 +239,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         for (int e = 0; e < 4; e += 2) {
                             const int j = g8 * 8 + e * 2;
                             const float4 bq = ld_shared_f4(sb + (uint32_t)(cb * 32 + j) * 4);
-                            const float x0 = fmaxf(__uint_as_float(v[j]) + bq.x, 0.f), x1 = fmaxf(__uint_as_float(v[j + 1]) + bq.y, 0.f);
-                            const float x2 = fmaxf(__uint_as_float(v[j + 2]) + bq.z, 0.f), x3 = fmaxf(__uint_as_float(v[j + 3]) + bq.w, 0.f);
+                            const float is = out.inv_in_scale;
+                            const float x0 = fmaxf(fmaf(__uint_as_float(v[j]), is, bq.x), 0.f), x1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), is, bq.y), 0.f);
+                            const float x2 = fmaxf(fmaf(__uint_as_float(v[j + 2]), is, bq.z), 0.f), x3 = fmaxf(fmaf(__uint_as_float(v[j + 3]), is, bq.w), 0.f);
                             const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
                             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                             const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
@@ -523,6 +525,21 @@ bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, i
     return r == CUDA_SUCCESS;
 }
 
+// 8-bit operand (e4m3 copies of activations, nrv_fused_pair.cu F8): rows of K bytes, box = 128 bytes x box_rows, 128-byte swizzle --
+// the same 16 KB tile geometry as a K = 64 fp16 tile, so the UMMA descriptors and k-step offsets (32 B) are shared
+bool make_tmap_u8_k128(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)K};
+    cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <int TN, bool FUSE2>
 static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                           const GemmOut& o, int num_sms, cudaStream_t st) {
@@ -541,10 +558,10 @@ static int launch_gemm_tn(const __half* a_hi, const __half* a_lo, const __half* 
 
 int launch_gemm_f16x3(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo, int64_t M, int N, int K,
                       float* c, const float* bias, int mode, int T, int64_t nw, int n_per_dir, int relu, int num_sms,
-                      cudaStream_t st, const __half* w2t_hi, const __half* w2t_lo, const float* b2) {
+                      cudaStream_t st, const __half* w2t_hi, const __half* w2t_lo, const float* b2, float in_scale) {
     if (M <= 0) return 0;
     if (K % G_KC != 0 || K <= 0 || N <= 0) return -1;
-    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2};
+    GemmOut o{c, bias, mode, T, nw, n_per_dir, relu, w2t_hi, w2t_lo, b2, 1.f / in_scale};
     // CTA-pair kernel (B resident, 8 epilogue warps) unless NRV_GEMM=single: proj2 36.7 -> 30.8 ms, proj3 21.3 -> 17.9 ms per step
     const bool use_pair = !(getenv("NRV_GEMM") && !strcmp(getenv("NRV_GEMM"), "single"));
     if (mode == 1 && use_pair && N % 256 == 0 && n_per_dir % 256 == 0 && M % G_TM == 0 && K <= 256) {

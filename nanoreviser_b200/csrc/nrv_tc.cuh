@@ -215,6 +215,18 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, kind::f8f6f4: A and B are 8-bit floats (format codes in the instruction descriptor: E4M3 = 0, i.e. the descriptor of
+// umma_idesc_f16_f32 is also the E4M3 x E4M3 -> F32 descriptor), one instruction covers K = 32 (32 bytes of a K-major row) at
+// twice the fp16 rate
+__device__ __forceinline__ void umma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // the mbarrier at this offset in BOTH CTAs arrives when all tcgen05 ops issued so far have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
@@ -253,6 +265,16 @@ __device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same with an 8-bit A tile (kind::f8f6f4), verified by tools/ts_probe/ts_probe8.cu: 32-bit column c = the four K-consecutive bytes
+// k = 4c .. 4c + 3; one K = 32 step = 8 columns
+__device__ __forceinline__ void umma_f8_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }

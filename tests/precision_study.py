@@ -96,11 +96,17 @@ def bn_affine(bn):
     return inv, b - m * inv
 
 
+BASE_MODE = ["f32"]
+REC_MODE = [None]      # --rec-mode: how the recurrent product h @ Wr of the emulated layers is evaluated (default: same as the projection)
+
+
 def lstm_dir(mode, x, wk, wr, bias, reverse, xs_hi, xs_lo):
     """x [B, T, in] (fp32 torch) -> [B, T, u]; h is in [-1, 1]: 8-bit copies scaled by 2^8 (hi) / 2^19 (lo)"""
     B, T, _ = x.shape
     u = wr["W"].shape[0]
     zin = mode.mm(x.reshape(B * T, -1), wk, xs_hi, xs_lo).reshape(B, T, 4 * u) + bias
+    if REC_MODE[0] and mode.name != "f32":
+        mode = Mode(REC_MODE[0])
     h = torch.zeros(B, u)
     c = torch.zeros(B, u)
     out = torch.empty(B, T, u)
@@ -133,10 +139,10 @@ class Net:
                         off = np.concatenate([off, np.zeros(64)])
                     b = b + off @ wk
                     wk = wk * inv[:, None]
-                md = mode if li in tensor_layers else f32m
+                md = mode if li in tensor_layers else (Mode(BASE_MODE[0]) if li >= 1 else f32m)
                 dirs.append((md, md.prep_w(wk), md.prep_w(d.recurrent), t32(b)))
             self.layers.append(dirs)
-        hm = mode if tensor_heads else f32m
+        hm = mode if tensor_heads else Mode(BASE_MODE[0])
         self.hm = hm
         self.d1 = hm.prep_w(m.dense1_k)
         self.d2 = hm.prep_w(m.dense2_k)
@@ -179,7 +185,11 @@ def main():
     ap.add_argument("--layers", nargs="+", type=int, default=[1, 2, 3], help="LSTM layers on the emulated tensor path")
     ap.add_argument("--max-windows", type=int, default=0)
     ap.add_argument("--no-heads", action="store_true", help="dense heads in fp32")
+    ap.add_argument("--rec-mode", default=None, help="mode of the recurrent products (e.g. f16x3 while the projections use e4m3)")
+    ap.add_argument("--base-mode", default="f16x3", help="mode of the tensor layers NOT listed in --layers (the GPU default is f16x3)")
     a = ap.parse_args()
+    REC_MODE[0] = a.rec_mode
+    BASE_MODE[0] = a.base_mode
     files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "fast5", "*.fast5")))
     for sp in a.species:
         m1, m2 = weights.load_species(sp, os.path.join(ROOT, "model"))
