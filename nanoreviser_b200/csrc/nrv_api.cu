@@ -90,14 +90,15 @@ struct nrv_handle {
     cudaStream_t copy_stream = nullptr;
     Arena d_shift, d_scale, d_base_read,
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_wq[2],
-        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin;
+        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin, d_tile_base;
     IoSlot& io() { return slot[cur]; }
     int in_flight() const { int n = 0; for (const IoSlot& s : slot) n += s.ticket != 0; return n; }
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
     int num_sms = 148;
     int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
     int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
-    int f8_rnn2 = 1;        // total_rnn2's projection correction passes in e4m3 (kind::f8f6f4); NRV_F8=0 keeps them fp16
+    int f8_rnn2 = 1;        // total_rnn2's correction passes in e4m3 (kind::f8f6f4); NRV_F8=0 keeps them fp16
+    int sig_table = 1;      // fused total_rnn1 reads the CNN features of boundary-free tiles straight from the per-base table; NRV_SIGTAB=0: gather all
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
@@ -407,25 +408,45 @@ __global__ void set_half_column_kernel(__half* a, int64_t rows, int ld, int col,
     if (r < rows) a[r * ld + col] = __float2half_rn(v);
 }
 
-__global__ void gather_sig_kernel(const __half* __restrict__ sf_hi, const __half* __restrict__ sf_lo,
-                                  const int32_t* __restrict__ win_base, int64_t n_win, int64_t nwp, int T, int ld,
-                                  __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
-    // columns [128, 192) of total_rnn1's input row (t, w) = CNN features of base win_base[w] + t; 8 x 16 B per half array
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t item = i >> 3;
-    const int q = (int)(i & 7);
-    if (item >= n_win * T) return;
-    const int t = (int)(item / n_win);
-    const int64_t w = item - (int64_t)t * n_win;
-    const int64_t b = (int64_t)win_base[w] + t;
-    const int64_t row = (int64_t)t * nwp + w;
-    reinterpret_cast<uint4*>(a_hi + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_hi + b * NRV_SIGFEAT) + q);
-    reinterpret_cast<uint4*>(a_lo + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_lo + b * NRV_SIGFEAT) + q);
+// tile_base[tile] = first base of the tile's 128 windows if their bases are consecutive (no read boundary inside the tile), else -1.
+// For such a tile the rows (t, w) of total_rnn1's CNN-feature columns are 128 CONSECUTIVE rows of the per-base feature table
+// starting at tile_base + t: the fused layer kernel loads them with one TMA box straight from the table (nrv_fused_pair.cu) and
+// the gather below skips the tile.  win_base is increasing inside a batch (jumps of W at read boundaries), so "consecutive" is one
+// subtraction.
+__global__ void tile_base_kernel(const int32_t* __restrict__ win_base, int64_t n_win, int32_t* __restrict__ tile_base, int64_t n_tiles) {
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= n_tiles) return;
+    const int64_t w0 = tile * 128, w1 = min(w0 + 127, n_win - 1);
+    int32_t tb = -1;
+    if (w0 < n_win) {
+        const int32_t b0 = win_base[w0];
+        if ((int64_t)win_base[w1] - b0 == w1 - w0) tb = b0;
+    }
+    tile_base[tile] = tb;
+}
+
+// columns [128, 192) of total_rnn1's input row (t, w) = CNN features of base win_base[w] + t; 8 x 16 B per half array.
+// One CTA per (tile of 128 windows, t); tile_base != nullptr: tiles with consecutive bases are skipped (read from the table instead)
+__global__ void __launch_bounds__(256) gather_sig_kernel(const __half* __restrict__ sf_hi, const __half* __restrict__ sf_lo,
+                                  const int32_t* __restrict__ win_base, int64_t n_win, int64_t nwp, int ld,
+                                  const int32_t* __restrict__ tile_base, __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+    const int64_t tile = blockIdx.x;
+    const int t = blockIdx.y;
+    if (tile_base && tile_base[tile] >= 0) return;
+    for (int i = threadIdx.x; i < 128 * 8; i += 256) {
+        const int64_t w = tile * 128 + (i >> 3);
+        const int q = i & 7;
+        if (w >= n_win) break;
+        const int64_t b = (int64_t)win_base[w] + t;
+        const int64_t row = (int64_t)t * nwp + w;
+        reinterpret_cast<uint4*>(a_hi + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_hi + b * NRV_SIGFEAT) + q);
+        reinterpret_cast<uint4*>(a_lo + row * ld + 128)[q] = __ldg(reinterpret_cast<const uint4*>(sf_lo + b * NRV_SIGFEAT) + q);
+    }
 }
 
 // Both models over all windows, chunk by chunk.  x [n_bases][6]; sig_feat[m] [n_bases][64] (+ fp16 pairs).
 int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const float* x, float* const sig_feat[2],
-               float* const probs[2], uint8_t* const labels[2]) {
+               float* const probs[2], uint8_t* const labels[2], int64_t n_bases) {
     const int T = h->window;
     const int64_t CH = std::min<int64_t>(h->chunk_windows, std::max<int64_t>(n_win, 1));
     const int64_t rows = ((CH + 127) / 128 * 128) * T;     // padded time-major rows of one chunk
@@ -450,6 +471,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
             CU(h, h->d_a4[k].ensure((size_t)rows * 128 * 2));
         }
         CU(h, h->d_a2[0].ensure((size_t)rows * 192 * 2)); CU(h, h->d_a2[1].ensure((size_t)rows * 192 * 2));
+        CU(h, h->d_tile_base.ensure((size_t)(rows / T / 128 + 1) * 4));
         CU(h, h->d_a3[0].ensure((size_t)rows * 256 * 2)); CU(h, h->d_a3[1].ensure((size_t)rows * 256 * 2));
         // fp32 gate pre-activations exist only on the split (GEMM + recurrence) paths; the fused layer kernels never materialise them
         if (!h->trnn1_fused || !h->trnn2_fused) CU(h, h->d_zin.ensure((size_t)rows * 1024 * sizeof(float)));
@@ -491,6 +513,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 float* zin = h->d_zin.as<float>();
                 int n;
                 const int f8 = h->f8_rnn2 && h->trnn1_fused && h->trnn2_fused;
+                const bool sig_table = h->sig_table && h->trnn1_fused && n_bases > 0;
+                int32_t* tile_base = h->d_tile_base.as<int32_t>();
                 // read_rnn1 (u = 16, K = 6: fp32 SIMT, fused) -> BN(h), columns [0,32) of a 64-wide zero-padded operand.
                 // The cluster-of-4 kernel of total_rnn1 can only use 128 of the 148 SMs (32 co-resident clusters) and read_rnn1 is a
                 // grid of small CTAs, so the read_rnn1 of the NEXT (chunk, model) is launched on a side stream as soon as read_rnn11 of
@@ -522,9 +546,15 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                 {   // total_rnn1 (K = 192, u = 128): gather the CNN features, then the fused layer kernel (or projection GEMM + recurrence)
                     {
                         StageTimer tm(h, ST_PROJ2);
-                        const int64_t items = nw * T * 8;
-                        gather_sig_kernel<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(
-                            h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, T, 192, a2h, a2l);
+                        // tiles without a read boundary take their CNN features straight from the per-base table (TMA in the fused
+                        // kernel); only the others are gathered into columns [128, 192) of a2
+                        const int64_t n_tiles = nwp >> 7;
+                        if (sig_table && mi == 0) {
+                            tile_base_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, h->stream>>>(win_base + c0, nw, tile_base, n_tiles);
+                            h->launches += 1;
+                        }
+                        gather_sig_kernel<<<dim3((unsigned)n_tiles, (unsigned)T), 256, 0, h->stream>>>(
+                            h->d_sfh[mi].as<__half>(), h->d_sfl[mi].as<__half>(), win_base + c0, nw, nwp, 192, sig_table ? tile_base : nullptr, a2h, a2l);
                         h->launches += 1;
                         if (overlap) {
                             // next iteration in launch order: the other model of this chunk, or model 1 of the next chunk.  The side stream has the
@@ -550,6 +580,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
                     io.out_f8 = f8 != 0;       // total_rnn2 runs its correction passes in e4m3: a3h = fp16(h) 2^12, a3l = the 8-bit copies
+                    if (sig_table) { io.sf_hi = h->d_sfh[mi].as<__half>(); io.sf_lo = h->d_sfl[mi].as<__half>(); io.sf_rows = n_bases; io.tile_base = tile_base; }
                     if (h->trnn1_fused) n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
                     else n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
                                             : launch_lstm_rec_tc128(M.lstm[2], io, nwp, T, h->stream);
@@ -794,7 +825,7 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
         }
     }
     float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
-    rc = run_models(h, o.n_win, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels);
+    rc = run_models(h, o.n_win, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels, o.n_bases);
     if (rc) return rc;
     // ---- K4: decode --------------------------------------------------------------------------------
     const int64_t n_tiles = decode_tile_count(o.n_bases);
@@ -930,6 +961,8 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     const char* t1 = getenv("NRV_TRNN1");
     if (t1 && !strcmp(t1, "split")) h->trnn1_fused = 0;
     if (t1 && !strcmp(t1, "fused")) h->trnn1_fused = 1;
+    const char* sge = getenv("NRV_SIGTAB");
+    if (sge && !strcmp(sge, "0")) h->sig_table = 0;
     const char* f8e = getenv("NRV_F8");
     if (f8e && !strcmp(f8e, "0")) h->f8_rnn2 = 0;
     const char* r128 = getenv("NRV_REC128");
@@ -951,7 +984,7 @@ void nrv_destroy(nrv_handle* h) {
                        &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_wq[0], &h->d_wq[1],
                        &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
                        &h->d_sfl[1], &h->d_a1[0], &h->d_a1[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_a4[0],
-                       &h->d_a4[1], &h->d_zin};
+                       &h->d_a4[1], &h->d_zin, &h->d_tile_base};
     for (Arena* a : arenas) a->release();
     for (nrv_handle::IoSlot& S : h->slot) {
         Arena* io[] = {&S.d_signal, &S.d_starts, &S.d_bases, &S.d_evm, &S.d_evs, &S.d_lastdur, &S.d_off, &S.d_qual_in,
@@ -1069,7 +1102,7 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
     float* probs[2] = {h->d_probs[0].as<float>(), h->d_probs[1].as<float>()};
     uint8_t* labels[2] = {nullptr, nullptr};
-    int rc = run_models(h, n, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels);
+    int rc = run_models(h, n, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels, nb);
     if (rc) return rc;
     if (p1) CU(h, cudaMemcpyAsync(p1, probs[0], (size_t)n * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
     if (p2) CU(h, cudaMemcpyAsync(p2, probs[1], (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, h->stream));

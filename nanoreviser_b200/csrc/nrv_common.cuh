@@ -61,6 +61,9 @@ struct LstmIo {
     __half* out_lo = nullptr;
     int out_ld = 0;
     int64_t out_nwp = 0;               // != 0: time-major padded rows, row(t, w) = t*out_nwp + w
+    // fused total_rnn1: CNN-feature columns of boundary-free window tiles come straight from the per-base table [sf_rows][64]
+    // (fp16 hi / lo); tile_base[tile] = table row of the tile's first window at t = 0, or -1 (then a2's columns [128, 192) are used)
+    const __half* sf_hi = nullptr; const __half* sf_lo = nullptr; int64_t sf_rows = 0; const int32_t* tile_base = nullptr;
     bool out_f8 = false;               // fused total_rnn1 feeding an F8 total_rnn2: out_hi = fp16(h) 2^12 and out_lo holds, per 4 units,
                                        // the 8 bytes {e4m3(h_lo 2^19) x 4, e4m3(h 2^8) x 4} (same bytes per row as the fp16 lo part)
 };

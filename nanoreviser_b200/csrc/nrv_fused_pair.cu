@@ -226,7 +226,11 @@ __global__ void __launch_bounds__(FP_THREADS, 1)
 lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
                        const __half* __restrict__ wr_lo, const float* __restrict__ bias,
                        const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int T, float acc_scale) {
+                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ld, int64_t nwp, int T, float acc_scale,
+                       // total_rnn1 only: tile_base != nullptr and tile_base[tile] >= 0 -> the last K-chunk (CNN features) of that window
+                       // tile is rows tile_base[tile] + t .. + 127 of the per-base feature table (tm_sf_hi / tm_sf_lo) instead of x
+                       const __grid_constant__ CUtensorMap tm_sf_hi, const __grid_constant__ CUtensorMap tm_sf_lo,
+                       const int32_t* __restrict__ tile_base) {
     static_assert(!F8 || UT == 64, "F8 is built for total_rnn2 (no exchange of 8-bit copies yet)");
     static_assert(!(F8 && OUT8), "an F8 layer's own output is the scaled fp16 pair");
     using Cfg = FpCfg<KIN, UT>;
@@ -276,6 +280,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         for (int i = 0; i < FP_EPI_WARPS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
         fence_mbar_init();
         tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo);
+        if (tile_base) { tma_prefetch_desc(&tm_sf_hi); tma_prefetch_desc(&tm_sf_lo); }
     }
     if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
     if (threadIdx.x < 256) {       // hard_sigmoid(z + b) = sat(0.2 z + (0.2 b + 0.5)): the gates i, f, o keep the folded constant
@@ -314,18 +319,24 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
             int stage = 0; uint32_t phase = 0;
             for (int64_t tp = cl0; tp < n_pairs; tp += cl_stride) {
                 const int64_t wtile = min(tp * 2 + (int64_t)r, ntw - 1);
+                const int tb = tile_base ? __ldg(tile_base + wtile) : -1;      // >= 0: CNN features of this tile from the per-base table
                 for (int s = 0; s < T; ++s) {
                     const int t = dir ? (T - 1 - s) : s;
                     const int grow = (int)(t * nwp + wtile * 128);
                     if (s + 1 < T) {                                       // next step's tiles -> L2 (the layer input comes from HBM: ring
                         const int gnext = grow + (dir ? -1 : 1) * (int)nwp;   // loads then see L2 latency, which 3-4 stages cover)
-                        for (int i = 0; i < KC; ++i) { tma_prefetch_2d(&tm_x_lo, i * XLO_W, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                        const int kx = tb >= 0 ? KC - 1 : KC;
+                        for (int i = 0; i < kx; ++i) { tma_prefetch_2d(&tm_x_lo, i * XLO_W, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                        if (tb >= 0) { tma_prefetch_2d(&tm_sf_lo, 0, tb + t + (dir ? -1 : 1)); tma_prefetch_2d(&tm_sf_hi, 0, tb + t + (dir ? -1 : 1)); }
                     }
                     for (int i = 0; i < 2 * KC; ++i) {                     // (K-chunk, part): lo tile (F8: the 8-bit copies) first, then hi
                         FP_WAIT(&empty[stage], phase ^ 1, 1, (uint32_t)s);
                         if (r == 0) mbar_arrive_expect_tx(&full[stage], 2 * FP_TILE);
-                        tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_x_hi : &tm_x_lo, &full[stage], leader,
-                                         (i >> 1) * ((i & 1) ? 64 : XLO_W), grow);
+                        if (tb >= 0 && (i >> 1) == KC - 1)
+                            tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_sf_hi : &tm_sf_lo, &full[stage], leader, 0, tb + t);
+                        else
+                            tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_x_hi : &tm_x_lo, &full[stage], leader,
+                                             (i >> 1) * ((i & 1) ? 64 : XLO_W), grow);
                         if (++stage == FP_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -621,6 +632,9 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     } else {
         if (!make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, KIN, 128)) return -2;
     }
+    CUtensorMap tsh = txh, tsl = txl;                 // per-base CNN-feature table (total_rnn1 only)
+    const bool sig_table = UT == 128 && io.tile_base && io.sf_hi && io.sf_lo && io.sf_rows > 0;
+    if (sig_table && (!make_tmap_f16_k64(&tsh, io.sf_hi, io.sf_rows, 64, 128) || !make_tmap_f16_k64(&tsl, io.sf_lo, io.sf_rows, 64, 128))) return -2;
     auto kern = lstm_fused_pair_kernel<KIN, UT, F8, OUT8>;
     static PerDevice per_dev;                     // co-resident clusters on the current device (per template instance)
     int& max_clusters = per_dev.cur();
@@ -654,7 +668,7 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     const __half* wr_hi = F8 ? (const __half*)L.f8_wr_hi : (const __half*)L.rt_hi;
     const __half* wr_lo = F8 ? reinterpret_cast<const __half*>(L.f8_wr8) : (const __half*)L.rt_lo;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wk_hi, wk_lo, wr_hi, wr_lo, (const float*)L.bias_tc, txh, txl, io.out_hi, io.out_lo,
-                                             io.out_ld, nwp, T, F8 ? L.f8_acc_scale : 1.0f);
+                                             io.out_ld, nwp, T, F8 ? L.f8_acc_scale : 1.0f, tsh, tsl, sig_table ? io.tile_base : (const int32_t*)nullptr);
     if (e != cudaSuccess) {
         fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: launch (grid %u x 2, cluster %d, %zu B smem): %s\n", KIN, UT, cfg.gridDim.x, CS,
                 (size_t)Cfg::SMEM, cudaGetErrorString(e));
