@@ -792,7 +792,7 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
     if (rc) return rc;
     // ---- K2: CNN per base, both models -------------------------------------------------------
     for (int mi = 0; mi < 2; ++mi) {
-        CU(h, h->d_sigfeat[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 4 + 16));
+        if (h->path == 0) CU(h, h->d_sigfeat[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 4 + 16));   // fp32 copy: SIMT path only
         CU(h, h->d_sfh[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 2 + 16));
         CU(h, h->d_sfl[mi].ensure((size_t)o.n_bases * NRV_SIGFEAT * 2 + 16));
     }
@@ -802,7 +802,8 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
         __half* sfl[2] = {h->d_sfl[0].as<__half>(), h->d_sfl[1].as<__half>()};
         h->launches += launch_cnn(&h->m[0], &h->m[1], d.signal, o.d_sig_off, d.starts, o.d_base_off,
                                   h->d_base_read.as<int32_t>(), h->d_shift.as<double>(), h->d_scale.as<double>(), nullptr,
-                                  o.n_bases, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), sfh, sfl, h->stream);
+                                  o.n_bases, h->path == 0 ? h->d_sigfeat[0].as<float>() : nullptr,
+                                  h->path == 0 ? h->d_sigfeat[1].as<float>() : nullptr, sfh, sfl, h->stream);
     }
     // ---- K3: window map + Bi-LSTM stack + heads --------------------------------------------------
     CU(h, h->d_win_base.ensure((size_t)o.n_win * 4 + 16));
@@ -1084,7 +1085,7 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     CU(h, h->d_x.ensure((size_t)nb * 6 * 4));
     CU(h, h->d_win_base.ensure((size_t)n * 4));
     for (int mi = 0; mi < 2; ++mi) {
-        CU(h, h->d_sigfeat[mi].ensure((size_t)nb * NRV_SIGFEAT * 4));
+        if (h->path == 0) CU(h, h->d_sigfeat[mi].ensure((size_t)nb * NRV_SIGFEAT * 4));
         CU(h, h->d_sfh[mi].ensure((size_t)nb * NRV_SIGFEAT * 2 + 16));
         CU(h, h->d_sfl[mi].ensure((size_t)nb * NRV_SIGFEAT * 2 + 16));
     }
@@ -1097,7 +1098,8 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     iota_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_win_base.as<int32_t>(), n, W);
     h->launches += 1;
     h->launches += launch_cnn(&h->m[0], &h->m[1], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                              h->d_sigwin.as<float>(), nb, h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>(), sfh, sfl,
+                              h->d_sigwin.as<float>(), nb, h->path == 0 ? h->d_sigfeat[0].as<float>() : nullptr,
+                              h->path == 0 ? h->d_sigfeat[1].as<float>() : nullptr, sfh, sfl,
                               h->stream);
     float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
     float* probs[2] = {h->d_probs[0].as<float>(), h->d_probs[1].as<float>()};

@@ -22,6 +22,10 @@ struct CnnSmem {
     __half fh[CNN_TB][FLAT_LDH];    // flatten(conv stack) as an fp16 (hi, lo) pair: A operand of the tensor-core dense
     __half fl[CNN_TB][FLAT_LDH];
     float w[264];
+    // per base of the tile (stage A): first sample of the window in the batch signal, samples available, left padding, shift, scale
+    long long g_lo[CNN_TB];
+    int g_len[CNN_TB], g_left[CNN_TB];
+    float g_shift[CNN_TB], g_scale[CNN_TB];
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t (&r)[4]) {
@@ -36,18 +40,19 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 
 __device__ __forceinline__ float clamp_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
+// One CTA = 32 bases, BOTH models: the window gather + normalisation (stage A) is shared, the conv stack and the dense run once per
+// model on the same windows (the reference evaluates the two networks on identical inputs).
 __global__ void __launch_bounds__(CNN_THREADS, 2)
-cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
+cnn_kernel(CnnDev W0, CnnDev W1, int n_models, const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
            const int32_t* __restrict__ starts, const int32_t* __restrict__ base_read,
            const double* __restrict__ shift, const double* __restrict__ scale,
-           const float* __restrict__ explicit_win, int64_t n_bases, float* __restrict__ sig_feat,
-           __half* __restrict__ sf_hi, __half* __restrict__ sf_lo) {
+           const float* __restrict__ explicit_win, int64_t n_bases, float* __restrict__ sig_feat0, float* __restrict__ sig_feat1,
+           __half* __restrict__ sf_hi0, __half* __restrict__ sf_lo0, __half* __restrict__ sf_hi1, __half* __restrict__ sf_lo1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CnnSmem& s = *reinterpret_cast<CnnSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const int64_t j0 = (int64_t)blockIdx.x * CNN_TB;
 
-    for (int i = tid; i < 264; i += CNN_THREADS) s.w[i] = W.blob[i];
     // zero halos of win and c1
     for (int i = tid; i < CNN_TB * 2; i += CNN_THREADS) {
         const int b = i >> 1, e = (i & 1) ? WIN_LD - 1 : 0;
@@ -56,30 +61,39 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
         for (int c = 0; c < NRV_CNN_CH; ++c) s.c1[b][e][c] = 0.f;
     }
     // ---- stage A: gather + normalise + symmetric zero pad ----------------------------------
+    // (x - shift) / scale: the reference divides in fp64 and the network casts to fp32.  x is an int16, shift a multiple of 0.5 and
+    // scale (the MAD, no 1.4826 factor) a multiple of 0.25, so numerator and denominator are exact in fp32 and ONE correctly rounded
+    // fp32 division gives the same bits: the quotient of two such numbers cannot come within 2^-43 (relative) of an fp32 rounding
+    // boundary without hitting it, so rounding the fp64 quotient (2^-53) to fp32 is the same as rounding the exact quotient.
+    if (!explicit_win && tid < CNN_TB) {
+        const int64_t j = j0 + tid;
+        long long lo = 0; int len = 0, left = 0; float sh = 0.f, sc = 1.f;
+        if (j < n_bases) {
+            const int r = base_read[j];
+            const long long o0 = sig_off[r], S = sig_off[r + 1] - o0;
+            const long long st = starts[j];
+            lo = (st - 25 <= 0) ? 0 : st - 25;
+            long long hi = (st + 25 >= S) ? S : st + 25;
+            if (hi < lo) hi = lo;
+            len = (int)(hi - lo);
+            left = (NRV_SIG - len + 1) / 2;
+            lo += o0;
+            sh = (float)shift[r]; sc = (float)scale[r];
+        }
+        s.g_lo[tid] = lo; s.g_len[tid] = len; s.g_left[tid] = left; s.g_shift[tid] = sh; s.g_scale[tid] = sc;
+    }
+    __syncthreads();
     for (int i = tid; i < CNN_TB * NRV_SIG; i += CNN_THREADS) {
         const int b = i / NRV_SIG, p = i - b * NRV_SIG;
-        const int64_t j = j0 + b;
         float v = 0.f;
-        if (j < n_bases) {
-            if (explicit_win) {
-                v = explicit_win[j * NRV_SIG + p];
-            } else {
-                const int r = base_read[j];
-                const int16_t* sig = signal + sig_off[r];
-                const long long S = sig_off[r + 1] - sig_off[r];
-                const long long st = starts[j];
-                const long long lo = (st - 25 <= 0) ? 0 : st - 25;
-                long long hi = (st + 25 >= S) ? S : st + 25;
-                if (hi < lo) hi = lo;
-                const int len = (int)(hi - lo);
-                const int left = (NRV_SIG - len + 1) / 2;
-                if (p >= left && p < left + len)
-                    v = (float)(((double)sig[lo + (p - left)] - shift[r]) / scale[r]);
-            }
+        if (explicit_win) {
+            if (j0 + b < n_bases) v = explicit_win[(j0 + b) * NRV_SIG + p];
+        } else {
+            const int q = p - s.g_left[b];
+            if (q >= 0 && q < s.g_len[b]) v = __fdiv_rn((float)signal[s.g_lo[b] + q] - s.g_shift[b], s.g_scale[b]);
         }
         s.win[b][p + 1] = v;
     }
-    __syncthreads();
     const float* w1 = s.w;            // [3][8]
     const float* b1 = s.w + 24;
     const float* s1 = s.w + 32;
@@ -88,6 +102,14 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
     const float* b2 = s.w + 240;
     const float* s2 = s.w + 248;
     const float* t2 = s.w + 256;
+    for (int mi = 0; mi < n_models; ++mi) {
+    const CnnDev& W = mi ? W1 : W0;
+    float* const sig_feat = mi ? sig_feat1 : sig_feat0;
+    __half* const sf_hi = mi ? sf_hi1 : sf_hi0;
+    __half* const sf_lo = mi ? sf_lo1 : sf_lo0;
+    __syncthreads();                  // windows written (mi = 0) / the previous model's dense has read its flatten tile
+    for (int i = tid; i < 264; i += CNN_THREADS) s.w[i] = W.blob[i];
+    __syncthreads();
     // ---- stage B: conv1 + relu + BN1 ---------------------------------------------------------
     for (int i = tid; i < CNN_TB * NRV_SIG; i += CNN_THREADS) {
         const int b = i / NRV_SIG, p = i - b * NRV_SIG;
@@ -189,7 +211,7 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
                 const int64_t j = j0 + mt * 16 + hh * 8 + (lane >> 2);
                 if (j < n_bases) {
                     const float y0 = acc[mt][hh * 2], y1 = acc[mt][hh * 2 + 1];
-                    *reinterpret_cast<float2*>(sig_feat + j * NRV_SIGFEAT + col) = make_float2(y0, y1);
+                    if (sig_feat) *reinterpret_cast<float2*>(sig_feat + j * NRV_SIGFEAT + col) = make_float2(y0, y1);
                     if (sf_hi) {   // fp16 (hi, lo) copy: A operand of the tensor-core projection of total_rnn1's per-base part
                         const float c0 = clamp_f16(y0), c1 = clamp_f16(y1);
                         const __half2 h = __floats2half2_rn(c0, c1);
@@ -200,30 +222,21 @@ cnn_kernel(CnnDev W, const int16_t* __restrict__ signal, const int64_t* __restri
                 }
             }
     }
+    }       // models
 }
 
 int launch_cnn(const ModelDev* m1, const ModelDev* m2, const int16_t* signal, const int64_t* sig_off,
                const int32_t* starts, const int64_t* /*base_off*/, const int32_t* base_read,
                const double* shift, const double* scale, const float* explicit_win, int64_t n_bases,
                float* sig_feat1, float* sig_feat2, __half* const sf_hi[2], __half* const sf_lo[2], cudaStream_t st) {
-    if (n_bases <= 0) return 0;
+    if (n_bases <= 0 || !m1) return 0;
     static PerDevice attr_set;
     if (attr_set.first()) cudaFuncSetAttribute(cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CnnSmem));
     const unsigned grid = (unsigned)((n_bases + CNN_TB - 1) / CNN_TB);
-    int n = 0;
-    if (m1 && sig_feat1) {
-        cnn_kernel<<<grid, CNN_THREADS, sizeof(CnnSmem), st>>>(m1->cnn, signal, sig_off, starts, base_read, shift,
-                                                                scale, explicit_win, n_bases, sig_feat1, sf_hi ? sf_hi[0] : nullptr,
-                                                                sf_lo ? sf_lo[0] : nullptr);
-        ++n;
-    }
-    if (m2 && sig_feat2) {
-        cnn_kernel<<<grid, CNN_THREADS, sizeof(CnnSmem), st>>>(m2->cnn, signal, sig_off, starts, base_read, shift,
-                                                                scale, explicit_win, n_bases, sig_feat2, sf_hi ? sf_hi[1] : nullptr,
-                                                                sf_lo ? sf_lo[1] : nullptr);
-        ++n;
-    }
-    return n;
+    cnn_kernel<<<grid, CNN_THREADS, sizeof(CnnSmem), st>>>(m1->cnn, m2 ? m2->cnn : m1->cnn, m2 ? 2 : 1, signal, sig_off, starts, base_read, shift, scale,
+                                                            explicit_win, n_bases, sig_feat1, sig_feat2, sf_hi ? sf_hi[0] : nullptr,
+                                                            sf_lo ? sf_lo[0] : nullptr, sf_hi ? sf_hi[1] : nullptr, sf_lo ? sf_lo[1] : nullptr);
+    return 1;
 }
 
 }  // namespace nrv
