@@ -168,7 +168,8 @@ def run_worker(args, file_list, device, logger=None):
         todo_python = list(slab)
         if native:
             paths = [os.path.join(args.fast5_base_dir, f) for f in slab]
-            batch, fstatus, read_file, _a0 = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads)
+            batch, fstatus, read_file, _a0, members = engine.ingest_fast5(paths, args.basecall_group, args.basecall_subgroup, nthreads,
+                                                                          with_names=True)
             todo_python = [f for f, st in zip(slab, fstatus) if st != engine.INGEST_OK]
             if fastq and batch.n_reads and batch.qual is None:
                 # the native reader attaches the basecaller's Phred scores when EVERY read of the slab has a Fastq dataset that
@@ -182,7 +183,8 @@ def run_worker(args, file_list, device, logger=None):
                 with ThreadPoolExecutor(max_workers=nthreads) as ex:
                     batch.qual = np.concatenate(list(ex.map(phred, range(batch.n_reads))))
             if batch.n_reads:
-                units.append((batch, [slab[int(i)] for i in read_file]))
+                # a read out of a multi-read container is named after its member (read_<id>), any other after its file (:137)
+                units.append((batch, [members[k] + '.fast5' if members[k] else slab[int(i)] for k, i in enumerate(read_file)]))
         if todo_python:
             with ThreadPoolExecutor(max_workers=nthreads) as ex:
                 loaded = list(ex.map(lambda f: _ingest(args, f), todo_python))

@@ -194,11 +194,15 @@ int nrv_debug_gemm(nrv_handle* h, int64_t M, int N, int K, const float* A, const
 
 /* ---- A1 at GPU rate: multi-threaded native fast5 ingest ----------------------------
  * Replaces get_read_data(fast5_fn, basecall_group, basecall_subgroup) (nanorev_fast5_handeler.py:39-150) for a LIST of
- * single-read fast5 files: own HDF5-subset reader + zlib inflate + event collapse (:84-118) on n_threads host threads
- * (0 = all cores), packing the reads that succeed straight into the CSR batch above (signal = raw[a0:], NanoReviser.py:120).
+ * fast5 files: own HDF5-subset reader, chunk decoding (deflate, or ONT's VBZ filter 32020 = zig-zag delta + streamvbyte +
+ * zstd, the plugin the reference bundles under nanorevutils/utils/lib) and the event collapse (:84-118) on n_threads host
+ * threads (0 = all cores), packing the reads that succeed straight into the CSR batch above (signal = raw[a0:],
+ * NanoReviser.py:120).  Legacy Albacore <= 0.0 tables (float64 `start` seconds rescaled with the raw read's start_time,
+ * :65-73) are decoded as the reference does.  A multi-read container (/read_<id>/{Raw/Signal, Analyses/...}; the reference
+ * itself only opens single-read files, :132-133) yields one read per member, see nrv_ingest_read_names.
  * Host-only (no CUDA call).  Per-file status mirrors the exceptions of the reference; NRV_INGEST_UNSUPPORTED marks inputs
- * outside the native subset (Albacore <= 0.0 event tables :65-72, float starts, non-deflate filters, multi-read files),
- * which the caller must route through the Python reader (nanoreviser_b200/fast5.py) -- nothing is guessed. */
+ * outside the native subset (other filters, float32 / integer legacy columns, big-endian types ...), which the caller must
+ * route through the Python reader (nanoreviser_b200/fast5.py) -- nothing is guessed. */
 #define NRV_INGEST_OK            0
 #define NRV_INGEST_OPEN_FAILED   1   /* "Error opening file. Likely a corrupted file." (:59-61) */
 #define NRV_INGEST_NO_EVENTS     2   /* "No events or corrupted events in file" (:76-77) */
@@ -219,6 +223,9 @@ int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* base
  * Fastq dataset that lines up, else NULL. */
 int nrv_ingest_view(const nrv_ingest* r, nrv_batch* batch, const int32_t** file_status, const int64_t** read_file,
                     const int64_t** a0);
+/* names[n_reads]: the member name (read_<id>) of every packed read that came from a multi-read container, "" for reads of
+ * single-read files (those are named after their file, NanoReviser.py:137).  Valid until nrv_ingest_free. */
+int nrv_ingest_read_names(const nrv_ingest* r, const char* const** names);
 void nrv_ingest_free(nrv_ingest* r);
 
 #ifdef __cplusplus

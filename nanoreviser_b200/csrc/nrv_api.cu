@@ -90,7 +90,7 @@ struct nrv_handle {
     cudaStream_t copy_stream = nullptr;
     Arena d_shift, d_scale, d_base_read,
         d_win_base, d_x, d_sigfeat[2], d_act[4], d_probs[2], d_y[2], d_counts, d_tiles, d_wq[2],
-        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin, d_tile_base;
+        d_segmean, d_segstd, d_sigwin, d_sfh[2], d_sfl[2], d_a1[2], d_a2[2], d_a3[2], d_a4[2], d_zin, d_tile_base, d_ghist;
     IoSlot& io() { return slot[cur]; }
     int in_flight() const { int n = 0; for (const IoSlot& s : slot) n += s.ticket != 0; return n; }
     int path = 1;           // 0: fp32 SIMT everywhere; 1: tcgen05 projections for total_rnn1/total_rnn2 (NRV_PATH)
@@ -98,6 +98,7 @@ struct nrv_handle {
     int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
     int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
     int f8_rnn2 = 1;        // total_rnn2's correction passes in e4m3 (kind::f8f6f4); NRV_F8=0 keeps them fp16
+    unsigned decode_epoch = 0;   // launch number of the single-pass decode (nrv_decode.cu), 1 .. 2^22 - 2
     int sig_table = 1;      // fused total_rnn1 reads the CNN features of boundary-free tiles straight from the per-base table; NRV_SIGTAB=0: gather all
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
@@ -651,34 +652,49 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
 struct Offsets {
     int64_t n_reads = 0, n_samples = 0, n_bases = 0, n_win = 0;
     const int64_t *d_sig_off = nullptr, *d_base_off = nullptr, *d_win_off = nullptr;
+    // read_stats: reads longer than one segment merge their histograms in global memory (slot = index among those reads, else -1)
+    const int32_t* d_hist_slot = nullptr;
+    int64_t n_multi = 0;
+    int max_segs = 1;
 };
 
-// host offsets -> pinned staging -> device; also derives the window CSR.
+// host offsets -> pinned staging -> device; also derives the window CSR and the histogram slots of read_stats.
 int stage_offsets(nrv_handle* h, int64_t R, const int64_t* sig_off, const int64_t* base_off, Offsets* o, cudaStream_t st) {
     const size_t n = (size_t)R + 1;
     nrv_handle::IoSlot& S = h->io();
     // the upload that last used this slot's pinned staging buffer must be done before it is overwritten: wait for THAT copy
     // (an event recorded right after it, NRV_SLOTS batches ago) -- not for the stream, which would drain the batch in flight
     CU(h, cudaEventSynchronize(S.ev_h2d));
-    CU(h, S.h_off.ensure(3 * n * sizeof(int64_t)));
-    CU(h, S.d_off.ensure(3 * n * sizeof(int64_t)));
+    const size_t bytes = 3 * n * sizeof(int64_t) + n * sizeof(int32_t);
+    CU(h, S.h_off.ensure(bytes));
+    CU(h, S.d_off.ensure(bytes));
     int64_t* hs = S.h_off.as<int64_t>();
     int64_t* hb = hs + n;
     int64_t* hw = hb + n;
+    int32_t* hslot = reinterpret_cast<int32_t*>(hw + n);
     for (size_t i = 0; i < n; ++i) { hs[i] = sig_off ? sig_off[i] : 0; hb[i] = base_off[i]; }
     hw[0] = 0;
+    const int64_t seg = read_stats_segment();
+    int64_t n_multi = 0, max_segs = 1;
     for (int64_t r = 0; r < R; ++r) {
         if (hb[r + 1] < hb[r] || hs[r + 1] < hs[r]) return fail(h, NRV_E_INVALID, "offsets must be non-decreasing");
         const int64_t N = hb[r + 1] - hb[r];
         hw[r + 1] = hw[r] + std::max<int64_t>(N - h->window, 0);
+        const int64_t nseg = (hs[r + 1] - hs[r] + seg - 1) / seg;
+        hslot[r] = nseg > 1 ? (int32_t)n_multi++ : -1;
+        max_segs = std::max(max_segs, nseg);
     }
+    hslot[R] = -1;
     if (hb[0] != 0 || hs[0] != 0) return fail(h, NRV_E_INVALID, "offsets must start at 0");
-    CU(h, cudaMemcpyAsync(S.d_off.p, hs, 3 * n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (max_segs > 65535) return fail(h, NRV_E_INVALID, "a read has more than 2^31 samples");
+    CU(h, cudaMemcpyAsync(S.d_off.p, hs, bytes, cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(S.ev_h2d, st));
     o->n_reads = R; o->n_samples = hs[R]; o->n_bases = hb[R]; o->n_win = hw[R];
     o->d_sig_off = S.d_off.as<int64_t>();
     o->d_base_off = o->d_sig_off + n;
     o->d_win_off = o->d_base_off + n;
+    o->d_hist_slot = reinterpret_cast<const int32_t*>(o->d_win_off + n);
+    o->n_multi = n_multi; o->max_segs = (int)max_segs;
     if (o->n_bases >= (int64_t)INT32_MAX || o->n_samples >= ((int64_t)1 << 40))
         return fail(h, NRV_E_INVALID, "batch too large (total bases must be < 2^31)");
     return NRV_OK;
@@ -726,7 +742,12 @@ int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x,
     if (want_x) CU(h, h->d_x.ensure((size_t)o.n_bases * 6 * 4 + 16));
     {
         StageTimer tm(h, ST_STATS);
+        // scratch histograms of the reads that span several segments: zero on (re)allocation, the kernel leaves them zeroed
+        const size_t before = h->d_ghist.cap;
+        CU(h, h->d_ghist.ensure(read_stats_hist_bytes(o.n_multi)));
+        if (h->d_ghist.cap != before) CU(h, cudaMemsetAsync(h->d_ghist.p, 0, h->d_ghist.cap, h->stream));
         h->launches += launch_read_stats(d.signal, o.d_sig_off, o.d_base_off, d.starts, d.last_dur, h->window, o.n_reads,
+                                         o.d_hist_slot, h->d_ghist.p, o.n_multi, o.max_segs,
                                          h->d_shift.as<double>(), h->d_scale.as<double>(), h->io().d_status.as<int32_t>(),
                                          h->stream);
         h->launches += launch_base_read_map(o.d_base_off, o.n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
@@ -741,6 +762,17 @@ int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x,
     CU(h, cudaGetLastError());
     return NRV_OK;
 }
+
+// K4 scratch: tile states + ticket counter of the single-pass decode (zeroed when (re)allocated and when the epoch wraps)
+int decode_scratch(nrv_handle* h, int64_t n_tiles, unsigned* epoch) {
+    const size_t before = h->d_tiles.cap;
+    CU(h, h->d_tiles.ensure((size_t)(n_tiles + 1) * 8 + 16));
+    h->decode_epoch = h->decode_epoch % 0x3ffffeu + 1;
+    if (h->d_tiles.cap != before || h->decode_epoch == 1) CU(h, cudaMemsetAsync(h->d_tiles.p, 0, h->d_tiles.cap, h->stream));
+    *epoch = h->decode_epoch;
+    return NRV_OK;
+}
+
 
 // Pick the slot for a new batch.  Sync entry points (nrv_segment, nrv_decode, nrv_predict_windows) need an idle handle.
 int begin_batch(nrv_handle* h, bool need_idle) {
@@ -829,9 +861,9 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
     rc = run_models(h, o.n_win, h->d_win_base.as<int32_t>(), h->d_x.as<float>(), sf, probs, labels, o.n_bases);
     if (rc) return rc;
     // ---- K4: decode --------------------------------------------------------------------------------
-    const int64_t n_tiles = decode_tile_count(o.n_bases);
-    CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
-    CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
+    unsigned dec_epoch = 0;
+    rc = decode_scratch(h, decode_tile_count(o.n_bases), &dec_epoch);
+    if (rc) return rc;
     CU(h, S.d_flag.ensure(16));
     CU(h, cudaMemsetAsync(S.d_flag.p, 0, 4, h->stream));
     uint8_t* d_rev; int64_t* d_outoff;
@@ -861,7 +893,7 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
             }
         }
         const int n = launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
-                                    S.d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, h->d_counts.as<int32_t>(),
+                                    S.d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, dec_epoch,
                                     h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, S.d_flag.as<int>(),
                                     h->stream, wq[0], wq[1], d_qual_in, d_revq);
         if (n < 0) return fail(h, NRV_E_INVALID, "decode: qualities requested without per-window scores");
@@ -985,7 +1017,7 @@ void nrv_destroy(nrv_handle* h) {
                        &h->d_probs[1], &h->d_y[0], &h->d_y[1], &h->d_counts, &h->d_tiles, &h->d_wq[0], &h->d_wq[1],
                        &h->d_segmean, &h->d_segstd, &h->d_sigwin, &h->d_sfh[0], &h->d_sfh[1], &h->d_sfl[0],
                        &h->d_sfl[1], &h->d_a1[0], &h->d_a1[1], &h->d_a2[0], &h->d_a2[1], &h->d_a3[0], &h->d_a3[1], &h->d_a4[0],
-                       &h->d_a4[1], &h->d_zin, &h->d_tile_base};
+                       &h->d_a4[1], &h->d_zin, &h->d_tile_base, &h->d_ghist};
     for (Arena* a : arenas) a->release();
     for (nrv_handle::IoSlot& S : h->slot) {
         Arena* io[] = {&S.d_signal, &S.d_starts, &S.d_bases, &S.d_evm, &S.d_evs, &S.d_lastdur, &S.d_off, &S.d_qual_in,
@@ -1133,9 +1165,11 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
     CU(h, h->d_y[1].ensure((size_t)o.n_win + 16));
     CU(h, S.d_status.ensure((size_t)n_reads * 4 + 16));
     CU(h, h->d_base_read.ensure((size_t)o.n_bases * 4 + 16));
-    const int64_t n_tiles = decode_tile_count(o.n_bases);
-    CU(h, h->d_counts.ensure((size_t)n_tiles * 4 + 16));
-    CU(h, h->d_tiles.ensure((size_t)n_tiles * 8 + 16));
+    unsigned dec_epoch = 0;
+    {
+        const int rc2 = decode_scratch(h, decode_tile_count(o.n_bases), &dec_epoch);
+        if (rc2) return rc2;
+    }
     CU(h, S.d_flag.ensure(16));
     CU(h, S.h_flag.ensure(16));
     CU(h, S.d_revised.ensure((size_t)revised_cap + 16));
@@ -1149,7 +1183,7 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
     h->launches += launch_base_read_map(o.d_base_off, n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
     h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), S.d_bases.as<uint8_t>(),
                                  h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), S.d_status.as<int32_t>(), n_reads,
-                                 o.n_bases, h->window, h->d_counts.as<int32_t>(), h->d_tiles.as<int64_t>(),
+                                 o.n_bases, h->window, dec_epoch, h->d_tiles.as<int64_t>(),
                                  S.d_revised.as<uint8_t>(), revised_cap, S.d_outoff.as<int64_t>(), S.d_flag.as<int>(),
                                  h->stream);
     CU(h, cudaMemcpyAsync(out_off, S.d_outoff.p, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -97,7 +97,10 @@ struct ModelDev {
 // nrv_segment.cu
 int launch_read_stats(const int16_t* signal, const int64_t* sig_off, const int64_t* base_off,
                       const int32_t* starts, const int32_t* last_dur, int window, int64_t n_reads,
+                      const int32_t* hist_slot, void* ghist, int64_t n_multi, int max_segs,
                       double* shift, double* scale, int32_t* status, cudaStream_t st);
+size_t read_stats_hist_bytes(int64_t n_multi);      // zeroed scratch for the reads that span several segments
+int read_stats_segment();                            // samples per CTA
 int launch_base_features(const int16_t* signal, const int64_t* sig_off, const int32_t* starts,
                          const int64_t* base_off, const uint8_t* bases, const float* ev_mean,
                          const float* ev_std, const int32_t* last_dur, const int32_t* base_read,
@@ -153,7 +156,7 @@ int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int
 // nrv_decode.cu
 int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,
                   const uint8_t* bases, const uint8_t* y1, const uint8_t* y2, const int32_t* status,
-                  int64_t n_reads, int64_t n_bases, int window, int32_t* counts_tmp, int64_t* tile_tmp,
+                  int64_t n_reads, int64_t n_bases, int window, unsigned epoch, int64_t* tile_tmp,
                   uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st,
                   const uint8_t* q1 = nullptr, const uint8_t* q2 = nullptr, const uint8_t* qual_in = nullptr,
                   uint8_t* revised_qual = nullptr);

@@ -9,17 +9,22 @@
 // HDF5 subset: superblock v0, object header v1 (+ continuation blocks), symbol-table groups
 // (B-tree v1 / SNOD / local heap), dataspace v1/v2, datatypes int / float / fixed string / compound v1 / vlen string
 // (global heap, for the `version` attribute), layout v3 contiguous + rank-1 chunked (B-tree v1 type 1) with the deflate
-// filter (zlib), attribute v1.  Anything outside the subset -- legacy event tables (Albacore <= 0.0, :65-72), float
-// `start` columns, other filters (VBZ), multi-read files -- is NOT guessed at: the file gets status
-// NRV_INGEST_UNSUPPORTED and the caller routes it through the Python reader (nanoreviser_b200/fast5.py), which follows
-// the reference branch by branch.  Errors the reference raises map to the other status codes.
+// filter (zlib) or ONT's VBZ filter (id 32020: zig-zag delta + streamvbyte + zstd; libzstd.so.1 is loaded at run time),
+// attribute v1.  Legacy event tables (Albacore <= 0.0, :65-72: float64 `start` in seconds, rescaled with the raw read's
+// `start_time`) are decoded like the reference does; multi-read containers (/read_<id>/{Raw/Signal, Analyses/...}, which the
+// reference itself cannot open) yield one read per member.  Anything else outside the subset is NOT guessed at: the file gets
+// status NRV_INGEST_UNSUPPORTED and the caller routes it through the Python reader (nanoreviser_b200/fast5.py), which
+// follows the reference branch by branch.  Errors the reference raises map to the other status codes.
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <dlfcn.h>
+#include <math.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -238,6 +243,72 @@ bool version_le_zero(const std::string& v) {
     return !std::lexicographical_compare(zero.begin(), zero.end(), parts.begin(), parts.end());
 }
 
+// ---- VBZ (HDF5 filter 32020, nanoporetech/vbz_compression; the reference bundles the plugin binary under nanorevutils/utils/lib).
+// chunk = u32 decompressed byte count, then -- inside a zstd frame unless cd_values[3] == 0 -- streamvbyte: ceil(n / 4) control
+// bytes (2 bits per value, low bits first: byte count - 1), then the values' little-endian bytes; with cd_values[2] the values are
+// zig-zag coded deltas.  cd_values = {version, integer size, zig-zag flag, zstd level}; versions 0 and 1 do not differ for 2-byte
+// integers.  Pinned against outputs of the plugin binary itself (tests/golden/make_variant_fixtures.py, tests/test_ingest_variants.py).
+struct Zstd {
+    unsigned long long (*frame_size)(const void*, size_t) = nullptr;
+    size_t (*decompress)(void*, size_t, const void*, size_t) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+};
+const Zstd& zstd_lib() {
+    static Zstd z;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return;
+        z.frame_size = reinterpret_cast<unsigned long long (*)(const void*, size_t)>(dlsym(h, "ZSTD_getFrameContentSize"));
+        z.decompress = reinterpret_cast<size_t (*)(void*, size_t, const void*, size_t)>(dlsym(h, "ZSTD_decompress"));
+        z.is_error = reinterpret_cast<unsigned (*)(size_t)>(dlsym(h, "ZSTD_isError"));
+        z.ok = z.frame_size && z.decompress && z.is_error;
+    });
+    return z;
+}
+
+struct Filter { int id = 0; uint32_t ncd = 0; uint32_t cd[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+
+// one VBZ chunk of int16 samples -> dst (at most max_samples); returns the number of samples produced
+size_t vbz_decode_i16(const uint8_t* src, size_t n, const Filter& f, int16_t* dst, size_t max_samples, std::vector<uint8_t>& tmp) {
+    if (f.ncd < 3 || f.cd[1] != 2) throw Fail{NRV_INGEST_UNSUPPORTED};      // 2-byte integers only (fast5 signals)
+    const bool zigzag = f.cd[2] != 0;
+    const uint32_t zlevel = f.ncd > 3 ? f.cd[3] : 1;
+    if (n < 4) throw Fail{NRV_INGEST_CORRUPT};
+    uint32_t out_bytes;
+    memcpy(&out_bytes, src, 4);
+    const size_t count = out_bytes / 2;
+    const uint8_t* body = src + 4;
+    size_t blen = n - 4;
+    if (zlevel) {
+        const Zstd& z = zstd_lib();
+        if (!z.ok) throw Fail{NRV_INGEST_UNSUPPORTED};                        // no libzstd on this host: the Python reader reports it
+        const unsigned long long fs = z.frame_size(body, blen);
+        if (fs > (5ull * count + 16)) throw Fail{NRV_INGEST_CORRUPT};         // also catches ZSTD_CONTENTSIZE_UNKNOWN / _ERROR
+        tmp.resize((size_t)fs + 8);
+        const size_t r = z.decompress(tmp.data(), (size_t)fs, body, blen);
+        if (z.is_error(r) || r != fs) throw Fail{NRV_INGEST_CORRUPT};
+        body = tmp.data(); blen = (size_t)fs;
+    }
+    const size_t nctl = (count + 3) / 4;
+    if (blen < nctl) throw Fail{NRV_INGEST_CORRUPT};
+    const uint8_t* data = body + nctl;
+    size_t avail = blen - nctl, pos = 0;
+    uint32_t prev = 0;
+    const size_t n_out = std::min(count, max_samples);
+    for (size_t i = 0; i < n_out; ++i) {
+        const int len = ((body[i >> 2] >> ((i & 3) * 2)) & 3) + 1;
+        if (pos + (size_t)len > avail) throw Fail{NRV_INGEST_CORRUPT};
+        uint32_t v = 0;
+        for (int k = 0; k < len; ++k) v |= (uint32_t)data[pos + k] << (8 * k);
+        pos += (size_t)len;
+        if (zigzag) { prev += (v >> 1) ^ (0u - (v & 1)); v = prev; }
+        dst[i] = (int16_t)(uint16_t)v;
+    }
+    return n_out;
+}
+
 struct ReadOut {
     int status = NRV_INGEST_OPEN_FAILED;
     int64_t a0 = 0;
@@ -247,6 +318,7 @@ struct ReadOut {
     std::vector<float> ev_mean, ev_std;
     std::vector<int16_t> signal;       // raw[a0:]
     std::vector<uint8_t> qual;         // basecaller Phred scores of the bases (empty when the Fastq dataset is absent / does not line up)
+    std::string name;                  // multi-read containers: the member's name (read_<id>); empty for single-read files
 };
 
 double load_real(const uint8_t* p, const Member& m) {
@@ -265,32 +337,60 @@ int64_t load_int(const uint8_t* p, const Member& m) {
     throw Fail{NRV_INGEST_UNSUPPORTED};
 }
 
-void read_one(const char* path, const std::string& group, const std::string& subgroup, ReadOut& out, std::vector<uint8_t>& filebuf,
-              std::vector<uint8_t>& scratch) {
+// integer attribute `name` of the object at `addr` (attribute v1); false if absent
+bool int_attr(const H5& h, uint64_t addr, const char* name, int64_t* out) {
+    for (const Msg& m : h.object_header(addr)) {
+        if (m.type != 0x000C) continue;
+        if (h.b.u8(m.off) != 1) throw Fail{NRV_INGEST_UNSUPPORTED};
+        const uint16_t nsz = h.b.u16(m.off + 2), dtsz = h.b.u16(m.off + 4), dssz = h.b.u16(m.off + 6);
+        uint64_t p = m.off + 8;
+        h.b.need(p, nsz);
+        const std::string nm((const char*)h.b.p + p, strnlen((const char*)h.b.p + p, nsz));
+        p += pad8(nsz);
+        if (nm != name) continue;
+        const Dtype dt = parse_dtype(h.b, p, nullptr);
+        p += pad8(dtsz) + pad8(dssz);
+        if (dt.cls != 0) throw Fail{NRV_INGEST_UNSUPPORTED};
+        Member mm; mm.cls = 0; mm.size = dt.size; mm.is_signed = dt.is_signed;
+        h.b.need(p, dt.size);
+        *out = load_int(h.b.p + p, mm);
+        return true;
+    }
+    return false;
+}
+
+// One read.  `top` = the object that holds Analyses/ (the file's root group, or a read_<id> member of a multi-read container);
+// `multi`: the signal is top/Raw/Signal and the raw attributes sit on top/Raw, instead of /Raw/Reads/<first>/Signal (:132-133).
+void parse_read(const H5& h, uint64_t top, bool multi, const std::string& group, const std::string& subgroup, ReadOut& out,
+                std::vector<uint8_t>& scratch) {
     out = ReadOut();
-    // ---- whole file into memory (single-read fast5: 0.1 - 1 MB) ----
-    FILE* fp = fopen(path, "rb");
-    if (!fp) { out.status = NRV_INGEST_OPEN_FAILED; return; }
-    fseek(fp, 0, SEEK_END);
-    const long fsz = ftell(fp);
-    fseek(fp, 0, SEEK_SET);
-    if (fsz < 96) { fclose(fp); out.status = NRV_INGEST_OPEN_FAILED; return; }
-    filebuf.resize((size_t)fsz);
-    const size_t got = fread(filebuf.data(), 1, (size_t)fsz, fp);
-    fclose(fp);
-    if (got != (size_t)fsz) { out.status = NRV_INGEST_OPEN_FAILED; return; }
-    H5 h;
-    h.b.p = filebuf.data(); h.b.n = filebuf.size();
-    static const uint8_t SIG[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
-    if (memcmp(h.b.p, SIG, 8)) { out.status = NRV_INGEST_OPEN_FAILED; return; }           // "Error opening file" (:59-61)
     try {
-        if (h.b.u8(8) != 0 || h.b.u8(13) != 8 || h.b.u8(14) != 8) throw Fail{NRV_INGEST_UNSUPPORTED};
-        const uint64_t root = h.b.u64(64);
+        const uint64_t root = top;
+        // ---- raw read (:130-135): first child of /Raw/Reads; located first because a legacy table needs its start_time ----
+        uint64_t raddr = UNDEF, saddr = UNDEF, rattr = UNDEF;
+        int raw_fail = 0;
+        try {
+            if (multi) {
+                if (!h.resolve(root, "Raw", &rattr) || !h.child(rattr, "Signal", &saddr)) throw Fail{NRV_INGEST_NO_SIGNAL};
+            } else {
+                std::vector<std::pair<std::string, uint64_t>> reads;
+                if (!h.resolve(root, "/Raw/Reads", &raddr)) throw Fail{NRV_INGEST_NO_SIGNAL};
+                h.group_members(h.object_header(raddr), reads);
+                if (reads.empty()) throw Fail{NRV_INGEST_NO_SIGNAL};
+                if (reads.size() > 1) std::sort(reads.begin(), reads.end());               // h5py iterates members by name
+                rattr = reads[0].second;
+                if (!h.child(rattr, "Signal", &saddr)) throw Fail{NRV_INGEST_NO_SIGNAL};
+            }
+        } catch (Fail f) {
+            raw_fail = f.code == NRV_INGEST_UNSUPPORTED ? NRV_INGEST_UNSUPPORTED : NRV_INGEST_NO_SIGNAL;   // reported after the event stage, as the reference does
+        }
         // ---- events (:63-77) ----
         uint64_t gaddr, eaddr;
         int stage = NRV_INGEST_NO_EVENTS;
+        bool legacy = false;
+        int64_t start_time = 0;
         try {
-            if (!h.resolve(root, "/Analyses/" + group, &gaddr)) throw Fail{NRV_INGEST_NO_EVENTS};
+            if (!h.resolve(root, "Analyses/" + group, &gaddr)) throw Fail{NRV_INGEST_NO_EVENTS};
             std::string version = "0.0";
             for (const Msg& m : h.object_header(gaddr)) {
                 if (m.type != 0x000C) continue;
@@ -307,7 +407,11 @@ void read_one(const char* path, const std::string& group, const std::string& sub
                 else if (dt.cls == 3) { h.b.need(p, dt.size); version.assign((const char*)h.b.p + p, strnlen((const char*)h.b.p + p, dt.size)); }
                 else throw Fail{NRV_INGEST_UNSUPPORTED};
             }
-            if (version_le_zero(version)) throw Fail{NRV_INGEST_UNSUPPORTED};             // legacy rescaling branch (:69-72)
+            if (version_le_zero(version)) {                                                // legacy rescaling branch (:65-73)
+                legacy = true;
+                // raw_attrs = attrs of the first raw read; a missing read or start_time is the reference's "No events" error (:76-78)
+                if (rattr == UNDEF || !int_attr(h, rattr, "start_time", &start_time)) throw Fail{NRV_INGEST_NO_EVENTS};
+            }
             if (!h.resolve(gaddr, subgroup + "/Events", &eaddr)) throw Fail{NRV_INGEST_NO_EVENTS};
         } catch (Fail f) {
             throw Fail{f.code == NRV_INGEST_UNSUPPORTED ? NRV_INGEST_UNSUPPORTED : stage};
@@ -334,7 +438,11 @@ void read_one(const char* path, const std::string& group, const std::string& sub
             else if (kv.first == "move") m_move = kv.second;
         }
         if (!m_mean.present || !m_start.present || !m_stdv.present || !m_state.present || !m_move.present) throw Fail{NRV_INGEST_NO_EVENTS};
-        if (m_start.cls != 0) throw Fail{NRV_INGEST_UNSUPPORTED};                          // float starts: legacy tables
+        // legacy tables hold `start` in seconds as float64: start * 4000 - start_time, written back into the float64 column and
+        // truncated by int() (:71,:93).  Any other combination (integer starts in a legacy file, float32 / float starts in a
+        // current one) goes to the Python reader, which has numpy's casting rules
+        const bool fstart = m_start.cls == 1 && m_start.size == 8;
+        if (legacy ? !fstart : m_start.cls != 0) throw Fail{NRV_INGEST_UNSUPPORTED};
         if (m_state.cls != 3 || m_state.size < 3) throw Fail{NRV_INGEST_UNSUPPORTED};
         // every member the collapse reads must lie inside one record (a corrupt compound type must not send the loops below
         // past the file buffer)
@@ -358,7 +466,14 @@ void read_one(const char* path, const std::string& group, const std::string& sub
             const uint8_t* r = ev + i * itemsize;
             const int64_t mv = load_int(r + m_move.offset, m_move);
             if (mv == 0) continue;
-            const int64_t st = load_int(r + m_start.offset, m_start);
+            int64_t st;
+            if (legacy) {
+                const double sv = load_real(r + m_start.offset, m_start) * 4000.0 - (double)start_time;
+                if (!(fabs(sv) < 9.0e15)) throw Fail{NRV_INGEST_CORRUPT};
+                st = (int64_t)sv;                                                              // int(): truncation toward zero
+            } else {
+                st = load_int(r + m_start.offset, m_start);
+            }
             const float mean = (float)load_real(r + m_mean.offset, m_mean), sd = (float)load_real(r + m_stdv.offset, m_stdv);
             const uint8_t* ms = r + m_state.offset;
             if (mv == 2) {
@@ -369,23 +484,13 @@ void read_one(const char* path, const std::string& group, const std::string& sub
             }
         }
         const int last_dur = (start[nb - 1] - start[nb - 2] < 5) ? 3 : 5;                  // :121-126
-        // ---- raw signal (:130-135): first child of /Raw/Reads ----
-        uint64_t raddr, saddr;
-        std::vector<std::pair<std::string, uint64_t>> reads;
-        try {
-            if (!h.resolve(root, "/Raw/Reads", &raddr)) throw Fail{NRV_INGEST_NO_SIGNAL};
-            h.group_members(h.object_header(raddr), reads);
-            if (reads.empty()) throw Fail{NRV_INGEST_NO_SIGNAL};
-            if (reads.size() > 1) std::sort(reads.begin(), reads.end());                   // h5py iterates members by name
-            if (!h.child(reads[0].second, "Signal", &saddr)) throw Fail{NRV_INGEST_NO_SIGNAL};
-        } catch (Fail f) {
-            throw Fail{f.code == NRV_INGEST_UNSUPPORTED ? NRV_INGEST_UNSUPPORTED : NRV_INGEST_NO_SIGNAL};
-        }
+        // ---- raw signal (:130-135) ----
+        if (raw_fail) throw Fail{raw_fail};
         std::vector<uint64_t> sdims;
         Dtype sdt;
         int layout_cls = -1;
         uint64_t lay_off = 0;
-        std::vector<int> filters;
+        std::vector<Filter> filters;
         for (const Msg& m : h.object_header(saddr)) {
             if (m.type == 0x0001) parse_dataspace(h.b, m.off, sdims);
             else if (m.type == 0x0003) sdt = parse_dtype(h.b, m.off, nullptr);
@@ -396,8 +501,10 @@ void read_one(const char* path, const std::string& group, const std::string& sub
                 uint64_t p = m.off + 8;
                 for (int i = 0; i < nf; ++i) {
                     const uint16_t fid = h.b.u16(p), name_len = h.b.u16(p + 2), ncd = h.b.u16(p + 6);
+                    Filter f; f.id = fid; f.ncd = std::min<uint32_t>(ncd, 8);
+                    for (uint32_t c = 0; c < f.ncd; ++c) f.cd[c] = h.b.u32(p + 8 + pad8(name_len) + 4ull * c);
                     p += 8 + pad8(name_len) + 4ull * ncd + ((ncd & 1) ? 4 : 0);
-                    filters.push_back(fid);
+                    filters.push_back(f);
                 }
             }
         }
@@ -419,7 +526,7 @@ void read_one(const char* path, const std::string& group, const std::string& sub
             const uint32_t cdim = h.b.u32(lay_off + 11), esize = h.b.u32(lay_off + 15);
             if (esize != 2) throw Fail{NRV_INGEST_UNSUPPORTED};
             if (cdim == 0 || cdim > (1u << 28)) throw Fail{NRV_INGEST_CORRUPT};
-            for (int f : filters) if (f != 1) throw Fail{NRV_INGEST_UNSUPPORTED};         // deflate only (no VBZ 32020)
+            for (const Filter& f : filters) if (f.id != 1 && f.id != 32020) throw Fail{NRV_INGEST_UNSUPPORTED};   // deflate or VBZ
             if (filters.size() > 1) throw Fail{NRV_INGEST_UNSUPPORTED};
             if (btree != UNDEF) {
                 // chunk B-tree v1 (node type 1): keys {u32 size, u32 filter mask, ndims x u64 offsets}, children = chunk addresses
@@ -443,7 +550,9 @@ void read_one(const char* path, const std::string& group, const std::string& sub
                         if (off0 >= S) continue;
                         h.b.need(childaddr, csize);
                         const uint64_t room = (S - off0) * 2;
-                        if (!filters.empty() && !(fmask & 1)) {
+                        if (!filters.empty() && !(fmask & 1) && filters[0].id == 32020) {
+                            vbz_decode_i16(h.b.p + childaddr, csize, filters[0], sig.data() + off0, (size_t)(S - off0), scratch);
+                        } else if (!filters.empty() && !(fmask & 1)) {
                             // the chunk may be larger than the dataset and the inflated payload shorter than the chunk
                             scratch.resize((size_t)cdim * 2);
                             z_stream zs;
@@ -524,6 +633,63 @@ void read_one(const char* path, const std::string& group, const std::string& sub
     }
 }
 
+// One file: a single-read fast5 (one ReadOut) or a multi-read container (one ReadOut per read_<id> member, in name order).
+// file status: the read's status for a single-read file; for a container NRV_INGEST_OK if at least one member decoded, else the
+// first member's failure.
+void read_file(const char* path, const std::string& group, const std::string& subgroup, std::vector<ReadOut>& outs, int* file_status,
+               std::vector<uint8_t>& filebuf, std::vector<uint8_t>& scratch) {
+    outs.clear();
+    *file_status = NRV_INGEST_OPEN_FAILED;
+    // ---- whole file into memory (single-read fast5: 0.1 - 1 MB) ----
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return;
+    fseek(fp, 0, SEEK_END);
+    const long fsz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (fsz < 96) { fclose(fp); return; }
+    filebuf.resize((size_t)fsz);
+    const size_t got = fread(filebuf.data(), 1, (size_t)fsz, fp);
+    fclose(fp);
+    if (got != (size_t)fsz) return;
+    H5 h;
+    h.b.p = filebuf.data(); h.b.n = filebuf.size();
+    static const uint8_t SIG[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (memcmp(h.b.p, SIG, 8)) return;                                                      // "Error opening file" (:59-61)
+    std::vector<std::pair<std::string, uint64_t>> top;
+    uint64_t root = 0;
+    try {
+        if (h.b.u8(8) != 0 || h.b.u8(13) != 8 || h.b.u8(14) != 8) throw Fail{NRV_INGEST_UNSUPPORTED};
+        root = h.b.u64(64);
+        h.group_members(h.object_header(root), top);
+    } catch (Fail f) {
+        *file_status = f.code;
+        return;
+    } catch (...) {
+        *file_status = NRV_INGEST_CORRUPT;
+        return;
+    }
+    bool has_raw = false, has_read = false;
+    for (auto& kv : top) { has_raw |= kv.first == "Raw" || kv.first == "Analyses"; has_read |= kv.first.compare(0, 5, "read_") == 0; }
+    if (has_raw || !has_read) {
+        outs.resize(1);
+        parse_read(h, root, false, group, subgroup, outs[0], scratch);
+        *file_status = outs[0].status;
+        if (outs[0].status != NRV_INGEST_OK) outs.clear();
+        return;
+    }
+    std::sort(top.begin(), top.end());
+    int first_fail = NRV_INGEST_NO_EVENTS;
+    bool any_fail = false;
+    for (auto& kv : top) {
+        if (kv.first.compare(0, 5, "read_") != 0) continue;
+        ReadOut r;
+        parse_read(h, kv.second, true, group, subgroup, r, scratch);
+        if (r.status == NRV_INGEST_OK) { r.name = kv.first; outs.push_back(std::move(r)); }
+        else if (!any_fail) { any_fail = true; first_fail = r.status; }
+    }
+    *file_status = outs.empty() ? first_fail : NRV_INGEST_OK;
+}
+
 }  // namespace
 
 struct nrv_ingest {
@@ -536,6 +702,8 @@ struct nrv_ingest {
     std::vector<uint8_t> bases;
     std::vector<float> ev_mean, ev_std;
     std::vector<uint8_t> qual;             // [n_bases] basecaller Phred scores, or empty when any packed read has none
+    std::vector<std::string> names;        // [n_reads] member name inside a multi-read container, "" for a single-read file
+    std::vector<const char*> name_ptrs;
 };
 
 extern "C" {
@@ -544,7 +712,8 @@ int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* grou
                      nrv_ingest** out) {
     if (!out || n_files < 0 || (n_files > 0 && !paths)) return NRV_E_INVALID;
     const std::string g = group ? group : "Basecall_1D_000", sg = subgroup ? subgroup : "BaseCalled_template";
-    std::vector<ReadOut> per((size_t)n_files);
+    std::vector<std::vector<ReadOut>> per((size_t)n_files);
+    std::vector<int> fstat((size_t)n_files, NRV_INGEST_OPEN_FAILED);
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n_files));
     std::atomic<int64_t> next{0};
@@ -553,7 +722,7 @@ int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* grou
         for (;;) {
             const int64_t i = next.fetch_add(1);
             if (i >= n_files) break;
-            read_one(paths[i], g, sg, per[(size_t)i], filebuf, scratch);
+            read_file(paths[i], g, sg, per[(size_t)i], &fstat[(size_t)i], filebuf, scratch);
         }
     };
     std::vector<std::thread> pool;
@@ -565,33 +734,44 @@ int nrv_ingest_fast5(const char* const* paths, int64_t n_files, const char* grou
     r->file_status.resize((size_t)n_files);
     r->sig_off.push_back(0); r->base_off.push_back(0);
     int64_t ns = 0, nb = 0, nr = 0;
+    bool all_qual = true;
     for (int64_t i = 0; i < n_files; ++i) {
-        r->file_status[(size_t)i] = per[(size_t)i].status;
-        if (per[(size_t)i].status == NRV_INGEST_OK) { ns += (int64_t)per[(size_t)i].signal.size(); nb += (int64_t)per[(size_t)i].starts.size(); ++nr; }
+        r->file_status[(size_t)i] = fstat[(size_t)i];
+        for (const ReadOut& p : per[(size_t)i]) {
+            ns += (int64_t)p.signal.size(); nb += (int64_t)p.starts.size(); ++nr;
+            if (p.qual.size() != p.starts.size()) all_qual = false;
+        }
     }
+    all_qual = all_qual && nr > 0;
     r->signal.resize((size_t)ns); r->starts.resize((size_t)nb); r->bases.resize((size_t)nb);
     r->ev_mean.resize((size_t)nb); r->ev_std.resize((size_t)nb);
-    r->last_dur.reserve((size_t)nr); r->a0.reserve((size_t)nr); r->read_file.reserve((size_t)nr);
-    bool all_qual = nr > 0;
-    for (int64_t i = 0; i < n_files; ++i)
-        if (per[(size_t)i].status == NRV_INGEST_OK && per[(size_t)i].qual.size() != per[(size_t)i].starts.size()) all_qual = false;
+    r->last_dur.reserve((size_t)nr); r->a0.reserve((size_t)nr); r->read_file.reserve((size_t)nr); r->names.reserve((size_t)nr);
     if (all_qual) r->qual.resize((size_t)nb);
     int64_t so = 0, bo = 0;
     for (int64_t i = 0; i < n_files; ++i) {
-        ReadOut& p = per[(size_t)i];
-        if (p.status != NRV_INGEST_OK) continue;
-        if (all_qual) memcpy(r->qual.data() + bo, p.qual.data(), p.qual.size());
-        memcpy(r->signal.data() + so, p.signal.data(), p.signal.size() * 2);
-        memcpy(r->starts.data() + bo, p.starts.data(), p.starts.size() * 4);
-        memcpy(r->bases.data() + bo, p.bases.data(), p.bases.size());
-        memcpy(r->ev_mean.data() + bo, p.ev_mean.data(), p.ev_mean.size() * 4);
-        memcpy(r->ev_std.data() + bo, p.ev_std.data(), p.ev_std.size() * 4);
-        so += (int64_t)p.signal.size(); bo += (int64_t)p.starts.size();
-        r->sig_off.push_back(so); r->base_off.push_back(bo);
-        r->last_dur.push_back(p.last_dur); r->a0.push_back(p.a0); r->read_file.push_back(i);
-        ReadOut().signal.swap(p.signal);           // release per-file copies as we go
+        for (ReadOut& p : per[(size_t)i]) {
+            if (all_qual) memcpy(r->qual.data() + bo, p.qual.data(), p.qual.size());
+            memcpy(r->signal.data() + so, p.signal.data(), p.signal.size() * 2);
+            memcpy(r->starts.data() + bo, p.starts.data(), p.starts.size() * 4);
+            memcpy(r->bases.data() + bo, p.bases.data(), p.bases.size());
+            memcpy(r->ev_mean.data() + bo, p.ev_mean.data(), p.ev_mean.size() * 4);
+            memcpy(r->ev_std.data() + bo, p.ev_std.data(), p.ev_std.size() * 4);
+            so += (int64_t)p.signal.size(); bo += (int64_t)p.starts.size();
+            r->sig_off.push_back(so); r->base_off.push_back(bo);
+            r->last_dur.push_back(p.last_dur); r->a0.push_back(p.a0); r->read_file.push_back(i);
+            r->names.push_back(p.name);
+            ReadOut().signal.swap(p.signal);           // release per-file copies as we go
+        }
     }
+    r->name_ptrs.resize(r->names.size());
+    for (size_t i = 0; i < r->names.size(); ++i) r->name_ptrs[i] = r->names[i].c_str();
     *out = r;
+    return NRV_OK;
+}
+
+int nrv_ingest_read_names(const nrv_ingest* r, const char* const** names) {
+    if (!r || !names) return NRV_E_INVALID;
+    *names = r->name_ptrs.data();
     return NRV_OK;
 }
 

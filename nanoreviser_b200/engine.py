@@ -59,7 +59,7 @@ EXPORTS = ("nrv_create", "nrv_destroy", "nrv_last_error", "nrv_version", "nrv_la
            "nrv_stage_count", "nrv_stage_name", "nrv_set_stage_timing", "nrv_get_stage_ms", "nrv_get_stage_launches", "nrv_stream", "nrv_synchronize", "nrv_segment",
            "nrv_predict_windows", "nrv_decode", "nrv_revise_batch", "nrv_revise_batch_device", "nrv_submit_batch",
            "nrv_wait_batch", "nrv_debug_gemm",
-           "nrv_ingest_fast5", "nrv_ingest_view", "nrv_ingest_free")
+           "nrv_ingest_fast5", "nrv_ingest_view", "nrv_ingest_read_names", "nrv_ingest_free")
 
 _lib = None
 
@@ -119,6 +119,8 @@ def load_library(path: Optional[str] = None):
     lib.nrv_ingest_fast5.restype = C.c_int
     lib.nrv_ingest_view.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.nrv_ingest_view.restype = C.c_int
+    lib.nrv_ingest_read_names.argtypes = [vp, C.POINTER(C.POINTER(C.c_char_p))]
+    lib.nrv_ingest_read_names.restype = C.c_int
     lib.nrv_ingest_free.argtypes = [vp]
     lib.nrv_ingest_free.restype = None
     if path is None:
@@ -131,11 +133,13 @@ INGEST_OK, INGEST_OPEN_FAILED, INGEST_NO_EVENTS, INGEST_TOO_SHORT, INGEST_NO_SIG
 
 
 def ingest_fast5(paths: Sequence[str], basecall_group: str = "Basecall_1D_000", basecall_subgroup: str = "BaseCalled_template",
-                 threads: int = 0):
-    """Native multi-threaded ``get_read_data`` over a list of single-read fast5 files (include/nrv.h: nrv_ingest_fast5).
+                 threads: int = 0, with_names: bool = False):
+    """Native multi-threaded ``get_read_data`` over a list of fast5 files (include/nrv.h: nrv_ingest_fast5): single-read files
+    (deflate or VBZ signal, current or legacy event tables) and multi-read containers (one read per member).
 
-    -> ``(batch, file_status int32[n_files], read_file int64[n_reads], a0 int64[n_reads])``: ``batch`` holds the reads whose
-    status is 0, in file order; the arrays are copies owned by numpy.  Host-only: works without a GPU."""
+    -> ``(batch, file_status int32[n_files], read_file int64[n_reads], a0 int64[n_reads])``: ``batch`` holds the reads that
+    decoded, in file order; the arrays are copies owned by numpy.  ``with_names=True`` appends ``names``: the member name of
+    every read that came out of a multi-read container, ``""`` for single-read files.  Host-only: works without a GPU."""
     lib = load_library()
     n = len(paths)
     arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
@@ -161,7 +165,13 @@ def ingest_fast5(paths: Sequence[str], basecall_group: str = "Basecall_1D_000", 
         batch = Batch(view(cb.signal, ns, np.int16), sig_off, view(cb.starts, nb, np.int32), base_off,
                       view(cb.bases, nb, np.uint8), view(cb.ev_mean, nb, np.float32), view(cb.ev_std, nb, np.float32),
                       view(cb.last_dur, R, np.int32), view(cb.qual, nb, np.uint8) if cb.qual else None)
-        return batch, view(fs.value, n, np.int32), view(rf.value, R, np.int64), view(a0.value, R, np.int64)
+        out = (batch, view(fs.value, n, np.int32), view(rf.value, R, np.int64), view(a0.value, R, np.int64))
+        if with_names:
+            np_ = C.POINTER(C.c_char_p)()
+            if lib.nrv_ingest_read_names(h, C.byref(np_)) != 0:
+                raise NrvError("nrv_ingest_read_names failed")
+            out = out + ([np_[i].decode() for i in range(R)],)
+        return out
     finally:
         lib.nrv_ingest_free(h)
 

@@ -83,19 +83,32 @@ def collapse_events(ev_start, ev_mean, ev_stdv, ev_state, ev_move):
     return start, bases, np.asarray(ev_mean)[src].astype(np.float32), np.asarray(ev_stdv)[src].astype(np.float32)
 
 
+def list_members(fast5_fn):
+    """Members of a multi-read container (root groups named read_<id>), in name order; [] for a single-read file."""
+    with h5mini.File(fast5_fn, "r") as f:
+        keys = f.keys()
+    if "Raw" in keys or "Analyses" in keys:
+        return []
+    return sorted(k for k in keys if k.startswith("read_"))
+
+
 def read_fast5_arrays(fast5_fn, basecall_group="Basecall_1D_000",
-                      basecall_subgroup="BaseCalled_template") -> ReadArrays:
+                      basecall_subgroup="BaseCalled_template", member=None) -> ReadArrays:
+    """``member``: a read_<id> group of a multi-read container (an extension: the reference opens single-read files only,
+    fast5_handeler.py:132-133); its layout is <member>/Analyses/... and <member>/Raw/Signal."""
     try:
         f = h5mini.File(fast5_fn, "r")
     except Exception:
         raise NotImplementedError("Error opening file. Likely a corrupted file.")
+    top = "/" + member if member else ""
     try:
-        grp = f["/Analyses/" + basecall_group]
+        grp = f[top + "/Analyses/" + basecall_group]
         ver = grp.attrs["version"] if "version" in grp.attrs else "0.0"
-        called = f["/Analyses/" + basecall_group + "/" + basecall_subgroup + "/Events"][()]
+        called = f[top + "/Analyses/" + basecall_group + "/" + basecall_subgroup + "/Events"][()]
         ev_start = called["start"]
         if _version_le_zero(ver):
-            raw_attrs = dict(list(f["/Raw/Reads/"].values())[0].attrs.items())
+            raw = f[top + "/Raw"] if member else list(f["/Raw/Reads/"].values())[0]
+            raw_attrs = dict(raw.attrs.items())
             ev_start = (ev_start * 4000 - raw_attrs["start_time"]).astype(ev_start.dtype)
     except Exception:
         f.close()
@@ -109,8 +122,11 @@ def read_fast5_arrays(fast5_fn, basecall_group="Basecall_1D_000",
     length[:-1] = np.diff(start)
     length[-1] = 3.0 if start[-1] - start[-2] < 5 else 5.0
     try:
-        read_name = list(f["/Raw/Reads/"].items())[0][0]
-        signal = f["/Raw/Reads/" + str(read_name) + "/Signal"][()]
+        if member:
+            signal = f[top + "/Raw/Signal"][()]
+        else:
+            read_name = list(f["/Raw/Reads/"].items())[0][0]
+            signal = f["/Raw/Reads/" + str(read_name) + "/Signal"][()]
     except Exception:
         f.close()
         raise RuntimeError("No signal stored in the file")
@@ -119,7 +135,7 @@ def read_fast5_arrays(fast5_fn, basecall_group="Basecall_1D_000",
         raise RuntimeError("Signal is shorter than the Events")
     a0 = int(start[0])
     import os
-    return ReadArrays(name=os.path.basename(str(fast5_fn)), a0=a0, starts=start - a0, length=length,
+    return ReadArrays(name=member if member else os.path.basename(str(fast5_fn)), a0=a0, starts=start - a0, length=length,
                       bases=bases, signal=np.ascontiguousarray(signal, dtype=np.int16),
                       ev_mean=ab_mean, ev_std=ab_std)
 

@@ -4,7 +4,8 @@ Covers exactly the subset that Keras-2.2.4 ``save_weights`` files and Albacore
 single-read ``.fast5`` files use: superblock v0, object
 header v1 (+ continuation blocks), symbol-table groups (B-tree v1 / SNOD / local
 heap), dataspace v1, datatypes fixed/float/string/compound-v1/vlen-string,
-layout v3 contiguous + chunked (B-tree v1 node type 1) with the deflate filter,
+layout v3 contiguous + chunked (B-tree v1 node type 1) with the deflate filter or
+ONT's VBZ filter (id 32020: zig-zag delta + streamvbyte + zstd, see vbz_decompress),
 attribute v1, global heap (vlen string attributes).
 
 This replaces the ``h5py.File`` calls of the reference at
@@ -26,6 +27,77 @@ _UNDEF = 0xFFFFFFFFFFFFFFFF
 
 class H5Error(RuntimeError):
     pass
+
+
+# ---- VBZ (HDF5 filter 32020, nanoporetech/vbz_compression; the reference bundles its plugin binary as
+# nanorevutils/utils/lib/libvbz_hdf_plugin.so*).  Chunk = u32 decompressed byte count, then -- inside a zstd frame unless
+# cd_values[3] == 0 -- streamvbyte: ceil(n / 4) control bytes (2 bits per value, low bits first: bytes - 1), then the values'
+# little-endian bytes.  cd_values = [version, integer size, zig-zag delta flag, zstd level].  The format was pinned by running the
+# plugin binary on chosen inputs (tests/golden/make_variant_fixtures.py); versions 0 and 1 are identical for 2- and 4-byte
+# integers (version 1 only changes 1-byte data, which fast5 signals are not).
+_zstd = None
+
+
+def _zstd_decompress(frame: bytes) -> bytes:
+    global _zstd
+    import ctypes
+    if _zstd is None:
+        try:
+            lib = ctypes.CDLL("libzstd.so.1")
+        except OSError as e:
+            raise H5Error("VBZ-compressed dataset: libzstd.so.1 is not available (%s)" % e)
+        lib.ZSTD_getFrameContentSize.restype = ctypes.c_ulonglong
+        lib.ZSTD_getFrameContentSize.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        lib.ZSTD_decompress.restype = ctypes.c_size_t
+        lib.ZSTD_decompress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+        lib.ZSTD_isError.restype = ctypes.c_uint
+        lib.ZSTD_isError.argtypes = [ctypes.c_size_t]
+        _zstd = lib
+    n = _zstd.ZSTD_getFrameContentSize(frame, len(frame))
+    if n >= 0xFFFFFFFFFFFFFFFE or n > (1 << 31):
+        raise H5Error("VBZ: bad zstd frame")
+    out = ctypes.create_string_buffer(max(int(n), 1))
+    r = _zstd.ZSTD_decompress(out, int(n), frame, len(frame))
+    if _zstd.ZSTD_isError(r) or r != n:
+        raise H5Error("VBZ: zstd decompression failed")
+    return out.raw[:int(n)]
+
+
+def streamvbyte_decode(body: bytes, count: int) -> np.ndarray:
+    """count uint32 values from a streamvbyte stream (vectorised: lengths from the control bytes, then one gather per byte lane)"""
+    nctl = (count + 3) // 4
+    if len(body) < nctl:
+        raise H5Error("VBZ: truncated control bytes")
+    ctl = np.frombuffer(body, dtype=np.uint8, count=nctl)
+    codes = ((ctl[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(-1)[:count].astype(np.int64)
+    off = np.zeros(count + 1, dtype=np.int64)
+    np.cumsum(codes + 1, out=off[1:])
+    data = np.frombuffer(body, dtype=np.uint8, offset=nctl)
+    if off[-1] > len(data):
+        raise H5Error("VBZ: truncated data bytes")
+    data = np.concatenate([data, np.zeros(4, np.uint8)])
+    vals = np.zeros(count, dtype=np.uint32)
+    for k in range(4):
+        vals |= np.where(codes >= k, data[off[:-1] + k].astype(np.uint32) << np.uint32(8 * k), np.uint32(0))
+    return vals
+
+
+def vbz_decompress(payload: bytes, cd) -> bytes:
+    if len(cd) < 3 or len(payload) < 4:
+        raise H5Error("VBZ: bad filter parameters")
+    isz, zigzag = int(cd[1]), int(cd[2])
+    zlevel = int(cd[3]) if len(cd) > 3 else 1
+    if isz not in (2, 4):
+        raise H5Error("VBZ: integer size %d unsupported" % isz)
+    n_bytes = struct.unpack_from("<I", payload, 0)[0]
+    body = payload[4:]
+    if zlevel:
+        body = _zstd_decompress(body)
+    vals = streamvbyte_decode(body, n_bytes // isz)
+    if zigzag:
+        d = (vals >> np.uint32(1)) ^ (np.uint32(0) - (vals & np.uint32(1)))
+        vals = np.cumsum(d, dtype=np.uint32)
+    return vals.astype("<u%d" % isz).tobytes()
 
 
 def _pad8(n: int) -> int:
@@ -152,8 +224,9 @@ class Dataset(_Object):
         for _ in range(n):
             fid, name_len, _flags, ncd = struct.unpack_from("<HHHH", data, p)
             p += 8 + _pad8(name_len)
+            cd = struct.unpack_from("<%dI" % ncd, data, p)
             p += 4 * ncd + (4 if ncd % 2 else 0)
-            out.append(fid)
+            out.append((fid, cd))
         return out
 
     def __len__(self):
@@ -205,13 +278,15 @@ class Dataset(_Object):
             return bytes(out)
         for (csize, fmask, offs, caddr) in self._f._iter_chunks(btree, ndims):
             payload = self._f._buf[caddr:caddr + csize]
-            for i, fid in enumerate(reversed(self._filters)):
+            for i, (fid, cd) in enumerate(reversed(self._filters)):
                 if fmask & (1 << (len(self._filters) - 1 - i)):
                     continue
                 if fid == 1:
                     payload = zlib.decompress(payload)
+                elif fid == 32020:
+                    payload = vbz_decompress(payload, cd)
                 else:
-                    raise H5Error("HDF5 filter id %d unsupported (only deflate)" % fid)
+                    raise H5Error("HDF5 filter id %d unsupported (deflate and VBZ only)" % fid)
             start = offs[0] * esize
             # chunk may be larger than the dataset and the payload shorter than the chunk
             n = min(len(payload), nbytes - start)

@@ -250,3 +250,23 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
         assert int(got[cname + ".sizeof"]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_fp32_division_reproduces_the_fp64_quotient_cast_to_fp32():
+    """K2's window normalisation (nrv_cnn.cu stage A) divides (x - shift) by scale ONCE in fp32, where the reference divides in
+    fp64 (preprocessing.py:119) and Keras casts to fp32.  x is an int16, shift = np.median a multiple of 0.5, scale = the MAD a
+    multiple of 0.25: both operands are exact in fp32 and the quotient of two such numbers never comes within the fp64 rounding
+    error of an fp32 rounding boundary, so both routes give the same bits.  Checked on 20 M random operand pairs plus the
+    exhaustive numerator range for a few denominators."""
+    rng = np.random.default_rng(7)
+    n = 20_000_000
+    num = (rng.integers(-2 * 65535, 2 * 65535 + 1, n) / 2.0)                 # x - shift: half-integers in [-65535, 65535]
+    den = (rng.integers(1, 4 * 65535 + 1, n) / 4.0)                          # MAD: quarter-integers in (0, 65535]
+    ref = (num / den).astype(np.float32)                                      # fp64 quotient, one cast
+    got = num.astype(np.float32) / den.astype(np.float32)                     # one fp32 division of exact operands
+    assert num.astype(np.float32).astype(np.float64).tobytes() == num.tobytes()
+    assert den.astype(np.float32).astype(np.float64).tobytes() == den.tobytes()
+    assert got.dtype == np.float32 and np.array_equal(ref, got)
+    allnum = np.arange(-2 * 65535, 2 * 65535 + 1) / 2.0
+    for d in (0.25, 0.75, 3.0, 7.25, 13.5, 77.75, 12345.25, 65535.75):
+        assert np.array_equal((allnum / d).astype(np.float32), allnum.astype(np.float32) / np.float32(d))

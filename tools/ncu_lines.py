@@ -29,7 +29,18 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
             line_of[int(m.group(1), 16)] = cur
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+# a report with several kernels is a sequence of blocks ("Kernel Name", name / header / lines): take the block whose demangled name
+# contains NCU_KERNEL (default: the first block)
+blocks, cur_b = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_b = [r]
+        blocks.append(cur_b)
+    elif cur_b is not None:
+        cur_b.append(r)
+want = os.environ.get("NCU_KERNEL", "")
+blk = next((b for b in blocks if want in b[0][1]), blocks[0])
+hdr, data = blk[1], [r for r in blk[2:] if r]
 ia, isamp, isrc = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Source")
 stalls = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not" not in h]
 base = min(int(r[ia], 16) for r in data)
