@@ -318,6 +318,12 @@ __device__ __forceinline__ float base_colour(uint8_t b) {   // preprocessing.py:
 
 constexpr int LONG_SEG = 128;
 
+// (double)x for a 32-bit integer without the conversion instruction (I2F.F64 runs on the quarter-rate XU pipe and was 51 % of this
+// kernel's time, one per sample): 2^52 + 2^31 + x is exactly representable, its bits are 0x43300000 : (x ^ 0x80000000)
+__device__ __forceinline__ double int_to_double(int x) {
+    return __hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 __global__ void __launch_bounds__(256)
 base_features_kernel(const int16_t* __restrict__ signal, const int64_t* __restrict__ sig_off,
                      const int32_t* __restrict__ starts, const int64_t* __restrict__ base_off,
@@ -351,7 +357,7 @@ base_features_kernel(const int16_t* __restrict__ signal, const int64_t* __restri
         for (long long i = st; i < en; ++i) s += sig[i];
         mean = (double)s / (double)n;                    // np.mean: exact integer sum / n
         double q = 0.0;
-        for (long long i = st; i < en; ++i) { double d = (double)sig[i] - mean; q += d * d; }
+        for (long long i = st; i < en; ++i) { double d = int_to_double(sig[i]) - mean; q += d * d; }
         var = q / (double)n;                             // np.std: sqrt(mean(|x - mean|^2)), ddof = 0
     }
     // stalled bases (hundreds to ~1e5 samples): the whole warp walks the segment together
@@ -368,7 +374,7 @@ base_features_kernel(const int16_t* __restrict__ signal, const int64_t* __restri
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const double m = (double)s / (double)(sen - sst);
         double q = 0.0;
-        for (long long i = sst + lane; i < sen; i += 32) { double d = (double)ssig[i] - m; q += d * d; }
+        for (long long i = sst + lane; i < sen; i += 32) { double d = int_to_double(ssig[i]) - m; q += d * d; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         if (lane == src) { mean = m; var = q / (double)(sen - sst); }
