@@ -440,8 +440,9 @@ def main():
             if fused2:
                 macs.pop("proj3")
                 macs["rec3"] = 1_802_240
+                f8 = os.environ.get("NRV_F8", "1") != "0" and fused1
                 names["rec3"] = ("lstm_fused_pair_kernel<256,64> (total_rnn2 projection+recurrence fused, tcgen05 cta_group::2, "
-                                 "h in TMEM, 3-pass split-fp16)")
+                                 "h in TMEM, " + ("1 fp16 + 1 e4m3 (kind::f8f6f4) MMA per K-step)" if f8 else "3-pass split-fp16)"))
         else:
             macs = {"lstm0": 30_976, "rec1": 540_672, "rec2": 3_604_480, "rec3": 1_802_240, "heads": 228_544}
             names = {k: "lstm_layer_kernel (fp32 SIMT, fused projection+recurrence)" for k in macs}
@@ -502,7 +503,7 @@ def main():
                     "all_model_kernels": kernels}
         # K1 (segmentation) and K4 (decode) are the HBM-bound kernels of SURVEY.md section 8(d)
         hbm_kernels = {}
-        for k, nbytes in (("read_stats", 2 * n_samp * 2),                       # median pass + MAD pass over int16
+        for k, nbytes in (("read_stats", n_samp * 2),                           # ONE pass over the int16 samples (median and MAD from the histogram)
                           ("base_features", 2 * n_samp + n_bases * (4 + 1 + 8 + 24)),   # samples, starts, base, ev_mean/std, 6 features
                           ("decode", n_bases * (2 + 1 + 2) + 8 * n_reads_rank)):
             t_ms = stage_ms.get(k, 0.0)
@@ -528,7 +529,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16x3/f32acc", "data": "synthetic",
-                "dtype_note": "tensor-core products are three fp16 passes (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo) with fp32 accumulation; "
+                "dtype_note": "tensor-core products are three fp16 passes (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo) with fp32 accumulation; in total_rnn2 "
+                              "the two correction passes run as one e4m3 product (kind::f8f6f4) on 8-bit copies with power-of-two scales; "
                               "segmentation statistics in fp64, indices / decode in integers",
                 "config": workload_config(cfg, species, world, per_rank, batch_budget,
                                           int(round(sum(len(j["L"]) for j in jobs) / JOBS)), n_win),
