@@ -16,9 +16,15 @@ constexpr int CNN_THREADS = 256;
 constexpr int WIN_LD = 52;          // 50 + zero halo on both sides ('same' padding)
 constexpr int FLAT_LDH = 408;       // halves per row of the flattened tile: 816 B rows -> conflict-free ldmatrix
 
+constexpr int C1_ROWS = CNN_TB * WIN_LD;      // conv1 output rows (base, padded position), 8 channels each
 struct CnnSmem {
     float win[CNN_TB][WIN_LD];
-    float c1[CNN_TB][WIN_LD][NRV_CNN_CH];
+    // conv1 output as an fp16 (hi, lo) pair, row R = b * 52 + padded position stored at [R + 1] (16 bytes per row; one zero row in
+    // front and behind, zero halo rows inside).  The im2col row of output (b, p) for the k = 3 convolution -- taps (p-1, p, p+1) x 8
+    // channels -- is then the 48 CONTIGUOUS bytes starting at stored row R: conv2 is a [1664 x 24] x [24 x 8] GEMM whose A operand
+    // ldmatrix reads straight from this array with overlapping rows (row stride 16 B).
+    __half c1h[C1_ROWS + 2][NRV_CNN_CH];
+    __half c1l[C1_ROWS + 2][NRV_CNN_CH];
     __half fh[CNN_TB][FLAT_LDH];    // flatten(conv stack) as an fp16 (hi, lo) pair: A operand of the tensor-core dense
     __half fl[CNN_TB][FLAT_LDH];
     float w[264];
@@ -38,7 +44,23 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
+__device__ __forceinline__ void ldmatrix_x2(uint32_t saddr, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+}
+// D(16x8, fp32) += A(16x8, fp16, row) . B(8x8, fp16, col)
+__device__ __forceinline__ void mma_1688(float (&d)[4], const uint32_t (&a)[2], uint32_t b) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(b));
+}
+
 __device__ __forceinline__ float clamp_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // One CTA = 32 bases, BOTH models: the window gather + normalisation (stage A) is shared, the conv stack and the dense run once per
 // model on the same windows (the reference evaluates the two networks on identical inputs).
@@ -53,12 +75,16 @@ cnn_kernel(CnnDev W0, CnnDev W1, int n_models, const int16_t* __restrict__ signa
     const int tid = threadIdx.x;
     const int64_t j0 = (int64_t)blockIdx.x * CNN_TB;
 
-    // zero halos of win and c1
+    // zero halos of win; zero rows of the conv1 array (pad rows, halo positions 0 and 51 of every base): never written afterwards
     for (int i = tid; i < CNN_TB * 2; i += CNN_THREADS) {
         const int b = i >> 1, e = (i & 1) ? WIN_LD - 1 : 0;
         s.win[b][e] = 0.f;
-#pragma unroll
-        for (int c = 0; c < NRV_CNN_CH; ++c) s.c1[b][e][c] = 0.f;
+        *reinterpret_cast<uint4*>(&s.c1h[1 + b * WIN_LD + e][0]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&s.c1l[1 + b * WIN_LD + e][0]) = make_uint4(0, 0, 0, 0);
+    }
+    if (tid < 2) {
+        *reinterpret_cast<uint4*>(&s.c1h[tid ? C1_ROWS + 1 : 0][0]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&s.c1l[tid ? C1_ROWS + 1 : 0][0]) = make_uint4(0, 0, 0, 0);
     }
     // ---- stage A: gather + normalise + symmetric zero pad ----------------------------------
     // (x - shift) / scale: the reference divides in fp64 and the network casts to fp32.  x is an int16, shift a multiple of 0.5 and
@@ -124,56 +150,60 @@ cnn_kernel(CnnDev W0, CnnDev W1, int n_models, const int16_t* __restrict__ signa
             a = fmaxf(a, 0.f);
             o[c] = fmaf(a, s1[c], t1[c]);
         }
-        *reinterpret_cast<float4*>(&s.c1[b][p + 1][0]) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(&s.c1[b][p + 1][4]) = make_float4(o[4], o[5], o[6], o[7]);
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int c = 0; c < NRV_CNN_CH; c += 2) split2(clamp_f16(o[c]), clamp_f16(o[c + 1]), ph[c >> 1], pl[c >> 1]);
+        *reinterpret_cast<uint4*>(&s.c1h[1 + b * WIN_LD + p + 1][0]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(&s.c1l[1 + b * WIN_LD + p + 1][0]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
     __syncthreads();
     // ---- stage C: conv2 + relu + BN2 + Add(input) -> flat[b][pos*8 + ch] as fp16 (hi, lo) ------
-    // Two positions per thread: every weight broadcast (LDS.128) feeds 8 FMAs and every input row is shared by the two
-    // outputs it touches (one position per thread was shared-memory-bound: 1 LDS per FMA).
-    for (int i = tid; i < CNN_TB * (NRV_SIG / 2); i += CNN_THREADS) {
-        const int b = i / (NRV_SIG / 2), p0 = (i - b * (NRV_SIG / 2)) * 2;
-        float in[4][NRV_CNN_CH];
+    // im2col GEMM on the tensor cores (mma.sync m16n8k16 for taps 0-1, m16n8k8 for tap 2; split-fp16 x 3, fp32 accumulate): 104 tiles
+    // of 16 rows over the 1664 (base, padded position) rows, 13 per warp; halo rows are computed and dropped.
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        // B fragments of this lane: B[k][n] = w2[k * 8 + n], k = tap * 8 + cin, n = cout = lane / 4
+        uint32_t bh[3], bl[3];
+        {
+            const int n = lane >> 2, k0 = (lane & 3) * 2;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float4 lo4 = *reinterpret_cast<const float4*>(&s.c1[b][p0 + r][0]);
-            const float4 hi4 = *reinterpret_cast<const float4*>(&s.c1[b][p0 + r][4]);
-            in[r][0] = lo4.x; in[r][1] = lo4.y; in[r][2] = lo4.z; in[r][3] = lo4.w;
-            in[r][4] = hi4.x; in[r][5] = hi4.y; in[r][6] = hi4.z; in[r][7] = hi4.w;
+            for (int j = 0; j < 3; ++j) split2(w2[(j * 8 + k0) * 8 + n], w2[(j * 8 + k0 + 1) * 8 + n], bh[j], bl[j]);
         }
-        float acc[2][NRV_CNN_CH];
+        const int co = (lane & 3) * 2;
+        const float bias0 = b2[co], bias1 = b2[co + 1], sc0 = s2[co], sc1 = s2[co + 1], sh0 = t2[co], sh1 = t2[co + 1];
+        const uint32_t c1h0 = (uint32_t)__cvta_generic_to_shared(&s.c1h[0][0]), c1l0 = (uint32_t)__cvta_generic_to_shared(&s.c1l[0][0]);
+        const uint32_t arow = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * 16;
+        const float* winflat = &s.win[0][0];
+        for (int tile = warp; tile < C1_ROWS / 16; tile += CNN_THREADS / 32) {
+            const int R0 = tile * 16;
+            const uint32_t a16 = (uint32_t)R0 * 16 + arow + (uint32_t)(lane >> 4) * 16, a8 = (uint32_t)R0 * 16 + arow + 32;
+            uint32_t ah[4], al[4], th[2], tl[2];
+            ldmatrix_x4(c1h0 + a16, ah);
+            ldmatrix_x4(c1l0 + a16, al);
+            ldmatrix_x2(c1h0 + a8, th);
+            ldmatrix_x2(c1l0 + a8, tl);
+            float acc[4] = {bias0, bias1, bias0, bias1};
+            mma_16816(acc, al, make_uint2(bh[0], bh[1]));
+            mma_16816(acc, ah, make_uint2(bl[0], bl[1]));
+            mma_16816(acc, ah, make_uint2(bh[0], bh[1]));
+            mma_1688(acc, tl, bh[2]);
+            mma_1688(acc, th, bl[2]);
+            mma_1688(acc, th, bh[2]);
 #pragma unroll
-        for (int c = 0; c < NRV_CNN_CH; ++c) acc[0][c] = acc[1][c] = b2[c];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-            for (int ci = 0; ci < NRV_CNN_CH; ++ci) {
-                const float4 wa = *reinterpret_cast<const float4*>(w2 + (k * 8 + ci) * 8);
-                const float4 wb = *reinterpret_cast<const float4*>(w2 + (k * 8 + ci) * 8 + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int co = 0; co < NRV_CNN_CH; ++co) {
-                    acc[0][co] = fmaf(in[k][ci], wv[co], acc[0][co]);
-                    acc[1][co] = fmaf(in[k + 1][ci], wv[co], acc[1][co]);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int R = R0 + (lane >> 2) + hh * 8;
+                const int bb = R / WIN_LD, pp = R - bb * WIN_LD;          // padded position 1..50 = position 0..49
+                if (pp >= 1 && pp <= NRV_SIG) {
+                    const float xin = winflat[R];
+                    // clamped to the fp16 range: an outlier spike on a quiet read (tiny MAD) must saturate, not become inf - inf = NaN
+                    const float y0 = clamp_f16(fmaf(fmaxf(acc[hh * 2], 0.f), sc0, sh0) + xin);
+                    const float y1 = clamp_f16(fmaf(fmaxf(acc[hh * 2 + 1], 0.f), sc1, sh1) + xin);
+                    uint32_t h2, l2;
+                    split2(y0, y1, h2, l2);
+                    *reinterpret_cast<uint32_t*>(&s.fh[bb][(pp - 1) * 8 + co]) = h2;
+                    *reinterpret_cast<uint32_t*>(&s.fl[bb][(pp - 1) * 8 + co]) = l2;
                 }
             }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float xin = s.win[b][p0 + j + 1];
-            uint32_t ph[4], pl[4];
-#pragma unroll
-            for (int c = 0; c < NRV_CNN_CH; c += 2) {
-                // clamped to the fp16 range: an outlier spike on a quiet read (tiny MAD) must saturate, not become inf - inf = NaN
-                const float y0 = clamp_f16(fmaf(fmaxf(acc[j][c], 0.f), s2[c], t2[c]) + xin);
-                const float y1 = clamp_f16(fmaf(fmaxf(acc[j][c + 1], 0.f), s2[c + 1], t2[c + 1]) + xin);
-                const __half2 h = __floats2half2_rn(y0, y1);
-                const float2 f = __half22float2(h);
-                const __half2 l = __floats2half2_rn(y0 - f.x, y1 - f.y);
-                ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&h); pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-            }
-            *reinterpret_cast<uint4*>(&s.fh[b][(p0 + j) * 8]) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<uint4*>(&s.fl[b][(p0 + j) * 8]) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
     }
     __syncthreads();

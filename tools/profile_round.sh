@@ -1,4 +1,5 @@
 #!/bin/bash
+# (gpurun copies back at most 64 MiB: the two big --set full reports are ~37 + 7 + 5 MB; the SASS summary is made locally by tools/sass_summary.py)
 # Round profile set (run on the GPU box): bench lines (ours, reference arm, cfg5), ncu launch list, ncu --set full of one launch of
 # every kernel of the path, CLI end to end, cfg4 batch sweep.  usage: profile_round.sh <tag>   (outputs: gpurun_out/<tag>_*)
 tag=${1:-r02}
@@ -19,5 +20,4 @@ python tools/bench_cli.py --files 10000 > $G/${tag}_cli.json 2> $G/${tag}_cli.er
 python tools/bench_cli.py --files 10000 --format fastq > $G/${tag}_cli_fastq.json 2> $G/${tag}_cli_fastq.err
 python tools/bench_cli.py --files 5 > $G/${tag}_cli_cfg1.json 2> $G/${tag}_cli_cfg1.err
 python tools/sweep_batch.py > $G/${tag}_batch_sweep.md 2> $G/${tag}_sweep.err
-cuobjdump -sass nanoreviser_b200/libnrv.so > $G/${tag}_sass.txt 2>/dev/null
 ls -la $G | grep ${tag}_
