@@ -176,26 +176,18 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
     out->cnn.blob = upload(h, blob, &e); if (e) goto cuda_fail;
     out->cnn.dense_k = upload(h, std::vector<float>(w->sig_dense_k, w->sig_dense_k + 400 * 64), &e); if (e) goto cuda_fail;
     out->cnn.dense_b = upload(h, std::vector<float>(w->sig_dense_b, w->sig_dense_b + 64), &e); if (e) goto cuda_fail;
-    {   // tensor-core (mma.sync) B fragments of the 400 -> 64 dense, split fp16 (hi, lo)
-        std::vector<uint2> fh(25 * 8 * 32), fl(25 * 8 * 32);
-        auto split = [&](int k, int n, uint16_t& hi, uint16_t& lo) {
-            const float wv = w->sig_dense_k[(size_t)k * 64 + n];
-            const __half a = __float2half_rn(wv);
-            const __half b = __float2half_rn(wv - __half2float(a));
-            hi = __half_as_ushort(a); lo = __half_as_ushort(b);
-        };
-        for (int kt = 0; kt < 25; ++kt)
-            for (int nt = 0; nt < 8; ++nt)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int n = nt * 8 + lane / 4, k0 = kt * 16 + (lane % 4) * 2;
-                    uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
-                    split(k0, n, h0, l0); split(k0 + 1, n, h1, l1); split(k0 + 8, n, h2, l2); split(k0 + 9, n, h3, l3);
-                    const size_t i = ((size_t)kt * 8 + nt) * 32 + lane;
-                    fh[i] = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-                    fl[i] = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
-                }
-        out->cnn.dfrag_hi = upload(h, fh, &e); if (e) goto cuda_fail;
-        out->cnn.dfrag_lo = upload(h, fl, &e); if (e) goto cuda_fail;
+    {   // Dense(400 -> 64) for the tcgen05 stage of nrv_cnn.cu: W^T [64 features][400] K-major, split fp16 (hi, lo); TMA streams it
+        // chunk by chunk (6 x 64 columns with the 128-byte swizzle, then 16 columns with the 32-byte swizzle)
+        std::vector<__half> th((size_t)64 * 400), tl(th.size());
+        for (int n = 0; n < 64; ++n)
+            for (int k = 0; k < 400; ++k) {
+                const float wv = w->sig_dense_k[(size_t)k * 64 + n];
+                const __half a = __float2half_rn(wv);
+                th[(size_t)n * 400 + k] = a;
+                tl[(size_t)n * 400 + k] = __float2half_rn(wv - __half2float(a));
+            }
+        out->cnn.dt_hi = upload(h, th, &e); if (e) goto cuda_fail;
+        out->cnn.dt_lo = upload(h, tl, &e); if (e) goto cuda_fail;
     }
     // ---- LSTM layers ----
     for (int l = 0; l < 4; ++l) {
@@ -832,10 +824,12 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
         StageTimer tm(h, ST_CNN);
         __half* sfh[2] = {h->d_sfh[0].as<__half>(), h->d_sfh[1].as<__half>()};
         __half* sfl[2] = {h->d_sfl[0].as<__half>(), h->d_sfl[1].as<__half>()};
-        h->launches += launch_cnn(&h->m[0], &h->m[1], d.signal, o.d_sig_off, d.starts, o.d_base_off,
+        const int nc = launch_cnn(&h->m[0], &h->m[1], d.signal, o.d_sig_off, d.starts, o.d_base_off,
                                   h->d_base_read.as<int32_t>(), h->d_shift.as<double>(), h->d_scale.as<double>(), nullptr,
                                   o.n_bases, h->path == 0 ? h->d_sigfeat[0].as<float>() : nullptr,
                                   h->path == 0 ? h->d_sigfeat[1].as<float>() : nullptr, sfh, sfl, h->stream);
+        if (nc < 0) return fail(h, NRV_E_CUDA, "CNN kernel could not be launched (tensor maps)");
+        h->launches += nc;
     }
     // ---- K3: window map + Bi-LSTM stack + heads --------------------------------------------------
     CU(h, h->d_win_base.ensure((size_t)o.n_win * 4 + 16));
@@ -1129,10 +1123,13 @@ int nrv_predict_windows(nrv_handle* h, int64_t n, const float* S, const float* X
     CU(h, cudaMemcpyAsync(h->d_x.p, X, (size_t)nb * 6 * 4, cudaMemcpyHostToDevice, h->stream));
     iota_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_win_base.as<int32_t>(), n, W);
     h->launches += 1;
-    h->launches += launch_cnn(&h->m[0], &h->m[1], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                              h->d_sigwin.as<float>(), nb, h->path == 0 ? h->d_sigfeat[0].as<float>() : nullptr,
-                              h->path == 0 ? h->d_sigfeat[1].as<float>() : nullptr, sfh, sfl,
-                              h->stream);
+    {
+        const int nc = launch_cnn(&h->m[0], &h->m[1], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  h->d_sigwin.as<float>(), nb, h->path == 0 ? h->d_sigfeat[0].as<float>() : nullptr,
+                                  h->path == 0 ? h->d_sigfeat[1].as<float>() : nullptr, sfh, sfl, h->stream);
+        if (nc < 0) return fail(h, NRV_E_CUDA, "CNN kernel could not be launched (tensor maps)");
+        h->launches += nc;
+    }
     float* sf[2] = {h->d_sigfeat[0].as<float>(), h->d_sigfeat[1].as<float>()};
     float* probs[2] = {h->d_probs[0].as<float>(), h->d_probs[1].as<float>()};
     uint8_t* labels[2] = {nullptr, nullptr};

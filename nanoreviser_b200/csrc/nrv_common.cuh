@@ -75,8 +75,8 @@ struct CnnDev {
     // [48..240) conv2_k[3][8][8]  [240..248) conv2_b  [248..256) bn2_scale  [256..264) bn2_shift
     float* dense_k;                    // [400][64]
     float* dense_b;                    // [64]
-    uint2* dfrag_hi;                   // Dense(400->64) kernel as mma.sync m16n8k16 B fragments, fp16 hi part:
-    uint2* dfrag_lo;                   //   [(kt*8 + nt)*32 + lane] = {W[k0+2c..+1][n], W[k0+8+2c..+1][n]}, n = nt*8 + lane/4, c = lane%4
+    __half* dt_hi;                     // Dense(400->64) kernel transposed, W^T [64][400] (K-major), fp16 hi / lo parts: the A operand of the
+    __half* dt_lo;                     // tcgen05 dense stage (TMA-streamed)
 };
 
 struct HeadsDev {
