@@ -123,6 +123,7 @@ def run_worker(args, file_list, device, logger=None):
                         per-read failure (NanoReviser.py:146-154)."""
     import queue
     import threading
+    t_worker0 = time.perf_counter()
     from nanoreviser_b200 import api, engine, fast5, weights, workqueue
     m1 = weights.load_model_weights(args.model1_predict_dir)
     m2 = weights.load_model_weights(args.model2_predict_dir)
@@ -226,18 +227,29 @@ def run_worker(args, file_list, device, logger=None):
     t_ingest.start()
     writers = ThreadPoolExecutor(max_workers=max(2, min(8, nthreads)))
     pending_writes = []
+    # where this thread's wall time goes (seconds): waiting for the ingest thread, for the GPU, for the writers
+    stats = {'t_worker_start': t_worker0, 'wait_ingest_s': 0.0, 'wait_gpu_s': 0.0, 'wait_writers_s': 0.0, 'batches': 0, 'bases': 0}
     with engine.Reviser(m1, m2, device=device) as rv:
+        stats['setup_s'] = time.perf_counter() - t_worker0        # weights, library, handle (CUDA context, weight re-packing)
         in_flight = []
 
         def drain_one():
             pend, names, sub = in_flight.pop(0)
+            t0 = time.perf_counter()
             out = rv.wait(pend)
+            t1 = time.perf_counter()
             pending_writes.append(writers.submit(write_batch, names, sub, out))
             while len(pending_writes) > 8:             # bound the memory held by finished batches
                 pending_writes.pop(0).result()
+            stats['wait_gpu_s'] += t1 - t0
+            stats['wait_writers_s'] += time.perf_counter() - t1
 
         while True:
+            t0 = time.perf_counter()
             units = q_in.get()
+            stats['wait_ingest_s'] += time.perf_counter() - t0
+            if 'first_slab_s' not in stats:
+                stats['first_slab_s'] = time.perf_counter() - t_worker0
             if units is None:
                 break
             if isinstance(units, BaseException):
@@ -250,13 +262,19 @@ def run_worker(args, file_list, device, logger=None):
                     if len(in_flight) == 2:
                         drain_one()
                     in_flight.append((rv.submit(sub, want_qual=fastq), [names[i] for i in idx], sub))
+                    stats['batches'] += 1
+                    stats['bases'] += int(sub.base_off[-1])
         while in_flight:
             drain_one()
+        stats['gpu_done_s'] = time.perf_counter() - t_worker0
+    t0 = time.perf_counter()
     for f in pending_writes:
         f.result()
     writers.shutdown(wait=True)
+    stats['wait_writers_s'] += time.perf_counter() - t0
     t_ingest.join()
-    return counts['ok'], counts['fallback'], counts['failed'], failed
+    stats['total_s'] = time.perf_counter() - t_worker0
+    return counts['ok'], counts['fallback'], counts['failed'], failed, stats
 
 
 def _worker_entry(payload):

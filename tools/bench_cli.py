@@ -58,13 +58,18 @@ def main():
     args = cli.get_args(argv)
     # warm-up run on one slab (CUDA context, module load, arenas) so that the steady number is not start-up
     t0 = time.perf_counter()
-    cli.main(args)
+    res = cli.main(args)
     wall = time.perf_counter() - t0
+    stats = [r[4] for r in res if len(r) > 4]
     n_out = len(os.listdir(dout))
     line = {"metric": "cli_e2e_revised_bases_per_sec", "files": a.files, "bases": total, "wall_s": wall,
             "value": total / wall, "unit": "bases/s", "devices": a.devices, "format": a.format, "outputs_written": n_out,
             "inputs": "copies" if a.copy else "hard links of the 5 unitest fast5", "host_cores": os.cpu_count(),
-            "note": "whole CLI run: weight load, handle creation, ingest, revise, write"}
+            "note": "whole CLI run: weight load, handle creation, ingest, revise, write",
+            # per worker: seconds of set-up (weights, CUDA context, handle), of waiting for the first ingest slab, and where the pipeline's
+            # main thread waited afterwards; steady = bases / (total - time to the first slab)
+            "workers": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items() if k != "t_worker_start"} for st in stats],
+            "steady_value": (sum(st["bases"] for st in stats) / max(max(st["total_s"] - st.get("first_slab_s", 0.0) for st in stats), 1e-9)) if stats else None}
     print(json.dumps(line), flush=True)
     shutil.rmtree(scratch, ignore_errors=True)
 
