@@ -279,7 +279,15 @@ def run_worker(args, file_list, device, logger=None):
 
 def _worker_entry(payload):
     args, files, device = payload
-    return run_worker(args, files, device, _test_logger() if args.test_mode else None)
+    # one process per GPU: expose only that GPU to the process before the CUDA driver initialises (cuInit enumerates every visible
+    # device; with 8 B200s and 8 processes starting at once that alone took ~10 s per worker), then address it as device 0
+    visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if visible:
+        ids = [v for v in visible.split(',') if v != '']
+        os.environ['CUDA_VISIBLE_DEVICES'] = ids[device] if device < len(ids) else str(device)
+    else:
+        os.environ['CUDA_VISIBLE_DEVICES'] = str(device)
+    return run_worker(args, files, 0, _test_logger() if args.test_mode else None)
 
 
 def main(ar_args):
