@@ -413,6 +413,33 @@ def test_cli_fasta_bytes_match_goldens(tmp_path, golden_dir, monkeypatch):
         assert (d <= 1).mean() >= 0.99 and (d == 0).mean() >= 0.95, (k, d.max(), (d == 0).mean())
 
 
+def test_cli_on_input_variants(tmp_path, golden_dir, monkeypatch):
+    """SURVEY.md section 8(f) ranks 1 and 3 end to end: the same read as a deflate, VBZ (filter 32020, three parameter sets) and legacy
+    Albacore <= 0.0 single-read fast5 and as a member of a multi-read container gives the same revised fasta through the CLI
+    (native ingest -> GPU -> writer), and that sequence is what the Python reader + api.revise_reads produce."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(root)
+    sys.path.insert(0, root)
+    import NanoReviser as cli
+    from nanoreviser_b200 import api, fast5
+    vdir = os.path.join(golden_dir, "fast5_variants")
+    out_dir = str(tmp_path) + "/"
+    res = cli.main(cli.get_args(["-d", vdir + "/", "-o", out_dir, "-F", "fasta", "-S", "ecoli", "--quiet"]))
+    assert sum(r[0] for r in res) == 7 and sum(r[1] for r in res) == 0          # vbz_chunks.npz is the one unreadable "fast5"
+    body = lambda fn: open(out_dir + fn).read().split("\n", 1)[1]
+    ref = body("plain_out.fasta")
+    for name in ("vbz_v0", "vbz_v1", "vbz_nozstd", "legacy"):
+        assert body(name + "_out.fasta") == ref, name
+    members = fast5.list_members(os.path.join(vdir, "multi.fast5"))
+    assert len(members) == 2 and body(members[0] + "_out.fasta") == ref
+    with api.init("ecoli") as rv:
+        r0 = fast5.read_fast5_arrays(os.path.join(vdir, "plain.fast5"))
+        r1 = fast5.read_fast5_arrays(os.path.join(vdir, "multi.fast5"), member=members[1])
+        out = api.revise_reads([r0, r1], reviser=rv)
+    assert ref.strip() == out.sequence(0) and body(members[1] + "_out.fasta").strip() == out.sequence(1)
+
+
 def test_stage_timing_api(reviser_by_species, reads):
     from nanoreviser_b200 import api
     rv = reviser_by_species("ecoli")
