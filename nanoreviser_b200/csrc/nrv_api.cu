@@ -98,6 +98,7 @@ struct nrv_handle {
     int trnn2_fused = 1;    // total_rnn2: 1 = fused CTA-pair kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN2=split)
     int trnn1_fused = 1;    // total_rnn1: 1 = fused cluster-of-4 kernel (nrv_fused_pair.cu); 0 = GEMM + recurrence (NRV_TRNN1=split)
     int f8_rnn2 = 1;        // total_rnn2's correction passes in e4m3 (kind::f8f6f4); NRV_F8=0 keeps them fp16
+    int f8_rnn1 = 1;        // total_rnn1's RECURRENT correction passes in e4m3 as well; NRV_F8=2 limits F8 to total_rnn2
     unsigned decode_epoch = 0;   // launch number of the single-pass decode (nrv_decode.cu), 1 .. 2^22 - 2
     int sig_table = 1;      // fused total_rnn1 reads the CNN features of boundary-free tiles straight from the per-base table; NRV_SIGTAB=0: gather all
     int rec128_pair = 1;    // u = 128 recurrence on CTA pairs (tcgen05 cta_group::2); NRV_REC128=single selects the 1-CTA kernel
@@ -278,49 +279,56 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.pb_hi = upload(h, bh, &e); if (e) goto cuda_fail;
             L.pb_lo = upload(h, bl, &e); if (e) goto cuda_fail;
             L.bias_tc = upload(h, bias_tc, &e); if (e) goto cuda_fail;
-            if (l == 3) {
-                // total_rnn2 with e4m3 correction passes (nrv_fused_pair.cu, F8): power-of-two operand scales so that every pass
-                // accumulates 2^S z.  b = floor(log2(448 / max|W|)) puts the largest weight just below the e4m3 maximum:
-                //   W_hi8 = e4m3(W_hi 2^b),  x_lo8 = e4m3(x_lo 2^19)          => S = 19 + b
-                //   W_hi16 = fp16(W 2^(S-12)),  x_hi16 = fp16(x) 2^12          (|W| 2^(S-12) <= 448 * 128 < 65504)
-                //   W_lo8 = e4m3(W_lo 2^(S-8)),  x_hi8 = e4m3(x 2^8)           (|W_lo| <= 2^-11 |W|  =>  <= 448)
+            if (l >= 2) {
+                // fused layers with e4m3 correction passes (nrv_fused_pair.cu, F8): the ACTIVATIONS keep their ordinary fp16 hi part
+                // (8-bit copies: x_lo 2^12 and x_hi), the WEIGHTS carry one power-of-two scale per layer so that every pass accumulates
+                // 2^S z.  b = floor(log2(448 / max|W|)) puts the largest weight just below the e4m3 maximum; S = 7 + b:
+                //   W16 (hi, lo) = fp16 pair of W 2^S                          (|W| 2^S <= 448 * 128 < 65504)
+                //   W_hi8 = e4m3(W_hi 2^(S-12)) = e4m3(W_hi 2^(b-5))            meets x_lo8 = e4m3(x_lo 2^12)
+                //   W_lo8 = e4m3(W_lo 2^S)       (|W_lo| <= 2^-11 |W| => <= 28)  meets x_hi8 = e4m3(x_hi)
                 // The 8-bit copies of one row are interleaved in groups of 4 inputs (LstmLayerDev::f8_wk8) exactly like the 8-bit copies
                 // of the activations, so both correction passes are ONE K-contiguous e4m3 product of twice the length.
+                // total_rnn2 (l = 3) runs projection and recurrence this way, total_rnn1 (l = 2) its recurrence (fp16 x 3 projection on
+                // the scaled fp16 pair).
                 double wmax = 1e-30;
                 for (float v : bt) wmax = std::max(wmax, (double)fabsf(v));
                 for (int d = 0; d < 2; ++d)
                     for (size_t i = 0; i < (size_t)u * 4 * u; ++i) wmax = std::max(wmax, (double)fabsf(w->lstm[l][d].recurrent[i]));
                 const int bexp = (int)floor(log2(448.0 / wmax));
-                const int S = 19 + bexp;
-                const double sq = ldexp(1.0, S - 12), s_hi8 = ldexp(1.0, S - 19), s_lo8 = ldexp(1.0, S - 8);
+                const int S = 7 + bexp;
+                const double sq = ldexp(1.0, S), s_hi8 = ldexp(1.0, S - 12), s_lo8 = ldexp(1.0, S);
                 auto e4m3 = [](double v) { return (uint8_t)__nv_cvt_float_to_fp8((float)v, __NV_SATFINITE, __NV_E4M3); };
-                // row-major [rows][K] fp32 values (already in the kernel's row order) -> fp16(W sq) and the interleaved 8-bit row
-                auto split8 = [&](const std::vector<float>& src, size_t rows, int K, std::vector<__half>& h16, std::vector<uint8_t>& q8) {
-                    h16.resize(rows * K); q8.resize(rows * 2 * K);
+                // row-major [rows][K] fp32 values (already in the kernel's row order) -> fp16 pair of W sq and the interleaved 8-bit row
+                auto split8 = [&](const std::vector<float>& src, size_t rows, int K, std::vector<__half>& h16, std::vector<__half>& l16,
+                                  std::vector<uint8_t>& q8) {
+                    h16.resize(rows * K); l16.resize(rows * K); q8.resize(rows * 2 * K);
                     for (size_t r = 0; r < rows; ++r)
                         for (int k = 0; k < K; ++k) {
                             const double wv = (double)src[r * K + k];
                             const __half hs = __float2half_rn((float)(wv * sq));
-                            const double hi = (double)__half2float(hs) / sq;
+                            const double his = (double)__half2float(hs);              // hi part, scaled
                             h16[r * K + k] = hs;
+                            l16[r * K + k] = __float2half_rn((float)(wv * sq - his));
                             uint8_t* g = &q8[r * 2 * K + (size_t)(k >> 2) * 8 + (k & 3)];
-                            g[0] = e4m3(hi * s_hi8);
-                            g[4] = e4m3((wv - hi) * s_lo8);
+                            g[0] = e4m3(his / sq * s_hi8);
+                            g[4] = e4m3((wv - his / sq) * s_lo8);
                         }
                 };
-                std::vector<__half> fh, rh;
+                std::vector<__half> fh, fl, rh, rl;
                 std::vector<uint8_t> f8, r8;
-                split8(bt, (size_t)2 * 4 * u, kin, fh, f8);
+                split8(bt, (size_t)2 * 4 * u, kin, fh, fl, f8);
                 std::vector<float> rt((size_t)2 * 4 * u * u);
                 for (int d = 0; d < 2; ++d)
                     for (int g = 0; g < 4; ++g)
                         for (int j = 0; j < u; ++j)
                             for (int k = 0; k < u; ++k)
                                 rt[((size_t)d * 4 * u + j * 4 + g) * u + k] = w->lstm[l][d].recurrent[(size_t)k * 4 * u + g * u + j];
-                split8(rt, (size_t)2 * 4 * u, u, rh, r8);
+                split8(rt, (size_t)2 * 4 * u, u, rh, rl, r8);
                 L.f8_wk_hi = upload(h, fh, &e); if (e) goto cuda_fail;
+                L.f8_wk_lo = upload(h, fl, &e); if (e) goto cuda_fail;
                 L.f8_wk8 = upload(h, f8, &e); if (e) goto cuda_fail;
                 L.f8_wr_hi = upload(h, rh, &e); if (e) goto cuda_fail;
+                L.f8_wr_lo = upload(h, rl, &e); if (e) goto cuda_fail;
                 L.f8_wr8 = upload(h, r8, &e); if (e) goto cuda_fail;
                 L.f8_acc_scale = (float)ldexp(1.0, -S);
             }
@@ -572,7 +580,8 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     }
                     StageTimer tm(h, ST_REC2);
                     LstmIo io; io.zin = zin; io.out_hi = a3h; io.out_lo = a3l; io.out_ld = 256;
-                    io.out_f8 = f8 != 0;       // total_rnn2 runs its correction passes in e4m3: a3h = fp16(h) 2^12, a3l = the 8-bit copies
+                    io.out_f8 = f8 != 0;       // total_rnn2 runs its correction passes in e4m3: a3h = fp16(h), a3l = the 8-bit copies
+                    io.rec_f8 = f8 != 0 && h->f8_rnn1;     // ... and so does total_rnn1's recurrence (the copies are then made once for both)
                     if (sig_table) { io.sf_hi = h->d_sfh[mi].as<__half>(); io.sf_lo = h->d_sfl[mi].as<__half>(); io.sf_rows = n_bases; io.tile_base = tile_base; }
                     if (h->trnn1_fused) n = launch_lstm_fused_pair128(M.lstm[2], a2h, a2l, io, nwp, T, h->num_sms, h->stream);
                     else n = h->rec128_pair ? launch_lstm_rec_tc128_pair(M.lstm[2], io, nwp, T, h->stream)
@@ -605,7 +614,7 @@ int run_models(nrv_handle* h, int64_t n_win, const int32_t* win_base, const floa
                     StageTimer tm(h, ST_HEADS_GEMM);
                     n = launch_gemm_f16x3(a4h, a4l, M.heads.d1t_hi, M.heads.d1t_lo, R, 128, 128, h->d_act[3].as<float>(),
                                           M.heads.d1b, 2, T, nwp, 128, 1, h->num_sms, h->stream, M.heads.d2t_hi, M.heads.d2t_lo,
-                                          M.heads.d2b, f8 ? 4096.f : 1.f);     // an F8 total_rnn2 writes h 2^12
+                                          M.heads.d2b);
                     if (n < 0) return fail(h, NRV_E_CUDA, "tcgen05 dense head could not be launched");
                     h->launches += n;
                 }
@@ -992,6 +1001,7 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (sge && !strcmp(sge, "0")) h->sig_table = 0;
     const char* f8e = getenv("NRV_F8");
     if (f8e && !strcmp(f8e, "0")) h->f8_rnn2 = 0;
+    if (f8e && !strcmp(f8e, "2")) h->f8_rnn1 = 0;
     const char* r128 = getenv("NRV_REC128");
     if (r128 && !strcmp(r128, "single")) h->rec128_pair = 0;
     h->num_sms = prop.multiProcessorCount;

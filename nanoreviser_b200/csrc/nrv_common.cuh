@@ -41,12 +41,12 @@ struct LstmLayerDev {
     float* bias_tc;
     // tensor-core recurrence operand: Wr^T [2 dirs][4u][u] fp16 (hi, lo), row = unit*4 + gate (layers 1..3)
     __half* rt_hi; __half* rt_lo;
-    // total_rnn2 with e4m3 correction passes (nrv_fused_pair.cu, F8): operands with power-of-two scales, accumulator = 2^S z.
-    //   f8_wk_hi = fp16(Wk 2^(S-12)) [2*4u][in] (rows as pb_hi),  f8_wr_hi = fp16(Wr 2^(S-12)) [2*4u][u] (rows as rt_hi)
+    // fused layers with e4m3 correction passes (nrv_fused_pair.cu, F8): weights with a power-of-two scale, accumulator = 2^S z.
+    //   f8_wk_hi / f8_wk_lo = fp16 pair of Wk 2^S [2*4u][in] (rows as pb_hi),  f8_wr_hi / f8_wr_lo = fp16 pair of Wr 2^S [2*4u][u]
     //   f8_wk8 / f8_wr8: the 8-bit copies for the two correction passes, [rows][2 in] / [rows][2 u] bytes, interleaved in groups
-    //   of 4 inputs: bytes 8g..8g+3 = e4m3(W_hi 2^(S-19)) (meets x_lo 2^19), bytes 8g+4..8g+7 = e4m3(W_lo 2^(S-8)) (meets x_hi 2^8)
-    __half* f8_wk_hi = nullptr; uint8_t* f8_wk8 = nullptr;
-    __half* f8_wr_hi = nullptr; uint8_t* f8_wr8 = nullptr;
+    //   of 4 inputs: bytes 8g..8g+3 = e4m3(W_hi 2^(S-12)) (meets x_lo 2^12), bytes 8g+4..8g+7 = e4m3(W_lo 2^S) (meets x_hi)
+    __half* f8_wk_hi = nullptr; __half* f8_wk_lo = nullptr; uint8_t* f8_wk8 = nullptr;
+    __half* f8_wr_hi = nullptr; __half* f8_wr_lo = nullptr; uint8_t* f8_wr8 = nullptr;
     float f8_acc_scale = 1.f;                                                // 2^-S
 };
 
@@ -64,8 +64,9 @@ struct LstmIo {
     // fused total_rnn1: CNN-feature columns of boundary-free window tiles come straight from the per-base table [sf_rows][64]
     // (fp16 hi / lo); tile_base[tile] = table row of the tile's first window at t = 0, or -1 (then a2's columns [128, 192) are used)
     const __half* sf_hi = nullptr; const __half* sf_lo = nullptr; int64_t sf_rows = 0; const int32_t* tile_base = nullptr;
-    bool out_f8 = false;               // fused total_rnn1 feeding an F8 total_rnn2: out_hi = fp16(h) 2^12 and out_lo holds, per 4 units,
-                                       // the 8 bytes {e4m3(h_lo 2^19) x 4, e4m3(h 2^8) x 4} (same bytes per row as the fp16 lo part)
+    bool rec_f8 = false;               // fused total_rnn1: its recurrence runs with e4m3 correction passes
+    bool out_f8 = false;               // fused total_rnn1 feeding an F8 total_rnn2: out_hi = fp16(h) and out_lo holds, per 4 units,
+                                       // the 8 bytes {e4m3(h_lo 2^12) x 4, e4m3(h_hi) x 4} (same bytes per row as the fp16 lo part)
 };
 
 struct CnnDev {

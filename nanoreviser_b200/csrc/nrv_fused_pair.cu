@@ -161,67 +161,51 @@ __device__ __forceinline__ void pack_h4(const float* hv, uint2& phi, uint2& plo)
     plo = make_uint2(pl[0], pl[1]);
 }
 
-// ---- 8-bit copies of activations for a layer that runs its correction passes in e4m3 (F8 below) ----
-// An activation x in [-1, 1] is handed over as  hi16 = fp16(x) 2^12  and, per group of 4 units, 8 bytes
-// {e4m3(x_lo 2^19) x 4, e4m3(x 2^8) x 4}: as many bytes per row as the fp16 lo part they replace.
-constexpr float F8_XS = 4096.f;                  // 2^12: scale of the fp16 hi part of an activation
-constexpr float F8_XLO = 524288.f;               // 2^19: scale of the e4m3 copy of the lo part
+// ---- 8-bit copies of activations for a product that runs its correction passes in e4m3 (F8 below) ----
+// An activation x is handed over as its ordinary fp16 hi part and, per group of 4 units, 8 bytes
+// {e4m3(x_lo 2^12) x 4, e4m3(x_hi) x 4}: as many bytes per row as the fp16 lo part they replace.
+constexpr float F8_XLO = 4096.f;                 // 2^12: scale of the e4m3 copy of the lo part (|x_lo| <= 2^-12 |x|)
 __device__ __forceinline__ uint32_t e4m3x2_f32(float a, float b) {
     return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
 }
 __device__ __forceinline__ uint32_t e4m3x2_h2(__half2 v) {
     return (uint32_t)__nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(v), __NV_SATFINITE, __NV_E4M3);
 }
-// 4 units of h for the kernel's OWN fp16 x 3 recurrence (hi2, lo2 as pack_h4) and for an F8 consumer (hs2 = fp16(h) 2^12, q2 = 8-bit copies)
-__device__ __forceinline__ void pack_h4_out8(const float* hv, uint2& phi, uint2& plo, uint2& phs, uint2& pq) {
-    uint32_t ph[2], pl[2], ps[2], l8[2], h8[2];
+// 4 units of h: fp16 hi (phi), fp16 lo (plo) and the 8-bit copies (pq).  WANT_LO = false skips the fp16 lo part (nobody reads it
+// when both the kernel's own recurrence and its consumer take the 8-bit copies)
+template <bool WANT_LO>
+__device__ __forceinline__ void pack_h4_f8(const float* hv, uint2& phi, uint2& plo, uint2& pq) {
+    uint32_t ph[2], pl[2] = {0, 0}, l8[2], h8[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
         const float2 hf = __half22float2(hi);
         const float l0 = hv[2 * p] - hf.x, l1 = hv[2 * p + 1] - hf.y;
         ph[p] = half2_bits(hi);
-        pl[p] = half2_bits(__floats2half2_rn(l0, l1));
-        ps[p] = half2_bits(__hmul2(hi, __float2half2_rn(F8_XS)));          // exact: a power of two, |h| < 1
+        if (WANT_LO) pl[p] = half2_bits(__floats2half2_rn(l0, l1));
         l8[p] = e4m3x2_f32(l0 * F8_XLO, l1 * F8_XLO);
-        h8[p] = e4m3x2_h2(__hmul2(hi, __float2half2_rn(256.f)));
+        h8[p] = e4m3x2_h2(hi);
     }
     phi = make_uint2(ph[0], ph[1]);
     plo = make_uint2(pl[0], pl[1]);
-    phs = make_uint2(ps[0], ps[1]);
-    pq = make_uint2(l8[0] | (l8[1] << 16), h8[0] | (h8[1] << 16));
-}
-// 4 units of h of an F8 layer: hs2 = fp16(h 2^12) and q2 = 8-bit copies (the operands of its own recurrence), ls2 = the fp16 lo
-// part at the same scale 2^12 (the layer's output is the pair hs2, ls2: the consumer undoes the scale)
-__device__ __forceinline__ void pack_h4_f8(const float* hv, uint2& phs, uint2& pls, uint2& pq) {
-    uint32_t ps[2], pl[2], l8[2], h8[2];
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const __half2 hs = __floats2half2_rn(hv[2 * p] * F8_XS, hv[2 * p + 1] * F8_XS);
-        const float2 hf = __half22float2(hs);
-        const float l0 = fmaf(hv[2 * p], F8_XS, -hf.x), l1 = fmaf(hv[2 * p + 1], F8_XS, -hf.y);     // lo 2^12, exact
-        ps[p] = half2_bits(hs);
-        pl[p] = half2_bits(__floats2half2_rn(l0, l1));
-        l8[p] = e4m3x2_f32(l0 * 128.f, l1 * 128.f);                          // lo 2^19
-        h8[p] = e4m3x2_h2(__hmul2(hs, __float2half2_rn(0.0625f)));           // h 2^8
-    }
-    phs = make_uint2(ps[0], ps[1]);
-    pls = make_uint2(pl[0], pl[1]);
     pq = make_uint2(l8[0] | (l8[1] << 16), h8[0] | (h8[1] << 16));
 }
 
-// F8 (total_rnn2): the two correction passes of every product (projection AND recurrence) run in e4m3 (tcgen05 kind::f8f6f4:
-// K = 32 bytes per instruction, twice the fp16 rate) on 8-bit copies of the operands: the producing epilogue writes
-// {e4m3(x_lo 2^19) x 4, e4m3(x 2^8) x 4} per group of 4 units in place of the fp16 lo part, pack_model lays the weights out the
-// same way ({e4m3(W_hi 2^(S-19)) x 4, e4m3(W_lo 2^(S-8)) x 4}), so x_lo . W_hi + x_hi . W_lo is ONE K-contiguous e4m3 product over
-// a 128-byte tile per 64 units: 2 instructions (1 fp16 + 1 e4m3) per K-step of 16 units instead of 3.  All operands carry power-of-two
-// scales chosen per layer so that every pass accumulates 2^S z into the same fp32 accumulator:
-//     fp16(x) 2^12 . fp16(W 2^(S-12))  +  e4m3(x_lo 2^19) . e4m3(W_hi 2^(S-19))  +  e4m3(x 2^8) . e4m3(W_lo 2^(S-8))
-// and the epilogue folds 2^-S into the gate constants (free).  In the F8 kernel `wk_lo`, `wr_lo`, `tm_x_lo` and the h_lo columns of TMEM
-// hold those 8-bit copies (same bytes per row / tile / column as the fp16 lo parts they replace), `wk_hi` / `wr_hi` the scaled fp16
-// weights.  OUT8: the CONSUMER is an F8 layer -- out_hi / out_lo receive that format instead of the plain fp16 pair.
-// Precision: tests/precision_study.py (max |dP| 1.1e-4 with total_rnn2 in this form) and DESIGN.md section 4.
-template <int KIN, int UT, bool F8, bool OUT8>
+// F8: the two correction passes of a product run as ONE e4m3 product (tcgen05 kind::f8f6f4: K = 32 bytes per instruction, twice the
+// fp16 rate) on 8-bit copies of the operands.  The producing epilogue writes {e4m3(x_lo 2^12) x 4, e4m3(x_hi) x 4} per group of 4
+// units in place of the fp16 lo part; pack_model lays the weights out the same way ({e4m3(W_hi 2^(S-12)) x 4, e4m3(W_lo 2^S) x 4}), so
+// x_lo . W_hi + x_hi . W_lo is one K-contiguous e4m3 product over a 128-byte tile per 64 units: 2 instructions (1 fp16 + 1 e4m3) per
+// K-step of 16 units instead of 3.  The fp16 hi parts of the ACTIVATIONS are the ordinary unscaled ones; the WEIGHTS carry power-of-two
+// scales chosen per layer (S = 7 + floor(log2(448 / max|W|))) so that every pass accumulates 2^S z into the same fp32 accumulator:
+//     fp16(x) . fp16(W 2^S)  +  e4m3(x_lo 2^12) . e4m3(W_hi 2^(S-12))  +  e4m3(x_hi) . e4m3(W_lo 2^S)
+// and the epilogue folds 2^-S into the gate constants (free).
+//   PF8: the PROJECTION runs this way (`wk_lo`, `tm_x_lo` hold the 8-bit copies; `wk_hi` the scaled fp16 weights);
+//   RF8: the RECURRENCE does (`wr_lo` and the h_lo columns of TMEM hold the 8-bit copies, and so do the halves two pairs exchange);
+//        with PF8 = false the projection stays fp16 x 3 on scaled weights (hi AND lo of W 2^S), so the layer's INPUT needs no copies;
+//   OUT8: the CONSUMER is a PF8 layer: out_lo receives the 8-bit copies (with RF8 they are the registers the recurrence uses anyway).
+// total_rnn2 = <PF8, RF8>, total_rnn1 = <RF8, OUT8>.  8-bit copies occupy the same bytes per row / tile / column as the fp16 lo parts
+// they replace.  Precision: tests/precision_study.py and DESIGN.md section 4.
+template <int KIN, int UT, bool PF8, bool RF8, bool OUT8>
 __global__ void __launch_bounds__(FP_THREADS, 1)
 lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
                        const __half* __restrict__ wr_lo, const float* __restrict__ bias,
@@ -231,13 +215,11 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                        // tile is rows tile_base[tile] + t .. + 127 of the per-base feature table (tm_sf_hi / tm_sf_lo) instead of x
                        const __grid_constant__ CUtensorMap tm_sf_hi, const __grid_constant__ CUtensorMap tm_sf_lo,
                        const int32_t* __restrict__ tile_base) {
-    static_assert(!F8 || UT == 64, "F8 is built for total_rnn2 (no exchange of 8-bit copies yet)");
-    static_assert(!(F8 && OUT8), "an F8 layer's own output is the scaled fp16 pair");
     using Cfg = FpCfg<KIN, UT>;
     constexpr int KC = Cfg::KC, NP = Cfg::NP, CS = 2 * NP, FP_STAGES = Cfg::STAGES;
     constexpr int NT = 4 * UT;                              // gate columns per direction
-    constexpr uint32_t H_HI = FP_H_COL, H_LO = FP_H_COL + UT / 2;      // F8: the H_LO columns hold the 8-bit copies of h
-    constexpr int XLO_W = F8 ? 128 : 64;                    // elements per 128-byte row of a lo tile (bytes / halves)
+    constexpr uint32_t H_HI = FP_H_COL, H_LO = FP_H_COL + UT / 2;      // RF8: the H_LO columns hold the 8-bit copies of h
+    constexpr int XLO_W = PF8 ? 128 : 64;                    // elements per 128-byte row of a lo tile (bytes / halves)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;                                    // [Wk chunk 0..KC-1 | Wr chunk 0..RC-1][hi | lo][128 rows][64]
@@ -292,7 +274,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
         const size_t grow0 = (size_t)dir * NT + p * 256 + r * 64;
         auto gcol = [](int row) { return (row >> 6) * 128 + (row & 63); };
         constexpr int CK = KIN / 8, CR = UT / 8;            // 16-byte chunks per row
-        // (F8: the lo parts are the interleaved 8-bit copies -- as many bytes per row as the fp16 lo part, same tiles)
+        // (PF8 / RF8: the lo parts are the interleaved 8-bit copies -- as many bytes per row as the fp16 lo part, same tiles)
         for (int i = threadIdx.x; i < 2 * 128 * CK; i += FP_THREADS) {
             const int c = i % CK, row = (i / CK) & 127, part = i / (CK * 128);
             const __half* src = (part ? wk_lo : wk_hi) + (grow0 + gcol(row)) * KIN;
@@ -373,7 +355,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #endif
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_lo = umma_desc_k_sw128(xa + k * 32);
-                                if constexpr (F8) {
+                                if constexpr (PF8) {
                                     umma_f8_ss_pair(d0, a_lo, umma_desc_k_sw128(wb_lo + k * 32), idesc, (kc | k) != 0);
                                     umma_f8_ss_pair(d1, a_lo, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, (kc | k) != 0);
                                 } else {
@@ -397,9 +379,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
 #else
                                 const uint32_t acc0 = 1u;
 #endif
-                                if constexpr (!F8) umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, acc0);
+                                if constexpr (!PF8) umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_lo + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d0, a_hi, umma_desc_k_sw128(wb_hi + k * 32), idesc, 1);
-                                if constexpr (!F8) umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, acc0);
+                                if constexpr (!PF8) umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_lo + BB + k * 32), idesc, acc0);
                                 umma_f16_ss_pair(d1, a_hi, umma_desc_k_sw128(wb_hi + BB + k * 32), idesc, 1);
                             }
                             umma_commit_mask(&empty[stage], mask);
@@ -424,7 +406,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                                 for (int blk = 0; blk < 2; ++blk) {
                                     const uint64_t b_hi = umma_desc_k_sw128(wr + blk * BB), b_lo = umma_desc_k_sw128(wr + FP_TILE + blk * BB);
                                     const uint32_t d = blk ? d1 : d0;
-                                    if constexpr (F8) {
+                                    if constexpr (RF8) {
                                         umma_f8_ts_pair(d, tmem_base + H_LO + k * 8, b_lo, idesc, 1);
                                     } else {
                                         umma_f16_ts_pair(d, tmem_base + H_LO + k * 8, b_hi, idesc, 1);
@@ -519,20 +501,24 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                 __half* ol = out_lo + orow + p * 64 + cg * 8;
                 // exchange in halves of 4 units, each handed to the bulk-copy engine as soon as it exists (2 x 256 B per warp): the DSMEM
                 // traffic is spread over the arithmetic instead of arriving as a 16 KB burst at the end of a block
-                // ph / pl: the operands of this kernel's own recurrence (TMEM, exchange); gh / gl: what goes to global memory --
-                // the same registers unless the consumer wants the F8 format (OUT8) or this layer is F8 itself (output = scaled fp16 pair)
+                // ph / pl: the operands of this kernel's own recurrence (TMEM, exchange): fp16 hi + fp16 lo, or with RF8 fp16 hi + 8-bit copies.
+                // Global memory gets the hi part and the lo format the CONSUMER reads (OUT8: 8-bit copies, else fp16 lo): the same
+                // registers when both agree, else gl
                 uint32_t ph[4], pl[4];
-                uint32_t gh[(OUT8 || F8) ? 4 : 1], gl[(OUT8 || F8) ? 4 : 1];
+                constexpr bool GL_OTHER = RF8 != OUT8;
+                uint32_t gl[GL_OTHER ? 4 : 1];
                 auto send_half = [&](int b, int half, const float* hv4, uint32_t wait_k) {      // wait_k != 0: first half of exchange phase wait_k
                     uint2 hi2, lo2;
-                    if constexpr (F8) {
-                        uint2 ls2;
-                        pack_h4_f8(hv4, hi2, ls2, lo2);          // TMEM: fp16(h 2^12) + 8-bit copies; global: fp16 pair at scale 2^12
-                        gl[half * 2] = ls2.x; gl[half * 2 + 1] = ls2.y;
-                    } else if constexpr (OUT8) {
-                        uint2 hs2, q2;
-                        pack_h4_out8(hv4, hi2, lo2, hs2, q2);
-                        gh[half * 2] = hs2.x; gh[half * 2 + 1] = hs2.y; gl[half * 2] = q2.x; gl[half * 2 + 1] = q2.y;
+                    if constexpr (RF8 || OUT8) {
+                        uint2 l16, q2;
+                        pack_h4_f8<GL_OTHER>(hv4, hi2, l16, q2);
+                        if constexpr (RF8) {
+                            lo2 = q2;
+                            if constexpr (GL_OTHER) { gl[half * 2] = l16.x; gl[half * 2 + 1] = l16.y; }
+                        } else {
+                            lo2 = l16;
+                            gl[half * 2] = q2.x; gl[half * 2 + 1] = q2.y;
+                        }
                     } else {
                         pack_h4(hv4, hi2, lo2);
                     }
@@ -556,16 +542,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     const uint4 phi = make_uint4(ph[0], ph[1], ph[2], ph[3]), plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     tmem_st_32x4(lane_addr + H_HI + own_col + b * 16, phi);
                     tmem_st_32x4(lane_addr + H_LO + own_col + b * 16, plo);
-                    if constexpr (OUT8) {
-                        *reinterpret_cast<uint4*>(oh + b * 32) = make_uint4(gh[0], gh[1], gh[2], gh[3]);
-                        *reinterpret_cast<uint4*>(ol + b * 32) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
-                    } else if constexpr (F8) {
-                        *reinterpret_cast<uint4*>(oh + b * 32) = phi;
-                        *reinterpret_cast<uint4*>(ol + b * 32) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
-                    } else {
-                        *reinterpret_cast<uint4*>(oh + b * 32) = phi;
-                        *reinterpret_cast<uint4*>(ol + b * 32) = plo;
-                    }
+                    *reinterpret_cast<uint4*>(oh + b * 32) = phi;
+                    if constexpr (GL_OTHER) *reinterpret_cast<uint4*>(ol + b * 32) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
+                    else *reinterpret_cast<uint4*>(ol + b * 32) = plo;
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -620,14 +599,15 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     if (warp == 0) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
-template <int KIN, int UT, bool F8, bool OUT8>
+template <int KIN, int UT, bool PF8, bool RF8, bool OUT8>
 static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                                int num_sms, cudaStream_t st) {
     using Cfg = FpCfg<KIN, UT>;
     constexpr int CS = 2 * Cfg::NP;
+    constexpr bool F8W = PF8 || RF8;                  // the layer's weights carry the scale 2^S (LstmLayerDev::f8_*)
     CUtensorMap txh, txl;
     if (!make_tmap_f16_k64(&txh, x_hi, (int64_t)T * nwp, KIN, 128)) return -2;
-    if (F8) {   // x_lo = the producing layer's 8-bit copies: rows of 2 KIN bytes, 128-byte boxes (= the 64 units of an fp16 K-chunk)
+    if (PF8) {   // x_lo = the producing layer's 8-bit copies: rows of 2 KIN bytes, 128-byte boxes (= the 64 units of an fp16 K-chunk)
         if (!make_tmap_u8_k128(&txl, x_lo, (int64_t)T * nwp, 2 * KIN, 128)) return -2;
     } else {
         if (!make_tmap_f16_k64(&txl, x_lo, (int64_t)T * nwp, KIN, 128)) return -2;
@@ -635,7 +615,7 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     CUtensorMap tsh = txh, tsl = txl;                 // per-base CNN-feature table (total_rnn1 only)
     const bool sig_table = UT == 128 && io.tile_base && io.sf_hi && io.sf_lo && io.sf_rows > 0;
     if (sig_table && (!make_tmap_f16_k64(&tsh, io.sf_hi, io.sf_rows, 64, 128) || !make_tmap_f16_k64(&tsl, io.sf_lo, io.sf_rows, 64, 128))) return -2;
-    auto kern = lstm_fused_pair_kernel<KIN, UT, F8, OUT8>;
+    auto kern = lstm_fused_pair_kernel<KIN, UT, PF8, RF8, OUT8>;
     static PerDevice per_dev;                     // co-resident clusters on the current device (per template instance)
     int& max_clusters = per_dev.cur();
     if (!max_clusters) {
@@ -652,7 +632,7 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
             cudaGetLastError(); n = num_sms / CS;
         }
         max_clusters = n;
-        if (getenv("NRV_VERBOSE")) fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d,%d>: cluster %d, %d co-resident clusters\n", KIN, UT, (int)F8, CS, n);
+        if (getenv("NRV_VERBOSE")) fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d,%d,%d,%d>: cluster %d, %d co-resident clusters\n", KIN, UT, (int)PF8, (int)RF8, (int)OUT8, CS, n);
     }
     const int64_t n_pairs = ((nwp >> 7) + 1) / 2;
     const int per_dir = std::max(1, max_clusters / 2);
@@ -663,12 +643,15 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     cfg.stream = st;
     cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CS; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
-    const __half* wk_hi = F8 ? (const __half*)L.f8_wk_hi : (const __half*)L.pb_hi;
-    const __half* wk_lo = F8 ? reinterpret_cast<const __half*>(L.f8_wk8) : (const __half*)L.pb_lo;
-    const __half* wr_hi = F8 ? (const __half*)L.f8_wr_hi : (const __half*)L.rt_hi;
-    const __half* wr_lo = F8 ? reinterpret_cast<const __half*>(L.f8_wr8) : (const __half*)L.rt_lo;
+    // scaled fp16 weights whenever one of the products runs F8 (one accumulator scale); the lo parts are fp16 for an fp16 x 3 product, the
+    // interleaved 8-bit copies for an F8 one
+    const __half* wk_hi = F8W ? (const __half*)L.f8_wk_hi : (const __half*)L.pb_hi;
+    const __half* wk_lo = PF8 ? reinterpret_cast<const __half*>(L.f8_wk8) : (F8W ? (const __half*)L.f8_wk_lo : (const __half*)L.pb_lo);
+    const __half* wr_hi = F8W ? (const __half*)L.f8_wr_hi : (const __half*)L.rt_hi;
+    const __half* wr_lo = RF8 ? reinterpret_cast<const __half*>(L.f8_wr8) : (F8W ? (const __half*)L.f8_wr_lo : (const __half*)L.rt_lo);
+    if (!wk_hi || !wk_lo || !wr_hi || !wr_lo) return -1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wk_hi, wk_lo, wr_hi, wr_lo, (const float*)L.bias_tc, txh, txl, io.out_hi, io.out_lo,
-                                             io.out_ld, nwp, T, F8 ? L.f8_acc_scale : 1.0f, tsh, tsl, sig_table ? io.tile_base : (const int32_t*)nullptr);
+                                             io.out_ld, nwp, T, F8W ? L.f8_acc_scale : 1.0f, tsh, tsl, sig_table ? io.tile_base : (const int32_t*)nullptr);
     if (e != cudaSuccess) {
         fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: launch (grid %u x 2, cluster %d, %zu B smem): %s\n", KIN, UT, cfg.gridDim.x, CS,
                 (size_t)Cfg::SMEM, cudaGetErrorString(e));
@@ -677,24 +660,24 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     return 1;
 }
 
-// total_rnn2: x = total_rnn1's output (K = 256), 64 units.  f8 != 0: x_hi is fp16(h) 2^12 and x_lo the 8-bit copies (see F8 above)
+// total_rnn2: x = total_rnn1's output (K = 256), 64 units.  f8 != 0: both products with e4m3 correction passes; x_lo = the 8-bit copies
 int launch_lstm_fused_pair64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
                              cudaStream_t st, int f8) {
     if (nwp <= 0) return 0;
     if (L.u != 64 || L.in_a != 256 || !L.rt_hi || !L.pb_hi || !L.bias_tc || !io.out_hi || !io.out_lo || (nwp & 127) || (io.out_ld & 7)) return -1;
-    if (f8) {
-        if (!L.f8_wk_hi || !L.f8_wk8 || !L.f8_wr_hi || !L.f8_wr8) return -1;
-        return launch_fused_pair_t<256, 64, true, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
-    }
-    return launch_fused_pair_t<256, 64, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (f8) return launch_fused_pair_t<256, 64, true, true, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    return launch_fused_pair_t<256, 64, false, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
 }
-// total_rnn1: x = [read_rnn11 | CNN features] (K = 192), 128 units, cluster of 4
+// total_rnn1: x = [read_rnn11 | CNN features] (K = 192), 128 units, cluster of 4.  io.out_f8: the consumer (total_rnn2) reads 8-bit copies;
+// io.rec_f8: the recurrence runs with e4m3 correction passes (the projection stays fp16 x 3: its inputs need no copies)
 int launch_lstm_fused_pair128(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T, int num_sms,
                               cudaStream_t st) {
     if (nwp <= 0) return 0;
     if (L.u != 128 || !L.rt_hi || !L.pb_hi || !L.bias_tc || !io.out_hi || !io.out_lo || (nwp & 127) || (io.out_ld & 7)) return -1;
-    if (io.out_f8) return launch_fused_pair_t<192, 128, false, true>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
-    return launch_fused_pair_t<192, 128, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (io.rec_f8 && io.out_f8) return launch_fused_pair_t<192, 128, false, true, true>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (io.rec_f8) return launch_fused_pair_t<192, 128, false, true, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    if (io.out_f8) return launch_fused_pair_t<192, 128, false, false, true>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
+    return launch_fused_pair_t<192, 128, false, false, false>(L, x_hi, x_lo, io, nwp, T, num_sms, st);
 }
 
 }  // namespace nrv

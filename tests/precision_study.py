@@ -58,6 +58,11 @@ class Mode:
         # power-of-two scales that put the largest |W_hi| / |W_lo| just below the e4m3 maximum
         sw = int(np.floor(np.log2(448.0 / max(wmax, 1e-30))))
         swl = int(np.floor(np.log2(448.0 / max(float(Wl.abs().max()), 1e-30))))
+        if W8_KERNEL_SCALES[0]:
+            # the kernel's scales (nrv_api.cu pack_model, F8): one accumulator scale S = 7 + b for all passes with UNSCALED fp16
+            # activations => W_hi8 = e4m3(W_hi 2^(b-5)) (meets x_lo 2^12), W_lo8 = e4m3(W_lo 2^(7+b)) (meets x_hi 2^0)
+            swl = sw + 7
+            sw = sw - 5
         return dict(W=W, Wh=Wh, Wl=Wl, sw=sw, swl=swl,
                     Wh8=q8(Wh, "e4m3", sw), Wl8=q8(Wl, "e4m3", swl),
                     Wh8_52=q8(Wh, "e5m2", sw), Wl8_52=q8(Wl, "e5m2", swl))
@@ -97,21 +102,25 @@ def bn_affine(bn):
 
 
 BASE_MODE = ["f32"]
+W8_KERNEL_SCALES = [False]
+H_SCALES = [8, 19]     # log2 scales of the 8-bit copies of h (hi, lo)
+PROJ_F16_LAYERS = []   # --proj-f16-layers: layers whose PROJECTION stays f16x3 while their recurrence runs the emulated mode
 REC_MODE = [None]      # --rec-mode: how the recurrent product h @ Wr of the emulated layers is evaluated (default: same as the projection)
 
 
-def lstm_dir(mode, x, wk, wr, bias, reverse, xs_hi, xs_lo):
+def lstm_dir(mode, x, wk, wr, bias, reverse, xs_hi, xs_lo, proj_f16=False):
     """x [B, T, in] (fp32 torch) -> [B, T, u]; h is in [-1, 1]: 8-bit copies scaled by 2^8 (hi) / 2^19 (lo)"""
     B, T, _ = x.shape
     u = wr["W"].shape[0]
-    zin = mode.mm(x.reshape(B * T, -1), wk, xs_hi, xs_lo).reshape(B, T, 4 * u) + bias
+    pm = Mode("f16x3") if (proj_f16 and mode.name != "f32") else mode
+    zin = pm.mm(x.reshape(B * T, -1), wk, xs_hi, xs_lo).reshape(B, T, 4 * u) + bias
     if REC_MODE[0] and mode.name != "f32":
         mode = Mode(REC_MODE[0])
     h = torch.zeros(B, u)
     c = torch.zeros(B, u)
     out = torch.empty(B, T, u)
     for t in (range(T - 1, -1, -1) if reverse else range(T)):
-        z = zin[:, t] + (mode.mm(h, wr, 8, 19) if (t != (T - 1 if reverse else 0)) else 0.0)
+        z = zin[:, t] + (mode.mm(h, wr, H_SCALES[0], H_SCALES[1]) if (t != (T - 1 if reverse else 0)) else 0.0)
         i, f = hard_sigmoid(z[:, :u]), hard_sigmoid(z[:, u:2 * u])
         g, o = torch.tanh(z[:, 2 * u:3 * u]), hard_sigmoid(z[:, 3 * u:])
         c = f * c + i * g
@@ -150,7 +159,7 @@ class Net:
     def bilstm(self, li, x, xs_hi=8, xs_lo=19):
         outs = []
         for k, (md, wk, wr, b) in enumerate(self.layers[li]):
-            outs.append(lstm_dir(md, x, wk, wr, b, k == 1, xs_hi, xs_lo))
+            outs.append(lstm_dir(md, x, wk, wr, b, k == 1, xs_hi, xs_lo, proj_f16=li in PROJ_F16_LAYERS))
         return torch.cat(outs, dim=-1)
 
     def forward(self, sig_feat, X):
@@ -165,7 +174,7 @@ class Net:
         fmax = float(tot.abs().max())
         s_hi = int(np.floor(np.log2(448.0 / max(fmax, 1.0))))
         t1 = self.bilstm(2, tot, s_hi, s_hi + 11)
-        t2 = self.bilstm(3, t1)
+        t2 = self.bilstm(3, t1, H_SCALES[0], H_SCALES[1])
         B, T, _ = t2.shape
         d = torch.relu(self.hm.mm(t2.reshape(B * T, -1), self.d1) + t32(m.dense1_b))
         dmax = float(d.abs().max())
@@ -186,10 +195,16 @@ def main():
     ap.add_argument("--max-windows", type=int, default=0)
     ap.add_argument("--no-heads", action="store_true", help="dense heads in fp32")
     ap.add_argument("--rec-mode", default=None, help="mode of the recurrent products (e.g. f16x3 while the projections use e4m3)")
+    ap.add_argument("--proj-f16-layers", nargs="*", type=int, default=[], help="layers whose projection stays f16x3 (only their recurrence is emulated)")
+    ap.add_argument("--h-scales", nargs=2, type=int, default=[8, 19], help="log2 scales of the 8-bit copies of h: hi, lo (default 8 19; the unified format is 1 12)")
+    ap.add_argument("--kernel-scales", action="store_true", help="8-bit weight scales as pack_model derives them (S = 7 + b, activations unscaled)")
     ap.add_argument("--base-mode", default="f16x3", help="mode of the tensor layers NOT listed in --layers (the GPU default is f16x3)")
     a = ap.parse_args()
     REC_MODE[0] = a.rec_mode
     BASE_MODE[0] = a.base_mode
+    PROJ_F16_LAYERS[:] = a.proj_f16_layers
+    W8_KERNEL_SCALES[0] = a.kernel_scales
+    H_SCALES[:] = a.h_scales
     files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "fast5", "*.fast5")))
     for sp in a.species:
         m1, m2 = weights.load_species(sp, os.path.join(ROOT, "model"))
