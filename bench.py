@@ -435,8 +435,10 @@ def main():
             if fused1:      # stage proj2 holds only the CNN-feature gather (no MACs); rec2 is the whole layer
                 macs.pop("proj2")
                 macs["rec2"] = 3_604_480
+                f8mode = os.environ.get("NRV_F8", "1")
                 names["rec2"] = ("lstm_fused_pair_kernel<192,128> (total_rnn1 projection+recurrence fused, tcgen05 cta_group::2, "
-                                 "cluster of 4, h in TMEM, 3-pass split-fp16)")
+                                 "cluster of 4, h in TMEM, " + ("3-pass split-fp16 projection, 1 fp16 + 1 e4m3 MMA per K-step in the recurrence)"
+                                                                if f8mode not in ("0", "2") and fused2 else "3-pass split-fp16)"))
             if fused2:
                 macs.pop("proj3")
                 macs["rec3"] = 1_802_240
@@ -495,7 +497,7 @@ def main():
                     "share_of_step": kernels[dom]["share_of_step"],
                     "hbm": {"achieved": kernels[dom].get("hbm_achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
                             "frac": kernels[dom].get("hbm_frac"), "bytes_per_launch": kernels[dom].get("hbm_bytes_per_launch")},
-                    "note": ("algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay fp32-equivalent "
+                    "note": ("algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes (2 fp16-equivalents where the corrections run in e4m3) per product to stay fp32-equivalent "
                              "(effective tensor ceiling = peak / 3) and runs under the 1000 W power cap; fused layers move only "
                              "x and h through HBM (see traffic)") if (fused1 or fused2) else
                             ("algorithmic FLOPs (1 pass); the kernel spends 3 fp16 MMA passes per product to stay "
@@ -529,8 +531,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16x3/f32acc", "data": "synthetic",
-                "dtype_note": "tensor-core products are three fp16 passes (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo) with fp32 accumulation; in total_rnn2 "
-                              "the two correction passes run as one e4m3 product (kind::f8f6f4) on 8-bit copies with power-of-two scales; "
+                "dtype_note": "tensor-core products are three fp16 passes (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo) with fp32 accumulation; in total_rnn2 and "
+                              "in the recurrence of total_rnn1 the two correction passes run as one e4m3 product (kind::f8f6f4) on 8-bit copies, "
+                              "weights scaled by a power of two per layer; "
                               "segmentation statistics in fp64, indices / decode in integers",
                 "config": workload_config(cfg, species, world, per_rank, batch_budget,
                                           int(round(sum(len(j["L"]) for j in jobs) / JOBS)), n_win),
