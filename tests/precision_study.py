@@ -173,7 +173,7 @@ class Net:
         tot = torch.cat([r2, sig_feat], dim=-1)
         fmax = float(tot.abs().max())
         s_hi = int(np.floor(np.log2(448.0 / max(fmax, 1.0))))
-        t1 = self.bilstm(2, tot, s_hi, s_hi + 11)
+        t1 = self.bilstm(2, tot, *((H_SCALES[0], H_SCALES[1]) if W8_KERNEL_SCALES[0] else (s_hi, s_hi + 11)))
         t2 = self.bilstm(3, t1, H_SCALES[0], H_SCALES[1])
         B, T, _ = t2.shape
         d = torch.relu(self.hm.mm(t2.reshape(B * T, -1), self.d1) + t32(m.dense1_b))
