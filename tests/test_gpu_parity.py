@@ -114,18 +114,23 @@ def test_median_mad_exact_random(reviser_by_species):
     rng = np.random.default_rng(11)
     sigs = [rng.integers(-32768, 32768, 10001).astype(np.int16), rng.integers(-32768, 32768, 10000).astype(np.int16),
             rng.integers(0, 3, 999).astype(np.int16), np.array([5, 7], np.int16), np.array([-3], np.int16),
-            rng.integers(400, 420, 50000).astype(np.int16), np.array([32767, -32768, 0, 1], np.int16)]
+            rng.integers(400, 420, 50000).astype(np.int16), np.array([32767, -32768, 0, 1], np.int16),
+            # reads longer than one 32,768-sample segment: histograms merged in global memory, the last CTA selects
+            rng.integers(-32768, 32768, 200001).astype(np.int16), rng.integers(-32768, 32768, 65536).astype(np.int16),
+            np.full(70000, -123, np.int16), rng.choice(np.array([-32768, 32767], np.int16), 98305),
+            (rng.normal(600, 60, 131072).clip(-32768, 32767)).astype(np.int16), rng.integers(0, 2, 32769).astype(np.int16)]
     R = len(sigs)
     sig_off = np.zeros(R + 1, np.int64); base_off = np.arange(R + 1, dtype=np.int64)
     for i, s in enumerate(sigs):
         sig_off[i + 1] = sig_off[i] + len(s)
     b = engine.Batch(np.concatenate(sigs), sig_off, np.zeros(R, np.int32), base_off, np.full(R, 65, np.uint8),
                      np.zeros(R, np.float32), np.zeros(R, np.float32), np.ones(R, np.int32))
-    shift, scale, *_ = rv.segment(b)
-    for i, s in enumerate(sigs):
-        f = s.astype(np.float64)
-        assert shift[i] == np.median(f), i
-        assert scale[i] == np.median(np.abs(f - np.median(f))), i
+    for rep in range(2):         # twice: the kernel must leave its global histograms and arrival counters zeroed
+        shift, scale, *_ = rv.segment(b)
+        for i, s in enumerate(sigs):
+            f = s.astype(np.float64)
+            assert shift[i] == np.median(f), (rep, i)
+            assert scale[i] == np.median(np.abs(f - np.median(f))), (rep, i)
 
 
 # --------------------------------------------------------------------------------------------------
