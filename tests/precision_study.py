@@ -103,6 +103,7 @@ def bn_affine(bn):
 
 BASE_MODE = ["f32"]
 W8_KERNEL_SCALES = [False]
+HEADS_D1_ONLY = [False]
 H_SCALES = [8, 19]     # log2 scales of the 8-bit copies of h (hi, lo)
 PROJ_F16_LAYERS = []   # --proj-f16-layers: layers whose PROJECTION stays f16x3 while their recurrence runs the emulated mode
 REC_MODE = [None]      # --rec-mode: how the recurrent product h @ Wr of the emulated layers is evaluated (default: same as the projection)
@@ -154,7 +155,8 @@ class Net:
         hm = mode if tensor_heads else Mode(BASE_MODE[0])
         self.hm = hm
         self.d1 = hm.prep_w(m.dense1_k)
-        self.d2 = hm.prep_w(m.dense2_k)
+        self.hm2 = Mode("f16x3") if (HEADS_D1_ONLY[0] and hm.name != "f32") else hm      # --heads-d1-only: dense2 stays f16x3
+        self.d2 = self.hm2.prep_w(m.dense2_k)
 
     def bilstm(self, li, x, xs_hi=8, xs_lo=19):
         outs = []
@@ -176,10 +178,10 @@ class Net:
         t1 = self.bilstm(2, tot, *((H_SCALES[0], H_SCALES[1]) if W8_KERNEL_SCALES[0] else (s_hi, s_hi + 11)))
         t2 = self.bilstm(3, t1, H_SCALES[0], H_SCALES[1])
         B, T, _ = t2.shape
-        d = torch.relu(self.hm.mm(t2.reshape(B * T, -1), self.d1) + t32(m.dense1_b))
+        d = torch.relu(self.hm.mm(t2.reshape(B * T, -1), self.d1, H_SCALES[0], H_SCALES[1]) + t32(m.dense1_b))
         dmax = float(d.abs().max())
         s_hi = int(np.floor(np.log2(448.0 / max(dmax, 1.0))))
-        d = torch.relu(self.hm.mm(d, self.d2, s_hi, s_hi + 11) + t32(m.dense2_b))
+        d = torch.relu(self.hm2.mm(d, self.d2, s_hi, s_hi + 11) + t32(m.dense2_b))
         d = torch.relu(d @ t32(m.main_k) + t32(m.main_b)).reshape(B, -1)
         feat = torch.relu(d @ t32(m.feat_k) + t32(m.feat_b))
         logits = feat @ t32(m.final_k) + t32(m.final_b)
@@ -197,6 +199,7 @@ def main():
     ap.add_argument("--rec-mode", default=None, help="mode of the recurrent products (e.g. f16x3 while the projections use e4m3)")
     ap.add_argument("--proj-f16-layers", nargs="*", type=int, default=[], help="layers whose projection stays f16x3 (only their recurrence is emulated)")
     ap.add_argument("--h-scales", nargs=2, type=int, default=[8, 19], help="log2 scales of the 8-bit copies of h: hi, lo (default 8 19; the unified format is 1 12)")
+    ap.add_argument("--heads-d1-only", action="store_true", help="of the dense head only the first dense (input h of total_rnn2) runs the emulated mode")
     ap.add_argument("--kernel-scales", action="store_true", help="8-bit weight scales as pack_model derives them (S = 7 + b, activations unscaled)")
     ap.add_argument("--base-mode", default="f16x3", help="mode of the tensor layers NOT listed in --layers (the GPU default is f16x3)")
     a = ap.parse_args()
@@ -204,6 +207,7 @@ def main():
     BASE_MODE[0] = a.base_mode
     PROJ_F16_LAYERS[:] = a.proj_f16_layers
     W8_KERNEL_SCALES[0] = a.kernel_scales
+    HEADS_D1_ONLY[0] = a.heads_d1_only
     H_SCALES[:] = a.h_scales
     files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "fast5", "*.fast5")))
     for sp in a.species:
