@@ -251,7 +251,7 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             }
             const int N2 = 2 * 4 * u;
             const int kin = (in + 63) / 64 * 64;
-            std::vector<float> bt((size_t)N2 * kin, 0.f), bias_tc(N2);
+            std::vector<float> bt((size_t)N2 * kin, 0.f), bias_tc(N2), bias_l1(N2);
             for (int d = 0; d < 2; ++d) {
                 const nrv_lstm_dir& src = w->lstm[l][d];
                 for (int g = 0; g < 4; ++g)
@@ -271,6 +271,7 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
                         if (l == 1) {   // fused kernel: the operand's column 32 is the constant 1.0, its weight row is the bias
                             bt[(size_t)n * kin + 32] = (float)bacc;
                             bias_tc[n] = 0.f;
+                            bias_l1[n] = (float)bacc;      // the ping-pong kernel multiplies only the 32 real columns and adds this in its epilogue
                         }
                     }
             }
@@ -282,6 +283,7 @@ int pack_model(nrv_handle* h, const nrv_model_weights* w, ModelDev* out) {
             L.pb_hi = upload(h, bh, &e); if (e) goto cuda_fail;
             L.pb_lo = upload(h, bl, &e); if (e) goto cuda_fail;
             L.bias_tc = upload(h, bias_tc, &e); if (e) goto cuda_fail;
+            if (l == 1) { L.bias_l1 = upload(h, bias_l1, &e); if (e) goto cuda_fail; }
             if (l >= 2) {
                 // fused layers with e4m3 correction passes (nrv_fused_pair.cu, F8): the ACTIVATIONS keep their ordinary fp16 hi part
                 // (8-bit copies: x_lo 2^12 and x_hi), the WEIGHTS carry one power-of-two scale per layer so that every pass accumulates

@@ -39,6 +39,7 @@ struct LstmLayerDev {
     __half* pb_hi; __half* pb_lo;      // main part (K = in_a)
     __half* sb_hi; __half* sb_lo;      // per-base part (K = in_b), layer 2 only
     float* bias_tc;
+    float* bias_l1 = nullptr;          // read_rnn11 only: the bias itself (the ping-pong kernel adds it in the epilogue; bias_tc is 0 there)
     // tensor-core recurrence operand: Wr^T [2 dirs][4u][u] fp16 (hi, lo), row = unit*4 + gate (layers 1..3)
     __half* rt_hi; __half* rt_lo;
     // fused layers with e4m3 correction passes (nrv_fused_pair.cu, F8): weights with a power-of-two scale, accumulator = 2^S z.

@@ -525,6 +525,20 @@ bool make_tmap_f16_k64(CUtensorMap* tm, const void* base, int64_t rows, int K, i
     return r == CUDA_SUCCESS;
 }
 
+// fp16 operand of 32 columns out of rows of K halves: box = 64 bytes x box_rows, 64-byte swizzle (nrv_rec_tc.cu, read_rnn11's x tiles)
+bool make_tmap_f16_k32_sw64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // fp16 operand tail of 16 columns (K = 16: one UMMA K-step): box = 32 bytes x box_rows, 32-byte swizzle (nrv_cnn.cu: columns
 // 384..399 of the Dense(400 -> 64) weights)
 bool make_tmap_f16_k16_sw32(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows) {

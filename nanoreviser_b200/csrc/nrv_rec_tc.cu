@@ -422,6 +422,233 @@ lstm_fused_tc64_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ============================================================================================================
+// read_rnn11, PING-PONG variant (round 2): TWO window tiles in flight per CTA.  The kernel above is bound by the chain
+// epilogue(s) -> last recurrent MMAs -> accumulator -> epilogue(s + 1) (tensor pipe 59 %): with a second, independent tile the
+// MMAs of one tile (projection + recurrence of its next step: 18 instructions) run while the 16 epilogue warps work on the
+// other, and the epilogue never waits.  Resources: two single-buffered accumulators = all 512 TMEM columns; two h tiles
+// (2 x 32 KB); the x tiles shrink to the 32 real input columns ([128][32] fp16, 64-byte swizzle, tools/ts_probe/sw64_probe.cu)
+// -- the constant-1 column that carried the bias is gone, the bias is added in the epilogue from shared memory -- which is what
+// makes room: 128 KB weights + 64 KB h + 32 KB x ring.  Schedule (all three roles agree on it): tiles are taken in pairs
+// (slot 0: 1st, 3rd, ... tile of this CTA; slot 1: 2nd, 4th, ...), steps alternate (slot 0, s), (slot 1, s), (slot 0, s + 1), ...
+// ============================================================================================================
+constexpr int PP_X_BYTES = 128 * 32 * 2;              // 8 KB per x tile part ([128 rows][32], SWIZZLE_64B)
+constexpr size_t PP_SMEM = 4 * RF_W_BYTES + 4 * RF_H_BYTES + RF_XS * 2 * PP_X_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+
+// One 32-column block (8 units x gates i,f,c,o) of the cell with the bias read from shared memory unit by unit (keeps the register
+// count of the two-tile epilogue at the 96 a 576-thread CTA allows): z = acc + b; c, h update; h -> fp16 (hi, lo) as 2 x 16 bytes.
+__device__ __forceinline__ void cell_block_sbias(const uint32_t (&v)[32], uint32_t sbias, float* c8, uint4& phi, uint4& plo) {
+    float hv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = ld_shared_f4(sbias + j * 16);
+        const float ig = hsig(__uint_as_float(v[4 * j + 0]) + b.x), fg = hsig(__uint_as_float(v[4 * j + 1]) + b.y);
+        const float gg = tanh_fast(__uint_as_float(v[4 * j + 2]) + b.z), og = hsig(__uint_as_float(v[4 * j + 3]) + b.w);
+        const float cn = fmaf(fg, c8[j], ig * gg);
+        c8[j] = cn;
+        hv[j] = og * tanh_fast(cn);
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const __half2 hi = __floats2half2_rn(hv[2 * p], hv[2 * p + 1]);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(hv[2 * p] - hf.x, hv[2 * p + 1] - hf.y);
+        ph[p] = half2_bits(hi); pl[p] = half2_bits(lo);
+    }
+    phi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    plo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;                     // 8-row groups of 64-byte rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                              // SWIZZLE_64B
+    return d;
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+lstm_fused_tc64_pp_kernel(const __half* __restrict__ wk_hi, const __half* __restrict__ wk_lo, const __half* __restrict__ wr_hi,
+                          const __half* __restrict__ wr_lo, const float* __restrict__ bias, const __grid_constant__ CUtensorMap tm_x_hi,
+                          const __grid_constant__ CUtensorMap tm_x_lo, const __grid_constant__ CUtensorMap tm_out_hi,
+                          const __grid_constant__ CUtensorMap tm_out_lo, int64_t nwp, int T) {
+    constexpr int U = 64, N = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                  // [Wk hi | Wk lo | Wr hi | Wr lo] x [256 rows][64] (of Wk only K < 32 is used)
+    uint8_t* s_h = smem + 4 * RF_W_BYTES;                 // [slot][hi | lo][128 rows][64]
+    uint8_t* s_x = s_h + 4 * RF_H_BYTES;                  // [stage][hi | lo][128 rows][32]
+    float* s_bias = reinterpret_cast<float*>(s_x + RF_XS * 2 * PP_X_BYTES);     // [256] gate columns (unit * 4 + gate) of this direction
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+    uint64_t* h_done = bars;                              // [2 slots] count RF_EPI_WARPS: h of the step is in the slot's tile, its accumulator is drained
+    uint64_t* acc_ready = bars + 2;                       // [2 slots] count 2: MMAs complete (commit) + the store of the previous h has left the tile
+    uint64_t* xfull = bars + 4;                           // [RF_XS]
+    uint64_t* xempty = bars + 4 + RF_XS;                  // [RF_XS] count 1 (commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * RF_XS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 2; ++j) { mbar_init(&h_done[j], RF_EPI_WARPS); mbar_init(&acc_ready[j], 2); }
+        for (int i = 0; i < RF_XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_out_hi); tma_prefetch_desc(&tm_out_lo);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    {
+        const __half* srcs[4] = {wk_hi + (size_t)dir * N * U, wk_lo + (size_t)dir * N * U, wr_hi + (size_t)dir * N * U,
+                                 wr_lo + (size_t)dir * N * U};
+        for (int i = threadIdx.x; i < 4 * N * 8; i += RF_THREADS) {
+            const int m = i / (N * 8), r = i - m * (N * 8);
+            *reinterpret_cast<uint4*>(s_w + m * RF_W_BYTES + sw128_offset(r >> 3, r & 7)) = __ldg(reinterpret_cast<const uint4*>(srcs[m]) + r);
+        }
+        if (threadIdx.x < N) s_bias[threadIdx.x] = __ldg(bias + dir * N + threadIdx.x);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's tiles: k-th tile = blockIdx.x + k * gridDim.x; slot j takes k = 2m + j
+    const int64_t ntw = nwp >> 7;
+    const int64_t n_mine = blockIdx.x < ntw ? (ntw - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t n_slot[2] = {(n_mine + 1) / 2, n_mine / 2};
+    auto tile_of = [&](int64_t m, int j) { return (int64_t)blockIdx.x + (2 * m + j) * (int64_t)gridDim.x; };
+
+    if (warp == 1) {
+        // ===================== TMA producer: x_t tiles in schedule order =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t m = 0; m < n_slot[0]; ++m)
+                for (int s = 0; s < T; ++s)
+                    for (int j = 0; j < 2; ++j) {
+                        if (m >= n_slot[j]) continue;
+                        const int t = dir ? (T - 1 - s) : s;
+                        const int grow = (int)(t * nwp + tile_of(m, j) * 128);
+                        mbar_wait(&xempty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&xfull[stage], 2 * PP_X_BYTES);
+                        tma_load_2d(s_x + (stage * 2 + 0) * PP_X_BYTES, &tm_x_hi, &xfull[stage], 0, grow);
+                        tma_load_2d(s_x + (stage * 2 + 1) * PP_X_BYTES, &tm_x_lo, &xfull[stage], 0, grow);
+                        if (++stage == RF_XS) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 0) {
+        // ===================== h store + MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_f16_f32(128, N);
+        const uint32_t w_base = smem_u32(s_w);
+        int xstage = 0; uint32_t xphase = 0;
+        int prev_row[2] = {-1, -1};                       // global row (t * nwp + tile * 128) of the h the slot's tile currently holds
+        for (int64_t m = 0; m < n_slot[0]; ++m)
+            for (int s = 0; s < T; ++s)
+                for (int j = 0; j < 2; ++j) {
+                    if (m >= n_slot[j]) continue;
+                    const uint32_t q = (uint32_t)(m * T + s);                  // step counter of the slot: every barrier of the slot completes once per step
+                    const uint32_t ha = smem_u32(s_h + j * 2 * RF_H_BYTES);
+                    const uint32_t d = tmem_base + (uint32_t)j * N;
+                    if (q > 0) {                                               // epilogue of the slot's previous step: h is in the tile, the accumulator drained
+                        mbar_wait(&h_done[j], (q - 1) & 1);
+                        tc_fence_after();
+                    }
+                    mbar_wait(&xfull[xstage], xphase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (q > 0) {
+                            tma_store_2d(&tm_out_hi, s_h + j * 2 * RF_H_BYTES, dir * U, prev_row[j]);
+                            tma_store_2d(&tm_out_lo, s_h + j * 2 * RF_H_BYTES + RF_H_BYTES, dir * U, prev_row[j]);
+                            tma_store_commit();
+                        }
+                        const uint32_t xa = smem_u32(s_x + (xstage * 2) * PP_X_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {                          // projection: K = 32
+                            const uint64_t a_hi = umma_desc_k_sw64(xa + k * 32), a_lo = umma_desc_k_sw64(xa + PP_X_BYTES + k * 32);
+                            const uint64_t b_hi = umma_desc_k_sw128(w_base + 0 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 1 * RF_W_BYTES + k * 32);
+                            umma_f16_ss(d, a_lo, b_hi, idesc, k != 0);
+                            umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                            umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                        }
+                        umma_commit(&xempty[xstage]);
+                        if (s > 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {                      // recurrence on h_{t-1} of this tile
+                                const uint64_t a_hi = umma_desc_k_sw128(ha + k * 32), a_lo = umma_desc_k_sw128(ha + RF_H_BYTES + k * 32);
+                                const uint64_t b_hi = umma_desc_k_sw128(w_base + 2 * RF_W_BYTES + k * 32), b_lo = umma_desc_k_sw128(w_base + 3 * RF_W_BYTES + k * 32);
+                                umma_f16_ss(d, a_lo, b_hi, idesc, 1);
+                                umma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                                umma_f16_ss(d, a_hi, b_hi, idesc, 1);
+                            }
+                        }
+                        umma_commit(&acc_ready[j]);
+                        tma_store_wait_read();                                 // the store of the previous h has read the tile ...
+                        mbar_arrive(&acc_ready[j]);                            // ... and with the MMAs complete the epilogue may overwrite it
+                    }
+                    __syncwarp();
+                    if (++xstage == RF_XS) { xstage = 0; xphase ^= 1; }
+                    const int t = dir ? (T - 1 - s) : s;
+                    prev_row[j] = (int)(t * nwp + tile_of(m, j) * 128);
+                }
+        // the last h of both slots
+        for (int j = 0; j < 2; ++j) {
+            if (n_slot[j] == 0) continue;
+            const uint32_t q = (uint32_t)(n_slot[j] * T);
+            mbar_wait(&h_done[j], (q - 1) & 1);
+            if (elect_one()) {
+                tma_store_2d(&tm_out_hi, s_h + j * 2 * RF_H_BYTES, dir * U, prev_row[j]);
+                tma_store_2d(&tm_out_lo, s_h + j * 2 * RF_H_BYTES + RF_H_BYTES, dir * U, prev_row[j]);
+                tma_store_commit();
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    } else {
+        // ===================== epilogue: warps 2..17; lane quarter = warp % 4, column group = (warp - 2) / 4 =====================
+        constexpr int NB = 2;                             // 32-column blocks per warp
+        const int q4 = warp & 3;
+        const int cg = (warp - 2) >> 2;                   // block cb: units cb*32 + cg*8 .. +8
+        const int row = q4 * 32 + lane;
+        float c[2][8 * NB];
+        for (int64_t m = 0; m < n_slot[0]; ++m)
+            for (int s = 0; s < T; ++s)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (m >= n_slot[j]) continue;
+                    const uint32_t q = (uint32_t)(m * T + s);
+                    if (s == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8 * NB; ++i) c[j][i] = 0.f;
+                    }
+                    const uint32_t sh_base = smem_u32(s_h + j * 2 * RF_H_BYTES);
+                    mbar_wait(&acc_ready[j], q & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int cb = 0; cb < NB; ++cb) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j * N + (uint32_t)((cb * 4 + cg) * 32), v);
+                        tmem_ld_wait();
+                        uint4 phi, plo;
+                        cell_block_sbias(v, smem_u32(s_bias + (cb * 4 + cg) * 32), &c[j][cb * 8], phi, plo);
+                        const uint32_t off = sw128_offset(row, cb * 4 + cg);
+                        st_shared_v4(sh_base + off, phi);
+                        st_shared_v4(sh_base + RF_H_BYTES + off, plo);
+                    }
+                    tc_fence_before();                    // our tcgen05.ld of this step precede the slot's next MMAs
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&h_done[j]);
+                }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+bool make_tmap_f16_k32_sw64(CUtensorMap* tm, const void* base, int64_t rows, int K, int box_rows);     // nrv_gemm.cu
+
 int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __half* x_lo, const LstmIo& io, int64_t nwp, int T,
                            cudaStream_t st) {
     if (nwp <= 0) return 0;
@@ -431,6 +658,16 @@ int launch_lstm_fused_tc64(const LstmLayerDev& L, const __half* x_hi, const __ha
         !make_tmap_f16_k64(&tmh, io.out_hi, (int64_t)T * nwp, io.out_ld, 128) ||
         !make_tmap_f16_k64(&tml, io.out_lo, (int64_t)T * nwp, io.out_ld, 128))
         return -2;
+    static const bool use_pp = !(getenv("NRV_RNN11") && !strcmp(getenv("NRV_RNN11"), "single"));
+    if (use_pp && L.bias_l1) {
+        CUtensorMap pxh, pxl;
+        if (!make_tmap_f16_k32_sw64(&pxh, x_hi, (int64_t)T * nwp, 64, 128) || !make_tmap_f16_k32_sw64(&pxl, x_lo, (int64_t)T * nwp, 64, 128)) return -2;
+        static PerDevice attr_pp;
+        if (attr_pp.first()) cudaFuncSetAttribute(lstm_fused_tc64_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SMEM);
+        dim3 grid((unsigned)std::min<int64_t>(nwp >> 7, 74), 2);
+        lstm_fused_tc64_pp_kernel<<<grid, RF_THREADS, PP_SMEM, st>>>(L.pb_hi, L.pb_lo, L.rt_hi, L.rt_lo, L.bias_l1, pxh, pxl, tmh, tml, nwp, T);
+        return 1;
+    }
     static PerDevice attr;
     if (attr.first()) cudaFuncSetAttribute(lstm_fused_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
     dim3 grid((unsigned)std::min<int64_t>(nwp >> 7, 74), 2);       // persistent: 148 CTAs, weights loaded once each

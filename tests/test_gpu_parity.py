@@ -586,6 +586,7 @@ def test_two_batches_in_flight_give_the_same_bytes(reviser_by_species, reads):
     {"NRV_TRNN1": "split", "NRV_TRNN2": "split", "NRV_GEMM": "single"},   # gemm_f16x3_kernel<256> projections
     {"NRV_OVERLAP": "0"},                                 # everything on one stream
     {"NRV_SIGTAB": "0"},                                  # CNN features of every tile gathered into a2 (no TMA from the per-base table)
+    {"NRV_RNN11": "single"},                              # read_rnn11 with one tile per CTA (lstm_fused_tc64_kernel) instead of the ping-pong kernel
     {"NRV_F8": "2"},                                      # F8 in total_rnn2 only: total_rnn1 = fp16 x 3 recurrence + 8-bit copies for its consumer
     {"NRV_F8": "0"},                                      # total_rnn2 with fp16 x 3 correction passes (lstm_fused_pair_kernel<.., false, false>)
 ], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
