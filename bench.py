@@ -428,7 +428,8 @@ def main():
                      "proj3": "gemm_f16x3_pair_kernel (total_rnn2 input projection, tcgen05 cta_group::2)",
                      "rec3": "lstm_rec_tc64_kernel (total_rnn2 recurrence, tcgen05)",
                      "proj1": "gemm_f16x3_kernel<256> (read_rnn11 input projection, tcgen05)",
-                     "rec1": "lstm_fused_tc64_kernel (read_rnn11 projection+recurrence, tcgen05)",
+                     "rec1": ("lstm_fused_tc64_kernel (read_rnn11 projection+recurrence, tcgen05)" if os.environ.get("NRV_RNN11") == "single" else
+                              "lstm_fused_tc64_pp_kernel (read_rnn11 projection+recurrence, tcgen05, two window tiles in flight per CTA)"),
                      "heads_gemm": "gemm_f16x3_kernel<128,FUSE2> (dense head 128->128->32, tcgen05)",
                      "heads": "heads_tail_thread_kernel (dense 32->6, flatten, feature, softmax, argmax; fp32 SIMT)",
                      "lstm0": "read_rnn1_kernel (read_rnn1, fp32 SIMT, one thread per window pair)"}

@@ -168,7 +168,11 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
 
 /* The whole path (A2..A10) for one ragged batch; replaces the body of provide_fasta between
  * get_read_data and prep_read_fasta.  Host buffers in, host buffers out; H2D and D2H copies
- * are inside; returns after the results are in the caller's buffers. */
+ * are inside; returns after the results are in the caller's buffers.
+ * Numerics: softmax outputs within 1e-3 of the float64 evaluation of the graph (lstmmodel.py:32-133).  Windows whose two
+ * best classes are closer than that tolerance are evaluated a second time in the library's most precise tensor-core mode
+ * before the argmax is taken, so that the labels -- and with them the revised sequence -- do not depend on the reduced-
+ * precision correction passes of the fast path (NRV_REFINE=0 switches this off). */
 int nrv_revise_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r);
 
 /* The same call split in two so that a host thread can keep TWO batches in flight (the reference gets its concurrency from a

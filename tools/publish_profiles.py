@@ -45,11 +45,13 @@ tb = lambda v, u: float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte":
 acc = {}
 for x in data:
     name = x[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("nrv::", "").replace(" ", "")
-    name = name.replace(",0,0>", ">").replace(",0,1>", ">").replace(",1,0>", ">").replace("<unnamed>::", "")       # F8 / OUT8 template flags
+    import re as _re
+    name = _re.sub(r"^(lstm_fused_pair_kernel<\d+,\d+)(,\d)+>", r"\1>", name).replace("<unnamed>::", "")       # PF8 / RF8 / OUT8 template flags
     t = tb(x[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + tb(x[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
     acc.setdefault(name, []).append(t)
 mean = {k: sum(v) / len(v) for k, v in acc.items()}
-stage_of = {"rec2": "lstm_fused_pair_kernel<192,128>", "rec3": "lstm_fused_pair_kernel<256,64>", "rec1": "lstm_fused_tc64_kernel",
+stage_of = {"rec2": "lstm_fused_pair_kernel<192,128>", "rec3": "lstm_fused_pair_kernel<256,64>",
+            "rec1": "lstm_fused_tc64_pp_kernel" if "lstm_fused_tc64_pp_kernel" in mean else "lstm_fused_tc64_kernel",
             "lstm0": "read_rnn1_kernel", "heads_gemm": "gemm_f16x3_kernel<128,1>", "heads": "heads_tail_thread_kernel<11>"}
 t = json.load(open(P + "/traffic_per_launch.json"))
 for s_, k in stage_of.items():
