@@ -129,15 +129,13 @@ template <int J0, int J1>
 __device__ __forceinline__ void cell_units(const uint32_t (&v)[32], uint32_t sbias, float* c8, float* hv, float zs, float zs02) {
 #pragma unroll
     for (int j = J0; j < J1; ++j) {
-        const float4 b = ld_shared_f4(sbias + j * 16);       // {0.2 b_i + 0.5, 0.2 b_f + 0.5, -2 log2(e) b_c, 0.2 b_o + 0.5}
+        const float4 b = ld_shared_f4(sbias + j * 16);       // {0.2 b_i + 0.5, 0.2 b_f + 0.5, b_c, 0.2 b_o + 0.5}
         const float ig = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 0]), b.x));
         const float fg = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 1]), b.y));
 #if defined(NRV_TANH_NR) && NRV_TANH_NR >= 1
-        const float gg = tanh_fast_nr(fmaf(zs, __uint_as_float(v[4 * j + 2]), b.z * (-1.f / 2.8853900817779268f)));
+        const float gg = tanh_fast_nr(fmaf(zs, __uint_as_float(v[4 * j + 2]), b.z));
 #else
-        // tanh(z) = 2 / (1 + 2^(-2 log2(e) z)) - 1 with the factor folded into the scale and the bias of gate c (one multiply
-        // less on the dependent chain of every unit)
-        const float gg = fmaf(2.f, rcp_approx(ex2_approx(fmaf(zs * -2.8853900817779268f, __uint_as_float(v[4 * j + 2]), b.z)) + 1.f), -1.f);
+        const float gg = tanh_fast(fmaf(zs, __uint_as_float(v[4 * j + 2]), b.z));
 #endif
         const float og = __saturatef(fmaf(zs02, __uint_as_float(v[4 * j + 3]), b.w));
         const float cn = fmaf(fg, c8[j], ig * gg);
@@ -269,7 +267,7 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
     if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
     if (threadIdx.x < 256) {       // hard_sigmoid(z + b) = sat(0.2 z + (0.2 b + 0.5)): the gates i, f, o keep the folded constant
         const float b = __ldg(bias + dir * NT + p * 256 + threadIdx.x);
-        s_bias[threadIdx.x] = (threadIdx.x & 3) == 2 ? b * -2.8853900817779268f : fmaf(0.2f, b, 0.5f);   // gate c: see cell_units
+        s_bias[threadIdx.x] = (threadIdx.x & 3) == 2 ? b : fmaf(0.2f, b, 0.5f);
     }
     {   // resident weights: this CTA's 128 gate columns, all of K, hi and lo.  Shared-memory row b*64 + j = gate column
         // b*128 + r*64 + j of the pair: an N = 128 MMA on unit block b takes rows [b*64, +64) from each CTA of the pair
