@@ -10,8 +10,9 @@ python bench.py --impl reference --steps 2 --warmup 1 > $G/${tag}_bench_referenc
 python bench.py --config cfg5 --steps 3 --warmup 3 --no-cpu-baseline > $G/${tag}_bench_cfg5.json 2> $G/${tag}_bench_cfg5.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $G/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --reads-per-step 16 --no-cpu-baseline > $G/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'read_rnn1|lstm_fused|gemm_f16x3|heads_tail|gather_sig|tile_base|cnn_kernel' \
+ncu --set full --clock-control none --import-source on -k regex:'read_rnn1|lstm_fused|gemm_f16x3|heads_tail|gather_sig|tile_base' \
     -s 12 -c 12 -o $G/${tag}_all -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $G/${tag}_all.log 2>&1
+bash tools/prof_cnn.sh ${tag}
 ncu --set full --clock-control none --import-source on -k regex:'read_stats|base_features|decode_|base_read_map|window_map' -s 5 -c 5 -o $G/${tag}_hbm -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $G/${tag}_hbm.log 2>&1
 ncu --set full --clock-control none -k regex:'read_stats|base_features|decode_' -s 3 -c 3 -o $G/${tag}_hbm_cfg5 -f \

@@ -14,6 +14,8 @@ for name in ("bench.json", "bench_reference.json", "bench_cfg5.json", "launches.
 run = lambda *a, **k: subprocess.run(list(a), capture_output=True, text=True, **k).stdout
 run(sys.executable, "profiles/summarize_ncu.py", G + "/%s_all.ncu-rep" % TAG, P + "/%s_ncu_summary.md" % TAG)
 run(sys.executable, "profiles/summarize_ncu.py", G + "/%s_hbm.ncu-rep" % TAG, P + "/%s_ncu_hbm_kernels.md" % TAG)
+if os.path.exists(G + "/%s_cnn.ncu-rep" % TAG):
+    run(sys.executable, "profiles/summarize_ncu.py", G + "/%s_cnn.ncu-rep" % TAG, P + "/%s_ncu_cnn.md" % TAG)
 if os.path.exists(G + "/%s_hbm_cfg5.ncu-rep" % TAG):
     run(sys.executable, "profiles/summarize_ncu.py", G + "/%s_hbm_cfg5.ncu-rep" % TAG, P + "/%s_ncu_hbm_kernels_cfg5.md" % TAG)
 run(sys.executable, "tools/sass_summary.py", P + "/%s_sass_summary.md" % TAG)
@@ -66,12 +68,14 @@ json.dump(t, open(P + "/traffic_per_launch.json", "w"), indent=1)
 # fused-layer stall summaries
 out = ["# per-source-line stall samples of the fused layer kernels (ncu --set full, gpurun_out/%s_all.ncu-rep; "
        "tools/ncu_top.py + tools/ncu_lines.py)" % TAG]
+def rep(want):                     # cnn_kernel runs before the model kernels of a step: its own capture (tools/prof_cnn.sh)
+    return G + ("/%s_cnn.ncu-rep" if "cnn" in want else "/%s_all.ncu-rep") % TAG
 for title, want, sub in (("<192,128,OUT8> (total_rnn1)", "(int)192", "ILi192ELi128ELb0ELb1E"), ("<256,64,F8> (total_rnn2)", "(int)256", "ILi256ELi64ELb1ELb0E"),
                          ("cnn_kernel (K2)", "cnn_kernel", "cnn_kernel")):
     env = dict(os.environ, NCU_KERNEL=want, NCU_FILTER="--kernel-name-base demangled --kernel-name regex:" + ("cnn_kernel" if "cnn" in want else want.replace("(int)", "")))
     out += ["", "## " + title, "```",
-            "\n".join(run(sys.executable, "tools/ncu_top.py", G + "/%s_all.ncu-rep" % TAG, "0", env=env).split("\n")[:22]),
-            "\n".join(l[:200] for l in run(sys.executable, "tools/ncu_lines.py", G + "/%s_all.ncu-rep" % TAG, sub, "22", env=env).split("\n")), "```"]
+            "\n".join(run(sys.executable, "tools/ncu_top.py", rep(want), "0", env=env).split("\n")[:22]),
+            "\n".join(l[:200] for l in run(sys.executable, "tools/ncu_lines.py", rep(want), sub, "22", env=env).split("\n")), "```"]
 open(P + "/%s_ncu_fused_layers.md" % TAG, "w").write("\n".join(out) + "\n")
 print("value %.4g e2e %.4g" % (d["value"], d["e2e"]["value"]), st)
 print({k: v for k, v in t.items() if not k.startswith("_")})
