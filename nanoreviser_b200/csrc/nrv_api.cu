@@ -820,8 +820,7 @@ int run_segment(nrv_handle* h, const DevBatch& d, const Offsets& o, bool want_x,
         h->launches += launch_read_stats(d.signal, o.d_sig_off, o.d_base_off, d.starts, d.last_dur, h->window, o.n_reads,
                                          o.d_hist_slot, h->d_ghist.p, o.n_multi, o.max_segs,
                                          h->d_shift.as<double>(), h->d_scale.as<double>(), h->io().d_status.as<int32_t>(),
-                                         h->stream);
-        h->launches += launch_base_read_map(o.d_base_off, o.n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
+                                         h->stream, h->d_base_read.as<int32_t>(), o.n_bases);      // + the base -> read map
     }
     {
         StageTimer tm(h, ST_FEAT);
@@ -975,8 +974,8 @@ int enqueue_batch(nrv_handle* h, const nrv_batch* b, nrv_result* r, bool host_io
                 h->launches += n;
             }
         }
-        const int n = launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), d.bases, labels[0], labels[1],
-                                    S.d_status.as<int32_t>(), o.n_reads, o.n_bases, h->window, dec_epoch,
+        const int n = launch_decode(o.d_base_off, o.d_win_off, d.bases, labels[0], labels[1],
+                                    S.d_status.as<int32_t>(), o.n_reads, o.n_bases, o.n_win, h->window, dec_epoch,
                                     h->d_tiles.as<int64_t>(), d_rev, r->revised_cap, d_outoff, S.d_flag.as<int>(),
                                     h->stream, wq[0], wq[1], d_qual_in, d_revq);
         if (n < 0) return fail(h, NRV_E_INVALID, "decode: qualities requested without per-window scores");
@@ -1271,12 +1270,14 @@ int nrv_decode(nrv_handle* h, int64_t n_reads, const int64_t* base_off, const ui
     CU(h, cudaMemcpyAsync(h->d_y[1].p, y2, (size_t)o.n_win, cudaMemcpyHostToDevice, h->stream));
     if (status) CU(h, cudaMemcpyAsync(S.d_status.p, status, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
     else CU(h, cudaMemsetAsync(S.d_status.p, 0, (size_t)n_reads * 4 + 16, h->stream));
-    h->launches += launch_base_read_map(o.d_base_off, n_reads, o.n_bases, h->d_base_read.as<int32_t>(), h->stream);
-    h->launches += launch_decode(o.d_base_off, o.d_win_off, h->d_base_read.as<int32_t>(), S.d_bases.as<uint8_t>(),
-                                 h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), S.d_status.as<int32_t>(), n_reads,
-                                 o.n_bases, h->window, dec_epoch, h->d_tiles.as<int64_t>(),
-                                 S.d_revised.as<uint8_t>(), revised_cap, S.d_outoff.as<int64_t>(), S.d_flag.as<int>(),
-                                 h->stream);
+    {
+        StageTimer tm(h, ST_DECODE);
+        h->launches += launch_decode(o.d_base_off, o.d_win_off, S.d_bases.as<uint8_t>(),
+                                     h->d_y[0].as<uint8_t>(), h->d_y[1].as<uint8_t>(), S.d_status.as<int32_t>(), n_reads,
+                                     o.n_bases, o.n_win, h->window, dec_epoch, h->d_tiles.as<int64_t>(),
+                                     S.d_revised.as<uint8_t>(), revised_cap, S.d_outoff.as<int64_t>(), S.d_flag.as<int>(),
+                                     h->stream);
+    }
     CU(h, cudaMemcpyAsync(out_off, S.d_outoff.p, (size_t)(n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(S.h_flag.p, S.d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

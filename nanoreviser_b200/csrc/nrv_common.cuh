@@ -100,7 +100,8 @@ struct ModelDev {
 int launch_read_stats(const int16_t* signal, const int64_t* sig_off, const int64_t* base_off,
                       const int32_t* starts, const int32_t* last_dur, int window, int64_t n_reads,
                       const int32_t* hist_slot, void* ghist, int64_t n_multi, int max_segs,
-                      double* shift, double* scale, int32_t* status, cudaStream_t st);
+                      double* shift, double* scale, int32_t* status, cudaStream_t st, int32_t* base_read = nullptr,
+                      int64_t n_bases = 0);   // base_read != null: also fills the base -> read map (launch_base_read_map not needed)
 size_t read_stats_hist_bytes(int64_t n_multi);      // zeroed scratch for the reads that span several segments
 int read_stats_segment();                            // samples per CTA
 int launch_base_features(const int16_t* signal, const int64_t* sig_off, const int32_t* starts,
@@ -156,9 +157,9 @@ int launch_heads(const HeadsDev& H, const float* act_in /*[n_win][T][128]*/, int
                  int64_t in_nwp /* != 0: act_in rows are time-major, row(t, w) = t*in_nwp + w */, cudaStream_t st);
 
 // nrv_decode.cu
-int launch_decode(const int64_t* base_off, const int64_t* win_off, const int32_t* base_read,
+int launch_decode(const int64_t* base_off, const int64_t* win_off,
                   const uint8_t* bases, const uint8_t* y1, const uint8_t* y2, const int32_t* status,
-                  int64_t n_reads, int64_t n_bases, int window, unsigned epoch, int64_t* tile_tmp,
+                  int64_t n_reads, int64_t n_bases, int64_t n_win, int window, unsigned epoch, int64_t* tile_tmp,
                   uint8_t* revised, int64_t revised_cap, int64_t* out_off, int* overflow_flag, cudaStream_t st,
                   const uint8_t* q1 = nullptr, const uint8_t* q2 = nullptr, const uint8_t* qual_in = nullptr,
                   uint8_t* revised_qual = nullptr);

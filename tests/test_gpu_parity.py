@@ -118,7 +118,17 @@ def test_median_mad_exact_random(reviser_by_species):
             # reads longer than one 32,768-sample segment: histograms merged in global memory, the last CTA selects
             rng.integers(-32768, 32768, 200001).astype(np.int16), rng.integers(-32768, 32768, 65536).astype(np.int16),
             np.full(70000, -123, np.int16), rng.choice(np.array([-32768, 32767], np.int16), 98305),
-            (rng.normal(600, 60, 131072).clip(-32768, 32767)).astype(np.int16), rng.integers(0, 2, 32769).astype(np.int16)]
+            (rng.normal(600, 60, 131072).clip(-32768, 32767)).astype(np.int16), rng.integers(0, 2, 32769).astype(np.int16),
+            # around the range of the compact histogram (-8191 .. 8190; beyond it values are clamped and the read is redone by the
+            # full-range kernel when the median or the MAD band touches the clamped bins): medians on the boundary, a median
+            # inside with the MAD band outside, spikes that must not matter, one- and multi-segment reads
+            rng.integers(-8200, -8180, 40001).astype(np.int16), rng.integers(8185, 8200, 40000).astype(np.int16),
+            rng.integers(-8193, -8189, 1001).astype(np.int16), rng.integers(8188, 8193, 1000).astype(np.int16),
+            np.concatenate([np.full(29999, 100), np.full(30000, 9000)]).astype(np.int16),
+            rng.permutation(np.concatenate([np.zeros(10001), np.full(10000, 16000), np.full(10000, -16000)])).astype(np.int16),
+            np.where(rng.random(100000) < 0.01, rng.choice([-20000, 20000], 100000), rng.normal(500, 50, 100000)).astype(np.int16),
+            np.where(rng.random(9000) < 0.3, 8191, rng.integers(8000, 8190, 9000)).astype(np.int16),
+            rng.permutation(np.concatenate([np.full(50001, 8189), np.full(25000, 8192), np.full(25000, 8186)])).astype(np.int16)]
     R = len(sigs)
     sig_off = np.zeros(R + 1, np.int64); base_off = np.arange(R + 1, dtype=np.int64)
     for i, s in enumerate(sigs):
@@ -195,19 +205,38 @@ def test_decode_vs_get_base_1(reviser_by_species):
     agree = rng.random(nw) < 0.6
     y2[agree] = np.clip(y1[agree].astype(int) - 1, 0, 4)
     status = np.zeros(len(lens), np.int32); status[7] = engine.NRV_READ_SCALE_ZERO
-    rev, off = rv.decode(base_off, bases, y1, y2, status)
-    w0 = 0
-    for i, n in enumerate(lens):
-        seq = bases[base_off[i]:base_off[i + 1]].tobytes().decode()
-        M = max(n - W, 0)
-        if M > 0 and status[i] == 0:
-            core = orc.get_base_1(list(seq[5:5 + M]), y1[w0:w0 + M].astype(int), y2[w0:w0 + M].astype(int) + 2)
-            want = seq[:5] + core + seq[5 + M:]
-        else:
-            want = seq
-        assert rev[off[i]:off[i + 1]].tobytes().decode() == want, i
-        w0 += M
-    assert off[-1] == len(rev)
+    def check(lens, base_off, bases, y1, y2, status):
+        rev, off = rv.decode(base_off, bases, y1, y2, status)
+        bef = (W - 1) // 2
+        w0 = 0
+        for i, n in enumerate(lens):
+            seq = bases[base_off[i]:base_off[i + 1]].tobytes().decode()
+            M = max(n - W, 0)
+            if M > 0 and status[i] == 0:
+                core = orc.get_base_1(list(seq[bef:bef + M]), y1[w0:w0 + M].astype(int), y2[w0:w0 + M].astype(int) + 2)
+                want = seq[:bef] + core + seq[bef + M:]
+            else:
+                want = seq
+            assert rev[off[i]:off[i + 1]].tobytes().decode() == want, i
+            w0 += M
+        assert off[-1] == len(rev)
+    check(lens, base_off, bases, y1, y2, status)
+    # (c) batches that span many decode tiles (4,096 bases each): reads ending anywhere inside a thread's 16 bases, runs of
+    # empty and window-less reads between long ones, failed reads, '-' bases, every label combination
+    for trial in range(4):
+        kinds = rng.integers(0, 6, size=60)
+        lens = [int({0: 0, 1: rng.integers(1, W + 1), 2: rng.integers(W + 1, 40), 3: rng.integers(40, 600),
+                     4: rng.integers(3000, 9000), 5: 4096 * int(rng.integers(1, 3)) + int(rng.integers(-2, 3))}[int(k)]) for k in kinds]
+        if trial == 3:
+            lens = [0, 0, 0] + lens + [0, 0]
+        base_off = np.zeros(len(lens) + 1, np.int64); base_off[1:] = np.cumsum(lens)
+        bases = rng.choice(np.frombuffer(b"ACGT-", np.uint8), size=int(base_off[-1]), p=[0.24, 0.24, 0.24, 0.24, 0.04])
+        nw = int(np.maximum(np.array(lens) - W, 0).sum())
+        y1 = rng.integers(0, 6, nw).astype(np.uint8); y2 = rng.integers(0, 5, nw).astype(np.uint8)
+        agree = rng.random(nw) < 0.6
+        y2[agree] = np.clip(y1[agree].astype(int) - 1, 0, 4)
+        status = (rng.random(len(lens)) < 0.15).astype(np.int32) * engine.NRV_READ_SCALE_ZERO
+        check(lens, base_off, bases, y1, y2, status)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -484,7 +513,7 @@ def test_stage_timing_api(reviser_by_species, reads):
     ms, nl = rv.stage_ms(), rv.stage_launches()
     rv.set_stage_timing(False)
     assert set(ms) == set(nl) and {"read_stats", "cnn", "rec2", "heads", "decode"} <= set(ms)
-    # decode is ONE kernel (count + look-back scan + scatter); read_stats = the one-pass histogram kernel + the base -> read map
+    # decode is ONE kernel (count + look-back scan + scatter); read_stats = the compact one-pass histogram kernel (which also writes the base -> read map) + the full-range fall-back
     assert sum(nl.values()) <= rv.launch_count - n0 and nl["decode"] == 1 and nl["read_stats"] == 2
     assert all(v >= 0 for v in ms.values()) and ms["rec2"] > 0
 
