@@ -319,6 +319,11 @@ read_stats_compact_kernel(const int16_t* __restrict__ signal, const int64_t* __r
     const int16_t* body = reinterpret_cast<const int16_t*>((reinterpret_cast<uintptr_t>(p0) + 15) & ~(uintptr_t)15);
     if (body > pend) body = pend;
     const int16_t* bend = body + ((pend - body) & ~(long long)7);
+    // the first two loads of every thread go out before anything else (software pipeline: two more are issued before these are used)
+    const int16_t* q = body + (long long)tid * 8;
+    constexpr long long QS = (long long)TH * 8;
+    uint4 va = q < bend ? __ldg(reinterpret_cast<const uint4*>(q)) : make_uint4(0, 0, 0, 0);
+    uint4 vb = q + QS < bend ? __ldg(reinterpret_cast<const uint4*>(q + QS)) : make_uint4(0, 0, 0, 0);
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.h);
         for (int i = tid; i < NB / 4; i += TH) h4[i] = make_uint4(0, 0, 0, 0);
@@ -330,12 +335,16 @@ read_stats_compact_kernel(const int16_t* __restrict__ signal, const int64_t* __r
     const long long b0 = base_off[r], nb = base_off[r + 1] - b0;
     {
         const long long s0 = nb * seg / nseg, s1 = nb * (seg + 1) / nseg;
+        const int ldur = last_dur[r];
+        bool lbad = false;
+#pragma unroll 4
         for (long long j = s0 + tid; j < s1; j += TH) {
             const long long st = starts[b0 + j];
-            const long long en = (j + 1 < nb) ? (long long)starts[b0 + j + 1] : st + last_dur[r];
-            if (st < 0 || en <= st || en > n) sm.bad = 1;
+            const long long en = (j + 1 < nb) ? (long long)starts[b0 + j + 1] : st + ldur;
+            lbad |= (st < 0 || en <= st || en > n);
             if (base_read) base_read[b0 + j] = r;
         }
+        if (lbad) sm.bad = 1;
     }
     {
         auto add = [&](int sv) { atomicAdd(&sm.h[min(max(sv + RC_OFF, 0), NB - 1)], 1u); };
@@ -345,13 +354,14 @@ read_stats_compact_kernel(const int16_t* __restrict__ signal, const int64_t* __r
             for (int e = 0; e < 4; ++e) { add((int)(int16_t)(w[e] & 0xffffu)); add((int)(int16_t)(w[e] >> 16)); }
         };
         if (p0 + tid < body) add(p0[tid]);                                   // head: fewer than 8 samples
-        const int16_t* q = body + (long long)tid * 8;
-        for (; q + (long long)TH * 8 < bend; q += (long long)TH * 16) {      // two loads in flight
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(q));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(q + (long long)TH * 8));
-            add8(a); add8(b);
+        for (; q < bend; q += 2 * QS) {
+            const int16_t* q2 = q + 2 * QS;
+            const uint4 na = q2 < bend ? __ldg(reinterpret_cast<const uint4*>(q2)) : make_uint4(0, 0, 0, 0);
+            const uint4 nb2 = q2 + QS < bend ? __ldg(reinterpret_cast<const uint4*>(q2 + QS)) : make_uint4(0, 0, 0, 0);
+            add8(va);
+            if (q + QS < bend) add8(vb);
+            va = na; vb = nb2;
         }
-        if (q < bend) add8(__ldg(reinterpret_cast<const uint4*>(q)));
         if (bend + tid < pend) add(bend[tid]);                               // tail
     }
     __syncthreads();

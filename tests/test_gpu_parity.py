@@ -618,6 +618,7 @@ def test_two_batches_in_flight_give_the_same_bytes(reviser_by_species, reads):
     {"NRV_RNN11": "single"},                              # read_rnn11 with one tile per CTA (lstm_fused_tc64_kernel) instead of the ping-pong kernel
     {"NRV_F8": "2"},                                      # F8 in total_rnn2 only: total_rnn1 = fp16 x 3 recurrence + 8-bit copies for its consumer
     {"NRV_F8": "0"},                                      # total_rnn2 with fp16 x 3 correction passes (lstm_fused_pair_kernel<.., false, false>)
+    {"NRV_READ_STATS": "full"},                           # every read through the full-range 65,536-bin read_stats_kernel (the fall-back)
 ], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_non_default_kernel_paths_match_goldens(weights_by_species, reads, golden_dir, monkeypatch, env):
     """Every kernel variant that an environment switch can select is held to the same bar as the default path on the
