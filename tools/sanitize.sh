@@ -14,3 +14,11 @@ echo "=== compute-sanitizer --tool memcheck : unitest set, ecoli (fused layers a
 timeout -k 10 600 compute-sanitizer --tool memcheck --print-limit 40 --log-file gpurun_out/san/unitest_memcheck.log \
     python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "revise_unitest_set_matches_goldens and ecoli" > gpurun_out/san/unitest_memcheck.out 2>&1
 echo "exit $?"; tail -n 3 gpurun_out/san/unitest_memcheck.out; tail -n 4 gpurun_out/san/unitest_memcheck.log
+# K1 / K4 at their edge cases: compact + full-range read_stats (multi-segment merges, clamped ends, fall-back), the staged
+# base_features, decode tiles that span reads / empty reads
+for tool in memcheck racecheck; do
+  echo "=== compute-sanitizer --tool $tool : K1 / K4 edge-case tests"
+  timeout -k 10 600 compute-sanitizer --tool $tool --print-limit 40 --log-file gpurun_out/san/k1k4_$tool.log \
+      python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "median_mad or segment_edge or decode_vs or segment_matches" > gpurun_out/san/k1k4_$tool.out 2>&1
+  echo "exit $?"; tail -n 3 gpurun_out/san/k1k4_$tool.out; tail -n 4 gpurun_out/san/k1k4_$tool.log
+done
