@@ -17,6 +17,7 @@ OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libnrv.so")
 
 SOURCES = ["nrv_segment.cu", "nrv_cnn.cu", "nrv_lstm.cu", "nrv_heads.cu", "nrv_decode.cu", "nrv_gemm.cu", "nrv_rec_tc.cu", "nrv_fused_pair.cu", "nrv_api.cu",
+           "nrv_train.cu",         # training operators (include/nrv_train.h)
            "nrv_ingest.cpp"]       # host-only C++ (native fast5 ingest); links zlib
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo"] + os.environ.get("NRV_EXTRA_NVCC", "").split() + [ "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -40,6 +41,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "nrv.h"))
+    headers.append(os.path.join(ROOT, "include", "nrv_train.h"))
     nvcc = _nvcc()
     jobs = []
     for src in SOURCES:

@@ -18,7 +18,7 @@ Mirrors, function by function (same names, arguments, return order and error beh
 The reference walks Python lists character by character; here the alignment columns are numpy byte arrays and the cleaning /
 windowing steps are vectorised.  Pinned against the reference's own functions on randomised alignments (both strands, H / S
 clips, I / D / N / P / = / X operations, leading and trailing non-match operations): tests/golden/make_trainprep_fixtures.py ->
-tests/golden/trainprep.npz, tests/test_trainprep.py.  Two quirks of the reference are kept on purpose and tested: a trailing
+tests/golden/trainprep.json, tests/test_trainprep.py.  Two quirks of the reference are kept on purpose and tested: a trailing
 non-match operation adds the length of the FIRST remaining operation to end_clipped_bases (alignutils.py:137), and the last
 alignment column is always kept by clean_read_map_ref, also when it is a deletion (preprocessing.py:75-78).
 """
@@ -257,7 +257,7 @@ def read_training_arrays(read, sam_record, genome_index, reviser) -> Dict[str, n
     b = engine.Batch(signal=np.ascontiguousarray(read.signal[int(a0):], np.int16),
                      sig_off=np.array([0, len(read.signal) - int(a0)], np.int64),
                      starts=np.ascontiguousarray(starts, np.int32), base_off=np.array([0, n], np.int64),
-                     bases=np.ascontiguousarray(c_read[:n] if len(c_read) >= n else np.resize(c_read, n), np.uint8),
+                     bases=np.ascontiguousarray(np.asarray(read.bases)[int(sc):int(sc) + n], np.uint8),
                      ev_mean=np.ascontiguousarray(ev_mean, np.float32), ev_std=np.ascontiguousarray(ev_std, np.float32),
                      last_dur=np.array([int(length[-1])], np.int32))
     shift, scale, seg_mean, seg_std, _x, win, _status = reviser.segment(b, want_windows=True)

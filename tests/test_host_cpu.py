@@ -149,6 +149,51 @@ def test_cabi_library_exports_every_declared_symbol():
     assert b"sm_100a" in engine.load_library().nrv_version()
 
 
+def test_training_cabi_exports_and_no_cpu_fallback():
+    """include/nrv_train.h: every declared operator is exported by the library and bound by train.py; without a GPU the training
+    model refuses to exist."""
+    import ctypes
+    import torch
+    from nanoreviser_b200 import engine, train
+    hdr = open(os.path.join(ROOT, "include", "nrv_train.h")).read()
+    declared = set(re.findall(r"\b(nrvt_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(train.TRAIN_EXPORTS), declared ^ set(train.TRAIN_EXPORTS)
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    if not torch.cuda.is_available():
+        with pytest.raises(train.TrainError, match="no CUDA device"):
+            train.TrainModel(window=11, n_class=6)
+    w = train.init_weights(13, 5, seed=1)
+    assert w.feat_k.shape == (78, 16) and w.final_k.shape == (16, 5) and w.lstm[2][0].kernel.shape == (192, 512)
+    assert np.allclose(w.lstm[1][1].recurrent @ w.lstm[1][1].recurrent.T, np.eye(64), atol=1e-5)        # orthogonal rows
+    assert w.lstm[0][0].bias[16:32].tolist() == [1.0] * 16 and w.lstm[0][0].bias[:16].tolist() == [0.0] * 16
+
+
+def test_saved_weight_file_is_keras_layout(tmp_path, weights_by_species):
+    """train.save_predict_weights writes what weights.load_model_weights (and the independent reader of tests/indep_keras.py) read:
+    a round trip of the shipped ecoli model reproduces every array bit for bit under the original dataset paths."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import indep_keras
+    from nanoreviser_b200 import train, weights
+    m1, _ = weights_by_species("ecoli")
+    fn = str(tmp_path / "rt.h5")
+    train.save_predict_weights(m1, fn)
+    back = weights.load_model_weights(fn)
+    for k, v in m1.__dict__.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, getattr(back, k)), k
+    for l in range(4):
+        for d in range(2):
+            for f in ("kernel", "recurrent", "bias"):
+                assert np.array_equal(getattr(m1.lstm[l][d], f), getattr(back.lstm[l][d], f))
+    orig = indep_keras.H5Scan(os.path.join(ROOT, "model", "ecoli", "ecoli_win13_50ep_model1.h5")).walk()
+    mine = indep_keras.H5Scan(fn).walk()
+    assert set(orig) == set(mine)
+    for k in orig:
+        assert np.array_equal(orig[k], mine[k]), k
+
+
 def test_no_cpu_fallback_without_device(weights_by_species):
     """Without a GPU the product fails loudly; it never routes through the oracle."""
     import torch
