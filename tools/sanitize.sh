@@ -22,3 +22,8 @@ for tool in memcheck racecheck; do
       python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "median_mad or segment_edge or decode_vs or segment_matches" > gpurun_out/san/k1k4_$tool.out 2>&1
   echo "exit $?"; tail -n 3 gpurun_out/san/k1k4_$tool.out; tail -n 4 gpurun_out/san/k1k4_$tool.log
 done
+# training operators: one gradient-parity test (every kernel of csrc/nrv_train.cu, both LSTM directions, all four layers)
+echo "=== compute-sanitizer --tool memcheck : training step"
+timeout -k 10 900 compute-sanitizer --tool memcheck --print-limit 40 --log-file gpurun_out/san/train_memcheck.log \
+    python -m pytest tests/test_train_gpu.py -x -q -m gpu -k "gradients_match and 1-keras" > gpurun_out/san/train_memcheck.out 2>&1
+echo "exit $?"; tail -n 3 gpurun_out/san/train_memcheck.out; tail -n 4 gpurun_out/san/train_memcheck.log
