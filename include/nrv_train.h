@@ -7,8 +7,9 @@
  * stream).  All calls are asynchronous on that stream and return 0, or a negative value when the launch was rejected
  * (nrvt_last_error() has the text).  Nothing here falls back to the CPU.
  *
- * A first, correct form: fp32 SIMT kernels, one launch per operator and LSTM timestep (a training step of 512 windows is
- * ~1.5 k launches); gradients are checked against an fp64 autograd graph of the same network in tests/test_train_gpu.py.
+ * A first, correct form: fp32 SIMT kernels, one launch per operator and LSTM timestep (a training step is ~600 calls, which
+ * train.py captures into a CUDA graph: nothing here allocates or synchronises, per-step scalars are read from device memory);
+ * gradients are checked against an fp64 autograd graph of the same network in tests/test_train_gpu.py.
  */
 #ifndef NRV_TRAIN_H
 #define NRV_TRAIN_H
@@ -72,12 +73,14 @@ int nrvt_softmax_ce(void* stream, const float* logits, const int32_t* labels, co
  * dcenters[y_i] -= the same (dcenters must be zeroed by the caller); stats[2] += sum_i l2_i. */
 int nrvt_center_loss(void* stream, const float* feat, const int32_t* labels, const float* centers, float* dfeat, float* dcenters,
                      float* stats, int B, int dim, float scale);
-/* keep-mask of Dropout(rate) for n elements: mask[i] = 1 with probability 1 - rate, a pure function of (seed, step, i). */
-int nrvt_dropout_mask(void* stream, uint8_t* mask, int64_t n, uint64_t seed, uint64_t step, float rate);
+/* keep-mask of Dropout(rate) for n elements: mask[i] = 1 with probability 1 - rate, a pure function of (seed, *step, i); the step
+ * number is read from DEVICE memory so that a captured CUDA graph of the training step draws a new mask at every replay. */
+int nrvt_dropout_mask(void* stream, uint8_t* mask, int64_t n, uint64_t seed, const int64_t* step, float rate);
 /* X *= mask * scale (mask: uint8 0/1): Dropout forward and backward. */
 int nrvt_dropout(void* stream, float* X, const uint8_t* mask, int64_t n, float scale);
-/* Keras 2.2.4 Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps), lr_t supplied by the caller. */
-int nrvt_adam(void* stream, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps);
+/* Keras 2.2.4 Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps); the bias-corrected step size
+ * lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) is read from DEVICE memory (one float, written by the caller before the step: graph replays). */
+int nrvt_adam(void* stream, float* p, const float* g, float* m, float* v, int64_t n, const float* lr_t, float b1, float b2, float eps);
 /* moving = momentum * moving + (1 - momentum) * batch (the BatchNormalization update ops). */
 int nrvt_ema(void* stream, float* moving, const float* batch, int64_t n, float momentum, float batch_scale);
 

@@ -35,15 +35,19 @@ inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1)
 // ---------------------------------------------------------------------------------------------------------------------------
 // GEMM: 64 x 64 tile of C per CTA, K in steps of 16, 4 x 4 outputs per thread
 // ---------------------------------------------------------------------------------------------------------------------------
-template <bool TA, bool TB>
+// SPLITK: blockIdx.z owns the K range [z * kchunk, (z + 1) * kchunk) and ADDS alpha * partial into C with atomics (C holds beta * C
+// already): the weight-gradient products X^T dZ have K = all rows of the batch (thousands) and a C of a few tiles only
+template <bool TA, bool TB, bool SPLITK>
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float beta,
-            float* __restrict__ C, int ldc) {
+            float* __restrict__ C, int ldc, int kchunk) {
     __shared__ float As[16][64 + 4], Bs[16][64 + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    const int kbeg = SPLITK ? blockIdx.z * kchunk : 0;
+    const int kend = SPLITK ? min(K, kbeg + kchunk) : K;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int idx = tid + i * 256;
@@ -51,14 +55,14 @@ gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int l
                 const int kk = TA ? idx >> 6 : idx & 15, mm = TA ? idx & 63 : idx >> 4;
                 const int gm = m0 + mm, gk = k0 + kk;
                 float v = 0.f;
-                if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+                if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
                 As[kk][mm] = v;
             }
             {   // B tile -> Bs[k][n]
                 const int kk = TB ? idx & 15 : idx >> 6, nn = TB ? idx >> 4 : idx & 63;
                 const int gn = n0 + nn, gk = k0 + kk;
                 float v = 0.f;
-                if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+                if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
                 Bs[kk][nn] = v;
             }
         }
@@ -84,9 +88,19 @@ gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int l
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             float* c = C + (size_t)gm * ldc + gn;
-            *c = beta == 0.f ? alpha * acc[i][j] : fmaf(alpha, acc[i][j], beta * *c);
+            if (SPLITK) atomicAdd(c, alpha * acc[i][j]);
+            else *c = beta == 0.f ? alpha * acc[i][j] : fmaf(alpha, acc[i][j], beta * *c);
         }
     }
+}
+
+// C[M,N] (ldc) *= beta (beta == 0: set to zero, also over NaNs)
+__global__ void scale2d_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    const int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
+    float* p = C + (size_t)r * ldc + c;
+    *p = beta == 0.f ? 0.f : beta * *p;
 }
 
 __global__ void bias_act_kernel(float* __restrict__ Y, int M, int N, int ldy, const float* __restrict__ bias, int relu) {
@@ -103,23 +117,23 @@ __global__ void relu_bwd_kernel(float* __restrict__ dY, const float* __restrict_
     if (i < n && !(Y[i] > 0.f)) dY[i] = 0.f;
 }
 
-// column sums: CTA = 32 columns x 8 row-lanes, rows strided over the grid's y dimension; double accumulation per CTA, one
-// atomic per column and CTA into a zeroed double scratch is avoided by a second tiny pass: here M <= a few 1e5, so one CTA
-// per 32 columns walks all rows
+// column sums: a CTA = 32 columns x 8 row-lanes over the rows [blockIdx.y * rchunk, +rchunk); double partial sums, one float atomic
+// per column and CTA into out (which holds beta * out already)
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ X, int M, int N, int ldx, float* __restrict__ out, float beta) {
+colsum_kernel(const float* __restrict__ X, int M, int N, int ldx, float* __restrict__ out, int rchunk) {
     __shared__ double part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rchunk, r1 = min(M, r0 + rchunk);
     double s = 0.0;
     if (c < N)
-        for (int r = rl; r < M; r += 8) s += (double)X[(size_t)r * ldx + c];
+        for (int r = r0 + rl; r < r1; r += 8) s += (double)X[(size_t)r * ldx + c];
     part[rl][threadIdx.x & 31] = s;
     __syncthreads();
     if (rl == 0 && c < N) {
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-        out[c] = beta == 0.f ? (float)t : (float)((double)beta * (double)out[c] + t);
+        atomicAdd(&out[c], (float)t);
     }
 }
 
@@ -386,9 +400,10 @@ __global__ void center_loss_kernel(const float* __restrict__ feat, const int32_t
 
 // keep-mask of Dropout(rate): a counter-based generator (the splitmix64 finaliser over (seed, step, element)), so that a step's
 // mask depends on nothing but those three numbers
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, uint64_t seed, uint64_t step, float rate) {
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, uint64_t seed, const int64_t* __restrict__ step_p, float rate) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint64_t step = (uint64_t)*step_p;
     uint64_t x = seed ^ (step * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)i * 0xD1B54A32D192ED03ull);
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
@@ -403,9 +418,10 @@ __global__ void dropout_kernel(float* __restrict__ X, const uint8_t* __restrict_
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                            float lr_t, float b1, float b2, float eps) {
+                            const float* __restrict__ lr_t_p, float b1, float b2, float eps) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float lr_t = *lr_t_p;
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -430,11 +446,19 @@ int nrvt_gemm(void* stream, int ta, int tb, int M, int N, int K, float alpha, co
               float beta, float* C, int ldc) {
     if (M <= 0 || N <= 0) return 0;
     if (K < 0 || !A || !B || !C) return bad("nrvt_gemm: bad arguments");
-    const dim3 grid((N + 63) / 64, (M + 63) / 64);
-    if (!ta && !tb) gemm_kernel<false, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (!ta && tb) gemm_kernel<false, true><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (ta && !tb) gemm_kernel<true, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else gemm_kernel<true, true><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    // few output tiles and a long K (the weight gradients): split K over the grid's z dimension
+    const int tiles = (int)(grid.x * grid.y);
+    if (ta && !tb && K >= 1024 && tiles < 148) {
+        const int splits = std::min((K + 255) / 256, std::max(1, 592 / tiles));
+        const int kchunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
+        grid.z = (K + kchunk - 1) / kchunk;
+        scale2d_kernel<<<blocks_for((int64_t)M * N, 256), 256, 0, S(stream)>>>(C, M, N, ldc, beta);
+        gemm_kernel<true, false, true><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kchunk);
+    } else if (!ta && !tb) gemm_kernel<false, false, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+    else if (!ta && tb) gemm_kernel<false, true, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+    else if (ta && !tb) gemm_kernel<true, false, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+    else gemm_kernel<true, true, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
     LAUNCH_CHECK("nrvt_gemm");
     return 0;
 }
@@ -455,7 +479,9 @@ int nrvt_relu_bwd(void* stream, float* dY, const float* Y, int64_t n) {
 
 int nrvt_colsum(void* stream, const float* X, int M, int N, int ldx, float* out, float beta) {
     if (N <= 0) return 0;
-    colsum_kernel<<<(N + 31) / 32, 256, 0, S(stream)>>>(X, M, N, ldx, out, beta);
+    const int rchunk = 512;
+    scale2d_kernel<<<blocks_for(N, 256), 256, 0, S(stream)>>>(out, 1, N, N, beta);
+    colsum_kernel<<<dim3((N + 31) / 32, (std::max(M, 1) + rchunk - 1) / rchunk), 256, 0, S(stream)>>>(X, M, N, ldx, out, rchunk);
     LAUNCH_CHECK("nrvt_colsum");
     return 0;
 }
@@ -577,7 +603,7 @@ int nrvt_center_loss(void* stream, const float* feat, const int32_t* labels, con
     return 0;
 }
 
-int nrvt_dropout_mask(void* stream, uint8_t* mask, int64_t n, uint64_t seed, uint64_t step, float rate) {
+int nrvt_dropout_mask(void* stream, uint8_t* mask, int64_t n, uint64_t seed, const int64_t* step, float rate) {
     if (n <= 0) return 0;
     dropout_mask_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(mask, n, seed, step, rate);
     LAUNCH_CHECK("nrvt_dropout_mask");
@@ -591,7 +617,7 @@ int nrvt_dropout(void* stream, float* X, const uint8_t* mask, int64_t n, float s
     return 0;
 }
 
-int nrvt_adam(void* stream, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps) {
+int nrvt_adam(void* stream, float* p, const float* g, float* m, float* v, int64_t n, const float* lr_t, float b1, float b2, float eps) {
     if (n <= 0) return 0;
     adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(p, g, m, v, n, lr_t, b1, b2, eps);
     LAUNCH_CHECK("nrvt_adam");

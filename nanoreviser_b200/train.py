@@ -73,9 +73,9 @@ def _lib():
         "nrvt_lstm_cell_bwd": [vp, f32p, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int],
         "nrvt_softmax_ce": [vp, f32p, vp, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float],
         "nrvt_center_loss": [vp, f32p, vp, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float],
-        "nrvt_dropout_mask": [vp, vp, i64, C.c_uint64, C.c_uint64, C.c_float],
+        "nrvt_dropout_mask": [vp, vp, i64, C.c_uint64, vp, C.c_float],
         "nrvt_dropout": [vp, f32p, vp, i64, C.c_float],
-        "nrvt_adam": [vp, f32p, f32p, f32p, f32p, i64, C.c_float, C.c_float, C.c_float, C.c_float],
+        "nrvt_adam": [vp, f32p, f32p, f32p, f32p, i64, f32p, C.c_float, C.c_float, C.c_float],
         "nrvt_ema": [vp, f32p, f32p, i64, C.c_float, C.c_float],
     }
     for name, args in sig.items():
@@ -173,8 +173,14 @@ class TrainModel:
         self.iterations = 0
         self.lr, self.beta1, self.beta2, self.eps = 1e-3, 0.9, 0.999, 1e-7
         self._buf: Dict[str, "torch.Tensor"] = {}
+        self._pool: Dict[tuple, "torch.Tensor"] = {}
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        # per-step scalars live on the device (the step is captured into a CUDA graph, where by-value arguments would freeze)
+        self._step_d = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._lr_t_d = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._graphs: Dict[tuple, dict] = {}
         self.launches = 0
+        self.use_graph = os.environ.get("NRV_TRAIN_GRAPH", "1") != "0"      # fit(): steps replayed from a CUDA graph
 
     # -- plumbing ------------------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -187,12 +193,17 @@ class TrainModel:
             raise TrainError("%s failed (%d): %s" % (name, rc, self.lib.nrvt_last_error().decode()))
 
     def buf(self, name, shape, dtype=None, zero=False):
+        """Named scratch tensor.  One tensor per (name, shape, dtype) is kept for the life of the model -- a captured CUDA graph holds
+        raw pointers into the buffers of its batch size, which therefore must survive passes with another batch size -- and
+        self._buf[name] is the one used last."""
         torch = self._torch
         dtype = dtype or torch.float32
-        t = self._buf.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.dev)
-            self._buf[name] = t
+        key = (name, tuple(int(v) for v in shape), dtype)
+        t = self._pool.get(key)
+        if t is None:
+            t = torch.empty(key[1], dtype=dtype, device=self.dev)
+            self._pool[key] = t
+        self._buf[name] = t
         if zero:
             t.zero_()
         return t
@@ -322,12 +333,26 @@ class TrainModel:
     def forward_backward(self, S, X, y, class_weight=None, training=True, dropout_mask=None):
         """One batch through the train model.  training=True: batch statistics, dropout, gradients left in self.g.
         Returns {'loss', 'final_out_loss', 'l2_loss1_loss', 'final_out_acc'} as device-side sums turned into batch means."""
-        torch = self._torch
         S_tm, X_tm, y_d, B, T = self._upload(S, X, y)
-        n = T * B
-        L, Cc = SIGNAL_LEN, CNN_CH
         if not training:
             return self._evaluate(S_tm, X_tm, y_d, B, T)
+        mask = None
+        if dropout_mask is not None:        # [B,T,50,8] booleans (tests): to the time-major order
+            mask = self._torch.from_numpy(np.ascontiguousarray(np.asarray(dropout_mask).transpose(1, 0, 2, 3)).astype(np.uint8)).to(self.dev)
+        self._step_d.fill_(self.iterations)
+        return self._metrics(self._train_device(S_tm, X_tm, y_d, B, T, self._class_weight_tensor(class_weight), mask), B)
+
+    def _class_weight_tensor(self, class_weight):
+        if class_weight is None or self.class_weight_mode != "applied":
+            return None
+        return self._torch.tensor([float(class_weight.get(k, 1.0)) for k in range(self.n_class)], dtype=self._torch.float32, device=self.dev)
+
+    def _train_device(self, S_tm, X_tm, y_d, B, T, cw, mask):
+        """Forward + backward of one batch, device work only (no allocation once the buffers exist, no synchronisation): this is
+        what a CUDA graph captures.  Returns the device tensor of the loss sums."""
+        torch = self._torch
+        n = T * B
+        L, Cc = SIGNAL_LEN, CNN_CH
         # ---- CNN branch (nanorevcnn.py:29-38, lstmmodel.py:35-41) on the n = T*B signals
         c1 = self.buf("c1", (n * L, Cc))
         self._call("nrvt_conv1d_fwd", self._ptr(S_tm), self._ptr(self.p["conv1_k"]), self._ptr(self.p["conv1_b"]), self._ptr(c1), n, L, 1, Cc)
@@ -336,12 +361,9 @@ class TrainModel:
         self._call("nrvt_conv1d_fwd", self._ptr(b1), self._ptr(self.p["conv2_k"]), self._ptr(self.p["conv2_b"]), self._ptr(c2), n, L, Cc, Cc)
         res = self._bn_fwd("bn2", c2, n * L, Cc, True)
         self._call("nrvt_add_bcast", self._ptr(res), self._ptr(S_tm), n * L, Cc)
-        if dropout_mask is None:
+        if mask is None:
             mask = self.buf("mask", (n * L, Cc), dtype=torch.uint8)
-            self._call("nrvt_dropout_mask", C.c_void_p(mask.data_ptr()), n * L * Cc, self.seed, self.iterations, DROPOUT)
-        else:       # [B,T,50,8] booleans (tests): to the time-major order
-            mask = torch.from_numpy(np.ascontiguousarray(np.asarray(dropout_mask).transpose(1, 0, 2, 3)).astype(np.uint8)).to(self.dev)
-        self._buf["mask"] = mask
+            self._call("nrvt_dropout_mask", C.c_void_p(mask.data_ptr()), n * L * Cc, self.seed, C.c_void_p(self._step_d.data_ptr()), DROPOUT)
         keep_scale = 1.0 / (1.0 - DROPOUT)
         self._call("nrvt_dropout", self._ptr(res), C.c_void_p(mask.data_ptr()), n * L * Cc, keep_scale)
         # ---- read branch: Bi-LSTM(16) -> BN -> Bi-LSTM(64) -> BN ; concat [read_rnn2 (128) | signal (64)]
@@ -369,10 +391,6 @@ class TrainModel:
         stats = self.buf("stats", (4,), zero=True)
         probs = self.buf("probs", (B, self.n_class))
         dlog = self.buf("dlogits", (B, self.n_class))
-        cw = None
-        if class_weight is not None and self.class_weight_mode == "applied":
-            cw = torch.tensor([float(class_weight.get(k, 1.0)) for k in range(self.n_class)], dtype=torch.float32, device=self.dev)
-        self._buf["cw"] = cw
         self._call("nrvt_softmax_ce", self._ptr(logits), C.c_void_p(y_d.data_ptr()), self._ptr(cw), self._ptr(probs), self._ptr(dlog),
                    self._ptr(stats), B, self.n_class, LOSS_WEIGHTS[0] / B)
         # ---- backward
@@ -410,7 +428,7 @@ class TrainModel:
         self._call("nrvt_conv1d_bwd", self._ptr(S_tm), self._ptr(self.p["conv1_k"]), self._ptr(c1), self._ptr(dc1), None,
                    self._ptr(self.g["conv1_k"]), self._ptr(self.g["conv1_b"]), n, L, 1, Cc)
         self._last_rows = {"bn1": n * L, "bn2": n * L, "bnr0": n, "bnr1": n, "bnr2": n}
-        return self._metrics(stats, B)
+        return stats
 
     @staticmethod
     def _metrics(stats, B):
@@ -464,24 +482,59 @@ class TrainModel:
         self.forward_backward(S, X, np.zeros(B), training=False)
         return self._buf["probs"].cpu().numpy()
 
-    def apply_gradients(self):
-        """One Adam step on every trainable parameter and the BatchNormalization moving-average updates of the last batch."""
-        self.iterations += 1
-        t = self.iterations
-        lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+    def _adam_step_size(self, t):
+        return self.lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+
+    def _apply_device(self):
+        """Adam on every trainable parameter + the BatchNormalization moving averages; step size from the device scalar"""
         for k, p in self.p.items():
             self._call("nrvt_adam", self._ptr(p), self._ptr(self.g[k]), self._ptr(self.m[k]), self._ptr(self.v[k]), p.numel(),
-                       lr_t, self.beta1, self.beta2, self.eps)
+                       self._ptr(self._lr_t_d), self.beta1, self.beta2, self.eps)
         for name, rows in self._last_rows.items():
             Cn = self.s[name + "_mean"].numel()
             self._call("nrvt_ema", self._ptr(self.s[name + "_mean"]), self._ptr(self._buf[name + "_bm"]), Cn, BN_MOMENTUM, 1.0)
             self._call("nrvt_ema", self._ptr(self.s[name + "_var"]), self._ptr(self._buf[name + "_bv"]), Cn, BN_MOMENTUM,
                        rows / (rows - (1.0 + BN_EPS)))
 
-    def train_on_batch(self, S, X, y, class_weight=None, dropout_mask=None):
-        out = self.forward_backward(S, X, y, class_weight, True, dropout_mask)
-        self.apply_gradients()
-        return out
+    def apply_gradients(self):
+        """One Adam step on every trainable parameter and the BatchNormalization moving-average updates of the last batch."""
+        self.iterations += 1
+        self._lr_t_d.fill_(self._adam_step_size(self.iterations))
+        self._apply_device()
+
+    def train_on_batch(self, S, X, y, class_weight=None, dropout_mask=None, graph=False):
+        """One training step.  graph=True: the device work of a step (forward, backward, Adam: ~600 launches) is captured into a
+        CUDA graph the third time a batch size is seen and replayed from then on; the inputs go into the graph's static tensors,
+        the step number (dropout mask) and the Adam step size into device scalars.  Same arithmetic either way."""
+        if not graph or dropout_mask is not None:
+            out = self.forward_backward(S, X, y, class_weight, True, dropout_mask)
+            self.apply_gradients()
+            return out
+        torch = self._torch
+        S_tm, X_tm, y_d, B, T = self._upload(S, X, y)
+        key = (B, T, self.class_weight_mode if class_weight is not None else None)
+        st = self._graphs.setdefault(key, {"seen": 0})
+        st["seen"] += 1
+        self._step_d.fill_(self.iterations)
+        self.iterations += 1
+        self._lr_t_d.fill_(self._adam_step_size(self.iterations))
+        if "graph" not in st:
+            if st["seen"] < 3:              # warm-up: every buffer of this batch size gets allocated outside the capture
+                stats = self._train_device(S_tm, X_tm, y_d, B, T, self._class_weight_tensor(class_weight), None)
+                self._apply_device()
+                return self._metrics(stats, B)
+            st["in"] = (S_tm.clone(), X_tm.clone(), y_d.clone())
+            st["cw"] = self._class_weight_tensor(class_weight)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["stats"] = self._train_device(st["in"][0], st["in"][1], st["in"][2], B, T, st["cw"], None)
+                self._apply_device()
+            st["graph"] = g                 # (the capture itself does not execute: the replay below is this batch's step)
+        for dst, src in zip(st["in"], (S_tm, X_tm, y_d)):
+            dst.copy_(src)
+        st["graph"].replay()
+        return self._metrics(st["stats"], B)
 
     # -- Model.fit -------------------------------------------------------------------------------------------------------------
     def fit(self, inputs, targets=None, class_weight=None, validation_split=0.0, shuffle=True, epochs=1, batch_size=32, verbose=1,
@@ -506,7 +559,7 @@ class TrainModel:
             acc = dict.fromkeys(keys, 0.0)
             for a in range(0, n_train, int(batch_size)):
                 idx = np.sort(order[a:a + int(batch_size)])
-                m = self.train_on_batch(S[idx], X[idx], y[idx], class_weight)
+                m = self.train_on_batch(S[idx], X[idx], y[idx], class_weight, graph=self.use_graph)
                 for k in keys:
                     acc[k] += m[k] * len(idx)
             row = {k: acc[k] / n_train for k in keys}

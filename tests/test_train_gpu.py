@@ -169,6 +169,35 @@ def test_adam_and_moving_average_updates(weights_by_species):
             assert np.allclose(tm.s[name + "_var"].cpu().numpy(), s0[name + "_var"], rtol=1e-5, atol=1e-6), (step, name)
 
 
+def test_graph_replay_equals_eager_steps(weights_by_species):
+    """train_on_batch(graph=True) -- the step captured into a CUDA graph on its third call and replayed afterwards, with a
+    validation pass of another batch size in between -- leaves the same parameters as the eager launches (same seeds, same masks:
+    the dropout mask is a function of (seed, step, element) read from device scalars)."""
+    import torch
+    from nanoreviser_b200 import train
+    w = weights_by_species("ecoli")[0]
+    rng = np.random.default_rng(23)
+    batches = [_inputs(rng, 32, w.window, w.n_class)[:3] for _ in range(6)]
+    Sv, Xv, yv, _ = _inputs(rng, 20, w.window, w.n_class)
+    models = []
+    for graph in (False, True):
+        tm = train.TrainModel(window=w.window, n_class=w.n_class, weights=w, seed=4)
+        losses = []
+        for k, (S, X, y) in enumerate(batches):
+            losses.append(tm.train_on_batch(S, X, y, graph=graph)["loss"])
+            if k == 3:
+                tm.forward_backward(Sv, Xv, yv, training=False)           # other shapes through the same named buffers
+        torch.cuda.synchronize()
+        models.append((tm, losses))
+    (a, la), (b, lb) = models
+    assert "graph" in next(iter(b._graphs.values())) and not a._graphs
+    assert np.allclose(la, lb, rtol=1e-5), (la, lb)
+    for k in a.p:
+        assert np.allclose(a.p[k].cpu().numpy(), b.p[k].cpu().numpy(), rtol=1e-5, atol=1e-7), k
+    for k in a.s:
+        assert np.allclose(a.s[k].cpu().numpy(), b.s[k].cpu().numpy(), rtol=1e-5, atol=1e-7), k
+
+
 def test_fit_learns_and_the_saved_weights_drive_the_inference_engine(tmp_path):
     """Model.fit semantics end to end on a learnable synthetic task (the label is a function of the centre base's colour column),
     then the Keras-layout weight file goes through weights.load_model_weights into the inference engine, whose probabilities
