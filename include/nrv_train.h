@@ -38,9 +38,10 @@ int nrvt_copy2d(void* stream, float* dst, int ldd, const float* src, int lds, in
 /* Conv1D(kernel 3, padding 'same', activation relu) over n sequences of L positions, channels last (nanorevcnn.py:24):
  * X [n,L,cin], W [3,cin,cout] (Keras layout), Y [n,L,cout]; cin, cout <= 8. */
 int nrvt_conv1d_fwd(void* stream, const float* X, const float* W, const float* b, float* Y, int n, int L, int cin, int cout);
-/* dY = gradient w.r.t. the relu output Y.  dX may be NULL (first layer).  dW [3,cin,cout] and db [cout] are OVERWRITTEN. */
+/* dY = gradient w.r.t. the relu output Y.  dX may be NULL (first layer).  dW [3,cin,cout] and db [cout] are OVERWRITTEN.
+ * work: >= 3*cin*cout + cout doubles of scratch. */
 int nrvt_conv1d_bwd(void* stream, const float* X, const float* W, const float* Y, const float* dY, float* dX, float* dW, float* db,
-                    int n, int L, int cin, int cout);
+                    double* work, int n, int L, int cin, int cout);
 /* Y[n,L,C] += X[n,L,1] broadcast over the channels (the Add() of identity_Block on a 1-channel input, nanorevcnn.py:37). */
 int nrvt_add_bcast(void* stream, float* Y, const float* X, int64_t rows, int C);
 

@@ -503,7 +503,7 @@ int nrvt_conv1d_fwd(void* stream, const float* X, const float* W, const float* b
 }
 
 int nrvt_conv1d_bwd(void* stream, const float* X, const float* W, const float* Y, const float* dY, float* dX, float* dW, float* db,
-                    int n, int L, int cin, int cout) {
+                    double* work, int n, int L, int cin, int cout) {
     if (cin < 1 || cin > 8 || cout < 1 || cout > 8 || L < 1 || L > 1024) return bad("nrvt_conv1d_bwd: cin, cout must be 1..8, L <= 1024");
     const int64_t rows = (int64_t)n * L;
     if (rows <= 0) return 0;
@@ -511,16 +511,13 @@ int nrvt_conv1d_bwd(void* stream, const float* X, const float* W, const float* Y
         conv1d_bwd_data_kernel<<<blocks_for(rows, 256), 256, 0, S(stream)>>>(W, Y, dY, dX, rows, L, cin, cout);
         LAUNCH_CHECK("nrvt_conv1d_bwd (data)");
     }
-    // weight / bias gradients through a double scratch (stream-ordered allocation: no state kept between calls)
-    double* acc = nullptr;
+    // weight / bias gradients accumulate in the caller's double scratch
+    if (!work) return bad("nrvt_conv1d_bwd: work is NULL");
     const int nacc = 3 * cin * cout + cout;
-    cudaError_t e = cudaMallocAsync(&acc, nacc * sizeof(double), S(stream));
-    if (e != cudaSuccess) return fail("nrvt_conv1d_bwd: scratch", e);
-    cudaMemsetAsync(acc, 0, nacc * sizeof(double), S(stream));
+    cudaMemsetAsync(work, 0, nacc * sizeof(double), S(stream));
     const size_t smem = ((size_t)(L + 2) * cin + (size_t)L * cout) * sizeof(float);
-    conv1d_bwd_w_kernel<<<(unsigned)std::min<int64_t>(n, 1184), 256, smem, S(stream)>>>(X, Y, dY, acc, n, L, cin, cout);
-    double_to_float_kernel<<<1, 256, 0, S(stream)>>>(acc, dW, 3 * cin * cout, db, cout);
-    cudaFreeAsync(acc, S(stream));
+    conv1d_bwd_w_kernel<<<(unsigned)std::min<int64_t>(n, 1184), 256, smem, S(stream)>>>(X, Y, dY, work, n, L, cin, cout);
+    double_to_float_kernel<<<1, 256, 0, S(stream)>>>(work, dW, 3 * cin * cout, db, cout);
     LAUNCH_CHECK("nrvt_conv1d_bwd (weights)");
     return 0;
 }

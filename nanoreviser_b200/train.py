@@ -64,7 +64,7 @@ def _lib():
         "nrvt_colsum": [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, C.c_float],
         "nrvt_copy2d": [vp, f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int],
         "nrvt_conv1d_fwd": [vp, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int],
-        "nrvt_conv1d_bwd": [vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int],
+        "nrvt_conv1d_bwd": [vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp, C.c_int, C.c_int, C.c_int, C.c_int],
         "nrvt_add_bcast": [vp, f32p, f32p, i64, C.c_int],
         "nrvt_bn_fwd": [vp, f32p, f32p, f32p, C.c_float, f32p, f32p, f32p, vp, i64, C.c_int],
         "nrvt_bn_apply": [vp, f32p, f32p, f32p, f32p, f32p, C.c_float, f32p, i64, C.c_int],
@@ -422,11 +422,12 @@ class TrainModel:
         self._call("nrvt_dropout", self._ptr(dres), C.c_void_p(mask.data_ptr()), n * L * Cc, keep_scale)
         dc2 = self._bn_bwd("bn2", c2, dres, n * L, Cc)
         db1 = self.buf("db1", (n * L, Cc))
+        work = self.buf("bn_work", (4 * 256,), dtype=torch.float64)
         self._call("nrvt_conv1d_bwd", self._ptr(b1), self._ptr(self.p["conv2_k"]), self._ptr(c2), self._ptr(dc2), self._ptr(db1),
-                   self._ptr(self.g["conv2_k"]), self._ptr(self.g["conv2_b"]), n, L, Cc, Cc)
+                   self._ptr(self.g["conv2_k"]), self._ptr(self.g["conv2_b"]), C.c_void_p(work.data_ptr()), n, L, Cc, Cc)
         dc1 = self._bn_bwd("bn1", c1, db1, n * L, Cc)
         self._call("nrvt_conv1d_bwd", self._ptr(S_tm), self._ptr(self.p["conv1_k"]), self._ptr(c1), self._ptr(dc1), None,
-                   self._ptr(self.g["conv1_k"]), self._ptr(self.g["conv1_b"]), n, L, 1, Cc)
+                   self._ptr(self.g["conv1_k"]), self._ptr(self.g["conv1_b"]), C.c_void_p(work.data_ptr()), n, L, 1, Cc)
         self._last_rows = {"bn1": n * L, "bn2": n * L, "bnr0": n, "bnr1": n, "bnr2": n}
         return stats
 
