@@ -150,7 +150,7 @@ def handel_input_fast5(fast5_fn_sg, args, genome_index, reviser):
 
 
 def train_preprocessing(args):
-    from nanoreviser_b200 import engine, trainprep, weights
+    from nanoreviser_b200 import engine, train, trainprep
     genome_index = trainprep.parse_fasta(args.genome_fn)
     if not args.test_mode:
         print(args.genome_fn, 'has been load......')
@@ -158,7 +158,7 @@ def train_preprocessing(args):
     if args.read_counts and args.read_counts < len(fns):
         fns = fns[:int(args.read_counts)]
     # the segmentation kernels belong to a handle; any weight set will do for it (only nrv_segment is used here)
-    m1, m2 = weights.load_species('ecoli')
+    m1, m2 = train.init_weights(11, 6), train.init_weights(11, 5)
     with engine.Reviser(m1, m2, device=args.device) as rv:
         for fn in fns:
             handel_input_fast5(fn, args, genome_index, rv)
