@@ -177,6 +177,35 @@ def test_predict_windows_vs_oracle(reviser_by_species, weights_by_species, reads
     assert np.abs(p2 - orc.forward_windows(m2, Sr, Xr, np.float32)).max() <= P_TOL_F32
 
 
+def test_outlier_spike_on_a_quiet_read_stays_finite(reviser_by_species, weights_by_species):
+    """A quiet read (MAD = 1) with a spike of ~30,000 normalised units: the fp32 reference graph stays finite, and so must the
+    split-fp16 path (values beyond the fp16 range saturate instead of becoming inf - inf = NaN).  Windows far from the spike equal
+    the oracle; windows that see it are valid probability rows."""
+    from oracle import nanorev_oracle as orc
+    from nanoreviser_b200 import engine, synth
+    rv = reviser_by_species("ecoli")
+    m1, m2 = weights_by_species("ecoli")
+    rng = np.random.default_rng(31)
+    sig, st, ba, em, es, ld = synth.make_read(220, 3, 9)
+    sig = (500 + rng.integers(-1, 2, sig.shape[0])).astype(np.int16)          # median 500, MAD 1
+    hit = int(st[110]) + 2
+    sig[hit:hit + 3] = 32000
+    b = engine.Batch(sig, np.array([0, len(sig)], np.int64), st.astype(np.int32), np.array([0, len(st)], np.int64), ba, em, es,
+                     np.array([ld], np.int32))
+    out = rv.revise_batch(b, want_labels=True, want_probs=True)
+    assert out.status.tolist() == [0]
+    for P in (out.p1, out.p2):
+        assert np.isfinite(P).all() and np.abs(P.sum(1) - 1.0).max() <= 1e-3
+    length = np.diff(np.concatenate([st, [st[-1] + ld]])).astype(np.float64)
+    res = orc.revise_arrays(m1, m2, [chr(c) for c in ba], st.astype(np.int64), length, sig, em, es, want=("probs",))
+    assert np.isfinite(res["P1"]).all() and np.isfinite(res["P2"]).all()
+    W = rv.window
+    far = np.abs(np.arange(len(st) - W) + W // 2 - 110) > 40                   # windows none of whose bases sees the spike
+    assert far.sum() > 80
+    assert np.abs(out.p1[far] - res["P1"][far]).max() <= P_TOL and np.abs(out.p2[far] - res["P2"][far]).max() <= P_TOL
+    assert np.array_equal(out.y1[far], res["y1"][far]) and np.array_equal(out.y2[far], res["y2"][far])
+
+
 # --------------------------------------------------------------------------------------------------
 # K4: decode vs the restated (and reference-pinned) get_base_1
 # --------------------------------------------------------------------------------------------------
