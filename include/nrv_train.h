@@ -71,7 +71,8 @@ int nrvt_lstm_cell_bwd(void* stream, const float* gates, const float* c_prev, co
 int nrvt_softmax_ce(void* stream, const float* logits, const int32_t* labels, const float* cw, float* probs, float* dlogits,
                     float* stats, int B, int nc, float scale);
 /* Center loss (lstmmodel.py:65-67): l2_i = sum_k (feat[i,k] - centers[y_i,k])^2.  dfeat += scale * 2 (feat - c_y);
- * dcenters[y_i] -= the same (dcenters must be zeroed by the caller); stats[2] += sum_i l2_i. */
+ * dcenters[y_i] -= the same (dcenters must be zeroed by the caller); stats[2] += sum_i l2_i; stats[3] += #(round(l2_i) == 0), the
+ * numerator of the 'accuracy' Keras reports for this output against its all-zero target (dim == 16 only). */
 int nrvt_center_loss(void* stream, const float* feat, const int32_t* labels, const float* centers, float* dfeat, float* dcenters,
                      float* stats, int B, int dim, float scale);
 /* keep-mask of Dropout(rate) for n elements: mask[i] = 1 with probability 1 - rate, a pure function of (seed, *step, i); the step

@@ -393,9 +393,17 @@ __global__ void center_loss_kernel(const float* __restrict__ feat, const int32_t
         dfeat[i] += g;
         atomicAdd(&dcenters[y * dim + k], -g);
     }
+    // per-sample sum over the dim (= 16: half a warp) lanes of a sample, then Keras' "accuracy" of this output against its all-zero
+    // target: binary_accuracy = mean(round(l2_i) == 0), round half to even
+    float per = l2;
+    if (dim == 16) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[2], l2);
+        for (int o = 8; o > 0; o >>= 1) per += __shfl_xor_sync(0xffffffffu, per, o);
+    }
+    float hit = (dim == 16 && (threadIdx.x & 15) == 0 && i < B * dim && per <= 0.5f) ? 1.f : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { l2 += __shfl_xor_sync(0xffffffffu, l2, o); hit += __shfl_xor_sync(0xffffffffu, hit, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[2], l2); atomicAdd(&stats[3], hit); }
 }
 
 // keep-mask of Dropout(rate): a counter-based generator (the splitmix64 finaliser over (seed, step, element)), so that a step's

@@ -8,7 +8,7 @@ The reference trains with Keras (NanoReviser_train.py:164-199):
     att_model_predict.save_weights(fn)
 
 :class:`TrainModel` is that object for this path: ``fit`` has Model.fit's arguments and returns the ``history`` dictionary
-(loss, final_out_loss, l2_loss1_loss, final_out_acc and their val_ twins), ``save_weights`` writes the predict model's weights
+(loss, final_out_loss, l2_loss1_loss, final_out_acc, l2_loss1_acc and their val_ twins), ``save_weights`` writes the predict model's weights
 in the Keras 2.2.4 HDF5 layout the inference path (weights.load_model_weights -> engine.Reviser) and Keras itself read.
 
 Every arithmetic step of a training step runs in the hand-written CUDA operators of csrc/nrv_train.cu (include/nrv_train.h):
@@ -332,7 +332,7 @@ class TrainModel:
 
     def forward_backward(self, S, X, y, class_weight=None, training=True, dropout_mask=None):
         """One batch through the train model.  training=True: batch statistics, dropout, gradients left in self.g.
-        Returns {'loss', 'final_out_loss', 'l2_loss1_loss', 'final_out_acc'} as device-side sums turned into batch means."""
+        Returns {'loss', 'final_out_loss', 'l2_loss1_loss', 'final_out_acc', 'l2_loss1_acc'} (device-side sums turned into batch means)."""
         S_tm, X_tm, y_d, B, T = self._upload(S, X, y)
         if not training:
             return self._evaluate(S_tm, X_tm, y_d, B, T)
@@ -433,9 +433,11 @@ class TrainModel:
 
     @staticmethod
     def _metrics(stats, B):
-        ce, hit, l2 = (float(v) for v in stats[:3].tolist())
+        ce, hit, l2, l2hit = (float(v) for v in stats[:4].tolist())
         ce, l2 = ce / B, l2 / B
-        return {"loss": LOSS_WEIGHTS[0] * ce + LOSS_WEIGHTS[1] * l2, "final_out_loss": ce, "l2_loss1_loss": l2, "final_out_acc": hit / B}
+        # (metrics=['accuracy'] applies to both outputs in Keras: the l2_loss1 output gets binary_accuracy against its zero target)
+        return {"loss": LOSS_WEIGHTS[0] * ce + LOSS_WEIGHTS[1] * l2, "final_out_loss": ce, "l2_loss1_loss": l2, "final_out_acc": hit / B,
+                "l2_loss1_acc": l2hit / B}
 
     def _evaluate(self, S_tm, X_tm, y_d, B, T):
         """Validation pass: the predict graph (moving statistics, no dropout) through the same operators."""
@@ -547,13 +549,13 @@ class TrainModel:
         S, X, y = inputs[0], inputs[1], np.asarray(inputs[2]).reshape(-1)
         S, X = np.asarray(S), np.asarray(X)
         N = X.shape[0]
-        n_val = int(N * float(validation_split)) if validation_split else 0
-        n_train = N - n_val
+        n_train = int(N * (1.0 - float(validation_split))) if validation_split else N      # keras/engine/training.py: split_at
+        n_val = N - n_train
         if n_train <= 0:
             raise ValueError("no training samples")
         rng = np.random.default_rng(seed)
         history: Dict[str, List[float]] = {}
-        keys = ("loss", "final_out_loss", "l2_loss1_loss", "final_out_acc")
+        keys = ("loss", "final_out_loss", "l2_loss1_loss", "final_out_acc", "l2_loss1_acc")
         for ep in range(int(epochs)):
             t0 = time.time()
             order = rng.permutation(n_train) if shuffle else np.arange(n_train)

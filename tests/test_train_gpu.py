@@ -78,7 +78,9 @@ def _ref_graph(torch, P, S, X, y, mask, cw, n_class, keep=None, gate_masks=None)
     logp = torch.log_softmax(logits, dim=1)
     w = cw[y] if cw is not None else torch.ones(B, dtype=X.dtype, device=X.device)
     ce = -(w * logp[torch.arange(B), y]).mean()
-    l2 = ((feat - P["centers"][y]) ** 2).sum(dim=1).mean()
+    l2_i = ((feat - P["centers"][y]) ** 2).sum(dim=1)
+    l2 = l2_i.mean()
+    stats["_l2_acc"] = float((l2_i.detach() <= 0.5).double().mean())
     return ce + 0.4 * l2, ce, l2, torch.softmax(logits, dim=1), stats
 
 
@@ -121,6 +123,7 @@ def test_gradients_match_fp64_autograd(weights_by_species, which, cw_mode):
                                             torch.tensor(y, device=dev), torch.tensor(mask, dtype=torch.float64, device=dev), cw, w.n_class,
                                             gate_masks=gate_masks)
     print("closest gate pre-activation to a hard_sigmoid kink: %.2e" % stats.pop("_kink"))
+    assert abs(m["l2_loss1_acc"] - stats.pop("_l2_acc")) <= 1.0 / B + 1e-9
     loss.backward()
     loss, ce, l2 = float(loss.detach()), float(ce.detach()), float(l2.detach())
     assert abs(m["loss"] - loss) <= 1e-4 * max(1.0, abs(loss)), (m, loss)
@@ -219,8 +222,9 @@ def test_fit_learns_and_the_saved_weights_drive_the_inference_engine(tmp_path):
         tm = train.TrainModel(window=T, n_class=n_class, seed=11)
         h = tm.fit([S[..., None], X, labels.reshape(-1, 1)], [labels, np.zeros((N, 1))], class_weight={0: 3, 1: 5, 2: 1, 3: 1, 4: 1, 5: 1},
                    validation_split=0.125, shuffle=True, epochs=EPOCHS, batch_size=64, verbose=0)
-        assert set(h) == {"loss", "final_out_loss", "l2_loss1_loss", "final_out_acc", "val_loss", "val_final_out_loss", "val_l2_loss1_loss",
-                          "val_final_out_acc"} and all(len(v) == EPOCHS for v in h.values())
+        assert set(h) == {"loss", "final_out_loss", "l2_loss1_loss", "final_out_acc", "l2_loss1_acc", "val_loss", "val_final_out_loss",
+                          "val_l2_loss1_loss", "val_final_out_acc", "val_l2_loss1_acc"} and all(len(v) == EPOCHS for v in h.values())
+        assert 0.0 <= h["l2_loss1_acc"][-1] <= 1.0
         print("model with %d classes: loss %.3f -> %.3f, acc %.3f -> %.3f, val_acc %.3f -> %.3f" % (
             n_class, h["loss"][0], h["loss"][-1], h["final_out_acc"][0], h["final_out_acc"][-1], h["val_final_out_acc"][0], h["val_final_out_acc"][-1]))
         # 525 Adam steps at Keras' default rate from a random initialisation: the task is learned, on held-out windows too
@@ -305,7 +309,7 @@ def test_cli_trains_both_models_from_fast5_and_sam(tmp_path, fast5_files):
         assert w.window == 11 and w.n_class == nc
         assert os.path.exists(os.path.join(mdl, "tiny", "training_model", "train_tiny_win11_2ep_%s.h5" % tag))
         rows = open(out + "tiny_win11_2ep_%s_hisroty.csv" % tag).read().strip().split("\n")
-        assert rows[0].split(",")[:4] == ["loss", "final_out_loss", "l2_loss1_loss", "final_out_acc"] and len(rows) == 3
+        assert rows[0].split(",")[:5] == ["loss", "final_out_loss", "l2_loss1_loss", "final_out_acc", "l2_loss1_acc"] and len(rows) == 3
         assert float(rows[2].split(",")[0]) < float(rows[1].split(",")[0])                   # the loss goes down
         import json
         assert json.load(open(out + "tiny_win11_2ep_%s_parameters.json" % tag))["epochs"] == 2
