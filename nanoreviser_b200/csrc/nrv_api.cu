@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "nrv_common.cuh"
+#include <nvtx3/nvToolsExt.h>    // header-only: ranges around the stages when NRV_NVTX=1 (ncu --nvtx, Nsight Systems)
 
 using namespace nrv;
 
@@ -108,6 +109,7 @@ struct nrv_handle {
     // stage timing: CUDA-event pairs recorded on the stream around every stage launch, never synchronised
     // on the hot path; folded into per-stage totals by nrv_get_stage_ms().
     bool timing = false;
+    bool nvtx = false;                    // NRV_NVTX=1: an NVTX range per stage scope (named like nrv_stage_name)
     float stage_ms[ST_COUNT] = {0};
     int64_t stage_launches[ST_COUNT] = {0};
     struct EvPair { cudaEvent_t a, b; int stage; };
@@ -383,6 +385,7 @@ cuda_fail:
 struct StageTimer {
     nrv_handle* h; int stage; int64_t launches0; ptrdiff_t slot = -1; cudaStream_t st;
     StageTimer(nrv_handle* h_, int s, cudaStream_t st_ = nullptr) : h(h_), stage(s), launches0(h_->launches), st(st_ ? st_ : h_->stream) {
+        if (h->nvtx) nvtxRangePushA(kStageNames[s]);
         if (!h->timing) return;
         if (h->ev_used == h->ev_pool.size()) {
             if (h->ev_pool.size() >= 8192 && h->timers_open == 0) h->fold_events();
@@ -399,6 +402,7 @@ struct StageTimer {
         ++h->timers_open;
     }
     ~StageTimer() {
+        if (h->nvtx) nvtxRangePop();
         h->stage_launches[stage] += h->launches - launches0;
         if (slot >= 0) { cudaEventRecord(h->ev_pool[slot].b, st); --h->timers_open; }
     }
@@ -1080,6 +1084,7 @@ int nrv_create(int device, const nrv_model_weights* m1, const nrv_model_weights*
     if (rfe && !strcmp(rfe, "0")) h->refine = 0;
     if (getenv("NRV_REFINE_TAU") && atof(getenv("NRV_REFINE_TAU")) > 0) h->refine_tau = (float)atof(getenv("NRV_REFINE_TAU"));
     if (getenv("NRV_REFINE_CAP") && atoi(getenv("NRV_REFINE_CAP")) > 0) h->refine_cap = atoi(getenv("NRV_REFINE_CAP"));
+    h->nvtx = getenv("NRV_NVTX") && atoi(getenv("NRV_NVTX")) != 0;
     const char* sge = getenv("NRV_SIGTAB");
     if (sge && !strcmp(sge, "0")) h->sig_table = 0;
     const char* f8e = getenv("NRV_F8");
