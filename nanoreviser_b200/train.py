@@ -347,36 +347,36 @@ class TrainModel:
             return None
         return self._torch.tensor([float(class_weight.get(k, 1.0)) for k in range(self.n_class)], dtype=self._torch.float32, device=self.dev)
 
-    def _train_device(self, S_tm, X_tm, y_d, B, T, cw, mask):
-        """Forward + backward of one batch, device work only (no allocation once the buffers exist, no synchronisation): this is
-        what a CUDA graph captures.  Returns the device tensor of the loss sums."""
+    def _forward(self, S_tm, X_tm, B, T, training, mask=None):
+        """The graph of lstmmodel.py:32-63 on time-major inputs.  training: batch statistics + dropout (train model), else moving
+        statistics, no dropout (predict model).  Returns the tensors the losses and the backward pass need."""
         torch = self._torch
         n = T * B
         L, Cc = SIGNAL_LEN, CNN_CH
         # ---- CNN branch (nanorevcnn.py:29-38, lstmmodel.py:35-41) on the n = T*B signals
         c1 = self.buf("c1", (n * L, Cc))
         self._call("nrvt_conv1d_fwd", self._ptr(S_tm), self._ptr(self.p["conv1_k"]), self._ptr(self.p["conv1_b"]), self._ptr(c1), n, L, 1, Cc)
-        b1 = self._bn_fwd("bn1", c1, n * L, Cc, True)
+        b1 = self._bn_fwd("bn1", c1, n * L, Cc, training)
         c2 = self.buf("c2", (n * L, Cc))
         self._call("nrvt_conv1d_fwd", self._ptr(b1), self._ptr(self.p["conv2_k"]), self._ptr(self.p["conv2_b"]), self._ptr(c2), n, L, Cc, Cc)
-        res = self._bn_fwd("bn2", c2, n * L, Cc, True)
+        res = self._bn_fwd("bn2", c2, n * L, Cc, training)
         self._call("nrvt_add_bcast", self._ptr(res), self._ptr(S_tm), n * L, Cc)
-        if mask is None:
-            mask = self.buf("mask", (n * L, Cc), dtype=torch.uint8)
-            self._call("nrvt_dropout_mask", C.c_void_p(mask.data_ptr()), n * L * Cc, self.seed, C.c_void_p(self._step_d.data_ptr()), DROPOUT)
-        keep_scale = 1.0 / (1.0 - DROPOUT)
-        self._call("nrvt_dropout", self._ptr(res), C.c_void_p(mask.data_ptr()), n * L * Cc, keep_scale)
+        if training:
+            if mask is None:
+                mask = self.buf("mask", (n * L, Cc), dtype=torch.uint8)
+                self._call("nrvt_dropout_mask", C.c_void_p(mask.data_ptr()), n * L * Cc, self.seed, C.c_void_p(self._step_d.data_ptr()), DROPOUT)
+            self._call("nrvt_dropout", self._ptr(res), C.c_void_p(mask.data_ptr()), n * L * Cc, 1.0 / (1.0 - DROPOUT))
         # ---- read branch: Bi-LSTM(16) -> BN -> Bi-LSTM(64) -> BN ; concat [read_rnn2 (128) | signal (64)]
         out0 = self._lstm_fwd(0, X_tm, 6, 6, T, B)
-        r1 = self._bn_fwd("bnr0", out0, n, 32, True)
+        r1 = self._bn_fwd("bnr0", out0, n, 32, training)
         out1 = self._lstm_fwd(1, r1, 32, 32, T, B)
-        r2 = self._bn_fwd("bnr1", out1, n, 128, True)
+        r2 = self._bn_fwd("bnr1", out1, n, 128, training)
         tot = self.buf("tot", (n, 192))
         self._call("nrvt_copy2d", self._ptr(tot), 192, self._ptr(r2), 128, n, 128, 0)
         self.gemm(0, 0, n, 64, L * Cc, res, L * Cc, self.p["sig_k"], 64, tot, 192, co=128)       # TD(Dense 64) straight into the concat
         self._call("nrvt_bias_act", self._ptr(tot, 128), n, 64, 192, self._ptr(self.p["sig_b"]), 0)
         out2 = self._lstm_fwd(2, tot, 192, 192, T, B)
-        t1 = self._bn_fwd("bnr2", out2, n, 256, True)
+        t1 = self._bn_fwd("bnr2", out2, n, 256, training)
         out3 = self._lstm_fwd(3, t1, 256, 256, T, B)
         # ---- heads (lstmmodel.py:55-63)
         d1 = self._dense_fwd("d1", out3, 128, n, 128, 128, True, "d1")
@@ -387,6 +387,20 @@ class TrainModel:
             self._call("nrvt_copy2d", self._ptr(flat, t * 6), T * 6, self._ptr(d3, t * B * 6), 6, B, 6, 0)
         feat = self._dense_fwd("f", flat, T * 6, B, T * 6, CENTER_DIM, True, "feat")
         logits = self._dense_fwd("o", feat, CENTER_DIM, B, CENTER_DIM, self.n_class, False, "logits")
+        return dict(c1=c1, b1=b1, c2=c2, res=res, mask=mask, out0=out0, r1=r1, out1=out1, tot=tot, out2=out2, t1=t1, out3=out3,
+                    d1=d1, d2=d2, d3=d3, flat=flat, feat=feat, logits=logits)
+
+    def _train_device(self, S_tm, X_tm, y_d, B, T, cw, mask):
+        """Forward + backward of one batch, device work only (no allocation once the buffers exist, no synchronisation): this is
+        what a CUDA graph captures.  Returns the device tensor of the loss sums."""
+        torch = self._torch
+        n = T * B
+        L, Cc = SIGNAL_LEN, CNN_CH
+        keep_scale = 1.0 / (1.0 - DROPOUT)
+        f = self._forward(S_tm, X_tm, B, T, True, mask)
+        c1, b1, c2, res, mask, out0, r1, out1, tot, out2, t1, out3 = (f[k] for k in ("c1", "b1", "c2", "res", "mask", "out0", "r1", "out1", "tot",
+                                                                                     "out2", "t1", "out3"))
+        d1, d2, d3, flat, feat, logits = (f[k] for k in ("d1", "d2", "d3", "flat", "feat", "logits"))
         # ---- losses: 1.0 * mean(w_y ce) + 0.4 * mean(l2)
         stats = self.buf("stats", (4,), zero=True)
         probs = self.buf("probs", (B, self.n_class))
@@ -440,42 +454,15 @@ class TrainModel:
                 "l2_loss1_acc": l2hit / B}
 
     def _evaluate(self, S_tm, X_tm, y_d, B, T):
-        """Validation pass: the predict graph (moving statistics, no dropout) through the same operators."""
-        n, L, Cc = T * B, SIGNAL_LEN, CNN_CH
-        bn_inf = lambda name, X, rows, Cn: self._bn_fwd(name, X, rows, Cn, False)
-        c1 = self.buf("c1", (n * L, Cc))
-        self._call("nrvt_conv1d_fwd", self._ptr(S_tm), self._ptr(self.p["conv1_k"]), self._ptr(self.p["conv1_b"]), self._ptr(c1), n, L, 1, Cc)
-        b1 = bn_inf("bn1", c1, n * L, Cc)
-        c2 = self.buf("c2", (n * L, Cc))
-        self._call("nrvt_conv1d_fwd", self._ptr(b1), self._ptr(self.p["conv2_k"]), self._ptr(self.p["conv2_b"]), self._ptr(c2), n, L, Cc, Cc)
-        res = bn_inf("bn2", c2, n * L, Cc)
-        self._call("nrvt_add_bcast", self._ptr(res), self._ptr(S_tm), n * L, Cc)
-        out0 = self._lstm_fwd(0, X_tm, 6, 6, T, B)
-        r1 = bn_inf("bnr0", out0, n, 32)
-        out1 = self._lstm_fwd(1, r1, 32, 32, T, B)
-        r2 = bn_inf("bnr1", out1, n, 128)
-        tot = self.buf("tot", (n, 192))
-        self._call("nrvt_copy2d", self._ptr(tot), 192, self._ptr(r2), 128, n, 128, 0)
-        self.gemm(0, 0, n, 64, L * Cc, res, L * Cc, self.p["sig_k"], 64, tot, 192, co=128)
-        self._call("nrvt_bias_act", self._ptr(tot, 128), n, 64, 192, self._ptr(self.p["sig_b"]), 0)
-        out2 = self._lstm_fwd(2, tot, 192, 192, T, B)
-        t1 = bn_inf("bnr2", out2, n, 256)
-        out3 = self._lstm_fwd(3, t1, 256, 256, T, B)
-        d1 = self._dense_fwd("d1", out3, 128, n, 128, 128, True, "d1")
-        d2 = self._dense_fwd("d2", d1, 128, n, 128, 32, True, "d2")
-        d3 = self._dense_fwd("m", d2, 32, n, 32, 6, True, "d3")
-        flat = self.buf("flat", (B, T * 6))
-        for t in range(T):
-            self._call("nrvt_copy2d", self._ptr(flat, t * 6), T * 6, self._ptr(d3, t * B * 6), 6, B, 6, 0)
-        feat = self._dense_fwd("f", flat, T * 6, B, T * 6, CENTER_DIM, True, "feat")
-        logits = self._dense_fwd("o", feat, CENTER_DIM, B, CENTER_DIM, self.n_class, False, "logits")
+        """Validation pass: the predict graph (moving statistics, no dropout) through the same operators, and the two loss terms."""
+        f = self._forward(S_tm, X_tm, B, T, False)
         stats = self.buf("stats", (4,), zero=True)
         probs = self.buf("probs", (B, self.n_class))
         dlog = self.buf("dlogits", (B, self.n_class))
-        self._call("nrvt_softmax_ce", self._ptr(logits), C.c_void_p(y_d.data_ptr()), None, self._ptr(probs), self._ptr(dlog), self._ptr(stats),
+        self._call("nrvt_softmax_ce", self._ptr(f["logits"]), C.c_void_p(y_d.data_ptr()), None, self._ptr(probs), self._ptr(dlog), self._ptr(stats),
                    B, self.n_class, 0.0)
         scratch_f, scratch_c = self.buf("ev_dfeat", (B, CENTER_DIM), zero=True), self.buf("ev_dcent", (self.n_class, CENTER_DIM), zero=True)
-        self._call("nrvt_center_loss", self._ptr(feat), C.c_void_p(y_d.data_ptr()), self._ptr(self.p["centers"]), self._ptr(scratch_f),
+        self._call("nrvt_center_loss", self._ptr(f["feat"]), C.c_void_p(y_d.data_ptr()), self._ptr(self.p["centers"]), self._ptr(scratch_f),
                    self._ptr(scratch_c), self._ptr(stats), B, CENTER_DIM, 0.0)
         return self._metrics(stats, B)
 
