@@ -7,7 +7,7 @@
  * stream).  All calls are asynchronous on that stream and return 0, or a negative value when the launch was rejected
  * (nrvt_last_error() has the text).  Nothing here falls back to the CPU.
  *
- * A first, correct form: fp32 SIMT kernels, one launch per operator and LSTM timestep (a training step is ~600 calls, which
+ * A first, correct form: one launch per operator and LSTM timestep (the GEMM on the tensor cores as 3 x TF32, the rest fp32 SIMT) (a training step is ~600 calls, which
  * train.py captures into a CUDA graph: nothing here allocates or synchronises, per-step scalars are read from device memory);
  * gradients are checked against an fp64 autograd graph of the same network in tests/test_train_gpu.py.
  */

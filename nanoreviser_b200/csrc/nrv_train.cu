@@ -1,8 +1,9 @@
 // Training operators (include/nrv_train.h): forward + backward of the layers of nanorevutils/lstmmodel.py:32-133 and
 // nanorevcnn.py:17-38 in training mode, the two losses of the train model (lstmmodel.py:65-74) and the Adam update.
-// fp32 SIMT kernels, one per operator; the orchestration (which tensors, which order) is nanoreviser_b200/train.py.
-// A training step is launch-bound at the reference's batch size (512 windows); these kernels are written for being
-// right first: tests/test_train_gpu.py holds every gradient against an fp64 autograd graph of the same network.
+// One kernel per operator (the GEMM on the tensor cores as 3 x TF32, the rest fp32 SIMT); the orchestration (which tensors, which
+// order, the CUDA graph around a step) is nanoreviser_b200/train.py.  A training step at the reference's batch size (512 windows) is a
+// chain of ~740 small dependent launches; these kernels are written for being right first: tests/test_train_gpu.py holds every
+// gradient against an fp64 autograd graph of the same network.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,18 +34,35 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// GEMM: 64 x 64 tile of C per CTA, K in steps of 16, 4 x 4 outputs per thread
+// GEMM: 64 x 64 tile of C per CTA, K in steps of 16.  The products run on the tensor cores as 3 x TF32 (mma.sync m16n8k8):
+// every fp32 operand is split into hi = tf32(x) and lo = tf32(x - hi) and a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo with fp32
+// accumulation, which keeps fp32-level accuracy (the gradient tests hold every tensor to 1e-3 of fp64 autograd, measured 1e-6 .. 3e-5).
+// 8 warps as 2 (M) x 4 (N): a warp owns a 32 x 16 sub-tile = 2 x 2 MMA tiles.
 // ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // SPLITK: blockIdx.z owns the K range [z * kchunk, (z + 1) * kchunk) and ADDS alpha * partial into C with atomics (C holds beta * C
 // already): the weight-gradient products X^T dZ have K = all rows of the batch (thousands) and a C of a few tiles only
 template <bool TA, bool TB, bool SPLITK>
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float beta,
             float* __restrict__ C, int ldc, int kchunk) {
-    __shared__ float As[16][64 + 4], Bs[16][64 + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int LD = 72;                               // row stride of the staged tiles: fragment loads hit 32 distinct banks
+    __shared__ float As[16][LD], Bs[16][LD];             // As[k][m], Bs[k][n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4] = {};
+    float acc[2][2][4] = {};
     const int kbeg = SPLITK ? blockIdx.z * kchunk : 0;
     const int kend = SPLITK ? min(K, kbeg + kchunk) : K;
     for (int k0 = kbeg; k0 < kend; k0 += 16) {
@@ -68,30 +86,47 @@ gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int l
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
+        for (int ks = 0; ks < 16; ks += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+            for (int mi = 0; mi < 2; ++mi) {             // A fragment (16 x 8, row): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)
+                const int r = wm + mi * 16 + g;
+                tf32_split(As[ks + t][r], ah[mi][0], al[mi][0]);
+                tf32_split(As[ks + t][r + 8], ah[mi][1], al[mi][1]);
+                tf32_split(As[ks + t + 4][r], ah[mi][2], al[mi][2]);
+                tf32_split(As[ks + t + 4][r + 8], ah[mi][3], al[mi][3]);
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int ni = 0; ni < 2; ++ni) {             // B fragment (8 x 8, col): b0 (k = t, n = g) b1 (k = t + 4, n = g)
+                const int c = wn + ni * 8 + g;
+                tf32_split(Bs[ks + t][c], bh[ni][0], bl[ni][0]);
+                tf32_split(Bs[ks + t + 4][c], bh[ni][1], bl[ni][1]);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+                    mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+                    mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+                }
         }
         __syncthreads();
     }
+    // C fragment: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn >= N) continue;
-            float* c = C + (size_t)gm * ldc + gn;
-            if (SPLITK) atomicAdd(c, alpha * acc[i][j]);
-            else *c = beta == 0.f ? alpha * acc[i][j] : fmaf(alpha, acc[i][j], beta * *c);
-        }
-    }
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = m0 + wm + mi * 16 + g + (e >> 1) * 8, gn = n0 + wn + ni * 8 + 2 * t + (e & 1);
+                if (gm >= M || gn >= N) continue;
+                float* c = C + (size_t)gm * ldc + gn;
+                const float v = acc[mi][ni][e];
+                if (SPLITK) atomicAdd(c, alpha * v);
+                else *c = beta == 0.f ? alpha * v : fmaf(alpha, v, beta * *c);
+            }
 }
 
 // C[M,N] (ldc) *= beta (beta == 0: set to zero, also over NaNs)
@@ -455,18 +490,27 @@ int nrvt_gemm(void* stream, int ta, int tb, int M, int N, int K, float alpha, co
     if (M <= 0 || N <= 0) return 0;
     if (K < 0 || !A || !B || !C) return bad("nrvt_gemm: bad arguments");
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    // few output tiles and a long K (the weight gradients): split K over the grid's z dimension
+    // few output tiles for the K at hand (the weight gradients: K = all rows of the batch; the per-timestep recurrent products:
+    // 16 tiles): split K over the grid's z dimension so that the launch fills the SMs
     const int tiles = (int)(grid.x * grid.y);
-    if (ta && !tb && K >= 1024 && tiles < 148) {
-        const int splits = std::min((K + 255) / 256, std::max(1, 592 / tiles));
-        const int kchunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
+    const int splits = std::min(K / 64, 592 / std::max(tiles, 1));
+    const bool splitk = tiles < 74 && splits >= 2;
+    int kchunk = 0;
+    if (splitk) {
+        kchunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
         grid.z = (K + kchunk - 1) / kchunk;
         scale2d_kernel<<<blocks_for((int64_t)M * N, 256), 256, 0, S(stream)>>>(C, M, N, ldc, beta);
-        gemm_kernel<true, false, true><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kchunk);
-    } else if (!ta && !tb) gemm_kernel<false, false, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
-    else if (!ta && tb) gemm_kernel<false, true, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
-    else if (ta && !tb) gemm_kernel<true, false, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
-    else gemm_kernel<true, true, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+    }
+#define NRVT_GEMM(TA_, TB_)                                                                                                         \
+    do {                                                                                                                            \
+        if (splitk) gemm_kernel<TA_, TB_, true><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kchunk); \
+        else gemm_kernel<TA_, TB_, false><<<grid, 256, 0, S(stream)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);            \
+    } while (0)
+    if (!ta && !tb) NRVT_GEMM(false, false);
+    else if (!ta && tb) NRVT_GEMM(false, true);
+    else if (ta && !tb) NRVT_GEMM(true, false);
+    else NRVT_GEMM(true, true);
+#undef NRVT_GEMM
     LAUNCH_CHECK("nrvt_gemm");
     return 0;
 }

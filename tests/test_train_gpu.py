@@ -175,7 +175,8 @@ def test_adam_and_moving_average_updates(weights_by_species):
 def test_graph_replay_equals_eager_steps(weights_by_species):
     """train_on_batch(graph=True) -- the step captured into a CUDA graph on its third call and replayed afterwards, with a
     validation pass of another batch size in between -- leaves the same parameters as the eager launches (same seeds, same masks:
-    the dropout mask is a function of (seed, step, element) read from device scalars)."""
+    the dropout mask is a function of (seed, step, element) read from device scalars).  "The same" is to fp32 rounding, not bitwise:
+    the split-K products accumulate with atomics, whose order differs from run to run (eager against eager as well)."""
     import torch
     from nanoreviser_b200 import train
     w = weights_by_species("ecoli")[0]
@@ -194,11 +195,11 @@ def test_graph_replay_equals_eager_steps(weights_by_species):
         models.append((tm, losses))
     (a, la), (b, lb) = models
     assert "graph" in next(iter(b._graphs.values())) and not a._graphs
-    assert np.allclose(la, lb, rtol=1e-5), (la, lb)
+    assert np.allclose(la, lb, rtol=1e-4), (la, lb)
     for k in a.p:
-        assert np.allclose(a.p[k].cpu().numpy(), b.p[k].cpu().numpy(), rtol=1e-5, atol=1e-7), k
+        assert np.allclose(a.p[k].cpu().numpy(), b.p[k].cpu().numpy(), rtol=1e-4, atol=2e-6), k
     for k in a.s:
-        assert np.allclose(a.s[k].cpu().numpy(), b.s[k].cpu().numpy(), rtol=1e-5, atol=1e-7), k
+        assert np.allclose(a.s[k].cpu().numpy(), b.s[k].cpu().numpy(), rtol=1e-4, atol=2e-6), k
 
 
 def test_fit_learns_and_the_saved_weights_drive_the_inference_engine(tmp_path):
