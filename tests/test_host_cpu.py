@@ -280,7 +280,8 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     mirrors = {"nrv_batch": engine._Batch, "nrv_result": engine._Result, "nrv_model_weights": engine._ModelWeights,
                "nrv_lstm_dir": engine._LstmDir}
-    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "nrv.h"', 'int main(void) {']
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "nrv.h"', '#include "nrv_train.h"   /* plain C as well */', 'int main(void) {',
+             '(void)sizeof(&nrvt_adam);   /* declared, not linked */']
     for cname, cls in mirrors.items():
         lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
         for fname, _ in cls._fields_:
