@@ -516,10 +516,17 @@ class TrainModel:
             st["in"] = (S_tm.clone(), X_tm.clone(), y_d.clone())
             st["cw"] = self._class_weight_tensor(class_weight)
             torch.cuda.synchronize(self.dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                st["stats"] = self._train_device(st["in"][0], st["in"][1], st["in"][2], B, T, st["cw"], None)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["stats"] = self._train_device(st["in"][0], st["in"][1], st["in"][2], B, T, st["cw"], None)
+                    self._apply_device()
+            except Exception as e:          # capture refused (nothing has executed): keep launching this batch size eagerly, loudly
+                print("[nanoreviser_b200.train] CUDA graph capture failed (%s); launching the steps one by one" % e)
+                st["seen"] = -(1 << 60)
+                stats = self._train_device(S_tm, X_tm, y_d, B, T, st["cw"], None)
                 self._apply_device()
+                return self._metrics(stats, B)
             st["graph"] = g                 # (the capture itself does not execute: the replay below is this batch's step)
         for dst, src in zip(st["in"], (S_tm, X_tm, y_d)):
             dst.copy_(src)
