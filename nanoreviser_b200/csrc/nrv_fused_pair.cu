@@ -109,6 +109,23 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, in
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy encodings as CUTLASS uses them: evict_first / evict_last, fraction 1)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_prefetch_2d_hint(const CUtensorMap* m, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint32_t bar_cta, int c0, int c1,
+                                                      uint64_t pol) {
+    asm volatile(
+        "{\n\t.reg .b32 remBar;\n\t"
+        "mapa.shared::cluster.u32 remBar, %2, %5;\n\t"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [remBar], "
+        "%6;\n\t}\n" ::"r"(tc::smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(bar_cta), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(cta));
@@ -214,7 +231,11 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                        // total_rnn1 only: tile_base != nullptr and tile_base[tile] >= 0 -> the last K-chunk (CNN features) of that window
                        // tile is rows tile_base[tile] + t .. + 127 of the per-base feature table (tm_sf_hi / tm_sf_lo) instead of x
                        const __grid_constant__ CUtensorMap tm_sf_hi, const __grid_constant__ CUtensorMap tm_sf_lo,
-                       const int32_t* __restrict__ tile_base) {
+                       const int32_t* __restrict__ tile_base,
+                       // != 0: L2 eviction hints on the x tiles.  The forward and the backward cluster of a window tile read x_t at steps t
+                       // and T-1-t: the first of the two readers asks L2 to keep the tile (evict_last), the second marks it dead
+                       // (evict_first) -- total_rnn2's working set per round (213 MB) does not fit L2 without that
+                       int l2hint) {
     using Cfg = FpCfg<KIN, UT>;
     constexpr int KC = Cfg::KC, NP = Cfg::NP, CS = 2 * NP, FP_STAGES = Cfg::STAGES;
     constexpr int NT = 4 * UT;                              // gate columns per direction
@@ -308,7 +329,12 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                     if (s + 1 < T) {                                       // next step's tiles -> L2 (the layer input comes from HBM: ring
                         const int gnext = grow + (dir ? -1 : 1) * (int)nwp;   // loads then see L2 latency, which 3-4 stages cover)
                         const int kx = tb >= 0 ? KC - 1 : KC;
-                        for (int i = 0; i < kx; ++i) { tma_prefetch_2d(&tm_x_lo, i * XLO_W, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                        if (l2hint) {
+                            const uint64_t pn = (2 * (s + 1) + 1 < T) ? L2_EVICT_LAST : L2_EVICT_FIRST;
+                            for (int i = 0; i < kx; ++i) { tma_prefetch_2d_hint(&tm_x_lo, i * XLO_W, gnext, pn); tma_prefetch_2d_hint(&tm_x_hi, i * 64, gnext, pn); }
+                        } else {
+                            for (int i = 0; i < kx; ++i) { tma_prefetch_2d(&tm_x_lo, i * XLO_W, gnext); tma_prefetch_2d(&tm_x_hi, i * 64, gnext); }
+                        }
                         if (tb >= 0) { tma_prefetch_2d(&tm_sf_lo, 0, tb + t + (dir ? -1 : 1)); tma_prefetch_2d(&tm_sf_hi, 0, tb + t + (dir ? -1 : 1)); }
                     }
                     for (int i = 0; i < 2 * KC; ++i) {                     // (K-chunk, part): lo tile (F8: the 8-bit copies) first, then hi
@@ -316,6 +342,9 @@ lstm_fused_pair_kernel(const __half* __restrict__ wk_hi, const __half* __restric
                         if (r == 0) mbar_arrive_expect_tx(&full[stage], 2 * FP_TILE);
                         if (tb >= 0 && (i >> 1) == KC - 1)
                             tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_sf_hi : &tm_sf_lo, &full[stage], leader, 0, tb + t);
+                        else if (l2hint)
+                            tma_load_2d_pair_hint(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_x_hi : &tm_x_lo, &full[stage], leader,
+                                                  (i >> 1) * ((i & 1) ? 64 : XLO_W), grow, (2 * s + 1 < T) ? L2_EVICT_LAST : L2_EVICT_FIRST);
                         else
                             tma_load_2d_pair(s_ring + (size_t)stage * FP_TILE, (i & 1) ? &tm_x_hi : &tm_x_lo, &full[stage], leader,
                                              (i >> 1) * ((i & 1) ? 64 : XLO_W), grow);
@@ -650,8 +679,12 @@ static int launch_fused_pair_t(const LstmLayerDev& L, const __half* x_hi, const 
     const __half* wr_hi = F8W ? (const __half*)L.f8_wr_hi : (const __half*)L.rt_hi;
     const __half* wr_lo = RF8 ? reinterpret_cast<const __half*>(L.f8_wr8) : (F8W ? (const __half*)L.f8_wr_lo : (const __half*)L.rt_lo);
     if (!wk_hi || !wk_lo || !wr_hi || !wr_lo) return -1;
+    // NRV_L2HINT=1: eviction hints on total_rnn2's input tiles (experiment switch, see the kernel parameter)
+    static const int l2hint_env = getenv("NRV_L2HINT") ? atoi(getenv("NRV_L2HINT")) : 0;
+    const int l2hint = (UT == 64) ? l2hint_env : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wk_hi, wk_lo, wr_hi, wr_lo, (const float*)L.bias_tc, txh, txl, io.out_hi, io.out_lo,
-                                             io.out_ld, nwp, T, F8W ? L.f8_acc_scale : 1.0f, tsh, tsl, sig_table ? io.tile_base : (const int32_t*)nullptr);
+                                             io.out_ld, nwp, T, F8W ? L.f8_acc_scale : 1.0f, tsh, tsl, sig_table ? io.tile_base : (const int32_t*)nullptr,
+                                             l2hint);
     if (e != cudaSuccess) {
         fprintf(stderr, "[nrv] lstm_fused_pair<%d,%d>: launch (grid %u x 2, cluster %d, %zu B smem): %s\n", KIN, UT, cfg.gridDim.x, CS,
                 (size_t)Cfg::SMEM, cudaGetErrorString(e));
