@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/nrv_train.h"
@@ -416,7 +417,7 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_
 
 __global__ void center_loss_kernel(const float* __restrict__ feat, const int32_t* __restrict__ labels, const float* __restrict__ centers,
                                    float* __restrict__ dfeat, float* __restrict__ dcenters, float* __restrict__ stats, int B, int dim,
-                                   float scale) {
+                                   float scale, int centers_elsewhere) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float l2 = 0.f;
     if (i < B * dim) {
@@ -426,7 +427,7 @@ __global__ void center_loss_kernel(const float* __restrict__ feat, const int32_t
         l2 = d * d;
         const float g = scale * 2.f * d;
         dfeat[i] += g;
-        atomicAdd(&dcenters[y * dim + k], -g);
+        if (!centers_elsewhere) atomicAdd(&dcenters[y * dim + k], -g);
     }
     // per-sample sum over the dim (= 16: half a warp) lanes of a sample, then Keras' "accuracy" of this output against its all-zero
     // target: binary_accuracy = mean(round(l2_i) == 0), round half to even
@@ -439,6 +440,18 @@ __global__ void center_loss_kernel(const float* __restrict__ feat, const int32_t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { l2 += __shfl_xor_sync(0xffffffffu, l2, o); hit += __shfl_xor_sync(0xffffffffu, hit, o); }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[2], l2); atomicAdd(&stats[3], hit); }
+}
+
+// deterministic form of the centre gradient: block c, thread k sums the samples of class c in batch order (one writer per entry)
+__global__ void center_grad_det_kernel(const float* __restrict__ feat, const int32_t* __restrict__ labels, const float* __restrict__ centers,
+                                       float* __restrict__ dcenters, int B, int dim, float scale) {
+    const int c = blockIdx.x, k = threadIdx.x;
+    if (k >= dim) return;
+    float acc = 0.f;
+    bool any = false;
+    for (int b = 0; b < B; ++b)
+        if (labels[b] == c) { any = true; acc -= scale * 2.f * (feat[b * dim + k] - centers[c * dim + k]); }
+    if (any) dcenters[c * dim + k] += acc;
 }
 
 // keep-mask of Dropout(rate): a counter-based generator (the splitmix64 finaliser over (seed, step, element)), so that a step's
@@ -479,6 +492,14 @@ __global__ void ema_kernel(float* __restrict__ moving, const float* __restrict__
 
 bool pow2_le_256(int C) { return C >= 1 && C <= 256 && (C & (C - 1)) == 0; }
 
+// NRV_TRAIN_DETERMINISTIC=1: no fp32 atomics (split-K products, row-chunked column sums), so that a step does the same float
+// additions in the same order on every run; ~2x slower.  (The double-precision atomics of the batch-norm / conv-weight reductions
+// stay: their order changes bits far below the float the sums are rounded to.)
+bool deterministic() {
+    static const bool d = getenv("NRV_TRAIN_DETERMINISTIC") && atoi(getenv("NRV_TRAIN_DETERMINISTIC")) != 0;
+    return d;
+}
+
 }  // namespace
 
 extern "C" {
@@ -494,7 +515,7 @@ int nrvt_gemm(void* stream, int ta, int tb, int M, int N, int K, float alpha, co
     // 16 tiles): split K over the grid's z dimension so that the launch fills the SMs
     const int tiles = (int)(grid.x * grid.y);
     const int splits = std::min(K / 64, 592 / std::max(tiles, 1));
-    const bool splitk = tiles < 74 && splits >= 2;
+    const bool splitk = tiles < 74 && splits >= 2 && !deterministic();
     int kchunk = 0;
     if (splitk) {
         kchunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
@@ -531,7 +552,7 @@ int nrvt_relu_bwd(void* stream, float* dY, const float* Y, int64_t n) {
 
 int nrvt_colsum(void* stream, const float* X, int M, int N, int ldx, float* out, float beta) {
     if (N <= 0) return 0;
-    const int rchunk = 512;
+    const int rchunk = deterministic() ? std::max(M, 1) : 512;
     scale2d_kernel<<<blocks_for(N, 256), 256, 0, S(stream)>>>(out, 1, N, N, beta);
     colsum_kernel<<<dim3((N + 31) / 32, (std::max(M, 1) + rchunk - 1) / rchunk), 256, 0, S(stream)>>>(X, M, N, ldx, out, rchunk);
     LAUNCH_CHECK("nrvt_colsum");
@@ -647,7 +668,9 @@ int nrvt_softmax_ce(void* stream, const float* logits, const int32_t* labels, co
 int nrvt_center_loss(void* stream, const float* feat, const int32_t* labels, const float* centers, float* dfeat, float* dcenters,
                      float* stats, int B, int dim, float scale) {
     if (B * dim <= 0) return 0;
-    center_loss_kernel<<<blocks_for((int64_t)B * dim, 128), 128, 0, S(stream)>>>(feat, labels, centers, dfeat, dcenters, stats, B, dim, scale);
+    const int det = deterministic() ? 1 : 0;
+    center_loss_kernel<<<blocks_for((int64_t)B * dim, 128), 128, 0, S(stream)>>>(feat, labels, centers, dfeat, dcenters, stats, B, dim, scale, det);
+    if (det && dim <= 1024) center_grad_det_kernel<<<8, dim, 0, S(stream)>>>(feat, labels, centers, dcenters, B, dim, scale);   // classes < 8 (nrvt_softmax_ce)
     LAUNCH_CHECK("nrvt_center_loss");
     return 0;
 }

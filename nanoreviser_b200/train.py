@@ -27,6 +27,8 @@ here); the gradients themselves are pinned against an fp
     ``{output_name: ...}`` and therefore applies NO class weights to either output; ``class_weight_mode='keras'`` (default)
     reproduces that, ``'applied'`` weights the cross-entropy samples the way the reference's author evidently intended;
   * Adam: lr 1e-3, beta 0.9 / 0.999, epsilon 1e-7, the bias correction folded into the step size (keras/optimizers.py Adam).
+Runs with the same seeds agree to fp32 rounding (split-K products accumulate with atomics); NRV_TRAIN_DETERMINISTIC=1 makes them
+bit-identical at about a third of the speed.
 """
 from __future__ import annotations
 

@@ -202,6 +202,36 @@ def test_graph_replay_equals_eager_steps(weights_by_species):
         assert np.allclose(a.s[k].cpu().numpy(), b.s[k].cpu().numpy(), rtol=1e-4, atol=2e-6), k
 
 
+def test_deterministic_mode_is_bitwise_reproducible():
+    """NRV_TRAIN_DETERMINISTIC=1 (no fp32 atomics: no split-K, whole-column sums, the centre gradient by one writer per entry):
+    two processes with the same seeds end with bit-identical parameters and moving statistics after five steps."""
+    import hashlib
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from nanoreviser_b200 import train\n"
+        "import test_train_gpu as T\n"
+        "rng = np.random.default_rng(2)\n"
+        "tm = train.TrainModel(window=11, n_class=6, seed=9)\n"
+        "for k in range(5):\n"
+        "    S, X, y, _ = T._inputs(rng, 48, 11, 6); X[..., 4:6] /= 100.0\n"
+        "    tm.train_on_batch(S, X, y, class_weight={0: 3, 1: 5}, graph=(k >= 1))\n"
+        "h = hashlib.sha256()\n"
+        "for d in (tm.p, tm.s):\n"
+        "    for k in sorted(d): h.update(d[k].cpu().numpy().tobytes())\n"
+        "print('HASH', h.hexdigest())\n") % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, NRV_TRAIN_DETERMINISTIC="1")
+    outs = []
+    for _ in range(2):
+        p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append([l for l in p.stdout.splitlines() if l.startswith("HASH")][0])
+    assert outs[0] == outs[1], outs
+
+
 def test_fit_learns_and_the_saved_weights_drive_the_inference_engine(tmp_path):
     """Model.fit semantics end to end on a learnable synthetic task (the label is a function of the centre base's colour column),
     then the Keras-layout weight file goes through weights.load_model_weights into the inference engine, whose probabilities
