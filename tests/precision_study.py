@@ -106,15 +106,26 @@ W8_KERNEL_SCALES = [False]
 HEADS_D1_ONLY = [False]
 H_SCALES = [8, 19]     # log2 scales of the 8-bit copies of h (hi, lo)
 PROJ_F16_LAYERS = []   # --proj-f16-layers: layers whose PROJECTION stays f16x3 while their recurrence runs the emulated mode
+PROJ_SPLIT = {}        # --proj-split LAYER COLS: that layer's projection runs the emulated mode on its first COLS input columns only (the
+                       # raw h of the layer below) and f16x3 on the rest (total_rnn1: the 64 CNN-feature columns, which are unbounded)
 REC_MODE = [None]      # --rec-mode: how the recurrent product h @ Wr of the emulated layers is evaluated (default: same as the projection)
 
 
-def lstm_dir(mode, x, wk, wr, bias, reverse, xs_hi, xs_lo, proj_f16=False):
+def _rows(w, a, b):
+    return {k: (v[a:b] if hasattr(v, "shape") and getattr(v, "ndim", 0) == 2 else v) for k, v in w.items()}
+
+
+def lstm_dir(mode, x, wk, wr, bias, reverse, xs_hi, xs_lo, proj_f16=False, split=0):
     """x [B, T, in] (fp32 torch) -> [B, T, u]; h is in [-1, 1]: 8-bit copies scaled by 2^8 (hi) / 2^19 (lo)"""
     B, T, _ = x.shape
     u = wr["W"].shape[0]
     pm = Mode("f16x3") if (proj_f16 and mode.name != "f32") else mode
-    zin = pm.mm(x.reshape(B * T, -1), wk, xs_hi, xs_lo).reshape(B, T, 4 * u) + bias
+    x2 = x.reshape(B * T, -1)
+    if split and mode.name not in ("f32", "f16x3"):
+        zin = (mode.mm(x2[:, :split], _rows(wk, 0, split), H_SCALES[0], H_SCALES[1]) +
+               Mode("f16x3").mm(x2[:, split:], _rows(wk, split, x2.shape[1]))).reshape(B, T, 4 * u) + bias
+    else:
+        zin = pm.mm(x2, wk, xs_hi, xs_lo).reshape(B, T, 4 * u) + bias
     if REC_MODE[0] and mode.name != "f32":
         mode = Mode(REC_MODE[0])
     h = torch.zeros(B, u)
@@ -161,7 +172,7 @@ class Net:
     def bilstm(self, li, x, xs_hi=8, xs_lo=19):
         outs = []
         for k, (md, wk, wr, b) in enumerate(self.layers[li]):
-            outs.append(lstm_dir(md, x, wk, wr, b, k == 1, xs_hi, xs_lo, proj_f16=li in PROJ_F16_LAYERS))
+            outs.append(lstm_dir(md, x, wk, wr, b, k == 1, xs_hi, xs_lo, proj_f16=li in PROJ_F16_LAYERS, split=PROJ_SPLIT.get(li, 0)))
         return torch.cat(outs, dim=-1)
 
     def forward(self, sig_feat, X):
@@ -201,11 +212,15 @@ def main():
     ap.add_argument("--h-scales", nargs=2, type=int, default=[8, 19], help="log2 scales of the 8-bit copies of h: hi, lo (default 8 19; the unified format is 1 12)")
     ap.add_argument("--heads-d1-only", action="store_true", help="of the dense head only the first dense (input h of total_rnn2) runs the emulated mode")
     ap.add_argument("--kernel-scales", action="store_true", help="8-bit weight scales as pack_model derives them (S = 7 + b, activations unscaled)")
+    ap.add_argument("--proj-split", nargs=2, type=int, default=None, metavar=("LAYER", "COLS"),
+                    help="that layer's projection: emulated mode on the first COLS input columns, f16x3 on the rest (overrides --proj-f16-layers for it)")
     ap.add_argument("--base-mode", default="f16x3", help="mode of the tensor layers NOT listed in --layers (the GPU default is f16x3)")
     a = ap.parse_args()
     REC_MODE[0] = a.rec_mode
     BASE_MODE[0] = a.base_mode
     PROJ_F16_LAYERS[:] = a.proj_f16_layers
+    if a.proj_split:
+        PROJ_SPLIT[a.proj_split[0]] = a.proj_split[1]
     W8_KERNEL_SCALES[0] = a.kernel_scales
     HEADS_D1_ONLY[0] = a.heads_d1_only
     H_SCALES[:] = a.h_scales
