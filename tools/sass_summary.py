@@ -10,7 +10,7 @@ counts, cur = collections.OrderedDict(), None
 for ln in sass.split("\n"):
     m = re.search(r"Function : (\S+)", ln)
     if m:
-        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0].replace("nrv::", "").replace("void ", "")
+        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "").split("(")[0].replace("nrv::", "").replace("void ", "")
         counts[cur] = collections.Counter()
         continue
     if cur is None:
